@@ -1,0 +1,241 @@
+// ORACLE (test infrastructure) — laserOdometry.cpp restated: TransformToStart (LO:77-95), Distance
+// (LO:153-162), graph_based_correspondence_vote_simple (LO:165-342) and one pass of the main loop
+// body (LO:425-896) for one synchronized set of feature clouds.
+//
+// fp conventions: association distances are fp32 expressions promoted to double on assignment
+// (LO:514-519 etc.); TransformToStart computes in fp64 and stores fp32; the vote is fp32 sqrt/exp.
+#include "orc_api.h"
+#include "orc_jet.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace orc {
+
+namespace {
+
+const double DISTANCE_SQ_THRESHOLD = 25;  // LO:29
+const double NEARBY_SCAN = 2.5;           // LO:30
+
+// LO:77-95 with DISTORTION 0 (s = 1.0)
+inline P4 transform_to_start(const P4& pi, const double para_q[4], const double para_t[3])
+{
+    const double s = 1.0;
+    const Quat<double> q_last_curr{para_q[0], para_q[1], para_q[2], para_q[3]};
+    const Quat<double> q_point_last = identity_slerp(s, q_last_curr);
+    const V3<double> t_point_last{s * para_t[0], s * para_t[1], s * para_t[2]};
+    const V3<double> point{pi.x, pi.y, pi.z};
+    const V3<double> un_point = rotate(q_point_last, point) + t_point_last;
+    return {(float)un_point.x, (float)un_point.y, (float)un_point.z, pi.i};
+}
+
+inline float Distance(const P4& a, const P4& b)  // LO:153-162
+{
+    float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    return std::sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+inline double sqdist(const P4& p, const P4& q)  // LO:514-519: fp32 expression, widened on assignment
+{
+    return (p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y) + (p.z - q.z) * (p.z - q.z);
+}
+
+struct compare_score {  // common.h:50-52
+    bool operator()(VertexVote const& ob1, VertexVote const& ob2) { return ob1.score > ob2.score; }
+};
+
+}  // namespace
+
+void graph_vote_simple(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected_idx,
+                       std::vector<float>* votes_out)
+{
+    const int cor_size_all = (int)correspondences.size();
+    const int number_of_region = corner_case ? 5 : 10;  // LO:179-188
+    const float score_threshold = 0.96;
+    if (votes_out) votes_out->assign(cor_size_all, 0.f);
+    for (int num_region = 0; num_region < number_of_region; num_region++) {  // LO:193
+        const int initial_pos = cor_size_all / number_of_region * (num_region);
+        const int end_pos = (num_region == number_of_region - 1) ? cor_size_all : cor_size_all / number_of_region * (num_region + 1);
+        const int cor_size = end_pos - initial_pos;
+        const CorreMatch* sel = correspondences.data() + initial_pos;
+        const float resolution = 1;
+        std::vector<VertexVote> vote_record(cor_size, VertexVote{0, 0.0f});
+        for (int i = 0; i < cor_size; i++) {  // LO:228-252 (the compatibility matrix is a dead store, LO:240-241)
+            vote_record[i].index = i;
+            for (int j = i + 1; j < cor_size; j++) {
+                const float s1 = Distance(sel[i].src, sel[j].src);
+                const float s2 = Distance(sel[i].tgt, sel[j].tgt);
+                const float dis_gap = std::abs(s1 - s2);
+                const float score = std::exp(-(dis_gap * dis_gap) / (resolution * resolution));
+                if (score < score_threshold) {
+                    vote_record[j].score += 1;
+                    vote_record[i].score += 1;
+                }
+            }
+        }
+        if (votes_out) for (int i = 0; i < cor_size; ++i) (*votes_out)[initial_pos + i] = vote_record[i].score;
+        std::sort(vote_record.begin(), vote_record.end(), compare_score());  // LO:255
+        // LO:257-330: the corner and plane branches are textually identical
+        const float selected_ratio = 0.90;
+        const float num_selected = selected_ratio * cor_size;
+        const float selected_count_ratio = 1;
+        const int donot_num_selected = (1 - selected_count_ratio) * cor_size;
+        for (int i = cor_size - 1; i >= 0; i--) {
+            if (i >= donot_num_selected) {
+                VertexVote obj;
+                if (sel[vote_record[i].index].index > (int)correspondences.size()) continue;
+                obj.index = sel[vote_record[i].index].index;
+                if (vote_record[i].score > num_selected) {
+                    obj.score = 0;
+                    break;
+                } else if (vote_record[i].score <= 50) {
+                    obj.score = 5.0;
+                } else {
+                    obj.score = 1;
+                }
+                selected_idx.push_back(obj);
+            }
+        }
+    }
+}
+
+void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<P4>& cornerPointsLessSharp,
+                    const std::vector<P4>& surfPointsFlat, const std::vector<P4>& surfPointsLessFlat)
+{
+    last_stats.clear();
+    if (!systemInited) {  // LO:427-431
+        systemInited = true;
+    } else {
+        const int cornerPointsSharpNum = (int)cornerPointsSharp.size();
+        const int surfPointsFlatNum = (int)surfPointsFlat.size();
+        const std::vector<P4>& laserCloudCornerLast = cornerLast;
+        const std::vector<P4>& laserCloudSurfLast = surfLast;
+        for (size_t opti_counter = 0; opti_counter < 3; ++opti_counter) {  // LO:439
+            OdomIterStats st{};
+            std::vector<ResidualBlock> problem;
+            last_corner_assoc.clear();
+            last_plane_assoc.clear();
+            int idx1[1];
+            float d1[1];
+
+            // LO:491-620 corner correspondences
+            for (int i = 0; i < cornerPointsSharpNum; ++i) {
+                const P4 pointSel = transform_to_start(cornerPointsSharp[i], para_q, para_t);
+                const float qf[3] = {pointSel.x, pointSel.y, pointSel.z};
+                if (kdCorner.knn(qf, 1, idx1, d1) < 1) continue;  // empty tree: PCL returns 0 neighbours
+                int closestPointInd = -1, minPointInd2 = -1;
+                if (d1[0] < DISTANCE_SQ_THRESHOLD) {
+                    closestPointInd = idx1[0];
+                    const int closestPointScanID = int(laserCloudCornerLast[closestPointInd].i);
+                    double minPointSqDis2 = DISTANCE_SQ_THRESHOLD;
+                    for (int j = closestPointInd + 1; j < (int)laserCloudCornerLast.size(); ++j) {  // increasing scan line
+                        if (int(laserCloudCornerLast[j].i) <= closestPointScanID) continue;
+                        if (int(laserCloudCornerLast[j].i) > (closestPointScanID + NEARBY_SCAN)) break;
+                        const double pointSqDis = sqdist(laserCloudCornerLast[j], pointSel);
+                        if (pointSqDis < minPointSqDis2) { minPointSqDis2 = pointSqDis; minPointInd2 = j; }
+                    }
+                    for (int j = closestPointInd - 1; j >= 0; --j) {  // decreasing scan line
+                        if (int(laserCloudCornerLast[j].i) >= closestPointScanID) continue;
+                        if (int(laserCloudCornerLast[j].i) < (closestPointScanID - NEARBY_SCAN)) break;
+                        const double pointSqDis = sqdist(laserCloudCornerLast[j], pointSel);
+                        if (pointSqDis < minPointSqDis2) { minPointSqDis2 = pointSqDis; minPointInd2 = j; }
+                    }
+                }
+                if (minPointInd2 >= 0) {  // LO:556-618
+                    const double cp[3] = {cornerPointsSharp[i].x, cornerPointsSharp[i].y, cornerPointsSharp[i].z};
+                    const double a[3] = {laserCloudCornerLast[closestPointInd].x, laserCloudCornerLast[closestPointInd].y, laserCloudCornerLast[closestPointInd].z};
+                    const double b[3] = {laserCloudCornerLast[minPointInd2].x, laserCloudCornerLast[minPointInd2].y, laserCloudCornerLast[minPointInd2].z};
+                    problem.push_back(make_edge(cp, a, b, 1.0));
+                    last_corner_assoc.push_back({i, closestPointInd, minPointInd2});
+                    st.corner_corr++;
+                }
+            }
+
+            // LO:653-793 plane correspondences
+            std::vector<CorreMatch> correspondences;
+            std::vector<ResidualBlock> plane_blocks;  // weight 1; re-weighted after the vote
+            std::vector<std::array<double, 12>> plane_pts;
+            int index = 0;
+            for (int i = 0; i < surfPointsFlatNum; ++i) {
+                const P4 pointSel = transform_to_start(surfPointsFlat[i], para_q, para_t);
+                const float qf[3] = {pointSel.x, pointSel.y, pointSel.z};
+                if (kdSurf.knn(qf, 1, idx1, d1) < 1) continue;
+                int closestPointInd = -1, minPointInd2 = -1, minPointInd3 = -1;
+                if (d1[0] < DISTANCE_SQ_THRESHOLD) {
+                    closestPointInd = idx1[0];
+                    const int closestPointScanID = int(laserCloudSurfLast[closestPointInd].i);
+                    double minPointSqDis2 = DISTANCE_SQ_THRESHOLD, minPointSqDis3 = DISTANCE_SQ_THRESHOLD;
+                    for (int j = closestPointInd + 1; j < (int)laserCloudSurfLast.size(); ++j) {
+                        if (int(laserCloudSurfLast[j].i) > (closestPointScanID + NEARBY_SCAN)) break;
+                        const double pointSqDis = sqdist(laserCloudSurfLast[j], pointSel);
+                        if (int(laserCloudSurfLast[j].i) <= closestPointScanID && pointSqDis < minPointSqDis2) {
+                            minPointSqDis2 = pointSqDis; minPointInd2 = j;
+                        } else if (int(laserCloudSurfLast[j].i) > closestPointScanID && pointSqDis < minPointSqDis3) {
+                            minPointSqDis3 = pointSqDis; minPointInd3 = j;
+                        }
+                    }
+                    for (int j = closestPointInd - 1; j >= 0; --j) {
+                        if (int(laserCloudSurfLast[j].i) < (closestPointScanID - NEARBY_SCAN)) break;
+                        const double pointSqDis = sqdist(laserCloudSurfLast[j], pointSel);
+                        if (int(laserCloudSurfLast[j].i) >= closestPointScanID && pointSqDis < minPointSqDis2) {
+                            minPointSqDis2 = pointSqDis; minPointInd2 = j;
+                        } else if (int(laserCloudSurfLast[j].i) < closestPointScanID && pointSqDis < minPointSqDis3) {
+                            minPointSqDis3 = pointSqDis; minPointInd3 = j;
+                        }
+                    }
+                    if (minPointInd2 >= 0 && minPointInd3 >= 0) {  // LO:723-791
+                        const P4& pa = laserCloudSurfLast[closestPointInd];
+                        const P4& pb = laserCloudSurfLast[minPointInd2];
+                        const P4& pc = laserCloudSurfLast[minPointInd3];
+                        plane_pts.push_back({(double)surfPointsFlat[i].x, (double)surfPointsFlat[i].y, (double)surfPointsFlat[i].z,
+                                             (double)pa.x, (double)pa.y, (double)pa.z, (double)pb.x, (double)pb.y, (double)pb.z,
+                                             (double)pc.x, (double)pc.y, (double)pc.z});
+                        CorreMatch cor;
+                        cor.index = index;
+                        cor.src = surfPointsFlat[i];
+                        cor.tgt = pa;
+                        cor.score = 0;
+                        cor.s = 1 / 1.0;
+                        correspondences.push_back(cor);
+                        index++;
+                        last_plane_assoc.push_back({i, closestPointInd, minPointInd2, minPointInd3});
+                        if (now_frame <= cfg.graph_from_frame) {  // LO:781-787
+                            const auto& pp = plane_pts.back();
+                            problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], 1.0, 1));
+                            st.plane_selected++;
+                        }
+                        st.plane_corr++;
+                    }
+                }
+            }
+            if (now_frame > cfg.graph_from_frame) {  // LO:794-810
+                std::vector<VertexVote> selected_idx;
+                graph_vote_simple(correspondences, false, selected_idx, nullptr);
+                for (size_t i = 0; i < selected_idx.size(); i++) {
+                    const auto& pp = plane_pts[selected_idx[i].index];
+                    problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], 1.0, selected_idx[i].score));
+                }
+                st.plane_selected = (int)selected_idx.size();
+            }
+            solve(problem, para_q, para_t, &st.solve, 4, true);  // LO:819-825
+            last_stats.push_back(st);
+        }
+        // LO:830-831
+        const Quat<double> qw{q_w_curr[0], q_w_curr[1], q_w_curr[2], q_w_curr[3]};
+        const Quat<double> ql{para_q[0], para_q[1], para_q[2], para_q[3]};
+        const V3<double> r = rotate(qw, V3<double>{para_t[0], para_t[1], para_t[2]});
+        t_w_curr[0] = t_w_curr[0] + r.x;
+        t_w_curr[1] = t_w_curr[1] + r.y;
+        t_w_curr[2] = t_w_curr[2] + r.z;
+        const Quat<double> qn = qmul(qw, ql);
+        q_w_curr[0] = qn.x; q_w_curr[1] = qn.y; q_w_curr[2] = qn.z; q_w_curr[3] = qn.w;
+    }
+    // LO:882-896: swap in the less-sharp / less-flat clouds and rebuild both kd-trees
+    cornerLast = cornerPointsLessSharp;
+    surfLast = surfPointsLessFlat;
+    kdCorner.build(cornerLast);
+    kdSurf.build(surfLast);
+    now_frame++;  // LO:926
+}
+
+}  // namespace orc
