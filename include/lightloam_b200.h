@@ -1,0 +1,127 @@
+/* lightloam_b200 — C ABI of the B200-native Light-LOAM per-scan hot path.
+ *
+ * The reference (BrenYi/Light-LOAM) has no plugin / FFI interface: the path is inlined in three ROS
+ * node bodies.  Each entry point below replaces one of those in-process bodies, cited by
+ * reference file:line (scanRegistration.cpp = SR, laserOdometry.cpp = LO, laserMapping.cpp = LM):
+ *
+ *   ll_extract_features   SR:100-377   everything between PointCloud2 decode and the 5 publishes
+ *   ll_odometry_step      LO:425-896   one pass of the odometry loop body incl. warm start + kd rebuild
+ *   ll_mapping_step       LM:1581-2168 one pass of process() between message decode and publish
+ *   ll_process_scans      the three chained on the device for `batch` independent scan streams
+ *
+ * Plain C99: opaque context, POD config, raw pointers + sizes, integer error codes, no exceptions.
+ * All `float*` clouds are packed x,y,z,intensity fp32 (16 B per point) unless a stride is given.
+ * A context is not thread-safe (the reference drives each node from one thread: SR:475, LO:380, LM:2397);
+ * different contexts are independent.  Every call is synchronous w.r.t. the context's CUDA stream
+ * unless stated otherwise.  There is no CPU fallback: without a CUDA device ll_create fails.
+ */
+#ifndef LIGHTLOAM_B200_H
+#define LIGHTLOAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LL_OK 0
+#define LL_E_INVAL (-1)      /* bad argument */
+#define LL_E_CAPACITY (-2)   /* input larger than the capacities given in ll_config */
+#define LL_E_CUDA (-3)       /* CUDA runtime error (message via ll_last_error) */
+#define LL_E_NCCL (-4)
+#define LL_E_EMPTY (-5)      /* no valid point in the scan (the reference would index points[0], SR:114) */
+#define LL_W_FEW_CORRESPONDENCES 1 /* warning, mirrors LO:814-817 / LM:2097-2100; results are still valid */
+
+typedef struct ll_ctx ll_ctx;
+
+/* ROS params + compile-time constants of the reference, one POD. */
+typedef struct ll_config {
+    int   scan_line;         /* SR:435  16 / 32 / 64 */
+    float minimum_range;     /* SR:438 */
+    float lower_bound;       /* SR:439  deg, 64-line formula */
+    float up_bound;          /* SR:440 */
+    float line_res;          /* LM:2363 mapping_line_resolution */
+    float plane_res;         /* LM:2364 mapping_plane_resolution */
+    int   skip_frame;        /* LO:350 (publication decimation only; kept for the nodes) */
+    int   graph_from_frame;  /* LO:781,794: planes are graph-voted when now_frame > this (5) */
+    int   device;            /* CUDA device ordinal */
+    int   batch;             /* number of independent scan streams ("lanes") processed per call */
+    int   max_points;        /* capacity: points per raw scan */
+    int   max_ring_points;   /* capacity: points in one ring after filtering */
+    int   map_capacity;      /* capacity: points per map cloud (corner / surf) in the 5x5x3 local map */
+    int   enable_mapping;    /* 0: ll_process_scans stops after odometry */
+    int   reserved[6];
+} ll_config;
+
+typedef struct ll_cloud_view {   /* caller-owned HOST memory */
+    const float* data;
+    int n;
+    int stride_bytes;            /* >= 12, multiple of 4; x,y,z at offsets 0,4,8 (PointCloud2 point_step) */
+} ll_cloud_view;
+
+typedef struct ll_cloud_out {    /* caller-owned HOST memory, float4 per point */
+    float* xyzi;
+    int n;                       /* out: points written */
+    int cap;                     /* in: capacity in points */
+} ll_cloud_out;
+
+typedef struct ll_stats {
+    int n_full, n_sharp, n_less_sharp, n_flat, n_less_flat;     /* last ll_extract_features / lane 0 */
+    int corner_corr[3], plane_corr[3], plane_selected[3];       /* per outer iteration of the last odometry step */
+    int lm_jacobian_evals[3], lm_cost_evals[3], lm_termination[3];
+    double initial_cost[3], final_cost[3];
+    int map_corner, map_surf, stack_corner, stack_surf, map_corner_corr, map_surf_corr;
+    int map_jacobian_evals[2], map_termination[2];
+    double map_initial_cost[2], map_final_cost[2];
+    int frame;                                                   /* now_frame of lane 0 */
+    int kernel_launches;                                         /* launches issued by the last call */
+} ll_stats;
+
+void ll_default_config(ll_config* cfg, int scan_line);   /* launch-file values for 16 / 32 / 64 lines */
+int  ll_create(const ll_config* cfg, ll_ctx** out);
+void ll_destroy(ll_ctx* ctx);
+const char* ll_strerror(int code);
+const char* ll_last_error(const ll_ctx* ctx);            /* detail of the last LL_E_CUDA */
+int  ll_get_last_stats(ll_ctx* ctx, ll_stats* out);
+int  ll_reset(ll_ctx* ctx);                              /* forget all streams' state (poses, last clouds, map) */
+
+/* SR:100-377.  Outputs may be NULL.  sharp_idx / less_sharp_idx / flat_idx are indices into `full`
+ * (capacities: 12 / 120 / 24 per ring).  Runs on lane 0. */
+int ll_extract_features(ll_ctx* ctx, ll_cloud_view scan, ll_cloud_out* full, ll_cloud_out* sharp, ll_cloud_out* less_sharp,
+                        ll_cloud_out* flat, ll_cloud_out* less_flat, int* sharp_idx, int* less_sharp_idx, int* flat_idx,
+                        float* curvature /* n_full floats or NULL */, int* ring_begin /* scan_line+1 or NULL */);
+
+/* LO:425-896 on lane 0 for one synchronized set of the four feature clouds (float4 xyzi, intensity =
+ * ring + 0.1*relTime).  Quaternions are x,y,z,w.  The first call only initialises (LO:427-431). */
+int ll_odometry_step(ll_ctx* ctx, ll_cloud_view sharp, ll_cloud_view less_sharp, ll_cloud_view flat, ll_cloud_view less_flat,
+                     double q_w_curr[4], double t_w_curr[3], double q_last_curr[4], double t_last_curr[3]);
+
+/* LM:1581-2168 on lane 0. */
+int ll_mapping_step(ll_ctx* ctx, ll_cloud_view corner_last, ll_cloud_view surf_last, const double q_wodom_curr[4],
+                    const double t_wodom_curr[3], double q_w_curr[4], double t_w_curr[3]);
+/* Pre-loads map-frame points into lane 0's cube map (config-3 style benchmarks; no reference equivalent). */
+int ll_map_insert(ll_ctx* ctx, ll_cloud_view corner, ll_cloud_view surf);
+
+/* Fused device pipeline: scan i of the call feeds lane i (n_scans <= batch).  Per lane the call is
+ * SR:100-377 -> LO:425-896 (-> LM:1581-2168 when enable_mapping), with features handed over in HBM.
+ * poses_out: n_scans x 14 doubles = odometry q_w_curr[4], t_w_curr[3], mapped q_w_curr[4], t_w_curr[3]
+ * (mapped = odometry when mapping is off). */
+int ll_process_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans, double* poses_out);
+/* The same split in two so a caller can keep inputs resident in HBM: stage = H2D only, run = kernels
+ * (+ D2H of the poses when poses_out != NULL). */
+int ll_stage_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);
+int ll_process_staged(ll_ctx* ctx, int n_scans, double* poses_out);
+
+/* Device-side timing of the last ll_process_staged / ll_process_scans: milliseconds between CUDA
+ * events recorded on the context stream around the feature, odometry and mapping kernel groups. */
+int ll_last_timings(ll_ctx* ctx, float ms[4] /* features, odometry, mapping, total */);
+/* Parity / debugging: association indices of the last outer iteration of lane `lane`.
+ * corner: n_sharp x {closest, minPointInd2} ; plane: n_flat x {closest, minPointInd2, minPointInd3, weight*1000}; -1 = none */
+int ll_debug_assoc(ll_ctx* ctx, int lane, int* corner, int corner_cap, int* plane, int plane_cap);
+/* Raw CUDA stream of the context (cudaStream_t as void*), so a host can order its own work after ours. */
+void* ll_cuda_stream(ll_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTLOAM_B200_H */

@@ -1,0 +1,218 @@
+"""ctypes binding of liblightloam_b200.so (include/lightloam_b200.h) — the same stub a maintainer of the
+reference would write over the C ABI.  Fails loudly when the CUDA library is missing: there is no CPU path.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblightloam_b200.so")
+_LIB = None
+
+LL_OK = 0
+LL_E_INVAL, LL_E_CAPACITY, LL_E_CUDA, LL_E_NCCL, LL_E_EMPTY = -1, -2, -3, -4, -5
+LL_W_FEW_CORRESPONDENCES = 1
+
+SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
+           "ll_extract_features", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
+           "ll_process_staged", "ll_last_timings", "ll_debug_assoc", "ll_cuda_stream"]
+
+
+class LLConfig(ctypes.Structure):
+    _fields_ = [("scan_line", ctypes.c_int), ("minimum_range", ctypes.c_float), ("lower_bound", ctypes.c_float),
+                ("up_bound", ctypes.c_float), ("line_res", ctypes.c_float), ("plane_res", ctypes.c_float),
+                ("skip_frame", ctypes.c_int), ("graph_from_frame", ctypes.c_int), ("device", ctypes.c_int),
+                ("batch", ctypes.c_int), ("max_points", ctypes.c_int), ("max_ring_points", ctypes.c_int),
+                ("map_capacity", ctypes.c_int), ("enable_mapping", ctypes.c_int), ("reserved", ctypes.c_int * 6)]
+
+
+class LLCloudView(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("n", ctypes.c_int), ("stride_bytes", ctypes.c_int)]
+
+
+class LLCloudOut(ctypes.Structure):
+    _fields_ = [("xyzi", ctypes.c_void_p), ("n", ctypes.c_int), ("cap", ctypes.c_int)]
+
+
+class LLStats(ctypes.Structure):
+    _fields_ = [("n_full", ctypes.c_int), ("n_sharp", ctypes.c_int), ("n_less_sharp", ctypes.c_int), ("n_flat", ctypes.c_int),
+                ("n_less_flat", ctypes.c_int), ("corner_corr", ctypes.c_int * 3), ("plane_corr", ctypes.c_int * 3),
+                ("plane_selected", ctypes.c_int * 3), ("lm_jacobian_evals", ctypes.c_int * 3), ("lm_cost_evals", ctypes.c_int * 3),
+                ("lm_termination", ctypes.c_int * 3), ("initial_cost", ctypes.c_double * 3), ("final_cost", ctypes.c_double * 3),
+                ("map_corner", ctypes.c_int), ("map_surf", ctypes.c_int), ("stack_corner", ctypes.c_int), ("stack_surf", ctypes.c_int),
+                ("map_corner_corr", ctypes.c_int), ("map_surf_corr", ctypes.c_int), ("map_jacobian_evals", ctypes.c_int * 2),
+                ("map_termination", ctypes.c_int * 2), ("map_initial_cost", ctypes.c_double * 2), ("map_final_cost", ctypes.c_double * 2),
+                ("frame", ctypes.c_int), ("kernel_launches", ctypes.c_int)]
+
+
+class LightLoamError(RuntimeError):
+    pass
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+
+
+def lib():
+    """Loads the CUDA library. Raises if it is missing — the product has no other path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise LightLoamError("liblightloam_b200.so not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.ll_strerror.restype = ctypes.c_char_p
+        L.ll_last_error.restype = ctypes.c_char_p
+        L.ll_last_error.argtypes = [ctypes.c_void_p]
+        L.ll_cuda_stream.restype = ctypes.c_void_p
+        L.ll_cuda_stream.argtypes = [ctypes.c_void_p]
+        L.ll_create.argtypes = [ctypes.POINTER(LLConfig), ctypes.POINTER(ctypes.c_void_p)]
+        L.ll_destroy.argtypes = [ctypes.c_void_p]
+        L.ll_reset.argtypes = [ctypes.c_void_p]
+        L.ll_get_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LLStats)]
+        L.ll_extract_features.argtypes = [ctypes.c_void_p, LLCloudView] + [ctypes.POINTER(LLCloudOut)] * 5 + [ctypes.c_void_p] * 5
+        L.ll_odometry_step.argtypes = [ctypes.c_void_p] + [LLCloudView] * 4 + [ctypes.c_void_p] * 4
+        L.ll_mapping_step.argtypes = [ctypes.c_void_p, LLCloudView, LLCloudView] + [ctypes.c_void_p] * 4
+        L.ll_map_insert.argtypes = [ctypes.c_void_p, LLCloudView, LLCloudView]
+        L.ll_process_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView), ctypes.c_void_p]
+        L.ll_stage_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
+        L.ll_process_staged.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.ll_last_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ll_debug_assoc.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        _LIB = L
+    return _LIB
+
+
+def default_config(scan_line=64, **overrides):
+    cfg = LLConfig()
+    lib().ll_default_config(ctypes.byref(cfg), scan_line)
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _view(a):
+    if a is None or len(a) == 0:
+        return LLCloudView(None, 0, 16)
+    assert a.dtype == np.float32 and a.ndim == 2 and a.flags["C_CONTIGUOUS"]
+    return LLCloudView(a.ctypes.data, a.shape[0], a.shape[1] * 4)
+
+
+class Context:
+    """One ll_ctx.  Mirrors the reference's three node bodies as methods."""
+
+    def __init__(self, cfg=None, **overrides):
+        self.L = lib()
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        h = ctypes.c_void_p()
+        rc = self.L.ll_create(ctypes.byref(self.cfg), ctypes.byref(h))
+        if rc != LL_OK:
+            raise LightLoamError("ll_create: %s" % self.L.ll_strerror(rc).decode())
+        self.h = h
+        self.R = self.cfg.scan_line
+        self.B = self.cfg.batch
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ll_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise LightLoamError("%s: %s (%s)" % (what, self.L.ll_strerror(rc).decode(), self.L.ll_last_error(self.h).decode()))
+        return rc
+
+    def reset(self):
+        self._check(self.L.ll_reset(self.h), "ll_reset")
+
+    def extract_features(self, points):
+        """scanRegistration.cpp:100-377. points: (n, 3..8) float32. Returns a dict like oracle/orc_py.extract_features."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        n, R = pts.shape[0], self.R
+        full = np.zeros((n, 4), np.float32)
+        sharp = np.zeros((R * 12, 4), np.float32)
+        lsharp = np.zeros((R * 120, 4), np.float32)
+        flat = np.zeros((R * 24, 4), np.float32)
+        lflat = np.zeros((n, 4), np.float32)
+        sidx = np.zeros(R * 12, np.int32)
+        lsidx = np.zeros(R * 120, np.int32)
+        fidx = np.zeros(R * 24, np.int32)
+        curv = np.zeros(n, np.float32)
+        rb = np.zeros(R + 1, np.int32)
+        outs = [LLCloudOut(a.ctypes.data, 0, a.shape[0]) for a in (full, sharp, lsharp, flat, lflat)]
+        rc = self.L.ll_extract_features(self.h, _view(pts), *[ctypes.byref(o) for o in outs], sidx.ctypes.data, lsidx.ctypes.data,
+                                        fidx.ctypes.data, curv.ctypes.data, rb.ctypes.data)
+        self._check(rc, "ll_extract_features")
+        nf, ns, nls, nfl, nlf = [o.n for o in outs]
+        return dict(full=full[:nf], ring_begin=rb, curvature=curv[:nf], sharp=sharp[:ns], less_sharp=lsharp[:nls], flat=flat[:nfl],
+                    less_flat=lflat[:nlf], sharp_idx=sidx[:ns], less_sharp_idx=lsidx[:nls], flat_idx=fidx[:nfl])
+
+    def odometry_step(self, sharp, less_sharp, flat, less_flat):
+        """laserOdometry.cpp:425-896 for one synchronized set of feature clouds (float32 (n,4))."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (sharp, less_sharp, flat, less_flat)]
+        qw, tw, ql, tl = np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(3)
+        rc = self.L.ll_odometry_step(self.h, *[_view(a) for a in arrs], qw.ctypes.data, tw.ctypes.data, ql.ctypes.data, tl.ctypes.data)
+        self._check(rc, "ll_odometry_step")
+        return dict(q_w=qw, t_w=tw, q_last=ql, t_last=tl, rc=rc)
+
+    def mapping_step(self, corner_last, surf_last, q_wodom, t_wodom):
+        """laserMapping.cpp:1581-2168."""
+        c = np.ascontiguousarray(corner_last, dtype=np.float32)
+        s = np.ascontiguousarray(surf_last, dtype=np.float32)
+        qi = np.ascontiguousarray(q_wodom, dtype=np.float64)
+        ti = np.ascontiguousarray(t_wodom, dtype=np.float64)
+        q, t = np.zeros(4), np.zeros(3)
+        rc = self.L.ll_mapping_step(self.h, _view(c), _view(s), qi.ctypes.data, ti.ctypes.data, q.ctypes.data, t.ctypes.data)
+        self._check(rc, "ll_mapping_step")
+        return dict(q=q, t=t, rc=rc)
+
+    def map_insert(self, corner, surf):
+        c = np.ascontiguousarray(corner, dtype=np.float32)
+        s = np.ascontiguousarray(surf, dtype=np.float32)
+        self._check(self.L.ll_map_insert(self.h, _view(c), _view(s)), "ll_map_insert")
+
+    def _views(self, scans):
+        self._keep = [np.ascontiguousarray(s, dtype=np.float32) for s in scans]
+        arr = (LLCloudView * len(scans))()
+        for i, a in enumerate(self._keep):
+            arr[i] = _view(a)
+        return arr
+
+    def process_scans(self, scans):
+        """Fused pipeline: scan i feeds lane i. Returns (n, 14) float64 poses."""
+        views = self._views(scans)
+        poses = np.zeros((len(scans), 14))
+        self._check(self.L.ll_process_scans(self.h, len(scans), views, poses.ctypes.data), "ll_process_scans")
+        return poses
+
+    def stage_scans(self, scans):
+        views = self._views(scans)
+        self._check(self.L.ll_stage_scans(self.h, len(scans), views), "ll_stage_scans")
+
+    def process_staged(self, n, want_poses=True):
+        poses = np.zeros((n, 14)) if want_poses else None
+        self._check(self.L.ll_process_staged(self.h, n, poses.ctypes.data if want_poses else None), "ll_process_staged")
+        return poses
+
+    def last_timings(self):
+        ms = np.zeros(4, np.float32)
+        self._check(self.L.ll_last_timings(self.h, ms.ctypes.data), "ll_last_timings")
+        return ms
+
+    def stats(self):
+        s = LLStats()
+        self._check(self.L.ll_get_last_stats(self.h, ctypes.byref(s)), "ll_get_last_stats")
+        return s
+
+    def debug_assoc(self, lane=0):
+        c = np.zeros((self.R * 12, 2), np.int32)
+        p = np.zeros((self.R * 24, 4), np.int32)
+        self._check(self.L.ll_debug_assoc(self.h, lane, c.ctypes.data, c.shape[0], p.ctypes.data, p.shape[0]), "ll_debug_assoc")
+        return c, p
+
+    def cuda_stream(self):
+        return self.L.ll_cuda_stream(self.h)

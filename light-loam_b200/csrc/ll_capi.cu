@@ -1,0 +1,418 @@
+// C ABI of liblightloam_b200 (include/lightloam_b200.h): context, staging, and the reference-facing calls.
+// No CPU fallback anywhere: every entry point runs the CUDA kernels or returns an error code.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "ll_ctx.h"
+
+size_t ll_feature_smem_bytes(int SCAP);
+
+namespace {
+
+struct ScanHdr { int n_raw, stride_words; };
+
+__global__ void k_set_scan_hdr(LaneState* lane, const ScanHdr* hdr, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_lanes) {
+        lane[b].n_raw = hdr[b].n_raw;
+        lane[b].stride_words = hdr[b].stride_words;
+        lane[b].err = 0;
+    }
+}
+
+__global__ void k_init_lanes(LaneState* lane, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_lanes) return;
+    LaneState z;
+    memset(&z, 0, sizeof(z));
+    z.para_q[3] = 1.0;  // LO:61
+    z.q_w[3] = 1.0;     // LO:57
+    z.map_par[3] = 1.0; // LM:81
+    z.q_wmap_wodom[3] = 1.0;  // LM:87
+    z.last_slot = 1;
+    z.cen[0] = 10; z.cen[1] = 10; z.cen[2] = 5;  // LM:42-44
+    lane[b] = z;
+}
+
+// odometry fed from host clouds: emulate what feature extraction leaves behind in the lane
+__global__ void k_set_feature_counts(LaneState* lane, int ns, int nls, int nf, int nlf)
+{
+    LaneState& L = lane[0];
+    L.cur = L.last_slot ^ 1;
+    L.n_sharp = ns; L.n_less_sharp = nls; L.n_flat = nf; L.n_less_flat = nlf;
+    L.err = 0;
+}
+
+int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <typename T>
+cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, n * sizeof(T)); }
+
+// smallest fp32 t >= 0 with expf(-t) < 0.96f under this host's libm: LO:239-242 decides votes with
+// `std::exp(-(gap*gap)) < 0.96f`; the device compares gap*gap >= t instead of evaluating exp.
+float calibrate_vote_threshold()
+{
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto flt = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    uint32_t lo = bits(0.03f);  // expf(-0.03) = 0.970 >= 0.96
+    uint32_t hi = bits(0.05f);  // expf(-0.05) = 0.951 <  0.96
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (expf(-flt(mid)) < 0.96f) hi = mid; else lo = mid;
+    }
+    return flt(hi);
+}
+
+int copy_view_to_device(ll_ctx* c, const ll_cloud_view& v, float4* dst, int cap)
+{
+    if (v.n < 0 || v.n > cap) return LL_E_CAPACITY;
+    if (v.n == 0) return LL_OK;
+    if (!v.data || v.stride_bytes < 12 || (v.stride_bytes & 3)) return LL_E_INVAL;
+    if (v.stride_bytes == 16) {
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        LL_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, 16, v.data, v.stride_bytes, 16 <= v.stride_bytes ? 16 : 12, v.n, cudaMemcpyHostToDevice, c->stream));
+    }
+    return LL_OK;
+}
+
+int copy_out(ll_ctx* c, ll_cloud_out* o, const float4* src, int n)
+{
+    if (!o) return LL_OK;
+    o->n = 0;
+    if (n > o->cap) return LL_E_CAPACITY;
+    if (n > 0 && o->xyzi) LL_CUDA_CHECK(c, cudaMemcpyAsync(o->xyzi, src, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    o->n = n;
+    return LL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ll_default_config(ll_config* cfg, int scan_line)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->scan_line = scan_line;
+    // launch/aloam_velodyne_HDL_64.launch:2-12 ; launch/aloam_velodyne_VLP_16.launch:3-13 (HDL-32 identical)
+    cfg->minimum_range = scan_line == 64 ? 5.0f : 0.3f;
+    cfg->lower_bound = -24.9f;  // SR:439
+    cfg->up_bound = 2.0f;       // SR:440
+    cfg->line_res = scan_line == 64 ? 0.4f : 0.2f;
+    cfg->plane_res = scan_line == 64 ? 0.8f : 0.4f;
+    cfg->skip_frame = 1;
+    cfg->graph_from_frame = 5;
+    cfg->device = 0;
+    cfg->batch = 1;
+    cfg->max_points = scan_line == 64 ? 131072 : (scan_line == 32 ? 73728 : 32768);
+    cfg->max_ring_points = 3083;
+    cfg->map_capacity = 1 << 20;
+    cfg->enable_mapping = 0;
+}
+
+const char* ll_strerror(int code)
+{
+    switch (code) {
+        case LL_OK: return "ok";
+        case LL_E_INVAL: return "invalid argument";
+        case LL_E_CAPACITY: return "input exceeds configured capacity";
+        case LL_E_CUDA: return "CUDA error";
+        case LL_E_NCCL: return "NCCL error";
+        case LL_E_EMPTY: return "scan has no valid point";
+        case LL_W_FEW_CORRESPONDENCES: return "warning: too few correspondences / map too small";
+        default: return "unknown error";
+    }
+}
+
+const char* ll_last_error(const ll_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+void ll_destroy(ll_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    ll_map_free(c);
+    void* ptrs[] = {c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_lf_tmp,
+                    c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
+                    c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted,
+                    c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->h_lane) cudaFreeHost(c->h_lane);
+    if (c->h_pose) cudaFreeHost(c->h_pose);
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ll_create(const ll_config* cfg, ll_ctx** out)
+{
+    if (!cfg || !out) return LL_E_INVAL;
+    *out = nullptr;
+    if (cfg->scan_line != 16 && cfg->scan_line != 32 && cfg->scan_line != 64) return LL_E_INVAL;  // SR:447-451
+    if (cfg->batch < 1 || cfg->batch > 4096 || cfg->max_points < 256 || cfg->max_ring_points < 17 || cfg->max_ring_points > 6 * 1024 + 11)
+        return LL_E_INVAL;
+    ll_ctx* c = new (std::nothrow) ll_ctx();
+    if (!c) return LL_E_INVAL;
+    c->cfg = *cfg;
+    c->B = cfg->batch;
+    c->R = cfg->scan_line;
+    c->Nmax = (cfg->max_points + LL_TILE - 1) / LL_TILE * LL_TILE;
+    c->NT = c->Nmax / LL_TILE;
+    c->SCAP = cfg->max_ring_points <= 6 * 512 + 11 ? 512 : 1024;
+    c->RCAP = 6 * c->SCAP + 16;
+    c->dev = cfg->device;
+    c->vote_t_min = calibrate_vote_threshold();
+#define CK(expr)                                                                     \
+    do {                                                                             \
+        cudaError_t e__ = (expr);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            fprintf(stderr, "lightloam_b200: %s: %s\n", #expr, cudaGetErrorString(e__)); \
+            ll_destroy(c);                                                           \
+            return LL_E_CUDA;                                                        \
+        }                                                                            \
+    } while (0)
+    CK(cudaSetDevice(c->dev));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    const size_t B = c->B, N = c->Nmax, R = c->R;
+    CK(dalloc(c->d_lane, B));
+    CK(cudaHostAlloc((void**)&c->h_lane, sizeof(LaneState) * B, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&c->h_pose, sizeof(double) * 14 * B, cudaHostAllocDefault));
+    CK(dalloc(c->d_pose, B * 14));
+    CK(cudaHostAlloc((void**)&c->h_hdr, sizeof(int) * 2 * B, cudaHostAllocDefault));
+    CK(dalloc(c->d_hdr, B * 2));
+    CK(dalloc(c->d_raw, B * N * 8));
+    CK(dalloc(c->d_ring8, B * N));
+    CK(dalloc(c->d_rank8, B * N));
+    CK(dalloc(c->d_ori, B * N));
+    CK(dalloc(c->d_tile_hist, B * c->NT * R));
+    CK(dalloc(c->d_full, B * N));
+    CK(dalloc(c->d_curv, B * N));
+    CK(dalloc(c->d_lf_tmp, B * N));
+    CK(dalloc(c->d_ring_lists, B * R * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING)));
+    CK(dalloc(c->d_ring_counts, B * R * 4));
+    CK(dalloc(c->d_sharp, B * R * LL_SHARP_PER_RING));
+    CK(dalloc(c->d_flat, B * R * LL_FLAT_PER_RING));
+    CK(dalloc(c->d_sharp_idx, B * R * LL_SHARP_PER_RING));
+    CK(dalloc(c->d_lsharp_idx, B * R * LL_LSHARP_PER_RING));
+    CK(dalloc(c->d_flat_idx, B * R * LL_FLAT_PER_RING));
+    for (int k = 0; k < 2; ++k) {
+        CK(dalloc(c->d_lsharp[k], B * R * LL_LSHARP_PER_RING));
+        CK(dalloc(c->d_lflat[k], B * N));
+    }
+    // hashed grids over the previous frame's less-sharp / less-flat clouds; cell 1.01 m so that the 5 m
+    // acceptance radius (LO:29) is covered by at most 5 shells
+    c->g_corner.T = pow2ceil(2 * (int)R * LL_LSHARP_PER_RING);
+    c->g_corner.cap = (int)R * LL_LSHARP_PER_RING;
+    c->g_surf.T = pow2ceil((int)N);
+    c->g_surf.cap = (int)N;
+    for (KnnGrid* g : {&c->g_corner, &c->g_surf}) {
+        g->h = 1.01f;
+        g->inv_h = 1.0f / g->h;
+        CK(dalloc(g->start, B * (size_t)(g->T + 1)));
+        CK(dalloc(g->cursor, B * (size_t)g->T));
+        CK(dalloc(g->sorted, B * (size_t)g->cap));
+    }
+    CK(dalloc(c->d_corner_assoc, B * R * LL_SHARP_PER_RING * 2));
+    CK(dalloc(c->d_plane_assoc, B * R * LL_FLAT_PER_RING * 4));
+    c->nblk_cap = (int)R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
+    CK(dalloc(c->d_blocks, B * (size_t)LL_BLOCK_DOUBLES * c->nblk_cap));
+    CK(cudaMemsetAsync(c->d_raw, 0, sizeof(uint32_t) * B * N * 8, c->stream));
+    k_init_lanes<<<(c->B + 63) / 64, 64, 0, c->stream>>>(c->d_lane, c->B);
+    CK(cudaGetLastError());
+    if (cfg->enable_mapping) {
+        const int rc = ll_map_alloc(c);
+        if (rc != LL_OK) { ll_destroy(c); return rc; }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+#undef CK
+    *out = c;
+    return LL_OK;
+}
+
+int ll_reset(ll_ctx* c)
+{
+    if (!c) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    k_init_lanes<<<(c->B + 63) / 64, 64, 0, c->stream>>>(c->d_lane, c->B);
+    if (c->map) { ll_map_free(c); const int rc = ll_map_alloc(c); if (rc) return rc; }
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LL_OK;
+}
+
+void* ll_cuda_stream(ll_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+static int fetch_lanes(ll_ctx* c, int n)
+{
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_lane, c->d_lane, sizeof(LaneState) * n, cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LL_OK;
+}
+
+int ll_stage_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
+{
+    if (!c || !scans || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    LL_CUDA_CHECK(c, cudaEventSynchronize(c->ev[4]));  // the previous staging must have consumed h_hdr
+    ScanHdr* hdr = reinterpret_cast<ScanHdr*>(c->h_hdr);
+    for (int i = 0; i < n_scans; ++i) {
+        const ll_cloud_view& v = scans[i];
+        if (!v.data || v.n < 1 || v.stride_bytes < 12 || v.stride_bytes > 32 || (v.stride_bytes & 3)) return LL_E_INVAL;
+        if (v.n > c->Nmax) return LL_E_CAPACITY;
+        hdr[i].n_raw = v.n;
+        hdr[i].stride_words = v.stride_bytes / 4;
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_raw + (size_t)i * c->Nmax * 8, v.data, (size_t)v.n * v.stride_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_hdr, hdr, sizeof(ScanHdr) * n_scans, cudaMemcpyHostToDevice, c->stream));
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[4], c->stream));
+    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, reinterpret_cast<const ScanHdr*>(c->d_hdr), n_scans);
+    LL_CUDA_CHECK(c, cudaGetLastError());
+    return LL_OK;
+}
+
+int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
+{
+    if (!c || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    c->launches = 0;
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[0], c->stream));
+    int rc = ll_launch_features(c, n_scans);
+    if (rc) return rc;
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[1], c->stream));
+    rc = ll_launch_odometry(c, n_scans);
+    if (rc) return rc;
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[2], c->stream));
+    if (c->cfg.enable_mapping) {
+        rc = ll_launch_mapping(c, n_scans);
+        if (rc) return rc;
+    }
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[3], c->stream));
+    if (poses_out) {
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 14 * n_scans, cudaMemcpyDeviceToHost, c->stream));
+        LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        memcpy(poses_out, c->h_pose, sizeof(double) * 14 * n_scans);
+    }
+    return LL_OK;
+}
+
+int ll_process_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans, double* poses_out)
+{
+    int rc = ll_stage_scans(c, n_scans, scans);
+    if (rc) return rc;
+    rc = ll_process_staged(c, n_scans, poses_out);
+    if (rc) return rc;
+    if (!poses_out) LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LL_OK;
+}
+
+int ll_last_timings(ll_ctx* c, float ms[4])
+{
+    if (!c || !ms) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaEventSynchronize(c->ev[3]));
+    LL_CUDA_CHECK(c, cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
+    LL_CUDA_CHECK(c, cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));
+    LL_CUDA_CHECK(c, cudaEventElapsedTime(&ms[2], c->ev[2], c->ev[3]));
+    LL_CUDA_CHECK(c, cudaEventElapsedTime(&ms[3], c->ev[0], c->ev[3]));
+    return LL_OK;
+}
+
+int ll_extract_features(ll_ctx* c, ll_cloud_view scan, ll_cloud_out* full, ll_cloud_out* sharp, ll_cloud_out* less_sharp, ll_cloud_out* flat,
+                        ll_cloud_out* less_flat, int* sharp_idx, int* less_sharp_idx, int* flat_idx, float* curvature, int* ring_begin)
+{
+    if (!c) return LL_E_INVAL;
+    int rc = ll_stage_scans(c, 1, &scan);
+    if (rc) return rc;
+    c->launches = 0;
+    rc = ll_launch_features(c, 1);
+    if (rc) return rc;
+    rc = fetch_lanes(c, 1);
+    if (rc) return rc;
+    const LaneState& L = c->h_lane[0];
+    if (L.err) return L.err;
+    const int cur = L.cur;
+    if ((rc = copy_out(c, full, c->d_full, L.n_full))) return rc;
+    if ((rc = copy_out(c, sharp, c->d_sharp, L.n_sharp))) return rc;
+    if ((rc = copy_out(c, less_sharp, c->d_lsharp[cur], L.n_less_sharp))) return rc;
+    if ((rc = copy_out(c, flat, c->d_flat, L.n_flat))) return rc;
+    if ((rc = copy_out(c, less_flat, c->d_lflat[cur], L.n_less_flat))) return rc;
+    cudaStream_t s = c->stream;
+    if (sharp_idx && L.n_sharp) LL_CUDA_CHECK(c, cudaMemcpyAsync(sharp_idx, c->d_sharp_idx, sizeof(int) * L.n_sharp, cudaMemcpyDeviceToHost, s));
+    if (less_sharp_idx && L.n_less_sharp) LL_CUDA_CHECK(c, cudaMemcpyAsync(less_sharp_idx, c->d_lsharp_idx, sizeof(int) * L.n_less_sharp, cudaMemcpyDeviceToHost, s));
+    if (flat_idx && L.n_flat) LL_CUDA_CHECK(c, cudaMemcpyAsync(flat_idx, c->d_flat_idx, sizeof(int) * L.n_flat, cudaMemcpyDeviceToHost, s));
+    if (curvature && L.n_full) LL_CUDA_CHECK(c, cudaMemcpyAsync(curvature, c->d_curv, sizeof(float) * L.n_full, cudaMemcpyDeviceToHost, s));
+    if (ring_begin) memcpy(ring_begin, L.ring_begin, sizeof(int) * (c->R + 1));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(s));
+    return LL_OK;
+}
+
+int ll_odometry_step(ll_ctx* c, ll_cloud_view sharp, ll_cloud_view less_sharp, ll_cloud_view flat, ll_cloud_view less_flat, double q_w_curr[4],
+                     double t_w_curr[3], double q_last_curr[4], double t_last_curr[3])
+{
+    if (!c) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    c->launches = 0;
+    int rc = fetch_lanes(c, 1);
+    if (rc) return rc;
+    const int nxt = c->h_lane[0].last_slot ^ 1;  // the slot k_set_feature_counts is about to select
+    if ((rc = copy_view_to_device(c, sharp, c->d_sharp, c->R * LL_SHARP_PER_RING))) return rc;
+    if ((rc = copy_view_to_device(c, less_sharp, c->d_lsharp[nxt], c->R * LL_LSHARP_PER_RING))) return rc;
+    if ((rc = copy_view_to_device(c, flat, c->d_flat, c->R * LL_FLAT_PER_RING))) return rc;
+    if ((rc = copy_view_to_device(c, less_flat, c->d_lflat[nxt], c->Nmax))) return rc;
+    k_set_feature_counts<<<1, 1, 0, c->stream>>>(c->d_lane, sharp.n, less_sharp.n, flat.n, less_flat.n);
+    if ((rc = ll_launch_odometry(c, 1))) return rc;
+    if ((rc = fetch_lanes(c, 1))) return rc;
+    const LaneState& L = c->h_lane[0];
+    if (q_w_curr) memcpy(q_w_curr, L.q_w, sizeof(double) * 4);
+    if (t_w_curr) memcpy(t_w_curr, L.t_w, sizeof(double) * 3);
+    if (q_last_curr) memcpy(q_last_curr, L.para_q, sizeof(double) * 4);
+    if (t_last_curr) memcpy(t_last_curr, L.para_t, sizeof(double) * 3);
+    if (L.err) return L.err;
+    if (L.now_frame > 1 && L.corner_corr[2] + L.plane_corr[2] < 10) return LL_W_FEW_CORRESPONDENCES;  // LO:814-817
+    return LL_OK;
+}
+
+int ll_get_last_stats(ll_ctx* c, ll_stats* o)
+{
+    if (!c || !o) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    const int rc = fetch_lanes(c, 1);
+    if (rc) return rc;
+    const LaneState& L = c->h_lane[0];
+    memset(o, 0, sizeof(*o));
+    o->n_full = L.n_full; o->n_sharp = L.n_sharp; o->n_less_sharp = L.n_less_sharp; o->n_flat = L.n_flat; o->n_less_flat = L.n_less_flat;
+    for (int k = 0; k < 3; ++k) {
+        o->corner_corr[k] = L.corner_corr[k]; o->plane_corr[k] = L.plane_corr[k]; o->plane_selected[k] = L.plane_sel[k];
+        o->lm_jacobian_evals[k] = L.jac_evals[k]; o->lm_cost_evals[k] = L.cost_evals[k]; o->lm_termination[k] = L.termination[k];
+        o->initial_cost[k] = L.initial_cost[k]; o->final_cost[k] = L.final_cost[k];
+    }
+    o->map_corner = L.n_map_corner; o->map_surf = L.n_map_surf; o->stack_corner = L.n_stack_corner; o->stack_surf = L.n_stack_surf;
+    o->map_corner_corr = L.n_map_corner_corr; o->map_surf_corr = L.n_map_surf_corr;
+    for (int k = 0; k < 2; ++k) {
+        o->map_jacobian_evals[k] = L.jac_evals[3 + k]; o->map_termination[k] = L.termination[3 + k];
+        o->map_initial_cost[k] = L.initial_cost[3 + k]; o->map_final_cost[k] = L.final_cost[3 + k];
+    }
+    o->frame = L.now_frame;
+    o->kernel_launches = c->launches;
+    return LL_OK;
+}
+
+int ll_debug_assoc(ll_ctx* c, int lane, int* corner, int corner_cap, int* plane, int plane_cap)
+{
+    if (!c || lane < 0 || lane >= c->B) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    const int nc = c->R * LL_SHARP_PER_RING, np = c->R * LL_FLAT_PER_RING;
+    if (corner) LL_CUDA_CHECK(c, cudaMemcpyAsync(corner, c->d_corner_assoc + (size_t)lane * nc * 2, sizeof(int) * 2 * (corner_cap < nc ? corner_cap : nc), cudaMemcpyDeviceToHost, c->stream));
+    if (plane) LL_CUDA_CHECK(c, cudaMemcpyAsync(plane, c->d_plane_assoc + (size_t)lane * np * 4, sizeof(int) * 4 * (plane_cap < np ? plane_cap : np), cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return LL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Private context layout of liblightloam_b200 (host + device side).  Not part of the C ABI.
+//
+// Data layout in HBM (per lane = one independent scan stream; all arrays are [batch][...] slabs so one
+// launch covers every lane with blockIdx.y / blockIdx.z = lane):
+//   raw        : the caller's point records as uploaded (stride words per point)
+//   ring8/rank8: per raw point ring id (int8, -1 = dropped) and rank inside its 256-point tile
+//   tile_hist  : [tiles][rings] counts -> exclusive offsets (stable counting sort by ring, SR:133-221)
+//   full       : ring-sorted float4 x,y,z,intensity (= laserCloud, SR:215-221)
+//   curv       : fp32 curvature per full point (SR:225-235)
+//   ring lists : per ring picked indices (sharp 12, less-sharp 120, flat 24) + per-ring voxel-DS output
+//   compact    : sharp / less_sharp / flat / less_flat clouds in the reference's publish order
+//   last[2]    : ping-pong copies of less_sharp / less_flat = laserCloudCornerLast / SurfLast (LO:882-891)
+//   grid       : hashed uniform grid (bucket_start + bucket-sorted float4 with the original index in .w)
+//                that replaces kdtreeCornerLast / kdtreeSurfLast (LO:895-896) and the map kd-trees
+//   assoc/blocks: correspondence indices and fp64 residual-block records for the LM solve
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/lightloam_b200.h"
+
+#define LL_TILE 256          // points per counting-sort tile
+#define LL_MAX_RINGS 64
+#define LL_SHARP_PER_RING 12     // 6 sectors x 2   (SR:270-275)
+#define LL_LSHARP_PER_RING 120   // 6 sectors x 20  (SR:276-280)
+#define LL_FLAT_PER_RING 24      // 6 sectors x 4   (SR:327-331)
+#define LL_BLOCK_DOUBLES 12      // residual-block record: type, cp[3], p0[3], p1[3], w, pad
+
+struct LaneState {
+    // --- scan registration ---
+    int n_raw, stride_words;
+    int first_valid, last_valid;     // first / last index surviving the NaN + range filters (SR:109-110)
+    int half_idx;                    // index of the point that flips halfPassed (SR:189-192), INT_MAX if none
+    float start_ori, end_ori;        // SR:114-126
+    int n_full;
+    int ring_begin[LL_MAX_RINGS + 1];
+    int n_sharp, n_less_sharp, n_flat, n_less_flat;
+    int less_flat_ring_begin[LL_MAX_RINGS + 1];
+    // --- odometry ---
+    int inited, now_frame;           // LO:33, LO:377
+    int cur;                         // ping-pong slot written by the latest extraction / upload (= last_slot ^ 1)
+    int last_slot;                   // slot holding laserCloudCornerLast / SurfLast (registered by k_odom_finalize)
+    int n_last_corner, n_last_surf;  // sizes of laserCloudCornerLast / laserCloudSurfLast
+    double para_q[4], para_t[3];     // LO:61-62 (x,y,z,w)
+    double q_w[4], t_w[3];           // LO:57-58
+    int n_corner_corr, n_plane_corr, n_plane_sel, n_blocks;
+    // solver summary per outer iteration (3 odometry + 2 mapping)
+    double initial_cost[5], final_cost[5];
+    int jac_evals[5], cost_evals[5], termination[5];
+    int corner_corr[3], plane_corr[3], plane_sel[3];
+    // --- mapping ---
+    double map_par[7];               // LM:81 parameters: q_w_curr (xyzw), t_w_curr
+    double q_wmap_wodom[4], t_wmap_wodom[3];  // LM:87-88
+    int cen[3];                      // laserCloudCenWidth/Height/Depth LM:42-44
+    int map_frame;
+    int n_map_corner, n_map_surf, n_stack_corner, n_stack_surf, n_map_corner_corr, n_map_surf_corr;
+    int err;                         // sticky device-side error (LL_E_*)
+};
+
+struct KnnGrid {
+    int T = 0;            // buckets per lane (power of two)
+    int cap = 0;          // points per lane
+    float h = 1.f, inv_h = 1.f;
+    int* start = nullptr;     // [B][T+1] exclusive bucket offsets
+    int* cursor = nullptr;    // [B][T]   counting / scatter cursors
+    float4* sorted = nullptr; // [B][cap] bucket-ordered points, .w = original index bits
+};
+
+struct ll_ctx {
+    ll_config cfg;
+    int B = 1, R = 64, Nmax = 0, NT = 0, RCAP = 0, SCAP = 0, KCAP = 0;
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string last_error;
+    int launches = 0;
+    float vote_t_min = 0.f;   // smallest fp32 t with expf(-t) < 0.96f on this host's libm (LO:239-242)
+
+    LaneState* d_lane = nullptr;
+    LaneState* h_lane = nullptr;   // pinned mirror
+    double* h_pose = nullptr;      // pinned [B][14]
+    double* d_pose = nullptr;      // [B][14]
+    int* h_hdr = nullptr;          // pinned [B][2] {n_raw, stride_words}
+    int* d_hdr = nullptr;          // [B][2]
+
+    uint32_t* d_raw = nullptr;     // [B][Nmax * 8] words (stride <= 32 B)
+    int8_t* d_ring8 = nullptr;     // [B][Nmax]
+    uint8_t* d_rank8 = nullptr;    // [B][Nmax]
+    float* d_ori = nullptr;        // [B][Nmax] -atan2(y,x) per raw point
+    int* d_tile_hist = nullptr;    // [B][NT][R]
+    float4* d_full = nullptr;      // [B][Nmax]
+    float* d_curv = nullptr;       // [B][Nmax]
+    float4* d_lf_tmp = nullptr;    // [B][Nmax] per-ring voxel-DS output parked at the ring's own offset
+    int* d_ring_lists = nullptr;   // [B][R][12 + 120 + 24]
+    int* d_ring_counts = nullptr;  // [B][R][4]  sharp, less_sharp, flat, less_flat
+    float4* d_sharp = nullptr;     // [B][R*12]
+    float4* d_flat = nullptr;      // [B][R*24]
+    int* d_sharp_idx = nullptr;    // [B][R*12]
+    int* d_lsharp_idx = nullptr;   // [B][R*120]
+    int* d_flat_idx = nullptr;     // [B][R*24]
+    float4* d_lsharp[2] = {nullptr, nullptr};  // [B][R*120]
+    float4* d_lflat[2] = {nullptr, nullptr};   // [B][Nmax]
+
+    KnnGrid g_corner, g_surf;      // over last less-sharp / less-flat
+    int* d_corner_assoc = nullptr; // [B][R*12][2]
+    int* d_plane_assoc = nullptr;  // [B][R*24][4]
+    double* d_blocks = nullptr;    // [B][nblk_cap][12]
+    int nblk_cap = 0;
+
+    // mapping (allocated when enable_mapping)
+    struct MapState* map = nullptr;
+};
+
+// error plumbing ---------------------------------------------------------------------------------------
+#define LL_CUDA_CHECK(ctx, expr)                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                  \
+            return LL_E_CUDA;                                                                         \
+        }                                                                                             \
+    } while (0)
+
+// kernel-group entry points (defined in the .cu files) ---------------------------------------------------
+int ll_launch_features(ll_ctx* c, int n_lanes);                 // SR:100-377 on lanes [0, n_lanes)
+int ll_launch_odometry(ll_ctx* c, int n_lanes);                 // LO:425-896
+int ll_launch_grid_build(ll_ctx* c, KnnGrid& g, const float4* pts, size_t lane_stride, const int* n_per_lane_field_dev,
+                         int field_offset_bytes, int n_lanes);
+int ll_map_alloc(ll_ctx* c);
+void ll_map_free(ll_ctx* c);
+int ll_launch_mapping(ll_ctx* c, int n_lanes);                  // LM:1581-2168
+int ll_map_insert_impl(ll_ctx* c, const float* corner, int nc, const float* surf, int ns);

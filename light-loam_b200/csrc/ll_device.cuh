@@ -1,0 +1,103 @@
+// Device helpers shared by the kernels.  The whole library is compiled with -fmad=false so that plain
+// fp32 / fp64 expressions keep the reference's x86-64 (no-FMA) rounding; fma() is used explicitly only
+// where parity does not depend on it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+
+#define LL_FULL_MASK 0xffffffffu
+#define LL_PI 3.14159265358979323846  // M_PI
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src)
+{
+    int lo = __shfl_sync(LL_FULL_MASK, (int)(unsigned)v, src);
+    int hi = __shfl_sync(LL_FULL_MASK, (int)(unsigned)(v >> 32), src);
+    return ((u64)(unsigned)hi << 32) | (unsigned)lo;
+}
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
+{
+    int lo = __shfl_xor_sync(LL_FULL_MASK, (int)(unsigned)v, m);
+    int hi = __shfl_xor_sync(LL_FULL_MASK, (int)(unsigned)(v >> 32), m);
+    return ((u64)(unsigned)hi << 32) | (unsigned)lo;
+}
+__device__ __forceinline__ u64 warp_min_u64(u64 v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { u64 o = shfl_xor_u64(v, m); v = o < v ? o : v; }
+    return v;
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m)
+{
+    return __longlong_as_double((long long)shfl_xor_u64((u64)__double_as_longlong(v), m));
+}
+__device__ __forceinline__ double shfl_down_f64(double v, int d)
+{
+    int lo = __shfl_down_sync(LL_FULL_MASK, __double2loint(v), d);
+    int hi = __shfl_down_sync(LL_FULL_MASK, __double2hiint(v), d);
+    return __hiloint2double(hi, lo);
+}
+
+// fp32 squared distance in the reference's order ((dx*dx)+(dy*dy))+(dz*dz), no FMA (-fmad=false).
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Eigen QuaternionBase::_transformVector in fp64: uv = 2 (u x v); v + w uv + u x uv  (q = x,y,z,w).
+__device__ __forceinline__ void quat_rotate(const double q[4], double vx, double vy, double vz, double& ox, double& oy, double& oz)
+{
+    double ux = q[1] * vz - q[2] * vy, uy = q[2] * vx - q[0] * vz, uz = q[0] * vy - q[1] * vx;
+    ux = ux + ux; uy = uy + uy; uz = uz + uz;
+    const double cx = q[1] * uz - q[2] * uy, cy = q[2] * ux - q[0] * uz, cz = q[0] * uy - q[1] * ux;
+    ox = (vx + q[3] * ux) + cx;
+    oy = (vy + q[3] * uy) + cy;
+    oz = (vz + q[3] * uz) + cz;
+}
+// Eigen quat_product a * b (Hamilton), x,y,z,w storage.
+__device__ __forceinline__ void quat_mul(const double a[4], const double b[4], double o[4])
+{
+    const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    const double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+
+// Exclusive scan of one int per thread over a block of NT threads (NT multiple of 32, <= 1024).
+// ws must hold 33 ints. Returns the exclusive prefix; *total receives the block sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* ws, int* total)
+{
+    const int lane = lane_id(), w = warp_id();
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+    __syncthreads();  // protect ws from a previous use
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        int s = lane < nw ? ws[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(LL_FULL_MASK, si, d); if (lane >= d) si += o; }
+        ws[lane] = si - s;
+        if (lane == 31) ws[32] = si;
+    }
+    __syncthreads();
+    const int r = ws[w] + incl - v;
+    if (total) *total = ws[32];
+    return r;
+}
+
+// hashed uniform grid: bucket of integer cell (ix,iy,iz), T = power of two
+__device__ __forceinline__ int cell_bucket(int ix, int iy, int iz, int Tmask)
+{
+    const unsigned h = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+    return (int)((h ^ (h >> 15)) & (unsigned)Tmask);
+}

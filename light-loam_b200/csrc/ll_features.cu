@@ -1,0 +1,639 @@
+// Feature extraction on the device — replaces scanRegistration.cpp:100-377 (`laserCloudHandler` body).
+//
+//   k_classify       SR:109-110 (NaN / range filter), SR:139-169 (ring id), SR:177 (-atan2)     coalesced, 1 thread / point
+//   k_halfpass_hist  SR:178-193 (which point flips halfPassed) + per-tile ring histogram / ranks
+//   k_ring_scan      SR:215-221 (ring offsets = stable counting sort by ring)
+//   k_scatter        SR:194-209 (relTime, intensity) + scatter into the ring-major cloud
+//   k_ring_features  SR:225-376: one CTA per (ring, lane): TMA bulk load of the ring into shared memory,
+//                    11-tap curvature, six in-smem sector sorts, warp-serial greedy pick with +-5
+//                    suppression, less-flat collection and pcl::VoxelGrid(0.2) per ring
+//   k_compact        concatenation of the per-ring outputs in the reference's publish order (SR:273-376)
+//
+// HBM-bound streaming work; no GEMM shape anywhere.  Algorithmic bytes per scan:
+// 16 P (raw) + 16 P (full) read+write in the sort, 16 P read + 4 P + features written by k_ring_features.
+#include <limits.h>
+#include <math.h>
+
+#include "ll_ctx.h"
+#include "ll_device.cuh"
+
+namespace {
+
+struct FeatParams {
+    LaneState* lane;
+    const uint32_t* raw;
+    int8_t* ring8;
+    uint8_t* rank8;
+    float* ori;
+    int* tile_hist;
+    float4* full;
+    float* curv;
+    float4* lf_tmp;
+    int* ring_lists;
+    int* ring_counts;
+    float4* sharp;
+    float4* flat;
+    int* sharp_idx;
+    int* lsharp_idx;
+    int* flat_idx;
+    float4* lsharp[2];
+    float4* lflat[2];
+    int Nmax, NT, R;
+    int scan_line;
+    float thres, lower_bound, up_bound, factor;
+    float inv_leaf;   // 1.0f / 0.2f
+    size_t raw_stride_words;  // per lane
+};
+
+// SR:114-126: endOri from the last valid point and startOri
+__device__ __forceinline__ float end_ori_of(float last_ori, float startOri)
+{
+    float endOri = (float)((double)last_ori + 2 * LL_PI);
+    if ((double)(endOri - startOri) > 3 * LL_PI)
+        endOri = (float)((double)endOri - 2 * LL_PI);
+    else if ((double)(endOri - startOri) < LL_PI)
+        endOri = (float)((double)endOri + 2 * LL_PI);
+    return endOri;
+}
+
+__global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
+{
+    const int b = blockIdx.y;
+    LaneState& L = P.lane[b];
+    const int n = L.n_raw, sw = L.stride_words;
+    const int i = blockIdx.x * LL_TILE + threadIdx.x;
+    bool valid = false;
+    int ring = -1;
+    float ori = 0.f;
+    if (i < n) {
+        const uint32_t* p = P.raw + (size_t)b * P.raw_stride_words + (size_t)i * sw;
+        const float x = __uint_as_float(p[0]), y = __uint_as_float(p[1]), z = __uint_as_float(p[2]);
+        valid = isfinite(x) && isfinite(y) && isfinite(z) && !(x * x + y * y + z * z < P.thres * P.thres);  // SR:72
+        if (valid) {
+            // SR:139: float atan / sqrt, * 180 in fp32, / M_PI in fp64, stored as float.
+            // atanf / atan2f are evaluated in fp64 and rounded once (correctly rounded fp32 result).
+            const float t = z / sqrtf(x * x + y * y);
+            const float a = (float)atan((double)t);
+            const float angle = (float)((double)(a * 180.0f) / LL_PI);
+            int scanID;
+            if (P.scan_line == 16) {
+                scanID = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
+                if (scanID > 15 || scanID < 0) scanID = -2;
+            } else if (P.scan_line == 32) {
+                scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+                if (scanID > 31 || scanID < 0) scanID = -2;
+            } else {
+                scanID = (int)((double)((angle - P.lower_bound) * P.factor) + 0.5);
+                if (scanID >= 64 || scanID < 0) scanID = -2;
+            }
+            ring = scanID;
+            ori = -(float)atan2((double)y, (double)x);  // SR:177
+        }
+    }
+    if (i < P.Nmax) {
+        P.ring8[(size_t)b * P.Nmax + i] = (int8_t)ring;
+        P.ori[(size_t)b * P.Nmax + i] = ori;
+    }
+    const int lo = __reduce_min_sync(LL_FULL_MASK, valid ? i : INT_MAX);
+    const int hi = __reduce_max_sync(LL_FULL_MASK, valid ? i : -1);
+    if (lane_id() == 0) {
+        if (lo != INT_MAX) atomicMin(&L.first_valid, lo);
+        if (hi >= 0) atomicMax(&L.last_valid, hi);
+    }
+}
+
+__global__ void __launch_bounds__(LL_TILE) k_halfpass_hist(FeatParams P)
+{
+    __shared__ int cnt[LL_TILE / 32][LL_MAX_RINGS];
+    const int b = blockIdx.y;
+    LaneState& L = P.lane[b];
+    const int i = blockIdx.x * LL_TILE + threadIdx.x;
+    const int w = warp_id(), lane = lane_id();
+    for (int k = threadIdx.x; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    int ring = -1;
+    if (i < L.n_raw) ring = P.ring8[(size_t)b * P.Nmax + i];
+    bool flag = false;
+    if (ring >= 0 && L.first_valid != INT_MAX) {
+        const float startOri = P.ori[(size_t)b * P.Nmax + L.first_valid];
+        float ori = P.ori[(size_t)b * P.Nmax + i];
+        // SR:180-192 in the !halfPassed state
+        if ((double)ori < (double)startOri - LL_PI / 2)
+            ori = (float)((double)ori + 2 * LL_PI);
+        else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
+            ori = (float)((double)ori - 2 * LL_PI);
+        flag = (double)(ori - startOri) > LL_PI;
+    }
+    const int fi = __reduce_min_sync(LL_FULL_MASK, flag ? i : INT_MAX);
+    if (lane == 0 && fi != INT_MAX) atomicMin(&L.half_idx, fi);
+
+    // stable rank inside the tile: warp match on the ring id, then prefix over the tile's warps
+    const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
+    const int rank_in_warp = __popc(m & ((1u << lane) - 1u));
+    if (ring >= 0 && rank_in_warp == 0) cnt[w][ring] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < P.R) {
+        int run = 0;
+        for (int ww = 0; ww < LL_TILE / 32; ++ww) { const int c = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += c; }
+        P.tile_hist[((size_t)b * P.NT + blockIdx.x) * P.R + threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (i < P.Nmax) P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(cnt[w][ring] + rank_in_warp) : 0;
+}
+
+// one CTA per lane: tile_hist[t][r] -> exclusive offset of tile t inside ring r; ring_begin[]; n_full
+__global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
+{
+    __shared__ int tot[LL_MAX_RINGS];
+    const int b = blockIdx.x;
+    LaneState& L = P.lane[b];
+    const int w = warp_id(), lane = lane_id();
+    const int ntiles = (L.n_raw + LL_TILE - 1) / LL_TILE;
+    const int per = (ntiles + 31) / 32;
+    for (int r = w; r < P.R; r += 32) {
+        int* col = P.tile_hist + (size_t)b * P.NT * P.R + r;
+        const int t0 = lane * per, t1 = min(t0 + per, ntiles);
+        int s = 0;
+        for (int t = t0; t < t1; ++t) s += col[(size_t)t * P.R];
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+        int run = incl - s;
+        for (int t = t0; t < t1; ++t) { const int c = col[(size_t)t * P.R]; col[(size_t)t * P.R] = run; run += c; }
+        if (lane == 31) tot[r] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int r = 0; r < P.R; ++r) { L.ring_begin[r] = run; run += tot[r]; }
+        L.ring_begin[P.R] = run;
+        L.n_full = run;
+        L.cur = L.last_slot ^ 1;  // this frame's less-sharp / less-flat go to the slot not holding the *Last clouds
+        if (L.first_valid != INT_MAX) {
+            L.start_ori = P.ori[(size_t)b * P.Nmax + L.first_valid];
+            L.end_ori = end_ori_of(P.ori[(size_t)b * P.Nmax + L.last_valid], L.start_ori);
+        } else {
+            L.err = LL_E_EMPTY;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LL_TILE) k_scatter(FeatParams P)
+{
+    const int b = blockIdx.y;
+    const LaneState& L = P.lane[b];
+    const int i = blockIdx.x * LL_TILE + threadIdx.x;
+    if (i >= L.n_raw) return;
+    const int ring = P.ring8[(size_t)b * P.Nmax + i];
+    if (ring < 0) return;
+    const float startOri = L.start_ori, endOri = L.end_ori;
+    float ori = P.ori[(size_t)b * P.Nmax + i];
+    if (i <= L.half_idx) {  // SR:178-193 (the flipping point itself still takes this branch)
+        if ((double)ori < (double)startOri - LL_PI / 2)
+            ori = (float)((double)ori + 2 * LL_PI);
+        else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
+            ori = (float)((double)ori - 2 * LL_PI);
+    } else {  // SR:194-205
+        ori = (float)((double)ori + 2 * LL_PI);
+        if ((double)ori < (double)endOri - LL_PI * 3 / 2)
+            ori = (float)((double)ori + 2 * LL_PI);
+        else if ((double)ori > (double)endOri + LL_PI / 2)
+            ori = (float)((double)ori - 2 * LL_PI);
+    }
+    const float relTime = (ori - startOri) / (endOri - startOri);          // SR:207
+    const float intensity = (float)((double)ring + 0.1 * (double)relTime);  // SR:208
+    const int pos = L.ring_begin[ring] + P.tile_hist[((size_t)b * P.NT + blockIdx.x) * P.R + ring] + P.rank8[(size_t)b * P.Nmax + i];
+    const uint32_t* p = P.raw + (size_t)b * P.raw_stride_words + (size_t)i * L.stride_words;
+    P.full[(size_t)b * P.Nmax + pos] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), intensity);
+}
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
+            smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// SR:288-311: +-5 neighbour suppression with the 0.05 m^2 consecutive-gap break. Called by warp 0 with the
+// picked local index `ind` (warp-uniform). Lanes 0..4 test l = +1..+5, lanes 8..12 test l = -1..-5.
+__device__ __forceinline__ void suppress_neighbours(const float4* pts, uint8_t* picked, int ind, int lane)
+{
+    bool brk = false;
+    int tgt = -1;
+    if (lane < 5) {
+        const int l = lane + 1;
+        const float4 a = pts[ind + l], c = pts[ind + l - 1];
+        brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
+        tgt = ind + l;
+    } else if (lane >= 8 && lane < 13) {
+        const int l = -(lane - 7);
+        const float4 a = pts[ind + l], c = pts[ind + l + 1];
+        brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
+        tgt = ind + l;
+    }
+    const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
+    const unsigned f = bm & 0x1Fu, r = (bm >> 8) & 0x1Fu;
+    const int nf = f ? __ffs(f) - 1 : 5, nr = r ? __ffs(r) - 1 : 5;
+    if (lane < 5 && lane < nf) picked[tgt] = 1;
+    if (lane >= 8 && lane < 13 && (lane - 8) < nr) picked[tgt] = 1;
+    __syncwarp();
+}
+
+template <int SCAP>
+__global__ void __launch_bounds__(512) k_ring_features(FeatParams P)
+{
+    constexpr int RCAP = 6 * SCAP + 16;
+    constexpr int KCAP = (RCAP <= 4096) ? 4096 : 8192;
+    constexpr int NTH = 512;
+    constexpr int CH = (RCAP + NTH - 1) / NTH;  // chunk of positions per thread for the ordered scans
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* pts = reinterpret_cast<float4*>(smem);
+    u64* keys = reinterpret_cast<u64*>(smem + (size_t)RCAP * 16);
+    uint8_t* picked = reinterpret_cast<uint8_t*>(keys + KCAP);
+    int8_t* label = reinterpret_cast<int8_t*>(picked + RCAP);
+    int* ws = reinterpret_cast<int*>(label + RCAP);  // RCAP multiple of 16 -> aligned
+    int* sp = ws + 40;                               // sector starts sp[0..6]
+    float* red = reinterpret_cast<float*>(sp + 8);   // 6 x 16 warp partials + 6 results
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 112);
+
+    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    LaneState& L = P.lane[b];
+    const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base, ntot = L.n_full;
+    int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
+    int* my_lists = P.ring_lists + ((size_t)b * P.R + r) * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING);
+    const float4* gfull = P.full + (size_t)b * P.Nmax;
+    float* gcurv = P.curv + (size_t)b * P.Nmax;
+
+    if (n - 11 < 6 || n > 6 * SCAP + 11) {  // SR:248 skip; or capacity overflow
+        if (tid == 0) {
+            my_counts[0] = my_counts[1] = my_counts[2] = my_counts[3] = 0;
+            if (n > 6 * SCAP + 11) L.err = LL_E_CAPACITY;
+        }
+        // curvature is still defined on these points (SR:225-235); emit it for parity dumps
+        for (int i = tid; i < n; i += NTH) {
+            const int g = base + i;
+            float c = 0.f;
+            if (g >= 5 && g < ntot - 5) {
+                float dx = gfull[g - 5].x, dy = gfull[g - 5].y, dz = gfull[g - 5].z;
+                for (int k = -4; k <= -1; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
+                dx = dx - 10 * gfull[g].x; dy = dy - 10 * gfull[g].y; dz = dz - 10 * gfull[g].z;
+                for (int k = 1; k <= 5; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
+                c = dx * dx + dy * dy + dz * dz;
+            }
+            gcurv[g] = c;
+        }
+        return;
+    }
+
+    // ---- TMA: one bulk copy of the ring's float4 slab into shared memory -----------------------------
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_bulk_g2s(pts, gfull + base, (uint32_t)n * 16u, bar);
+    // meanwhile: clear flags, sector geometry (SR:253-254 with ring-local indices)
+    for (int i = tid; i < RCAP; i += NTH) { picked[i] = 0; label[i] = 0; }
+    for (int i = tid; i < 6 * SCAP; i += NTH) keys[i] = ~0ull;
+    const int len = n - 11;
+    if (tid <= 6) sp[tid] = 5 + len * tid / 6;
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    // ---- curvature (SR:225-235) + sort keys -------------------------------------------------------------
+    for (int i = tid; i < n; i += NTH) {
+        float c = 0.f;
+        bool have = false;
+        if (i >= 5 && i < n - 5) {
+            float dx = pts[i - 5].x, dy = pts[i - 5].y, dz = pts[i - 5].z;
+#pragma unroll
+            for (int k = -4; k <= -1; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
+            { const float4 q = pts[i]; dx = dx - 10 * q.x; dy = dy - 10 * q.y; dz = dz - 10 * q.z; }
+#pragma unroll
+            for (int k = 1; k <= 5; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
+            c = dx * dx + dy * dy + dz * dz;
+            have = true;
+        } else {
+            // the reference's stencil runs over ring joins (global index); those values are never used by
+            // the picks (sectors keep a 5-point margin) but belong to the curvature array
+            const int g = base + i;
+            if (g >= 5 && g < ntot - 5) {
+                float dx = gfull[g - 5].x, dy = gfull[g - 5].y, dz = gfull[g - 5].z;
+                for (int k = -4; k <= -1; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
+                dx = dx - 10 * gfull[g].x; dy = dy - 10 * gfull[g].y; dz = dz - 10 * gfull[g].z;
+                for (int k = 1; k <= 5; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
+                c = dx * dx + dy * dy + dz * dz;
+            }
+        }
+        gcurv[base + i] = c;
+        if (have && i < n - 6) {  // sectors tile [5, n-6)
+            int j = 0;
+#pragma unroll
+            for (int q = 1; q < 6; ++q) j += (i >= sp[q]);
+            keys[j * SCAP + (i - sp[j])] = ((u64)__float_as_uint(c) << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+
+    // ---- six independent bitonic sorts (ascending curvature, ties by index), SR:257 --------------------
+    for (int k = 2; k <= SCAP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < 3 * SCAP; t += NTH) {
+                const int seg = t / (SCAP / 2), tl = t % (SCAP / 2);
+                const int i = ((tl & ~(j - 1)) << 1) | (tl & (j - 1));
+                u64* K = keys + seg * SCAP;
+                const u64 a = K[i], c = K[i | j];
+                const bool asc = (i & k) == 0;
+                if ((a > c) == asc) { K[i] = c; K[i | j] = a; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- greedy pick, sectors in order (SR:251-359); warp 0, window of 32 sorted candidates -----------
+    if (wid == 0) {
+        int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+        for (int j = 0; j < 6; ++j) {
+            const u64* seg = keys + j * SCAP;
+            const int size = sp[j + 1] - sp[j];
+            // corners: from the largest curvature down
+            int pos = size - 1, npick = 0;
+            while (pos >= 0) {
+                const int p = pos - lane;
+                const u64 key = p >= 0 ? seg[p] : 0ull;
+                const int idx = (int)(unsigned)key;
+                const bool over = p >= 0 && (double)__uint_as_float((unsigned)(key >> 32)) > 0.1;
+                const bool elig = over && picked[idx] == 0;
+                const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+                const unsigned nm = __ballot_sync(LL_FULL_MASK, p >= 0 && !over);
+                if (em == 0) {
+                    if (nm) break;  // reached curvature <= 0.1: nothing below can be picked
+                    pos -= 32;
+                    continue;
+                }
+                const int f = __ffs(em) - 1;
+                const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
+                ++npick;
+                if (npick > 20) break;  // SR:281-284
+                if (lane == 0) {
+                    if (npick <= 2) {
+                        label[ind] = 2;
+                        my_lists[n_sharp] = base + ind;
+                        my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
+                    } else {
+                        label[ind] = 1;
+                        my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
+                    }
+                    picked[ind] = 1;
+                }
+                if (npick <= 2) ++n_sharp;
+                ++n_lsharp;
+                __syncwarp();
+                suppress_neighbours(pts, picked, ind, lane);
+                pos -= f + 1;
+            }
+            // flats: from the smallest curvature up
+            pos = 0;
+            int nsm = 0;
+            while (pos < size) {
+                const int p = pos + lane;
+                const u64 key = p < size ? seg[p] : 0ull;
+                const int idx = (int)(unsigned)key;
+                const bool under = p < size && (double)__uint_as_float((unsigned)(key >> 32)) < 0.1;
+                const bool elig = under && picked[idx] == 0;
+                const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+                const unsigned nm = __ballot_sync(LL_FULL_MASK, p < size && !under);
+                if (em == 0) {
+                    if (nm) break;
+                    pos += 32;
+                    continue;
+                }
+                const int f = __ffs(em) - 1;
+                const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
+                if (lane == 0) {
+                    label[ind] = -1;
+                    my_lists[LL_SHARP_PER_RING + LL_LSHARP_PER_RING + n_flat] = base + ind;
+                }
+                ++n_flat;
+                ++nsm;
+                if (nsm >= 4) break;  // SR:328-331: before picked / suppression
+                if (lane == 0) picked[ind] = 1;
+                __syncwarp();
+                suppress_neighbours(pts, picked, ind, lane);
+                pos += f + 1;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) { my_counts[0] = n_sharp; my_counts[1] = n_lsharp; my_counts[2] = n_flat; }
+    }
+    __syncthreads();
+
+    // ---- less-flat = every sector point with label <= 0 (SR:361-367), then VoxelGrid(0.2) (SR:370-376) --
+    const int c0 = tid * CH, c1 = min(c0 + CH, n);
+    int mycnt = 0;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = c0; i < c1; ++i) {
+        if (i >= 5 && i < n - 6 && label[i] <= 0) {
+            ++mycnt;
+            const float4 q = pts[i];
+            mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
+            mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+        }
+    }
+    int m = 0;
+    const int off = block_exclusive_scan(mycnt, ws, &m);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(LL_FULL_MASK, mn[a], d));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(LL_FULL_MASK, mx[a], d));
+        }
+        if (lane == 0) { red[a * 16 + wid] = mn[a]; red[(3 + a) * 16 + wid] = mx[a]; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float v = red[tid * 16];
+        for (int k = 1; k < NTH / 32; ++k) v = tid < 3 ? fminf(v, red[tid * 16 + k]) : fmaxf(v, red[tid * 16 + k]);
+        red[96 + tid] = v;
+    }
+    __syncthreads();
+    if (m == 0) { if (tid == 0) my_counts[3] = 0; return; }
+    const float inv = P.inv_leaf;
+    const float bmn[3] = {red[96], red[97], red[98]}, bmx[3] = {red[99], red[100], red[101]};
+    const long long ddx = (long long)((bmx[0] - bmn[0]) * inv) + 1, ddy = (long long)((bmx[1] - bmn[1]) * inv) + 1,
+                    ddz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
+    float4* gout = P.lf_tmp + (size_t)b * P.Nmax + base;
+    if (ddx * ddy * ddz > (long long)INT_MAX) {  // PCL "leaf size too small": output = input
+        int o = off;
+        for (int i = c0; i < c1; ++i)
+            if (i >= 5 && i < n - 6 && label[i] <= 0) gout[o++] = pts[i];
+        if (tid == 0) my_counts[3] = m;
+        return;
+    }
+    const int min_b0 = (int)floorf(bmn[0] * inv), min_b1 = (int)floorf(bmn[1] * inv), min_b2 = (int)floorf(bmn[2] * inv);
+    const int div0 = (int)floorf(bmx[0] * inv) - min_b0 + 1, div1 = (int)floorf(bmx[1] * inv) - min_b1 + 1;
+    const int mul1 = div0, mul2 = div0 * div1;
+    int NS = 32;
+    while (NS < m) NS <<= 1;
+    {
+        int o = off;
+        for (int i = c0; i < c1; ++i)
+            if (i >= 5 && i < n - 6 && label[i] <= 0) {
+                const float4 q = pts[i];
+                const int i0 = (int)(floorf(q.x * inv) - (float)min_b0);
+                const int i1 = (int)(floorf(q.y * inv) - (float)min_b1);
+                const int i2 = (int)(floorf(q.z * inv) - (float)min_b2);
+                const int vidx = i0 + i1 * mul1 + i2 * mul2;
+                keys[o++] = ((u64)(unsigned)vidx << 32) | (unsigned)i;
+            }
+        for (int i = m + tid; i < NS; i += NTH) keys[i] = ~0ull;
+    }
+    __syncthreads();
+    for (int k = 2; k <= NS; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < NS / 2; t += NTH) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const u64 a = keys[i], c = keys[i | j];
+                const bool asc = (i & k) == 0;
+                if ((a > c) == asc) { keys[i] = c; keys[i | j] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // heads of equal-voxel runs; centroid of x,y,z,intensity summed in sorted (= input) order, fp32
+    const int p0 = tid * CH, p1 = min(p0 + CH, m);
+    int heads = 0;
+    for (int p = p0; p < p1; ++p) heads += (p == 0 || (unsigned)(keys[p] >> 32) != (unsigned)(keys[p - 1] >> 32));
+    int nvox = 0;
+    int o = block_exclusive_scan(heads, ws, &nvox);
+    for (int p = p0; p < p1; ++p) {
+        const unsigned v = (unsigned)(keys[p] >> 32);
+        if (p == 0 || v != (unsigned)(keys[p - 1] >> 32)) {
+            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+            int q = p;
+            for (; q < m && (unsigned)(keys[q] >> 32) == v; ++q) {
+                const float4 a = pts[(int)(unsigned)keys[q]];
+                sx += a.x; sy += a.y; sz += a.z; si += a.w;
+            }
+            const float cnt = (float)(q - p);
+            gout[o++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        }
+    }
+    if (tid == 0) my_counts[3] = nvox;
+}
+
+// one CTA per (ring, lane): offsets = sums over the earlier rings; copy lists / clouds to their compact places
+__global__ void __launch_bounds__(256) k_compact(FeatParams P)
+{
+    __shared__ int offs[4];
+    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    LaneState& L = P.lane[b];
+    const int* counts = P.ring_counts + (size_t)b * P.R * 4;
+    if (tid < 32) {
+        int s[4] = {0, 0, 0, 0};
+        for (int q = tid; q < r; q += 32)
+            for (int k = 0; k < 4; ++k) s[k] += counts[q * 4 + k];
+        for (int k = 0; k < 4; ++k) {
+            for (int d = 16; d > 0; d >>= 1) s[k] += __shfl_xor_sync(LL_FULL_MASK, s[k], d);
+            if (tid == 0) offs[k] = s[k];
+        }
+    }
+    __syncthreads();
+    const int* lists = P.ring_lists + ((size_t)b * P.R + r) * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING);
+    const float4* gfull = P.full + (size_t)b * P.Nmax;
+    const int cur = L.cur;
+    const int ns = counts[r * 4 + 0], nls = counts[r * 4 + 1], nf = counts[r * 4 + 2], nlf = counts[r * 4 + 3];
+    for (int k = tid; k < ns; k += blockDim.x) {
+        const int g = lists[k];
+        P.sharp[(size_t)b * P.R * LL_SHARP_PER_RING + offs[0] + k] = gfull[g];
+        P.sharp_idx[(size_t)b * P.R * LL_SHARP_PER_RING + offs[0] + k] = g;
+    }
+    for (int k = tid; k < nls; k += blockDim.x) {
+        const int g = lists[LL_SHARP_PER_RING + k];
+        P.lsharp[cur][(size_t)b * P.R * LL_LSHARP_PER_RING + offs[1] + k] = gfull[g];
+        P.lsharp_idx[(size_t)b * P.R * LL_LSHARP_PER_RING + offs[1] + k] = g;
+    }
+    for (int k = tid; k < nf; k += blockDim.x) {
+        const int g = lists[LL_SHARP_PER_RING + LL_LSHARP_PER_RING + k];
+        P.flat[(size_t)b * P.R * LL_FLAT_PER_RING + offs[2] + k] = gfull[g];
+        P.flat_idx[(size_t)b * P.R * LL_FLAT_PER_RING + offs[2] + k] = g;
+    }
+    const float4* src = P.lf_tmp + (size_t)b * P.Nmax + L.ring_begin[r];
+    float4* dst = P.lflat[cur] + (size_t)b * P.Nmax + offs[3];
+    for (int k = tid; k < nlf; k += blockDim.x) dst[k] = src[k];
+    if (tid == 0) {
+        L.less_flat_ring_begin[r] = offs[3];
+        if (r == P.R - 1) {
+            L.n_sharp = offs[0] + ns;
+            L.n_less_sharp = offs[1] + nls;
+            L.n_flat = offs[2] + nf;
+            L.n_less_flat = offs[3] + nlf;
+            L.less_flat_ring_begin[P.R] = offs[3] + nlf;
+        }
+    }
+}
+
+__global__ void k_reset_scan_state(LaneState* lane, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_lanes) {
+        lane[b].first_valid = INT_MAX;
+        lane[b].last_valid = -1;
+        lane[b].half_idx = INT_MAX;
+    }
+}
+
+}  // namespace
+
+size_t ll_feature_smem_bytes(int SCAP)
+{
+    const int RCAP = 6 * SCAP + 16, KCAP = RCAP <= 4096 ? 4096 : 8192;
+    return (size_t)RCAP * 16 + (size_t)KCAP * 8 + (size_t)RCAP * 2 + (40 + 8) * 4 + 112 * 4 + 16;
+}
+
+int ll_launch_features(ll_ctx* c, int n_lanes)
+{
+    FeatParams P;
+    P.lane = c->d_lane; P.raw = c->d_raw; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.ori = c->d_ori; P.tile_hist = c->d_tile_hist;
+    P.full = c->d_full; P.curv = c->d_curv; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
+    P.sharp = c->d_sharp; P.flat = c->d_flat; P.sharp_idx = c->d_sharp_idx; P.lsharp_idx = c->d_lsharp_idx; P.flat_idx = c->d_flat_idx;
+    P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
+    P.Nmax = c->Nmax; P.NT = c->NT; P.R = c->R; P.scan_line = c->cfg.scan_line;
+    P.thres = c->cfg.minimum_range; P.lower_bound = c->cfg.lower_bound; P.up_bound = c->cfg.up_bound;
+    P.factor = (c->cfg.scan_line - 1) / (c->cfg.up_bound - c->cfg.lower_bound);  // SR:441, fp32
+    P.inv_leaf = 1.0f / 0.2f;
+    P.raw_stride_words = (size_t)c->Nmax * 8;
+    cudaStream_t s = c->stream;
+    const dim3 tiles(c->NT, n_lanes);
+    k_reset_scan_state<<<(n_lanes + 127) / 128, 128, 0, s>>>(c->d_lane, n_lanes);
+    k_classify<<<tiles, LL_TILE, 0, s>>>(P);
+    k_halfpass_hist<<<tiles, LL_TILE, 0, s>>>(P);
+    k_ring_scan<<<n_lanes, 1024, 0, s>>>(P);
+    k_scatter<<<tiles, LL_TILE, 0, s>>>(P);
+    const size_t smem = ll_feature_smem_bytes(c->SCAP);
+    if (c->SCAP == 512) {
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_features<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ring_features<512><<<dim3(c->R, n_lanes), 512, smem, s>>>(P);
+    } else {
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_features<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ring_features<1024><<<dim3(c->R, n_lanes), 512, smem, s>>>(P);
+    }
+    k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P);
+    c->launches += 7;
+    LL_CUDA_CHECK(c, cudaGetLastError());
+    return LL_OK;
+}

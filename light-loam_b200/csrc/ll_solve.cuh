@@ -1,0 +1,336 @@
+// Fused residual + Jacobian + Huber + JtJ / Jtr reduction and the Levenberg-Marquardt controller — the
+// replacement for ceres::Solve on this path (LO:475-482, 819-825; LM:1865-1872, 2079-2087) and for the
+// autodiff cost functors of lidarFactor.hpp (LidarEdgeFactor LF:9-52, LidarPlaneFactor_modify LF:203-251,
+// LidarPlaneNormFactor LF:253-285).
+//
+// With DISTORTION 0 (LO:23) every live factor is r = f(lp), lp = R(q) cp + t, and composing the ambient
+// Jacobian with EigenQuaternionManifold's plus-Jacobian gives d lp / d delta = -2 [R cp]x, d lp / d t = I
+// (checked against the oracle's Jet autodiff in tests/).  Column order (dx,dy,dz,tx,ty,tz).
+//
+// Solver restated: TRUST_REGION + LEVENBERG_MARQUARDT, DENSE_QR replaced by a Cholesky solve of the 6x6
+// normal equations (the 28-double reduction 21 + 6 + 1 carries everything the controller needs), Jacobi
+// scaling from the first Jacobian, HuberLoss(0.1) with the rho'' <= 0 corrector, radius 1e4, accept if
+// rho > 1e-3, max 4 iterations, function / gradient / parameter tolerances 1e-6 / 1e-10 / 1e-8.
+//
+// One CTA per problem; LM_THREADS threads stride over the residual blocks; the reduction order is fixed
+// (lane tree, then warps in order), so results are run-to-run deterministic.
+#pragma once
+#include <float.h>
+
+#include "ll_ctx.h"
+#include "ll_device.cuh"
+
+#define LM_THREADS 512
+#define LM_NRED 28
+
+struct LmShared {
+    double x[7], cand[7];
+    double red[LM_THREADS / 32][LM_NRED];
+    double out[LM_NRED];
+    int go;
+};
+
+// residual-block record (SoA, stride = cap): [0] type, [1..3] cp, [4..6] p0, [7..9] p1, [10] w
+//   type 0 EDGE        p0 = a, p1 = b
+//   type 1 PLANE_MODIFY p0 = j, p1 = ljm_norm, w = weight
+//   type 2 PLANE_NORM   p0 = unit normal, w = negative_OA_dot_norm
+template <bool FULL>
+__device__ __forceinline__ void lm_accumulate(const double* blk, int cap, int nb, const double* x, double acc[LM_NRED])
+{
+#pragma unroll
+    for (int k = 0; k < LM_NRED; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < nb; i += LM_THREADS) {
+        const int type = (int)blk[i];
+        const double cpx = blk[1 * cap + i], cpy = blk[2 * cap + i], cpz = blk[3 * cap + i];
+        const double ax = blk[4 * cap + i], ay = blk[5 * cap + i], az = blk[6 * cap + i];
+        const double bx = blk[7 * cap + i], by = blk[8 * cap + i], bz = blk[9 * cap + i];
+        const double w = blk[10 * cap + i];
+        double Rx, Ry, Rz;
+        quat_rotate(x, cpx, cpy, cpz, Rx, Ry, Rz);
+        const double lx = Rx + x[4], ly = Ry + x[5], lz = Rz + x[6];
+        double r[3], D[3][3];
+        int nr;
+        if (type == 0) {
+            // r = ((lp - a) x (lp - b)) / |a - b| ; d r / d lp = [b - a]x / |a - b|
+            const double ux = lx - ax, uy = ly - ay, uz = lz - az, vx = lx - bx, vy = ly - by, vz = lz - bz;
+            const double dex = ax - bx, dey = ay - by, dez = az - bz;
+            const double dn = sqrt(dex * dex + dey * dey + dez * dez);
+            r[0] = (uy * vz - uz * vy) / dn;
+            r[1] = (uz * vx - ux * vz) / dn;
+            r[2] = (ux * vy - uy * vx) / dn;
+            const double ex = -dex / dn, ey = -dey / dn, ez = -dez / dn;
+            D[0][0] = 0; D[0][1] = -ez; D[0][2] = ey;
+            D[1][0] = ez; D[1][1] = 0; D[1][2] = -ex;
+            D[2][0] = -ey; D[2][1] = ex; D[2][2] = 0;
+            nr = 3;
+        } else if (type == 1) {
+            r[0] = ((lx - ax) * bx + (ly - ay) * by + (lz - az) * bz) * w;
+            D[0][0] = w * bx; D[0][1] = w * by; D[0][2] = w * bz;
+            nr = 1;
+        } else {
+            r[0] = (ax * lx + ay * ly + az * lz) + w;
+            D[0][0] = ax; D[0][1] = ay; D[0][2] = az;
+            nr = 1;
+        }
+        double s = 0.0;
+        for (int k = 0; k < nr; ++k) s += r[k] * r[k];
+        // HuberLoss(0.1): rho(s), rho'(s); Corrector with rho'' <= 0: scale r and J by sqrt(rho')
+        double rho0 = s, rho1 = 1.0;
+        if (s > 0.01) {
+            const double rr = sqrt(s);
+            rho0 = 2.0 * 0.1 * rr - 0.01;
+            rho1 = fmax(DBL_MIN, 0.1 / rr);
+        }
+        acc[27] += 0.5 * rho0;
+        if (FULL) {
+            const double sq = sqrt(rho1);
+            for (int k = 0; k < nr; ++k) {
+                // J row = D_k * [ -2 [R cp]x | I ]
+                const double d0 = D[k][0], d1 = D[k][1], d2 = D[k][2];
+                double J[6];
+                J[0] = (d1 * (-2.0 * Rz) + d2 * (2.0 * Ry)) * sq;
+                J[1] = (d0 * (2.0 * Rz) + d2 * (-2.0 * Rx)) * sq;
+                J[2] = (d0 * (-2.0 * Ry) + d1 * (2.0 * Rx)) * sq;
+                J[3] = d0 * sq; J[4] = d1 * sq; J[5] = d2 * sq;
+                const double rk = r[k] * sq;
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                    for (int c = a; c < 6; ++c) acc[q++] += J[a] * J[c];
+                }
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * rk;
+            }
+        }
+    }
+}
+
+// fixed-order block reduction of acc[first..LM_NRED) into S.out
+template <bool FULL>
+__device__ __forceinline__ void lm_reduce(LmShared& S, double acc[LM_NRED])
+{
+    const int lane = lane_id(), w = warp_id();
+#pragma unroll
+    for (int k = FULL ? 0 : 27; k < LM_NRED; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += shfl_down_f64(v, d);
+        if (lane == 0) S.red[w][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < LM_NRED && (FULL || threadIdx.x == 27)) {
+        double v = 0.0;
+        for (int ww = 0; ww < LM_THREADS / 32; ++ww) v += S.red[ww][threadIdx.x];
+        S.out[threadIdx.x] = v;
+    }
+    __syncthreads();
+}
+
+// EigenQuaternionManifold::Plus on q, Euclidean on t
+__device__ __forceinline__ void lm_plus(const double* x, const double* delta, double* out)
+{
+    const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+    if (nd == 0.0) {
+        for (int i = 0; i < 4; ++i) out[i] = x[i];
+    } else {
+        const double sbd = sin(nd) / nd;
+        const double dq[4] = {sbd * delta[0], sbd * delta[1], sbd * delta[2], cos(nd)};
+        quat_mul(dq, x, out);
+    }
+    for (int i = 0; i < 3; ++i) out[4 + i] = x[4 + i] + delta[3 + i];
+}
+
+// 6x6 SPD solve A y = b by Cholesky (A given as packed upper triangle row-major, 21 entries). false if not SPD.
+__device__ __forceinline__ bool chol6_solve(const double* Ap, const double* b, double* y)
+{
+    double Lm[6][6];
+    int q = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int c = a; c < 6; ++c) { Lm[a][c] = Ap[q]; Lm[c][a] = Ap[q]; ++q; }
+    for (int j = 0; j < 6; ++j) {
+        double d = Lm[j][j];
+        for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        Lm[j][j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = Lm[i][j];
+            for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
+            Lm[i][j] = s / d;
+        }
+    }
+    double z[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= Lm[i][k] * z[k];
+        z[i] = s / Lm[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = z[i];
+        for (int k = i + 1; k < 6; ++k) s -= Lm[k][i] * y[k];
+        y[i] = s / Lm[i][i];
+        if (!isfinite(y[i])) return false;
+    }
+    return true;
+}
+
+// The whole Solve. q_io / t_io point at the parameter blocks (global memory); all threads of the CTA call it.
+__device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot)
+{
+    __shared__ LmShared S;
+    const int tid = threadIdx.x;
+    if (tid < 4) S.x[tid] = q_io[tid];
+    if (tid >= 4 && tid < 7) S.x[tid] = t_io[tid - 4];
+    __syncthreads();
+    if (nb <= 0) {  // nothing to minimise: parameters untouched
+        if (tid == 0 && L) { L->initial_cost[slot] = 0; L->final_cost[slot] = 0; L->jac_evals[slot] = 0; L->cost_evals[slot] = 0; L->termination[slot] = -1; }
+        return;
+    }
+    double acc[LM_NRED];
+    // controller state (meaningful on thread 0 only)
+    double H[21], g[6], scale[6], diagonal[6], x_cost = 0, x_norm = 0, radius = 1e4, decrease_factor = 2.0, se_cost = 0;
+    double model_cost_change = 0, gmax = 0;
+    bool reuse_diagonal = false, last_successful = true, atleast_one = false;
+    int iteration = 0, invalid = 0, term = 0, jac_evals = 0, cost_evals = 0;
+    double initial_cost = 0;
+
+    auto norm7 = [](const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); };
+
+    // IterationZero: cost, gradient, Jacobian (as JtJ) at x
+    lm_accumulate<true>(blk, cap, nb, S.x, acc);
+    lm_reduce<true>(S, acc);
+    if (tid == 0) {
+        for (int k = 0; k < 21; ++k) H[k] = S.out[k];
+        for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
+        x_cost = S.out[27];
+        initial_cost = x_cost;
+        se_cost = x_cost;
+        jac_evals = 1;
+        x_norm = norm7(S.x);
+        const int dq[6] = {0, 6, 11, 15, 18, 20};  // packed index of the diagonal
+        for (int c = 0; c < 6; ++c) scale[c] = 1.0 / (1.0 + sqrt(H[dq[c]]));  // jacobi_scaling, first Jacobian only
+        double ng[6], xp[7];
+        for (int c = 0; c < 6; ++c) ng[c] = -g[c];
+        lm_plus(S.x, ng, xp);
+        gmax = 0;
+        for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(S.x[i] - xp[i]));
+    }
+    for (;;) {
+        // ---- thread 0: finalize previous iteration, compute the trust-region step ----------------------
+        if (tid == 0) {
+            int go = 1;  // 1: evaluate candidate cost, 0: stop
+            for (;;) {
+                if (iteration >= 4) { term = 0; go = 0; break; }                         // max_num_iterations (LO:822)
+                if (last_successful && gmax <= 1e-10) { term = 1; go = 0; break; }       // gradient_tolerance
+                if (radius <= 1e-32) { term = 4; go = 0; break; }                        // min_trust_region_radius
+                ++iteration;
+                const int dq[6] = {0, 6, 11, 15, 18, 20};
+                if (!reuse_diagonal)
+                    for (int c = 0; c < 6; ++c) diagonal[c] = fmin(fmax(H[dq[c]] * scale[c] * scale[c], 1e-6), 1e32);
+                // (S H S + D^2) y = S g ; step = -y
+                double A[21], rhs[6], y[6], step[6];
+                int q = 0;
+                for (int a = 0; a < 6; ++a)
+                    for (int c = a; c < 6; ++c) { A[q] = H[q] * scale[a] * scale[c]; ++q; }
+                for (int c = 0; c < 6; ++c) { A[dq[c]] += diagonal[c] / radius; rhs[c] = g[c] * scale[c]; }
+                const bool ok = chol6_solve(A, rhs, y);
+                reuse_diagonal = true;
+                bool valid = false;
+                if (ok) {
+                    for (int c = 0; c < 6; ++c) step[c] = -y[c];
+                    // model_cost_change = -(J step).(r + J step / 2) = -step.(S g) - step^T (S H S) step / 2
+                    double lin = 0, quad = 0;
+                    for (int c = 0; c < 6; ++c) lin += step[c] * rhs[c];
+                    q = 0;
+                    for (int a = 0; a < 6; ++a)
+                        for (int c = a; c < 6; ++c) {
+                            const double hv = H[q] * scale[a] * scale[c];
+                            quad += (a == c ? 1.0 : 2.0) * hv * step[a] * step[c];
+                            ++q;
+                        }
+                    model_cost_change = -lin - 0.5 * quad;
+                    valid = model_cost_change > 0.0;
+                }
+                if (!valid) {  // HandleInvalidStep
+                    last_successful = false;
+                    if (++invalid >= 5) { term = 5; go = 0; break; }
+                    radius *= 0.5;
+                    continue;
+                }
+                invalid = 0;
+                double delta[6];
+                for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
+                lm_plus(S.x, delta, S.cand);
+                break;
+            }
+            S.go = go;
+        }
+        __syncthreads();
+        if (!S.go) break;
+        // ---- all threads: cost at the candidate --------------------------------------------------------
+        lm_accumulate<false>(blk, cap, nb, S.cand, acc);
+        lm_reduce<false>(S, acc);
+        if (tid == 0) {
+            const double cand_cost = S.out[27];
+            ++cost_evals;
+            int go = 2;  // 2: accepted -> re-linearise, 1: rejected -> next step, 0: stop
+            double sn = 0;
+            for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
+            if (atleast_one && sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { term = 2; go = 0; }           // parameter_tolerance
+            else if (atleast_one && fabs(x_cost - cand_cost) <= 1e-6 * x_cost) { term = 3; go = 0; }  // function_tolerance
+            else {
+                const double rel = (se_cost - cand_cost) / model_cost_change;
+                if (rel > 1e-3) {  // min_relative_decrease: HandleSuccessfulStep
+                    for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
+                    x_norm = norm7(S.x);
+                    radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+                    radius = fmin(1e16, radius);
+                    decrease_factor = 2.0;
+                    reuse_diagonal = false;
+                    se_cost = cand_cost;
+                    atleast_one = true;
+                    last_successful = true;
+                    go = 2;
+                } else {  // StepRejected
+                    radius = radius / decrease_factor;
+                    decrease_factor *= 2.0;
+                    reuse_diagonal = true;
+                    last_successful = false;
+                    go = 1;
+                }
+            }
+            S.go = go;
+        }
+        __syncthreads();
+        const int go = S.go;
+        if (go == 0) break;
+        if (go == 2) {
+            lm_accumulate<true>(blk, cap, nb, S.x, acc);
+            lm_reduce<true>(S, acc);
+            if (tid == 0) {
+                for (int k = 0; k < 21; ++k) H[k] = S.out[k];
+                for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
+                x_cost = S.out[27];
+                ++jac_evals;
+                double ng[6], xp[7];
+                for (int c = 0; c < 6; ++c) ng[c] = -g[c];
+                lm_plus(S.x, ng, xp);
+                gmax = 0;
+                for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(S.x[i] - xp[i]));
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) q_io[i] = S.x[i];
+        for (int i = 0; i < 3; ++i) t_io[i] = S.x[4 + i];
+        if (L) {
+            L->initial_cost[slot] = initial_cost;
+            L->final_cost[slot] = x_cost;
+            L->jac_evals[slot] = jac_evals;
+            L->cost_evals[slot] = cost_evals;
+            L->termination[slot] = term;
+        }
+    }
+}
