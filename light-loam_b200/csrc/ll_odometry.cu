@@ -414,6 +414,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     cudaStream_t s = c->stream;
     const int nq = c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     const size_t prep_smem = (size_t)c->R * LL_FLAT_PER_RING * 8 * 4;
+    LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
         k_odom_assoc<<<dim3((nq + 7) / 8, n_lanes), 256, 0, s>>>(P);
