@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — scans/sec of the Light-LOAM per-scan hot path on B200.
+
+A "step" = one pass of the hot path (feature extraction SR:100-377 + scan-to-scan odometry LO:425-896:
+3 outer iterations x <= 5 LM linearisations) over one batch of `--batch` independent HDL-64 scan streams
+("lanes"), one new ~130k-point scan per lane per step.  Workload = BASELINE.json configs[1].
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N ...            the reference's CPU algorithm (oracle restatement;
+                                                           PCL/Ceres/ROS are not installable here) on the host cores
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scans/sec (HDL-64, 130k pts, 5 GN iters)"
+POOL_SCANS = 157          # one lap of the 25 m loop path at 1 m per scan: a cyclic scan sequence
+WORKLOAD = "HDL-64 single scan (~130k pts), 5 GN iters, scan-to-scan odometry on 1xB200 (BASELINE.json configs[1]), batched over independent scan streams"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def make_pool(ll, n):
+    return [ll.synth.scan(64, k, mode=1) for k in range(n)]
+
+
+def lane_ids(step, lanes, rank):
+    """Lane i of rank r walks the cyclic scan sequence from its own offset: independent streams, same work."""
+    base = (np.arange(lanes) + rank * lanes) * 7
+    return ((base + step) % POOL_SCANS).astype(np.int32)
+
+
+# per-scan algorithmic (compulsory) bytes of each kernel, from the measured point counts
+def algorithmic_bytes(counts):
+    Nr, P, nlf, nls, ns, nf = counts["n_raw"], counts["n_full"], counts["n_less_flat"], counts["n_less_sharp"], counts["n_sharp"], counts["n_flat"]
+    feats = 16 * (ns + nls + nf) + 4 * (ns + nls + nf)
+    return {
+        "k_classify": 16 * Nr + 5 * Nr,                      # read raw, write ring id (1 B) + azimuth (4 B)
+        "k_halfpass_hist": 5 * Nr + 1 * Nr + 4 * 64 * (Nr / 256.0),
+        "k_scatter": 16 * Nr + 6 * Nr + 16 * P,              # read raw + ring/ori/rank, write ring-sorted cloud
+        "k_ring_features": 16 * P + 4 * P + feats + 16 * nlf,  # read ring slabs, write curvature, picks, per-ring voxel DS
+        "k_compact": 2 * (16 * nlf) + 2 * feats,
+        "k_odom_assoc": 3 * 0 + 16 * (ns + nf) + 16 * (nls + nlf) + 8 * ns + 16 * nf,  # upper bound 16 (Q + M) per launch
+        "k_grid_count": 16 * (nls + nlf),
+        "k_grid_scatter": 32 * (nls + nlf),
+    }
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    ll = importlib.import_module("light-loam_b200")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+    ctx = ll.Context(scan_line=64, batch=B, device=local_rank)
+    pool = make_pool(ll, POOL_SCANS)
+    ctx.pool_upload(pool)
+    stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step = 0
+    W = max(args.warmup, 3)
+    # priming (state, not timing): the first frame only initialises (LO:427-431) and the graph vote starts at
+    # now_frame > 5 (LO:794); the timed steps must run the steady-state path
+    for _ in range(7 + W):
+        ctx.process_pool(lane_ids(step, B, rank), want_poses=False)
+        step += 1
+    # ---- value: inputs resident in HBM (scan pool), device-timed ----------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        ctx.process_pool(lane_ids(step, B, rank), want_poses=False)
+        step += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = ctx.stats().kernel_launches * args.steps
+    sampler.stop_flag = True
+    barrier()
+    ms_total = maxreduce(e0.elapsed_time(e1))
+    value = B * world * args.steps / (ms_total * 1e-3)
+    st = ctx.stats()
+    counts = {"n_raw": float(np.mean([len(p) for p in pool])), "n_full": st.n_full, "n_less_flat": st.n_less_flat,
+              "n_less_sharp": st.n_less_sharp, "n_sharp": st.n_sharp, "n_flat": st.n_flat}
+
+    # ---- e2e: host buffers through the public call, H2D of every scan + D2H of the poses in the timed region ---
+    pinned = [torch.empty((len(p), 4), dtype=torch.float32).pin_memory() for p in pool]
+    for t, p in zip(pinned, pool):
+        t.numpy()[:] = p
+    host = [t.numpy() for t in pinned]
+    for _ in range(3):
+        ids = lane_ids(step, B, rank)
+        ctx.process_scans([host[i] for i in ids])
+        step += 1
+    barrier()
+    h2d = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids = lane_ids(step, B, rank)
+        poses = ctx.process_scans([host[i] for i in ids])
+        h2d += sum(host[i].nbytes for i in ids)
+        step += 1
+    torch.cuda.synchronize()
+    e2e_s = maxreduce(time.perf_counter() - t0)
+    e2e_value = B * world * args.steps / e2e_s
+    assert np.isfinite(poses).all()
+
+    # ---- per-kernel device time (CUDA event pairs on the launching stream) -> roofline of the dominant kernel ----
+    ctx.profile_enable(True)
+    for _ in range(args.steps):
+        ctx.process_pool(lane_ids(step, B, rank), want_poses=False)
+        step += 1
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    total_prof = sum(v[0] for v in prof.values())
+    dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    peak, peak_src = peaks()
+    ab = algorithmic_bytes(counts)
+    per_kernel = {}
+    for name, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        avg_ms = ms / n
+        bytes_launch = ab.get(name, 0.0) * B
+        per_kernel[name] = {"ms_per_launch": round(avg_ms, 4), "launches_per_step": n / args.steps, "share": round(ms / total_prof, 4),
+                            "alg_gbs": round(bytes_launch / (avg_ms * 1e-3) / 1e9, 1) if bytes_launch else None}
+    dom_ms = prof[dom][0] / prof[dom][1]
+    achieved = ab.get(dom, 0.0) * B / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": int(ab.get(dom, 0.0) * B),
+                "ms_per_launch": round(dom_ms, 4), "share_of_step": round(prof[dom][0] / total_prof, 4), "kernels": per_kernel}
+
+    # ---- CPU baseline: the oracle port of the same path on one host core, bounded sample (rank 0, N = 1) ---------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_sample(pool, n_scans=args.cpu_scans)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (features, NN) + f64 (residuals, LM)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "lanes_per_gpu": B, "scans_per_step": B * world, "points_per_scan": int(counts["n_raw"]),
+                       "gn_linearisations_per_solve_max": 5, "outer_iterations": 3, "parallelism": "independent scan streams sharded per GPU, no data-path collective",
+                       "l2": "inputs larger than L2: %d lanes x %.2f MB raw scan = %.0f MB read per step (> 126 MB), no flush" % (B, counts["n_raw"] * 16 / 1e6, B * counts["n_raw"] * 16 / 1e6)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": B * 14 * 8},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(pool, n_scans):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc_py
+    pipe = orc_py.Pipeline(orc_py.config(64), with_mapping=False)
+    ms = []
+    for k in range(n_scans + 2):
+        r = pipe.step(pool[k % POOL_SCANS])
+        if k >= 2:
+            ms.append(r["ms"][:2].sum())
+    per = float(np.mean(ms)) * 1e-3
+    return {"value": round(1.0 / per, 2), "unit": "scans/s", "cores": 1, "kind": "port",
+            "sample": "%d consecutive scans of the same pool, oracle extract_features + odometry (restated reference CPU path; PCL/Ceres unavailable offline), steady_clock per stage" % n_scans}
+
+
+_G = {}
+
+
+def _ref_worker(arg):
+    wid, n_scans = arg
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc_py
+    pipe = orc_py.Pipeline(orc_py.config(64), with_mapping=False)
+    pool = _G["pool"]
+    off = (wid * 7) % POOL_SCANS
+    for k in range(2):  # init frame + one warm frame, untimed
+        pipe.step(pool[(off + k) % POOL_SCANS])
+    t0 = time.perf_counter()
+    for k in range(2, 2 + n_scans):
+        pipe.step(pool[(off + k) % POOL_SCANS])
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU algorithm for the path (oracle restatement: the reference cannot be compiled here),
+    one independent scan stream per host core, all cores."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    ll = importlib.import_module("light-loam_b200")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc_py
+    orc_py.build()
+    cores = os.cpu_count() or 1
+    _G["pool"] = make_pool(ll, POOL_SCANS)
+    per_step = 2  # scans per worker per step: a bounded sample of the workload
+    n_scans = per_step * (args.steps + max(args.warmup, 3))
+    ctxm = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctxm.Pool(cores) as pl:
+        times = pl.map(_ref_worker, [(w, n_scans) for w in range(cores)])
+    wall = max(times)
+    value = cores * n_scans / wall
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "scans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(wall / (args.steps + max(args.warmup, 3)) * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (features, NN) + f64 (residuals, LM)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "restated reference CPU path (PCL/Ceres/ROS unavailable offline), one scan stream per host core"},
+            "cpu_baseline": {"value": round(value, 2), "unit": "scans/s", "cores": cores, "kind": "port",
+                             "sample": "%d scans per core x %d cores, extract_features + odometry" % (n_scans, cores)},
+            "e2e": {"value": round(value, 2), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 2)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "64")), help="scan streams (lanes) per GPU")
+    ap.add_argument("--cpu-scans", type=int, default=200, help="scans in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,16 @@ int ll_process_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans, doubl
 int ll_stage_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);
 int ll_process_staged(ll_ctx* ctx, int n_scans, double* poses_out);
 
+/* Scan pool: upload many scans once (float4 records in HBM), then feed lane i from pooled scan scan_ids[i].
+ * Same per-lane semantics as ll_process_scans without the per-call H2D of the points. */
+int ll_pool_upload(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);
+int ll_process_pool(ll_ctx* ctx, int n_lanes, const int* scan_ids, double* poses_out);
+
+/* Per-kernel device timing: CUDA event pairs around every launch while enabled. ll_profile_read returns the
+ * number of kernel names written ('\n'-separated) with their accumulated milliseconds and launch counts. */
+int ll_profile_enable(ll_ctx* ctx, int on);
+int ll_profile_read(ll_ctx* ctx, char* names_buf, int buf_len, double* total_ms, int* launches, int cap);
+
 /* Device-side timing of the last ll_process_staged / ll_process_scans: milliseconds between CUDA
  * events recorded on the context stream around the feature, odometry and mapping kernel groups. */
 int ll_last_timings(ll_ctx* ctx, float ms[4] /* features, odometry, mapping, total */);

@@ -17,7 +17,8 @@ LL_W_FEW_CORRESPONDENCES = 1
 
 SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
            "ll_extract_features", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
-           "ll_process_staged", "ll_last_timings", "ll_debug_assoc", "ll_cuda_stream"]
+           "ll_process_staged", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
+           "ll_debug_assoc", "ll_cuda_stream"]
 
 
 class LLConfig(ctypes.Structure):
@@ -78,6 +79,10 @@ def lib():
         L.ll_process_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView), ctypes.c_void_p]
         L.ll_stage_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
         L.ll_process_staged.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.ll_pool_upload.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
+        L.ll_process_pool.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.ll_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.ll_profile_read.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.ll_last_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ll_debug_assoc.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         _LIB = L
@@ -197,6 +202,30 @@ class Context:
         poses = np.zeros((n, 14)) if want_poses else None
         self._check(self.L.ll_process_staged(self.h, n, poses.ctypes.data if want_poses else None), "ll_process_staged")
         return poses
+
+    def pool_upload(self, scans):
+        """Keeps the scans resident in HBM; lanes are then fed by scan id (process_pool)."""
+        views = self._views(scans)
+        self._check(self.L.ll_pool_upload(self.h, len(scans), views), "ll_pool_upload")
+        self._keep = None
+
+    def process_pool(self, scan_ids, want_poses=True):
+        ids = np.ascontiguousarray(scan_ids, dtype=np.int32)
+        poses = np.zeros((len(ids), 14)) if want_poses else None
+        self._check(self.L.ll_process_pool(self.h, len(ids), ids.ctypes.data, poses.ctypes.data if want_poses else None), "ll_process_pool")
+        return poses
+
+    def profile_enable(self, on=True):
+        self._check(self.L.ll_profile_enable(self.h, int(on)), "ll_profile_enable")
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} accumulated since profile_enable(True)."""
+        buf = ctypes.create_string_buffer(4096)
+        ms = np.zeros(64)
+        cnt = np.zeros(64, np.int32)
+        n = self._check(self.L.ll_profile_read(self.h, buf, 4096, ms.ctypes.data, cnt.ctypes.data, 64), "ll_profile_read")
+        names = buf.value.decode().split("\n")[:n]
+        return {names[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     def last_timings(self):
         ms = np.zeros(4, np.float32)

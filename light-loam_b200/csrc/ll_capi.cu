@@ -15,12 +15,24 @@ namespace {
 
 struct ScanHdr { int n_raw, stride_words; };
 
-__global__ void k_set_scan_hdr(LaneState* lane, const ScanHdr* hdr, int n_lanes)
+__global__ void k_set_scan_hdr(LaneState* lane, const ScanHdr* hdr, const uint32_t* raw, size_t lane_words, int n_lanes)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n_lanes) {
+        lane[b].raw = raw + (size_t)b * lane_words;
         lane[b].n_raw = hdr[b].n_raw;
         lane[b].stride_words = hdr[b].stride_words;
+        lane[b].err = 0;
+    }
+}
+
+__global__ void k_set_pool_hdr(LaneState* lane, const int* ids, const int* pool_n, const uint32_t* pool, size_t scan_words, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_lanes) {
+        lane[b].raw = pool + (size_t)ids[b] * scan_words;
+        lane[b].n_raw = pool_n[ids[b]];
+        lane[b].stride_words = 4;
         lane[b].err = 0;
     }
 }
@@ -139,7 +151,9 @@ void ll_destroy(ll_ctx* c)
     cudaSetDevice(c->dev);
     if (c->stream) cudaStreamSynchronize(c->stream);
     ll_map_free(c);
-    void* ptrs[] = {c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_lf_tmp,
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    if (c->h_ids) cudaFreeHost(c->h_ids);
+    void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted,
                     c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
@@ -273,7 +287,7 @@ int ll_stage_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
     }
     LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_hdr, hdr, sizeof(ScanHdr) * n_scans, cudaMemcpyHostToDevice, c->stream));
     LL_CUDA_CHECK(c, cudaEventRecord(c->ev[4], c->stream));
-    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, reinterpret_cast<const ScanHdr*>(c->d_hdr), n_scans);
+    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, reinterpret_cast<const ScanHdr*>(c->d_hdr), c->d_raw, (size_t)c->Nmax * 8, n_scans);
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }
@@ -282,6 +296,7 @@ int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
 {
     if (!c || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
     LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    if (c->prof) ll_prof_harvest(c);
     c->launches = 0;
     LL_CUDA_CHECK(c, cudaEventRecord(c->ev[0], c->stream));
     int rc = ll_launch_features(c, n_scans);
@@ -311,6 +326,86 @@ int ll_process_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans, double*
     if (rc) return rc;
     if (!poses_out) LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return LL_OK;
+}
+
+// ---- scan pool: keep many scans resident in HBM, feed lanes by scan id ------------------------------------
+int ll_pool_upload(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
+{
+    if (!c || !scans || n_scans < 1) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (n_scans > c->pool_cap) {
+        if (c->d_pool) cudaFree(c->d_pool);
+        if (c->d_pool_n) cudaFree(c->d_pool_n);
+        c->d_pool = nullptr; c->d_pool_n = nullptr; c->pool_cap = 0;
+        LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_pool, sizeof(uint32_t) * 4 * (size_t)c->Nmax * n_scans));
+        LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_pool_n, sizeof(int) * n_scans));
+        c->pool_cap = n_scans;
+    }
+    if (!c->h_ids) {
+        LL_CUDA_CHECK(c, cudaHostAlloc((void**)&c->h_ids, sizeof(int) * c->B, cudaHostAllocDefault));
+        LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_ids, sizeof(int) * c->B));
+    }
+    std::vector<int> ns(n_scans);
+    for (int i = 0; i < n_scans; ++i) {
+        const ll_cloud_view& v = scans[i];
+        if (!v.data || v.n < 1 || v.stride_bytes < 12 || (v.stride_bytes & 3)) return LL_E_INVAL;
+        if (v.n > c->Nmax) return LL_E_CAPACITY;
+        ns[i] = v.n;
+        uint32_t* dst = c->d_pool + (size_t)i * c->Nmax * 4;
+        if (v.stride_bytes == 16)
+            LL_CUDA_CHECK(c, cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
+        else
+            LL_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, 16, v.data, v.stride_bytes, v.stride_bytes < 16 ? 12 : 16, v.n, cudaMemcpyHostToDevice, c->stream));
+    }
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_pool_n, ns.data(), sizeof(int) * n_scans, cudaMemcpyHostToDevice, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->pool_n = n_scans;
+    return LL_OK;
+}
+
+int ll_process_pool(ll_ctx* c, int n_lanes, const int* scan_ids, double* poses_out)
+{
+    if (!c || !scan_ids || n_lanes < 1 || n_lanes > c->B || !c->d_pool) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    LL_CUDA_CHECK(c, cudaEventSynchronize(c->ev[4]));
+    for (int i = 0; i < n_lanes; ++i) {
+        if (scan_ids[i] < 0 || scan_ids[i] >= c->pool_n) return LL_E_INVAL;
+        c->h_ids[i] = scan_ids[i];
+    }
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_ids, c->h_ids, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, c->stream));
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[4], c->stream));
+    k_set_pool_hdr<<<(n_lanes + 63) / 64, 64, 0, c->stream>>>(c->d_lane, c->d_ids, c->d_pool_n, c->d_pool, (size_t)c->Nmax * 4, n_lanes);
+    return ll_process_staged(c, n_lanes, poses_out);
+}
+
+// ---- per-kernel device timing ---------------------------------------------------------------------------------
+int ll_profile_enable(ll_ctx* c, int on)
+{
+    if (!c) return LL_E_INVAL;
+    if (c->prof) ll_prof_harvest(c);
+    c->prof = on != 0;
+    c->prof_acc.clear();
+    return LL_OK;
+}
+// writes up to cap entries: names as a '\n'-separated list into names_buf; total ms and launches per name
+int ll_profile_read(ll_ctx* c, char* names_buf, int buf_len, double* total_ms, int* launches, int cap)
+{
+    if (!c || !names_buf || !total_ms || !launches) return LL_E_INVAL;
+    ll_prof_harvest(c);
+    int k = 0;
+    std::string names;
+    for (const auto& kv : c->prof_acc) {
+        if (k >= cap) break;
+        names += kv.first;
+        names += '\n';
+        total_ms[k] = kv.second.first;
+        launches[k] = kv.second.second;
+        ++k;
+    }
+    if ((int)names.size() + 1 > buf_len) return LL_E_CAPACITY;
+    memcpy(names_buf, names.c_str(), names.size() + 1);
+    return k;
 }
 
 int ll_last_timings(ll_ctx* c, float ms[4])
@@ -416,3 +511,18 @@ int ll_debug_assoc(ll_ctx* c, int lane, int* corner, int corner_cap, int* plane,
 }
 
 }  // extern "C"
+
+void ll_prof_harvest(ll_ctx* c)
+{
+    if (c->prof_name.empty()) return;
+    cudaEventSynchronize(c->prof_ev[2 * (c->prof_name.size() - 1) + 1]);
+    for (size_t k = 0; k < c->prof_name.size(); ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]) == cudaSuccess) {
+            auto& a = c->prof_acc[c->prof_name[k]];
+            a.first += ms;
+            a.second += 1;
+        }
+    }
+    c->prof_name.clear();
+}

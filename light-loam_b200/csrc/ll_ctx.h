@@ -17,7 +17,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/lightloam_b200.h"
 
@@ -30,6 +32,7 @@
 
 struct LaneState {
     // --- scan registration ---
+    const uint32_t* raw;             // this lane's raw point records (staging slab or scan pool)
     int n_raw, stride_words;
     int first_valid, last_valid;     // first / last index surviving the NaN + range filters (SR:109-110)
     int half_idx;                    // index of the point that flips halfPassed (SR:189-192), INT_MAX if none
@@ -109,6 +112,19 @@ struct ll_ctx {
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;
 
+    // scan pool: scans kept resident in HBM and referenced by id (ll_pool_upload / ll_process_pool)
+    uint32_t* d_pool = nullptr;    // [pool_cap][Nmax * 4] words (float4 records)
+    int* d_pool_n = nullptr;       // [pool_cap] points per pooled scan
+    int* h_ids = nullptr;          // pinned [B]
+    int* d_ids = nullptr;          // [B]
+    int pool_cap = 0, pool_n = 0;
+
+    // optional per-kernel device timing (ll_profile_enable): event pairs around every launch
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<const char*> prof_name;      // name per pair in flight
+    std::map<std::string, std::pair<double, int>> prof_acc;  // name -> (total ms, launches)
+
     // mapping (allocated when enable_mapping)
     struct MapState* map = nullptr;
 };
@@ -122,6 +138,31 @@ struct ll_ctx {
             return LL_E_CUDA;                                                                         \
         }                                                                                             \
     } while (0)
+
+// RAII event pair around one kernel launch when profiling is on
+struct LLProf {
+    ll_ctx* c;
+    bool on;
+    LLProf(ll_ctx* ctx, const char* name) : c(ctx), on(ctx->prof)
+    {
+        if (!on) return;
+        const size_t k = c->prof_name.size();
+        if (c->prof_ev.size() < 2 * (k + 1)) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            c->prof_ev.push_back(a);
+            c->prof_ev.push_back(b);
+        }
+        c->prof_name.push_back(name);
+        cudaEventRecord(c->prof_ev[2 * k], c->stream);
+    }
+    ~LLProf()
+    {
+        if (on) cudaEventRecord(c->prof_ev[2 * (c->prof_name.size() - 1) + 1], c->stream);
+    }
+};
+void ll_prof_harvest(ll_ctx* c);  // folds the in-flight event pairs into prof_acc (synchronises)
 
 // kernel-group entry points (defined in the .cu files) ---------------------------------------------------
 int ll_launch_features(ll_ctx* c, int n_lanes);                 // SR:100-377 on lanes [0, n_lanes)

@@ -21,7 +21,6 @@ namespace {
 
 struct FeatParams {
     LaneState* lane;
-    const uint32_t* raw;
     int8_t* ring8;
     uint8_t* rank8;
     float* ori;
@@ -42,7 +41,6 @@ struct FeatParams {
     int scan_line;
     float thres, lower_bound, up_bound, factor;
     float inv_leaf;   // 1.0f / 0.2f
-    size_t raw_stride_words;  // per lane
 };
 
 // SR:114-126: endOri from the last valid point and startOri
@@ -66,7 +64,7 @@ __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
     int ring = -1;
     float ori = 0.f;
     if (i < n) {
-        const uint32_t* p = P.raw + (size_t)b * P.raw_stride_words + (size_t)i * sw;
+        const uint32_t* p = L.raw + (size_t)i * sw;
         const float x = __uint_as_float(p[0]), y = __uint_as_float(p[1]), z = __uint_as_float(p[2]);
         valid = isfinite(x) && isfinite(y) && isfinite(z) && !(x * x + y * y + z * z < P.thres * P.thres);  // SR:72
         if (valid) {
@@ -203,7 +201,7 @@ __global__ void __launch_bounds__(LL_TILE) k_scatter(FeatParams P)
     const float relTime = (ori - startOri) / (endOri - startOri);          // SR:207
     const float intensity = (float)((double)ring + 0.1 * (double)relTime);  // SR:208
     const int pos = L.ring_begin[ring] + P.tile_hist[((size_t)b * P.NT + blockIdx.x) * P.R + ring] + P.rank8[(size_t)b * P.Nmax + i];
-    const uint32_t* p = P.raw + (size_t)b * P.raw_stride_words + (size_t)i * L.stride_words;
+    const uint32_t* p = L.raw + (size_t)i * L.stride_words;
     P.full[(size_t)b * P.Nmax + pos] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), intensity);
 }
 
@@ -608,7 +606,7 @@ size_t ll_feature_smem_bytes(int SCAP)
 int ll_launch_features(ll_ctx* c, int n_lanes)
 {
     FeatParams P;
-    P.lane = c->d_lane; P.raw = c->d_raw; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.ori = c->d_ori; P.tile_hist = c->d_tile_hist;
+    P.lane = c->d_lane; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.ori = c->d_ori; P.tile_hist = c->d_tile_hist;
     P.full = c->d_full; P.curv = c->d_curv; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
     P.sharp = c->d_sharp; P.flat = c->d_flat; P.sharp_idx = c->d_sharp_idx; P.lsharp_idx = c->d_lsharp_idx; P.flat_idx = c->d_flat_idx;
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
@@ -616,23 +614,24 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     P.thres = c->cfg.minimum_range; P.lower_bound = c->cfg.lower_bound; P.up_bound = c->cfg.up_bound;
     P.factor = (c->cfg.scan_line - 1) / (c->cfg.up_bound - c->cfg.lower_bound);  // SR:441, fp32
     P.inv_leaf = 1.0f / 0.2f;
-    P.raw_stride_words = (size_t)c->Nmax * 8;
     cudaStream_t s = c->stream;
     const dim3 tiles(c->NT, n_lanes);
-    k_reset_scan_state<<<(n_lanes + 127) / 128, 128, 0, s>>>(c->d_lane, n_lanes);
-    k_classify<<<tiles, LL_TILE, 0, s>>>(P);
-    k_halfpass_hist<<<tiles, LL_TILE, 0, s>>>(P);
-    k_ring_scan<<<n_lanes, 1024, 0, s>>>(P);
-    k_scatter<<<tiles, LL_TILE, 0, s>>>(P);
+    { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<(n_lanes + 127) / 128, 128, 0, s>>>(c->d_lane, n_lanes); }
+    { LLProf pr(c, "k_classify"); k_classify<<<tiles, LL_TILE, 0, s>>>(P); }
+    { LLProf pr(c, "k_halfpass_hist"); k_halfpass_hist<<<tiles, LL_TILE, 0, s>>>(P); }
+    { LLProf pr(c, "k_ring_scan"); k_ring_scan<<<n_lanes, 1024, 0, s>>>(P); }
+    { LLProf pr(c, "k_scatter"); k_scatter<<<tiles, LL_TILE, 0, s>>>(P); }
     const size_t smem = ll_feature_smem_bytes(c->SCAP);
     if (c->SCAP == 512) {
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_features<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LLProf pr(c, "k_ring_features");
         k_ring_features<512><<<dim3(c->R, n_lanes), 512, smem, s>>>(P);
     } else {
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_features<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LLProf pr(c, "k_ring_features");
         k_ring_features<1024><<<dim3(c->R, n_lanes), 512, smem, s>>>(P);
     }
-    k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P);
+    { LLProf pr(c, "k_compact"); k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P); }
     c->launches += 7;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;

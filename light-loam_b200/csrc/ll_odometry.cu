@@ -396,9 +396,9 @@ static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1,
     cudaStream_t s = c->stream;
     LL_CUDA_CHECK(c, cudaMemsetAsync(g.cursor, 0, sizeof(int) * (size_t)g.T * n_lanes, s));
     const int gx = (max_pts + 255) / 256 > 0 ? (max_pts + 255) / 256 : 1;
-    k_grid_count<<<dim3(gx < 296 ? gx : 296, n_lanes), 256, 0, s>>>(S, c->d_lane, g.cursor, g.T, g.inv_h);
-    k_grid_scan<<<n_lanes, 1024, 0, s>>>(g.cursor, g.start, g.T);
-    k_grid_scatter<<<dim3(gx < 296 ? gx : 296, n_lanes), 256, 0, s>>>(S, c->d_lane, g.cursor, g.sorted, g.T, g.cap, g.inv_h);
+    { LLProf pr(c, "k_grid_count"); k_grid_count<<<dim3(gx < 296 ? gx : 296, n_lanes), 256, 0, s>>>(S, c->d_lane, g.cursor, g.T, g.inv_h); }
+    { LLProf pr(c, "k_grid_scan"); k_grid_scan<<<n_lanes, 1024, 0, s>>>(g.cursor, g.start, g.T); }
+    { LLProf pr(c, "k_grid_scatter"); k_grid_scatter<<<dim3(gx < 296 ? gx : 296, n_lanes), 256, 0, s>>>(S, c->d_lane, g.cursor, g.sorted, g.T, g.cap, g.inv_h); }
     c->launches += 3;
     return LL_OK;
 }
@@ -417,12 +417,12 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
-        k_odom_assoc<<<dim3((nq + 7) / 8, n_lanes), 256, 0, s>>>(P);
-        k_odom_prep<<<n_lanes, PREP_THREADS, prep_smem, s>>>(P);
-        k_lm_solve_odom<<<n_lanes, LM_THREADS, 0, s>>>(P);
+        { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3((nq + 7) / 8, n_lanes), 256, 0, s>>>(P); }
+        { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, prep_smem, s>>>(P); }
+        { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, LM_THREADS, 0, s>>>(P); }
         c->launches += 3;
     }
-    k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes);
+    { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
     c->launches += 1;
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud on this frame's less-sharp / less-flat (LO:895-896)
     int rc = build_grid(c, c->g_corner, c->d_lsharp[0], c->d_lsharp[1], (size_t)c->R * LL_LSHARP_PER_RING, 0, n_lanes, c->R * LL_LSHARP_PER_RING);
