@@ -153,10 +153,10 @@ void ll_destroy(ll_ctx* c)
     ll_map_free(c);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->h_ids) cudaFreeHost(c->h_ids);
-    void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_lf_tmp,
+    void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
-                    c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted,
-                    c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
+                    c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted, c->g_corner.partial,
+                    c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_lane) cudaFreeHost(c->h_lane);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -210,6 +210,8 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_tile_hist, B * c->NT * R));
     CK(dalloc(c->d_full, B * N));
     CK(dalloc(c->d_curv, B * N));
+    CK(dalloc(c->d_label, B * N));
+    CK(dalloc(c->d_sorted16, B * N));
     CK(dalloc(c->d_lf_tmp, B * N));
     CK(dalloc(c->d_ring_lists, B * R * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING)));
     CK(dalloc(c->d_ring_counts, B * R * 4));
@@ -224,15 +226,16 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     }
     // hashed grids over the previous frame's less-sharp / less-flat clouds; cell 1.01 m so that the 5 m
     // acceptance radius (LO:29) is covered by at most 5 shells
-    c->g_corner.T = pow2ceil(2 * (int)R * LL_LSHARP_PER_RING);
+    c->g_corner.T = pow2ceil(2 * (int)R * LL_LSHARP_PER_RING) < 2048 ? 2048 : pow2ceil(2 * (int)R * LL_LSHARP_PER_RING);
     c->g_corner.cap = (int)R * LL_LSHARP_PER_RING;
-    c->g_surf.T = pow2ceil((int)N);
+    c->g_surf.T = pow2ceil((int)N / 2) < 2048 ? 2048 : pow2ceil((int)N / 2);
     c->g_surf.cap = (int)N;
     for (KnnGrid* g : {&c->g_corner, &c->g_surf}) {
         g->h = 1.01f;
         g->inv_h = 1.0f / g->h;
         CK(dalloc(g->start, B * (size_t)(g->T + 1)));
         CK(dalloc(g->cursor, B * (size_t)g->T));
+        CK(dalloc(g->partial, B * (size_t)(g->T / 2048 + 1)));
         CK(dalloc(g->sorted, B * (size_t)g->cap));
     }
     CK(dalloc(c->d_corner_assoc, B * R * LL_SHARP_PER_RING * 2));

@@ -46,6 +46,7 @@ struct LaneState {
     int cur;                         // ping-pong slot written by the latest extraction / upload (= last_slot ^ 1)
     int last_slot;                   // slot holding laserCloudCornerLast / SurfLast (registered by k_odom_finalize)
     int n_last_corner, n_last_surf;  // sizes of laserCloudCornerLast / laserCloudSurfLast
+    int mono_corner, mono_surf;      // 1: the *Last cloud is ring-monotone (int(intensity) non-decreasing, 0..255)
     double para_q[4], para_t[3];     // LO:61-62 (x,y,z,w)
     double q_w[4], t_w[3];           // LO:57-58
     int n_corner_corr, n_plane_corr, n_plane_sel, n_blocks;
@@ -68,6 +69,7 @@ struct KnnGrid {
     float h = 1.f, inv_h = 1.f;
     int* start = nullptr;     // [B][T+1] exclusive bucket offsets
     int* cursor = nullptr;    // [B][T]   counting / scatter cursors
+    int* partial = nullptr;   // [B][T / 2048] chunk sums for the two-level scan
     float4* sorted = nullptr; // [B][cap] bucket-ordered points, .w = original index bits
 };
 
@@ -95,6 +97,8 @@ struct ll_ctx {
     int* d_tile_hist = nullptr;    // [B][NT][R]
     float4* d_full = nullptr;      // [B][Nmax]
     float* d_curv = nullptr;       // [B][Nmax]
+    int8_t* d_label = nullptr;     // [B][Nmax] cloudLabel (SR:40)
+    uint16_t* d_sorted16 = nullptr;// [B][Nmax] per-sector sorted local index | curvature class bits
     float4* d_lf_tmp = nullptr;    // [B][Nmax] per-ring voxel-DS output parked at the ring's own offset
     int* d_ring_lists = nullptr;   // [B][R][12 + 120 + 24]
     int* d_ring_counts = nullptr;  // [B][R][4]  sharp, less_sharp, flat, less_flat

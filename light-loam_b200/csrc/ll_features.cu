@@ -4,9 +4,10 @@
 //   k_halfpass_hist  SR:178-193 (which point flips halfPassed) + per-tile ring histogram / ranks
 //   k_ring_scan      SR:215-221 (ring offsets = stable counting sort by ring)
 //   k_scatter        SR:194-209 (relTime, intensity) + scatter into the ring-major cloud
-//   k_ring_features  SR:225-376: one CTA per (ring, lane): TMA bulk load of the ring into shared memory,
-//                    11-tap curvature, six in-smem sector sorts, warp-serial greedy pick with +-5
-//                    suppression, less-flat collection and pcl::VoxelGrid(0.2) per ring
+//   k_ring_sort      SR:225-257: one CTA per (ring, lane): TMA bulk load of the ring into shared memory,
+//                    11-tap curvature, six in-smem sector sorts -> u16 sorted order per point
+//   k_ring_pick      SR:251-359: greedy pick with +-5 suppression, one warp per ring (order-dependent part)
+//   k_ring_lessflat  SR:361-376: less-flat collection and pcl::VoxelGrid(0.2) per ring
 //   k_compact        concatenation of the per-ring outputs in the reference's publish order (SR:273-376)
 //
 // HBM-bound streaming work; no GEMM shape anywhere.  Algorithmic bytes per scan:
@@ -27,6 +28,8 @@ struct FeatParams {
     int* tile_hist;
     float4* full;
     float* curv;
+    int8_t* label;       // [B][Nmax] SR:234/272/278/324
+    uint16_t* sorted16;  // [B][Nmax] per-sector sorted order + curvature class bits
     float4* lf_tmp;
     int* ring_lists;
     int* ring_counts;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(LL_TILE) k_halfpass_hist(FeatParams P)
     if (threadIdx.x < P.R) {
         int run = 0;
         for (int ww = 0; ww < LL_TILE / 32; ++ww) { const int c = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += c; }
-        P.tile_hist[((size_t)b * P.NT + blockIdx.x) * P.R + threadIdx.x] = run;
+        P.tile_hist[((size_t)b * P.R + threadIdx.x) * P.NT + blockIdx.x] = run;  // [lane][ring][tile]: scans run along tiles
     }
     __syncthreads();
     if (i < P.Nmax) P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(cnt[w][ring] + rank_in_warp) : 0;
@@ -149,15 +152,15 @@ __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
     const int ntiles = (L.n_raw + LL_TILE - 1) / LL_TILE;
     const int per = (ntiles + 31) / 32;
     for (int r = w; r < P.R; r += 32) {
-        int* col = P.tile_hist + (size_t)b * P.NT * P.R + r;
+        int* col = P.tile_hist + ((size_t)b * P.R + r) * P.NT;
         const int t0 = lane * per, t1 = min(t0 + per, ntiles);
         int s = 0;
-        for (int t = t0; t < t1; ++t) s += col[(size_t)t * P.R];
+        for (int t = t0; t < t1; ++t) s += col[t];
         int incl = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
         int run = incl - s;
-        for (int t = t0; t < t1; ++t) { const int c = col[(size_t)t * P.R]; col[(size_t)t * P.R] = run; run += c; }
+        for (int t = t0; t < t1; ++t) { const int c = col[t]; col[t] = run; run += c; }
         if (lane == 31) tot[r] = incl;
     }
     __syncthreads();
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(LL_TILE) k_scatter(FeatParams P)
     }
     const float relTime = (ori - startOri) / (endOri - startOri);          // SR:207
     const float intensity = (float)((double)ring + 0.1 * (double)relTime);  // SR:208
-    const int pos = L.ring_begin[ring] + P.tile_hist[((size_t)b * P.NT + blockIdx.x) * P.R + ring] + P.rank8[(size_t)b * P.Nmax + i];
+    const int pos = L.ring_begin[ring] + P.tile_hist[((size_t)b * P.R + ring) * P.NT + blockIdx.x] + P.rank8[(size_t)b * P.Nmax + i];
     const uint32_t* p = L.raw + (size_t)i * L.stride_words;
     P.full[(size_t)b * P.Nmax + pos] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), intensity);
 }
@@ -228,9 +231,108 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
-// SR:288-311: +-5 neighbour suppression with the 0.05 m^2 consecutive-gap break. Called by warp 0 with the
+// ---------------------------------------------------------------------------------------------------------
+// k_ring_sort: one CTA per (ring, lane).  TMA bulk load of the ring slab into shared memory, 11-tap curvature
+// (SR:225-235), six concurrent bitonic sector sorts on (curvature bits, index) keys (SR:257), then the sorted
+// order is written back as one u16 per point: local index | over(c > 0.1) << 14 | under(c < 0.1) << 15 —
+// everything the greedy pick needs to know about the curvature.
+// ---------------------------------------------------------------------------------------------------------
+template <int SCAP>
+__global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
+{
+    constexpr int RCAP = 6 * SCAP + 16;
+    constexpr int NTH = 512;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* pts = reinterpret_cast<float4*>(smem);
+    u64* keys = reinterpret_cast<u64*>(smem + (size_t)RCAP * 16);
+    int* sp = reinterpret_cast<int*>(keys + 6 * SCAP);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sp + 8);
+
+    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    LaneState& L = P.lane[b];
+    const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base, ntot = L.n_full;
+    const float4* gfull = P.full + (size_t)b * P.Nmax;
+    float* gcurv = P.curv + (size_t)b * P.Nmax;
+    int8_t* glabel = P.label + (size_t)b * P.Nmax;
+    uint16_t* gsorted = P.sorted16 + (size_t)b * P.Nmax;
+
+    auto global_curv = [&](int g) {  // the reference's stencil runs over ring joins (global index)
+        float c = 0.f;
+        if (g >= 5 && g < ntot - 5) {
+            float dx = gfull[g - 5].x, dy = gfull[g - 5].y, dz = gfull[g - 5].z;
+            for (int k = -4; k <= -1; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
+            dx = dx - 10 * gfull[g].x; dy = dy - 10 * gfull[g].y; dz = dz - 10 * gfull[g].z;
+            for (int k = 1; k <= 5; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
+            c = dx * dx + dy * dy + dz * dz;
+        }
+        return c;
+    };
+
+    if (n - 11 < 6 || n > 6 * SCAP + 11) {  // SR:248 skip; or capacity overflow
+        if (tid == 0 && n > 6 * SCAP + 11) L.err = LL_E_CAPACITY;
+        for (int i = tid; i < n; i += NTH) { gcurv[base + i] = global_curv(base + i); glabel[base + i] = 0; }
+        return;
+    }
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_bulk_g2s(pts, gfull + base, (uint32_t)n * 16u, bar);
+    for (int i = tid; i < 6 * SCAP; i += NTH) keys[i] = ~0ull;
+    const int len = n - 11;
+    if (tid <= 6) sp[tid] = 5 + len * tid / 6;  // SR:253-254 with ring-local indices
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    for (int i = tid; i < n; i += NTH) {
+        float c;
+        if (i >= 5 && i < n - 5) {
+            float dx = pts[i - 5].x, dy = pts[i - 5].y, dz = pts[i - 5].z;
+#pragma unroll
+            for (int k = -4; k <= -1; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
+            { const float4 q = pts[i]; dx = dx - 10 * q.x; dy = dy - 10 * q.y; dz = dz - 10 * q.z; }
+#pragma unroll
+            for (int k = 1; k <= 5; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
+            c = dx * dx + dy * dy + dz * dz;
+            if (i < n - 6) {  // sectors tile [5, n-6)
+                int j = 0;
+#pragma unroll
+                for (int q = 1; q < 6; ++q) j += (i >= sp[q]);
+                keys[j * SCAP + (i - sp[j])] = ((u64)__float_as_uint(c) << 32) | (unsigned)i;
+            }
+        } else {
+            c = global_curv(base + i);
+        }
+        gcurv[base + i] = c;
+        glabel[base + i] = 0;
+    }
+    __syncthreads();
+
+    for (int k = 2; k <= SCAP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < 3 * SCAP; t += NTH) {
+                const int seg = t / (SCAP / 2), tl = t % (SCAP / 2);
+                const int i = ((tl & ~(j - 1)) << 1) | (tl & (j - 1));
+                u64* K = keys + seg * SCAP;
+                const u64 a = K[i], c = K[i | j];
+                const bool asc = (i & k) == 0;
+                if ((a > c) == asc) { K[i] = c; K[i | j] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = 5 + tid; i < n - 6; i += NTH) {
+        int j = 0;
+#pragma unroll
+        for (int q = 1; q < 6; ++q) j += (i >= sp[q]);
+        const u64 key = keys[j * SCAP + (i - sp[j])];
+        const float c = __uint_as_float((unsigned)(key >> 32));
+        gsorted[base + i] = (uint16_t)((unsigned)key | ((double)c > 0.1 ? 0x4000u : 0u) | ((double)c < 0.1 ? 0x8000u : 0u));
+    }
+}
+
+// SR:288-311: +-5 neighbour suppression with the 0.05 m^2 consecutive-gap break. Called by one warp with the
 // picked local index `ind` (warp-uniform). Lanes 0..4 test l = +1..+5, lanes 8..12 test l = -1..-5.
-__device__ __forceinline__ void suppress_neighbours(const float4* pts, uint8_t* picked, int ind, int lane)
+__device__ __forceinline__ void suppress_neighbours(const float4* pts, unsigned* picked, int ind, int lane)
 {
     bool brk = false;
     int tgt = -1;
@@ -248,198 +350,136 @@ __device__ __forceinline__ void suppress_neighbours(const float4* pts, uint8_t* 
     const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
     const unsigned f = bm & 0x1Fu, r = (bm >> 8) & 0x1Fu;
     const int nf = f ? __ffs(f) - 1 : 5, nr = r ? __ffs(r) - 1 : 5;
-    if (lane < 5 && lane < nf) picked[tgt] = 1;
-    if (lane >= 8 && lane < 13 && (lane - 8) < nr) picked[tgt] = 1;
+    if ((lane < 5 && lane < nf) || (lane >= 8 && lane < 13 && (lane - 8) < nr)) atomicOr(&picked[tgt >> 5], 1u << (tgt & 31));
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_ring_pick: the greedy, order-dependent part of SR:251-359, one WARP per (ring, lane) so that thousands of
+// rings run concurrently.  State per warp: a picked bitmask in shared memory; sorted candidates (u16) and
+// the ring's points are read through L2.  Each ballot examines 32 sorted candidates at once.
+// ---------------------------------------------------------------------------------------------------------
+#define PICK_WARPS 4
 template <int SCAP>
-__global__ void __launch_bounds__(512) k_ring_features(FeatParams P)
+__global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int n_lanes)
+{
+    constexpr int RCAP = 6 * SCAP + 16;
+    constexpr int WORDS = (RCAP + 31) / 32;
+    __shared__ unsigned picked_all[PICK_WARPS][WORDS];
+    const int lane = lane_id(), wid = warp_id();
+    const int ring_lane = blockIdx.x * PICK_WARPS + wid;
+    if (ring_lane >= P.R * n_lanes) return;
+    const int b = ring_lane / P.R, r = ring_lane % P.R;
+    LaneState& L = P.lane[b];
+    const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base;
+    int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
+    int* my_lists = P.ring_lists + ((size_t)b * P.R + r) * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING);
+    if (n - 11 < 6 || n > 6 * SCAP + 11) {
+        if (lane == 0) { my_counts[0] = my_counts[1] = my_counts[2] = 0; }
+        return;
+    }
+    unsigned* picked = picked_all[wid];
+    for (int i = lane; i < WORDS; i += 32) picked[i] = 0;
+    __syncwarp();
+    const float4* pts = P.full + (size_t)b * P.Nmax + base;
+    const uint16_t* sorted = P.sorted16 + (size_t)b * P.Nmax + base;
+    int8_t* label = P.label + (size_t)b * P.Nmax + base;
+    const int len = n - 11;
+    int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+    for (int j = 0; j < 6; ++j) {
+        const int s0 = 5 + len * j / 6, size = 5 + len * (j + 1) / 6 - s0;
+        const uint16_t* seg = sorted + s0;
+        // corners: from the largest curvature down (SR:261-313)
+        int pos = size - 1, npick = 0;
+        while (pos >= 0) {
+            const int p = pos - lane;
+            const unsigned key = p >= 0 ? seg[p] : 0u;
+            const int idx = (int)(key & 0x3FFFu);
+            const bool over = p >= 0 && (key & 0x4000u);
+            const bool elig = over && !((picked[idx >> 5] >> (idx & 31)) & 1u);
+            const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+            const unsigned nm = __ballot_sync(LL_FULL_MASK, p >= 0 && !over);
+            if (em == 0) {
+                if (nm) break;  // reached curvature <= 0.1: nothing below can be picked
+                pos -= 32;
+                continue;
+            }
+            const int f = __ffs(em) - 1;
+            const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
+            ++npick;
+            if (npick > 20) break;  // SR:281-284
+            if (lane == 0) {
+                label[ind] = npick <= 2 ? 2 : 1;
+                if (npick <= 2) my_lists[n_sharp] = base + ind;
+                my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
+                picked[ind >> 5] |= 1u << (ind & 31);
+            }
+            if (npick <= 2) ++n_sharp;
+            ++n_lsharp;
+            __syncwarp();
+            suppress_neighbours(pts, picked, ind, lane);
+            pos -= f + 1;
+        }
+        // flats: from the smallest curvature up (SR:316-359)
+        pos = 0;
+        int nsm = 0;
+        while (pos < size) {
+            const int p = pos + lane;
+            const unsigned key = p < size ? seg[p] : 0u;
+            const int idx = (int)(key & 0x3FFFu);
+            const bool under = p < size && (key & 0x8000u);
+            const bool elig = under && !((picked[idx >> 5] >> (idx & 31)) & 1u);
+            const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+            const unsigned nm = __ballot_sync(LL_FULL_MASK, p < size && !under);
+            if (em == 0) {
+                if (nm) break;
+                pos += 32;
+                continue;
+            }
+            const int f = __ffs(em) - 1;
+            const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
+            if (lane == 0) {
+                label[ind] = -1;
+                my_lists[LL_SHARP_PER_RING + LL_LSHARP_PER_RING + n_flat] = base + ind;
+            }
+            ++n_flat;
+            ++nsm;
+            if (nsm >= 4) break;  // SR:328-331: before picked / suppression
+            if (lane == 0) picked[ind >> 5] |= 1u << (ind & 31);
+            __syncwarp();
+            suppress_neighbours(pts, picked, ind, lane);
+            pos += f + 1;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { my_counts[0] = n_sharp; my_counts[1] = n_lsharp; my_counts[2] = n_flat; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_ring_lessflat: less-flat = every sector point with label <= 0 (SR:361-367), then pcl::VoxelGrid(0.2) on
+// the ring (SR:370-376): bbox -> voxel id -> bitonic sort of (voxel id, index) -> run-sum centroids in
+// sorted (= input) order, fp32.  Points and labels are read through L2; only the sort keys live in smem.
+// ---------------------------------------------------------------------------------------------------------
+template <int SCAP>
+__global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
 {
     constexpr int RCAP = 6 * SCAP + 16;
     constexpr int KCAP = (RCAP <= 4096) ? 4096 : 8192;
     constexpr int NTH = 512;
-    constexpr int CH = (RCAP + NTH - 1) / NTH;  // chunk of positions per thread for the ordered scans
+    constexpr int CH = (RCAP + NTH - 1) / NTH;
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* pts = reinterpret_cast<float4*>(smem);
-    u64* keys = reinterpret_cast<u64*>(smem + (size_t)RCAP * 16);
-    uint8_t* picked = reinterpret_cast<uint8_t*>(keys + KCAP);
-    int8_t* label = reinterpret_cast<int8_t*>(picked + RCAP);
-    int* ws = reinterpret_cast<int*>(label + RCAP);  // RCAP multiple of 16 -> aligned
-    int* sp = ws + 40;                               // sector starts sp[0..6]
-    float* red = reinterpret_cast<float*>(sp + 8);   // 6 x 16 warp partials + 6 results
-    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 112);
+    u64* keys = reinterpret_cast<u64*>(smem);
+    int* ws = reinterpret_cast<int*>(keys + KCAP);
+    float* red = reinterpret_cast<float*>(ws + 40);
 
     const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     LaneState& L = P.lane[b];
-    const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base, ntot = L.n_full;
+    const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base;
     int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
-    int* my_lists = P.ring_lists + ((size_t)b * P.R + r) * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING);
-    const float4* gfull = P.full + (size_t)b * P.Nmax;
-    float* gcurv = P.curv + (size_t)b * P.Nmax;
+    if (n - 11 < 6 || n > 6 * SCAP + 11) { if (tid == 0) my_counts[3] = 0; return; }
+    const float4* pts = P.full + (size_t)b * P.Nmax + base;
+    const int8_t* label = P.label + (size_t)b * P.Nmax + base;
 
-    if (n - 11 < 6 || n > 6 * SCAP + 11) {  // SR:248 skip; or capacity overflow
-        if (tid == 0) {
-            my_counts[0] = my_counts[1] = my_counts[2] = my_counts[3] = 0;
-            if (n > 6 * SCAP + 11) L.err = LL_E_CAPACITY;
-        }
-        // curvature is still defined on these points (SR:225-235); emit it for parity dumps
-        for (int i = tid; i < n; i += NTH) {
-            const int g = base + i;
-            float c = 0.f;
-            if (g >= 5 && g < ntot - 5) {
-                float dx = gfull[g - 5].x, dy = gfull[g - 5].y, dz = gfull[g - 5].z;
-                for (int k = -4; k <= -1; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
-                dx = dx - 10 * gfull[g].x; dy = dy - 10 * gfull[g].y; dz = dz - 10 * gfull[g].z;
-                for (int k = 1; k <= 5; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
-                c = dx * dx + dy * dy + dz * dz;
-            }
-            gcurv[g] = c;
-        }
-        return;
-    }
-
-    // ---- TMA: one bulk copy of the ring's float4 slab into shared memory -----------------------------
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) tma_bulk_g2s(pts, gfull + base, (uint32_t)n * 16u, bar);
-    // meanwhile: clear flags, sector geometry (SR:253-254 with ring-local indices)
-    for (int i = tid; i < RCAP; i += NTH) { picked[i] = 0; label[i] = 0; }
-    for (int i = tid; i < 6 * SCAP; i += NTH) keys[i] = ~0ull;
-    const int len = n - 11;
-    if (tid <= 6) sp[tid] = 5 + len * tid / 6;
-    mbar_wait(bar, 0);
-    __syncthreads();
-
-    // ---- curvature (SR:225-235) + sort keys -------------------------------------------------------------
-    for (int i = tid; i < n; i += NTH) {
-        float c = 0.f;
-        bool have = false;
-        if (i >= 5 && i < n - 5) {
-            float dx = pts[i - 5].x, dy = pts[i - 5].y, dz = pts[i - 5].z;
-#pragma unroll
-            for (int k = -4; k <= -1; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
-            { const float4 q = pts[i]; dx = dx - 10 * q.x; dy = dy - 10 * q.y; dz = dz - 10 * q.z; }
-#pragma unroll
-            for (int k = 1; k <= 5; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
-            c = dx * dx + dy * dy + dz * dz;
-            have = true;
-        } else {
-            // the reference's stencil runs over ring joins (global index); those values are never used by
-            // the picks (sectors keep a 5-point margin) but belong to the curvature array
-            const int g = base + i;
-            if (g >= 5 && g < ntot - 5) {
-                float dx = gfull[g - 5].x, dy = gfull[g - 5].y, dz = gfull[g - 5].z;
-                for (int k = -4; k <= -1; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
-                dx = dx - 10 * gfull[g].x; dy = dy - 10 * gfull[g].y; dz = dz - 10 * gfull[g].z;
-                for (int k = 1; k <= 5; ++k) { dx = dx + gfull[g + k].x; dy = dy + gfull[g + k].y; dz = dz + gfull[g + k].z; }
-                c = dx * dx + dy * dy + dz * dz;
-            }
-        }
-        gcurv[base + i] = c;
-        if (have && i < n - 6) {  // sectors tile [5, n-6)
-            int j = 0;
-#pragma unroll
-            for (int q = 1; q < 6; ++q) j += (i >= sp[q]);
-            keys[j * SCAP + (i - sp[j])] = ((u64)__float_as_uint(c) << 32) | (unsigned)i;
-        }
-    }
-    __syncthreads();
-
-    // ---- six independent bitonic sorts (ascending curvature, ties by index), SR:257 --------------------
-    for (int k = 2; k <= SCAP; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < 3 * SCAP; t += NTH) {
-                const int seg = t / (SCAP / 2), tl = t % (SCAP / 2);
-                const int i = ((tl & ~(j - 1)) << 1) | (tl & (j - 1));
-                u64* K = keys + seg * SCAP;
-                const u64 a = K[i], c = K[i | j];
-                const bool asc = (i & k) == 0;
-                if ((a > c) == asc) { K[i] = c; K[i | j] = a; }
-            }
-            __syncthreads();
-        }
-    }
-
-    // ---- greedy pick, sectors in order (SR:251-359); warp 0, window of 32 sorted candidates -----------
-    if (wid == 0) {
-        int n_sharp = 0, n_lsharp = 0, n_flat = 0;
-        for (int j = 0; j < 6; ++j) {
-            const u64* seg = keys + j * SCAP;
-            const int size = sp[j + 1] - sp[j];
-            // corners: from the largest curvature down
-            int pos = size - 1, npick = 0;
-            while (pos >= 0) {
-                const int p = pos - lane;
-                const u64 key = p >= 0 ? seg[p] : 0ull;
-                const int idx = (int)(unsigned)key;
-                const bool over = p >= 0 && (double)__uint_as_float((unsigned)(key >> 32)) > 0.1;
-                const bool elig = over && picked[idx] == 0;
-                const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
-                const unsigned nm = __ballot_sync(LL_FULL_MASK, p >= 0 && !over);
-                if (em == 0) {
-                    if (nm) break;  // reached curvature <= 0.1: nothing below can be picked
-                    pos -= 32;
-                    continue;
-                }
-                const int f = __ffs(em) - 1;
-                const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
-                ++npick;
-                if (npick > 20) break;  // SR:281-284
-                if (lane == 0) {
-                    if (npick <= 2) {
-                        label[ind] = 2;
-                        my_lists[n_sharp] = base + ind;
-                        my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
-                    } else {
-                        label[ind] = 1;
-                        my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
-                    }
-                    picked[ind] = 1;
-                }
-                if (npick <= 2) ++n_sharp;
-                ++n_lsharp;
-                __syncwarp();
-                suppress_neighbours(pts, picked, ind, lane);
-                pos -= f + 1;
-            }
-            // flats: from the smallest curvature up
-            pos = 0;
-            int nsm = 0;
-            while (pos < size) {
-                const int p = pos + lane;
-                const u64 key = p < size ? seg[p] : 0ull;
-                const int idx = (int)(unsigned)key;
-                const bool under = p < size && (double)__uint_as_float((unsigned)(key >> 32)) < 0.1;
-                const bool elig = under && picked[idx] == 0;
-                const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
-                const unsigned nm = __ballot_sync(LL_FULL_MASK, p < size && !under);
-                if (em == 0) {
-                    if (nm) break;
-                    pos += 32;
-                    continue;
-                }
-                const int f = __ffs(em) - 1;
-                const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
-                if (lane == 0) {
-                    label[ind] = -1;
-                    my_lists[LL_SHARP_PER_RING + LL_LSHARP_PER_RING + n_flat] = base + ind;
-                }
-                ++n_flat;
-                ++nsm;
-                if (nsm >= 4) break;  // SR:328-331: before picked / suppression
-                if (lane == 0) picked[ind] = 1;
-                __syncwarp();
-                suppress_neighbours(pts, picked, ind, lane);
-                pos += f + 1;
-            }
-            __syncwarp();
-        }
-        if (lane == 0) { my_counts[0] = n_sharp; my_counts[1] = n_lsharp; my_counts[2] = n_flat; }
-    }
-    __syncthreads();
-
-    // ---- less-flat = every sector point with label <= 0 (SR:361-367), then VoxelGrid(0.2) (SR:370-376) --
     const int c0 = tid * CH, c1 = min(c0 + CH, n);
     int mycnt = 0;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -512,7 +552,6 @@ __global__ void __launch_bounds__(512) k_ring_features(FeatParams P)
             __syncthreads();
         }
     }
-    // heads of equal-voxel runs; centroid of x,y,z,intensity summed in sorted (= input) order, fp32
     const int p0 = tid * CH, p1 = min(p0 + CH, m);
     int heads = 0;
     for (int p = p0; p < p1; ++p) heads += (p == 0 || (unsigned)(keys[p] >> 32) != (unsigned)(keys[p - 1] >> 32));
@@ -597,17 +636,22 @@ __global__ void k_reset_scan_state(LaneState* lane, int n_lanes)
 
 }  // namespace
 
-size_t ll_feature_smem_bytes(int SCAP)
+size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + six sector key arrays + sector starts + mbarrier
+{
+    const int RCAP = 6 * SCAP + 16;
+    return (size_t)RCAP * 16 + (size_t)6 * SCAP * 8 + 8 * 4 + 16;
+}
+size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: voxel sort keys + scan / reduction scratch
 {
     const int RCAP = 6 * SCAP + 16, KCAP = RCAP <= 4096 ? 4096 : 8192;
-    return (size_t)RCAP * 16 + (size_t)KCAP * 8 + (size_t)RCAP * 2 + (40 + 8) * 4 + 112 * 4 + 16;
+    return (size_t)KCAP * 8 + 40 * 4 + 112 * 4;
 }
 
 int ll_launch_features(ll_ctx* c, int n_lanes)
 {
     FeatParams P;
     P.lane = c->d_lane; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.ori = c->d_ori; P.tile_hist = c->d_tile_hist;
-    P.full = c->d_full; P.curv = c->d_curv; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
+    P.full = c->d_full; P.curv = c->d_curv; P.label = c->d_label; P.sorted16 = c->d_sorted16; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
     P.sharp = c->d_sharp; P.flat = c->d_flat; P.sharp_idx = c->d_sharp_idx; P.lsharp_idx = c->d_lsharp_idx; P.flat_idx = c->d_flat_idx;
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
     P.Nmax = c->Nmax; P.NT = c->NT; P.R = c->R; P.scan_line = c->cfg.scan_line;
@@ -621,18 +665,25 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     { LLProf pr(c, "k_halfpass_hist"); k_halfpass_hist<<<tiles, LL_TILE, 0, s>>>(P); }
     { LLProf pr(c, "k_ring_scan"); k_ring_scan<<<n_lanes, 1024, 0, s>>>(P); }
     { LLProf pr(c, "k_scatter"); k_scatter<<<tiles, LL_TILE, 0, s>>>(P); }
-    const size_t smem = ll_feature_smem_bytes(c->SCAP);
+    const size_t smem_sort = ll_feature_smem_bytes(c->SCAP);
+    const size_t smem_lf = ll_lessflat_smem_bytes(c->SCAP);
+    const dim3 rings(c->R, n_lanes);
+    const int pick_blocks = (c->R * n_lanes + PICK_WARPS - 1) / PICK_WARPS;
     if (c->SCAP == 512) {
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_features<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LLProf pr(c, "k_ring_features");
-        k_ring_features<512><<<dim3(c->R, n_lanes), 512, smem, s>>>(P);
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
+        { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, 512, smem_sort, s>>>(P); }
+        { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, 0, s>>>(P, n_lanes); }
+        { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512><<<rings, 512, smem_lf, s>>>(P); }
     } else {
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_features<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LLProf pr(c, "k_ring_features");
-        k_ring_features<1024><<<dim3(c->R, n_lanes), 512, smem, s>>>(P);
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
+        { LLProf pr(c, "k_ring_sort"); k_ring_sort<1024><<<rings, 512, smem_sort, s>>>(P); }
+        { LLProf pr(c, "k_ring_pick"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, 0, s>>>(P, n_lanes); }
+        { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<1024><<<rings, 512, smem_lf, s>>>(P); }
     }
     { LLProf pr(c, "k_compact"); k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P); }
-    c->launches += 7;
+    c->launches += 9;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }

@@ -16,7 +16,7 @@
 
 struct GridView {
     const int* start;      // [T+1] for this lane
-    const float4* sorted;  // bucket-ordered points, .w = original index bits
+    const float4* sorted;  // bucket-ordered points, .w bits = original index (low 24) | ring id (high 8)
     int Tmask;
     float h, inv_h;
 };
@@ -60,56 +60,63 @@ __device__ __forceinline__ void warp_merge_topk(const WarpKnn<K>& loc, u64 out[K
     }
 }
 
-// Returns (warp-uniform) the K best keys with d2 < cutoff semantics left to the caller.
+// Streams every point of shell s (cells at Chebyshev distance s from (cx,cy,cz); s == 1 also covers s == 0)
+// through f(float4 point), 32 bucket headers per round, bucket ranges concatenated across the warp.
+template <typename F>
+__device__ __forceinline__ void grid_visit_shell(const GridView& g, int cx, int cy, int cz, int s, F&& f)
+{
+    const int lane = lane_id();
+    const int w = 2 * s + 1, ncell = w * w * w;
+    for (int e0 = 0; e0 < ncell; e0 += 32) {
+        const int e = e0 + lane;
+        int bucket = -1 - lane;  // distinct invalid ids so match_any never groups invalid lanes with valid ones
+        if (e < ncell) {
+            const int dx = e % w - s, dy = (e / w) % w - s, dz = e / (w * w) - s;
+            const int cheb = max(abs(dx), max(abs(dy), abs(dz)));
+            if (cheb == s || s == 1) bucket = cell_bucket(cx + dx, cy + dy, cz + dz, g.Tmask);
+        }
+        const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
+        int beg = 0, cnt = 0;
+        if (bucket >= 0 && (__ffs(grp) - 1) == lane) {
+            beg = g.start[bucket];
+            cnt = g.start[bucket + 1] - beg;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+        const int excl = incl - cnt;
+        const int total = __shfl_sync(LL_FULL_MASK, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int cand = lo + step;
+                const int pv = __shfl_sync(LL_FULL_MASK, excl, cand & 31);
+                if (cand < 32 && pv <= t) lo = cand;
+            }
+            const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
+            const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
+            if (t < total) f(g.sorted[cbeg + (t - cexc)]);
+        }
+    }
+}
+
+// Returns (warp-uniform) the K best keys; the caller applies its own d2 cutoff.
 // r_search: every neighbour with true distance < r_search is guaranteed to be considered.
 template <int K>
 __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, float qz, float r_search, u64 out[K])
 {
-    const int lane = lane_id();
     const float eps = 1e-3f;
     const int cx = (int)floorf(qx * g.inv_h), cy = (int)floorf(qy * g.inv_h), cz = (int)floorf(qz * g.inv_h);
     WarpKnn<K> loc;
     loc.init();
     const int smax = (int)ceilf((r_search + eps) * g.inv_h);
     for (int s = 1; s <= smax; ++s) {  // the first pass covers shells 0 and 1 (27 cells) at once
-        const int w = 2 * s + 1, ncell = w * w * w;
-        for (int e0 = 0; e0 < ncell; e0 += 32) {
-            const int e = e0 + lane;
-            int bucket = -1 - lane;  // distinct invalid ids so match_any never groups invalid lanes with valid ones
-            if (e < ncell) {
-                const int dx = e % w - s, dy = (e / w) % w - s, dz = e / (w * w) - s;
-                const int cheb = max(abs(dx), max(abs(dy), abs(dz)));
-                if (cheb == s || s == 1) bucket = cell_bucket(cx + dx, cy + dy, cz + dz, g.Tmask);
-            }
-            const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
-            int beg = 0, cnt = 0;
-            if (bucket >= 0 && (__ffs(grp) - 1) == lane) {
-                beg = g.start[bucket];
-                cnt = g.start[bucket + 1] - beg;
-            }
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
-            const int excl = incl - cnt;
-            const int total = __shfl_sync(LL_FULL_MASK, incl, 31);
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                int lo = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const int cand = lo + step;
-                    const int pv = __shfl_sync(LL_FULL_MASK, excl, cand & 31);
-                    if (cand < 32 && pv <= t) lo = cand;
-                }
-                const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
-                const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
-                if (t < total) {
-                    const float4 p = g.sorted[cbeg + (t - cexc)];
-                    const float d2 = sqdist3(qx, qy, qz, p.x, p.y, p.z);
-                    loc.insert(((u64)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w));
-                }
-            }
-        }
+        grid_visit_shell(g, cx, cy, cz, s, [&](const float4 p) {
+            const float d2 = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+            loc.insert(((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(p.w) & 0xFFFFFFu));
+        });
         warp_merge_topk<K>(loc, out);
         if (out[K - 1] != ~0ull) {
             const float kth = __uint_as_float((unsigned)(out[K - 1] >> 32));

@@ -44,33 +44,58 @@ __device__ __forceinline__ const float4* grid_src_pts(const GridSrc& S, const La
     return S.pts[slot] + (size_t)b * S.lane_stride;
 }
 
-__global__ void k_grid_count(GridSrc S, const LaneState* lane, int* cursor, int T, float inv_h)
+__global__ void k_grid_count(GridSrc S, LaneState* lane, int* cursor, int T, float inv_h)
 {
     const int b = blockIdx.y;
-    const LaneState& L = lane[b];
+    LaneState& L = lane[b];
     const int n = grid_src_count(S, L);
     const float4* pts = grid_src_pts(S, L, b);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
         const int bk = cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
         atomicAdd(&cursor[(size_t)b * T + bk], 1);
+        if (S.which < 2) {  // is the cloud ring-monotone? (LO:504-553 assumes it; the fast association path needs it)
+            const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
+            if (r0 < 0 || r0 > 255 || r1 < r0) { if (S.which == 0) L.mono_corner = 0; else L.mono_surf = 0; }
+        }
     }
 }
-// one CTA per lane: start[] = exclusive scan of the counts; cursor[] = start[] (scatter cursors)
-__global__ void __launch_bounds__(1024) k_grid_scan(int* cursor, int* start, int T)
+// two-level exclusive scan of the bucket counts: chunk sums, then per-chunk scan with its base
+#define GRID_CHUNK 2048
+__global__ void __launch_bounds__(256) k_grid_partial(const int* cursor, int* partial, int T)
 {
     __shared__ int ws[40];
-    const int b = blockIdx.x;
-    int* cur = cursor + (size_t)b * T;
-    int* st = start + (size_t)b * (T + 1);
-    const int per = T / 1024 > 0 ? T / 1024 : 1;
-    const int i0 = threadIdx.x * per, i1 = min(i0 + per, T);
+    const int b = blockIdx.y, nchunk = T / GRID_CHUNK;
+    const int* cur = cursor + (size_t)b * T + (size_t)blockIdx.x * GRID_CHUNK;
     int s = 0;
-    for (int i = i0; i < i1; ++i) s += cur[i];
+#pragma unroll
+    for (int k = 0; k < GRID_CHUNK / 256; ++k) s += cur[threadIdx.x * (GRID_CHUNK / 256) + k];
     int tot = 0;
-    int run = block_exclusive_scan(s, ws, &tot);
-    for (int i = i0; i < i1; ++i) { const int c = cur[i]; st[i] = run; cur[i] = run; run += c; }
-    if (threadIdx.x == 0) st[T] = tot;
+    block_exclusive_scan(s, ws, &tot);
+    if (threadIdx.x == 0) partial[(size_t)b * (nchunk + 1) + blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) k_grid_scan(int* cursor, int* start, const int* partial, int T)
+{
+    __shared__ int ws[40];
+    __shared__ int base_s;
+    const int b = blockIdx.y, nchunk = T / GRID_CHUNK, chunk = blockIdx.x;
+    if (threadIdx.x < 32) {
+        int v = 0;
+        for (int q = threadIdx.x; q < chunk; q += 32) v += partial[(size_t)b * (nchunk + 1) + q];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(LL_FULL_MASK, v, d);
+        if (threadIdx.x == 0) base_s = v;
+    }
+    int* cur = cursor + (size_t)b * T + (size_t)chunk * GRID_CHUNK;
+    int* st = start + (size_t)b * (T + 1) + (size_t)chunk * GRID_CHUNK;
+    const int per = GRID_CHUNK / 256, i0 = threadIdx.x * per;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) s += cur[i0 + k];
+    int tot = 0;
+    int run = block_exclusive_scan(s, ws, &tot) + base_s;  // the scan's barriers also publish base_s
+#pragma unroll
+    for (int k = 0; k < per; ++k) { const int c = cur[i0 + k]; st[i0 + k] = run; cur[i0 + k] = run; run += c; }
+    if (chunk == nchunk - 1 && threadIdx.x == 255) start[(size_t)b * (T + 1) + T] = run;
 }
 __global__ void k_grid_scatter(GridSrc S, const LaneState* lane, int* cursor, float4* sorted, int T, int cap, float inv_h)
 {
@@ -82,7 +107,9 @@ __global__ void k_grid_scatter(GridSrc S, const LaneState* lane, int* cursor, fl
         const float4 p = pts[i];
         const int bk = cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
         const int pos = atomicAdd(&cursor[(size_t)b * T + bk], 1);
-        sorted[(size_t)b * cap + pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        int ring = S.which < 2 ? (int)p.w : 0;
+        ring = ring < 0 ? 0 : (ring > 255 ? 255 : ring);
+        sorted[(size_t)b * cap + pos] = make_float4(p.x, p.y, p.z, __int_as_float((i & 0xFFFFFF) | (ring << 24)));
     }
 }
 
@@ -145,6 +172,32 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
         closest = (int)(unsigned)best[0];
         const int cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
         u64 k2 = ~0ull, k3 = ~0ull;              // (d2 bits << 32) | visit order  -> strict '<' of the serial loops
+        const unsigned down_base = (unsigned)n;
+        if (is_corner ? L.mono_corner : L.mono_surf) {
+            // Ring-monotone cloud (always the case for clouds produced by scanRegistration): the serial loops of
+            // LO:504-553 / LO:668-721 visit exactly the points whose ring lies in [cring-2, cring+2], so the same
+            // minima come out of a ring-filtered shell search over the grid; ties keep the loops' visit order.
+            const int cx = (int)floorf(qx * gv.inv_h), cy = (int)floorf(qy * gv.inv_h), cz = (int)floorf(qz * gv.inv_h);
+            const int smax = (int)ceilf((5.0f + 1e-3f) * gv.inv_h);
+            for (int s = 1; s <= smax; ++s) {
+                grid_visit_shell(gv, cx, cy, cz, s, [&](const float4 t) {
+                    const unsigned bits = (unsigned)__float_as_int(t.w);
+                    const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
+                    const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
+                    if (!((double)d2 < 25.0) || j == closest || rj < cring - 2 || rj > cring + 2) return;
+                    const unsigned rank = j > closest ? (unsigned)(j - (closest + 1)) : down_base + (unsigned)(closest - 1 - j);
+                    const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
+                    if (rj == cring) { if (!is_corner && key < k2) k2 = key; }
+                    else if (is_corner) { if (key < k2) k2 = key; }
+                    else if (key < k3) k3 = key;
+                });
+                const u64 m2 = warp_min_u64(k2), m3 = is_corner ? 0ull : warp_min_u64(k3);
+                const float safe = (float)s * gv.h - 1e-3f, safe2 = safe * safe;
+                const bool ok2 = m2 != ~0ull && __uint_as_float((unsigned)(m2 >> 32)) < safe2;
+                const bool ok3 = is_corner || (m3 != ~0ull && __uint_as_float((unsigned)(m3 >> 32)) < safe2);
+                if (ok2 && ok3) break;
+            }
+        } else {
         // increasing scan line (LO:504-527 / LO:668-693); lane order inside a chunk = visit order
         for (int j0 = closest + 1; j0 < n; j0 += 32) {
             const int j = j0 + lane;
@@ -171,7 +224,6 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
             if (bm) break;
         }
         // decreasing scan line (LO:530-553 / LO:696-721); visit order continues after the up-scan
-        const unsigned down_base = (unsigned)n;
         for (int j0 = closest - 1; j0 >= 0; j0 -= 32) {
             const int j = j0 - lane;
             bool brk = false;
@@ -196,6 +248,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
             if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
             if (bm) break;
         }
+        }  // literal scan loops
         k2 = warp_min_u64(k2);
         k3 = warp_min_u64(k3);
         auto decode = [&](u64 k) -> int {
@@ -377,6 +430,8 @@ __global__ void k_odom_finalize(LaneState* lane, double* pose_out, int n_lanes)
         L.q_w[0] = qn[0]; L.q_w[1] = qn[1]; L.q_w[2] = qn[2]; L.q_w[3] = qn[3];
     }
     L.last_slot = L.cur;  // LO:882-891 swap
+    L.mono_corner = 1;    // cleared by k_grid_count if the new *Last clouds are not ring-monotone
+    L.mono_surf = 1;
     L.n_last_corner = L.n_less_sharp;
     L.n_last_surf = L.n_less_flat;
     L.now_frame++;
@@ -397,9 +452,10 @@ static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1,
     LL_CUDA_CHECK(c, cudaMemsetAsync(g.cursor, 0, sizeof(int) * (size_t)g.T * n_lanes, s));
     const int gx = (max_pts + 255) / 256 > 0 ? (max_pts + 255) / 256 : 1;
     { LLProf pr(c, "k_grid_count"); k_grid_count<<<dim3(gx < 296 ? gx : 296, n_lanes), 256, 0, s>>>(S, c->d_lane, g.cursor, g.T, g.inv_h); }
-    { LLProf pr(c, "k_grid_scan"); k_grid_scan<<<n_lanes, 1024, 0, s>>>(g.cursor, g.start, g.T); }
+    { LLProf pr(c, "k_grid_partial"); k_grid_partial<<<dim3(g.T / GRID_CHUNK, n_lanes), 256, 0, s>>>(g.cursor, g.partial, g.T); }
+    { LLProf pr(c, "k_grid_scan"); k_grid_scan<<<dim3(g.T / GRID_CHUNK, n_lanes), 256, 0, s>>>(g.cursor, g.start, g.partial, g.T); }
     { LLProf pr(c, "k_grid_scatter"); k_grid_scatter<<<dim3(gx < 296 ? gx : 296, n_lanes), 256, 0, s>>>(S, c->d_lane, g.cursor, g.sorted, g.T, g.cap, g.inv_h); }
-    c->launches += 3;
+    c->launches += 4;
     return LL_OK;
 }
 

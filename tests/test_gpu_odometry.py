@@ -118,3 +118,29 @@ def test_too_few_correspondences_warning(ll):
     assert r1["rc"] == ll.capi.LL_W_FEW_CORRESPONDENCES
     assert np.array_equal(r1["t_w"], r0["t_w"]) and np.array_equal(r1["q_last"], [0, 0, 0, 1])
     ctx.close()
+
+
+def test_non_monotone_last_cloud_takes_literal_path(ll, orc):
+    """Clouds that are NOT ring-sorted (never produced by scanRegistration, but legal input on the topic) must go
+    through the literal scan loops of LO:504-553 / LO:668-721 and still match the oracle index for index."""
+    line = 16
+    ctx = ll.Context(scan_line=line)
+    ocfg = orc.config(line, voxel_stable=1)
+    odo = orc.Odometry(ocfg)
+    rng = np.random.default_rng(5)
+    for k in range(4):
+        f = orc.extract_features(ll.synth.scan(line, k), ocfg)
+        ls = f["less_sharp"][rng.permutation(len(f["less_sharp"]))]
+        lf = f["less_flat"].copy()
+        blocks = np.array_split(np.arange(len(lf)), 7)          # shuffle coarse blocks: locally sorted, globally not
+        lf = lf[np.concatenate([blocks[i] for i in rng.permutation(7)])]
+        po = odo.step(f["sharp"], ls, f["flat"], lf)
+        pg = ctx.odometry_step(f["sharp"], ls, f["flat"], lf)
+        assert np.abs(pg["t_w"] - po["t_w"]).max() < 1e-9 and np.abs(pg["q_w"] - po["q_w"]).max() < 1e-9, k
+        if k:
+            oc, op = odo.assoc(len(f["sharp"]), len(f["flat"]))
+            gc, gp = ctx.debug_assoc(0)
+            got_c = np.array([[i, a, b] for i, (a, b) in enumerate(gc[:len(f["sharp"])]) if b >= 0], np.int32).reshape(-1, 3)
+            got_p = np.array([[i, a, b, c] for i, (a, b, c, _) in enumerate(gp[:len(f["flat"])]) if a >= 0], np.int32).reshape(-1, 4)
+            assert np.array_equal(got_c, oc) and np.array_equal(got_p, op), k
+    ctx.close()
