@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every entry point runs the CUDA kernels or returns an error code.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -184,6 +185,7 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     c->RCAP = 6 * c->SCAP + 16;
     c->dev = cfg->device;
     c->vote_t_min = calibrate_vote_threshold();
+    if (const char* e = getenv("LL_PLANE_SHELLS")) c->plane_shells = atoi(e);
 #define CK(expr)                                                                     \
     do {                                                                             \
         cudaError_t e__ = (expr);                                                    \
@@ -232,6 +234,7 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     c->g_surf.cap = (int)N;
     for (KnnGrid* g : {&c->g_corner, &c->g_surf}) {
         g->h = 1.01f;
+        if (const char* e = getenv("LL_GRID_H")) { const float v = (float)atof(e); if (v > 0.05f && v < 10.f) g->h = v; }
         g->inv_h = 1.0f / g->h;
         CK(dalloc(g->start, B * (size_t)(g->T + 1)));
         CK(dalloc(g->cursor, B * (size_t)g->T));

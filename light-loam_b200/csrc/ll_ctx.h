@@ -81,6 +81,7 @@ struct ll_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     int launches = 0;
+    int plane_shells = 2;     // see k_odom_assoc (env LL_PLANE_SHELLS)
     float vote_t_min = 0.f;   // smallest fp32 t with expf(-t) < 0.96f on this host's libm (LO:239-242)
 
     LaneState* d_lane = nullptr;

@@ -131,6 +131,7 @@ struct OdomParams {
     int graph_from_frame;
     float vote_t_min;
     int outer;             // opti_counter
+    int plane_shells;      // grid shells tried for the 2nd / 3rd plane neighbour before the literal walk
 };
 
 __device__ __forceinline__ int last_slot(const LaneState& L) { return L.last_slot; }  // previous frame's clouds
@@ -173,13 +174,15 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
         const int cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
         u64 k2 = ~0ull, k3 = ~0ull;              // (d2 bits << 32) | visit order  -> strict '<' of the serial loops
         const unsigned down_base = (unsigned)n;
-        if (is_corner ? L.mono_corner : L.mono_surf) {
+        bool resolved = false;
+        if (!is_corner && L.mono_surf) {
             // Ring-monotone cloud (always the case for clouds produced by scanRegistration): the serial loops of
-            // LO:504-553 / LO:668-721 visit exactly the points whose ring lies in [cring-2, cring+2], so the same
-            // minima come out of a ring-filtered shell search over the grid; ties keep the loops' visit order.
+            // LO:668-721 visit exactly the points whose ring lies in [cring-2, cring+2], so the same minima come out
+            // of a ring-filtered shell search over the grid; ties keep the loops' visit order.  Only the first
+            // `plane_shells` shells are tried: when the 2nd / 3rd neighbour is farther than that (sparse ground
+            // rings) the literal walk below is cheaper, and it yields the same answer by construction.
             const int cx = (int)floorf(qx * gv.inv_h), cy = (int)floorf(qy * gv.inv_h), cz = (int)floorf(qz * gv.inv_h);
-            const int smax = (int)ceilf((5.0f + 1e-3f) * gv.inv_h);
-            for (int s = 1; s <= smax; ++s) {
+            for (int s = 1; s <= P.plane_shells && !resolved; ++s) {
                 grid_visit_shell(gv, cx, cy, cz, s, [&](const float4 t) {
                     const unsigned bits = (unsigned)__float_as_int(t.w);
                     const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
@@ -187,17 +190,17 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
                     if (!((double)d2 < 25.0) || j == closest || rj < cring - 2 || rj > cring + 2) return;
                     const unsigned rank = j > closest ? (unsigned)(j - (closest + 1)) : down_base + (unsigned)(closest - 1 - j);
                     const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
-                    if (rj == cring) { if (!is_corner && key < k2) k2 = key; }
-                    else if (is_corner) { if (key < k2) k2 = key; }
+                    if (rj == cring) { if (key < k2) k2 = key; }
                     else if (key < k3) k3 = key;
                 });
-                const u64 m2 = warp_min_u64(k2), m3 = is_corner ? 0ull : warp_min_u64(k3);
+                const u64 m2 = warp_min_u64(k2), m3 = warp_min_u64(k3);
                 const float safe = (float)s * gv.h - 1e-3f, safe2 = safe * safe;
-                const bool ok2 = m2 != ~0ull && __uint_as_float((unsigned)(m2 >> 32)) < safe2;
-                const bool ok3 = is_corner || (m3 != ~0ull && __uint_as_float((unsigned)(m3 >> 32)) < safe2);
-                if (ok2 && ok3) break;
+                resolved = m2 != ~0ull && __uint_as_float((unsigned)(m2 >> 32)) < safe2 && m3 != ~0ull &&
+                           __uint_as_float((unsigned)(m3 >> 32)) < safe2;
             }
-        } else {
+            if (!resolved) { k2 = ~0ull; k3 = ~0ull; }
+        }
+        if (!resolved) {
         // increasing scan line (LO:504-527 / LO:668-693); lane order inside a chunk = visit order
         for (int j0 = closest + 1; j0 < n; j0 += 32) {
             const int j = j0 + lane;
@@ -466,7 +469,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
     P.Nmax = c->Nmax; P.R = c->R; P.gc = c->g_corner; P.gs = c->g_surf;
     P.corner_assoc = c->d_corner_assoc; P.plane_assoc = c->d_plane_assoc; P.blocks = c->d_blocks; P.nblk_cap = c->nblk_cap;
-    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min;
+    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.plane_shells = c->plane_shells;
     cudaStream_t s = c->stream;
     const int nq = c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     const size_t prep_smem = (size_t)c->R * LL_FLAT_PER_RING * 8 * 4;
