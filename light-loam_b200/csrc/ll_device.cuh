@@ -101,3 +101,57 @@ __device__ __forceinline__ int cell_bucket(int ix, int iy, int iz, int Tmask)
     const unsigned h = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
     return (int)((h ^ (h >> 15)) & (unsigned)Tmask);
 }
+
+// ---- block-wide bitonic sort of 64-bit keys in shared memory --------------------------------------------------
+// Sorts every aligned segment of SEG keys (power of two >= 64, N a multiple of SEG) ascending.  Stages whose
+// partner distance is < 64 run in registers: a warp owns 64 consecutive keys (2 per lane) and exchanges them with
+// shuffles, so shared memory is touched once per "register phase" instead of once per stage (10 passes instead of
+// 45 for SEG = 512).  All threads of the block must call it; ends with a barrier.
+__device__ __forceinline__ void bitonic_reg_stages(u64& k0, u64& k1, int ibase, int kk, int jmax, int lane)
+{
+    // element indices: i0 = ibase + lane (slot 0), i1 = i0 + 32 (slot 1); stages j = jmax, jmax/2, ..., 1
+    for (int j = jmax; j > 0; j >>= 1) {
+        if (j == 32) {
+            const bool asc = ((ibase + lane) & kk) == 0;
+            if ((k0 > k1) == asc) { const u64 t = k0; k0 = k1; k1 = t; }
+        } else {
+            const bool lower = (lane & j) == 0;
+            const u64 o0 = shfl_xor_u64(k0, j), o1 = shfl_xor_u64(k1, j);
+            const bool asc0 = ((ibase + lane) & kk) == 0, asc1 = ((ibase + 32 + lane) & kk) == 0;
+            k0 = (lower == asc0) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+            k1 = (lower == asc1) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+        }
+    }
+}
+__device__ __forceinline__ void block_bitonic_sort_u64(u64* keys, int N, int SEG)
+{
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5, nchunk = N >> 6;
+    // phase 0: every 64-chunk fully sorted (k = 2..64) in registers, direction taken from the global network
+    for (int c = w; c < nchunk; c += nw) {
+        const int ibase = (c << 6) & (SEG - 1);
+        u64 k0 = keys[(c << 6) + lane], k1 = keys[(c << 6) + 32 + lane];
+        for (int kk = 2; kk <= 64; kk <<= 1) bitonic_reg_stages(k0, k1, ibase, SEG == 64 && kk == 64 ? 0 : kk, kk >> 1, lane);
+        keys[(c << 6) + lane] = k0;
+        keys[(c << 6) + 32 + lane] = k1;
+    }
+    __syncthreads();
+    for (int kk = 128; kk <= SEG; kk <<= 1) {
+        for (int j = kk >> 1; j >= 64; j >>= 1) {
+            for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const u64 a = keys[i], b = keys[i | j];
+                const bool asc = ((i & (SEG - 1)) & kk) == 0;
+                if ((a > b) == asc) { keys[i] = b; keys[i | j] = a; }
+            }
+            __syncthreads();
+        }
+        for (int c = w; c < nchunk; c += nw) {
+            const int ibase = (c << 6) & (SEG - 1);
+            u64 k0 = keys[(c << 6) + lane], k1 = keys[(c << 6) + 32 + lane];
+            bitonic_reg_stages(k0, k1, ibase, kk == SEG ? 0 : kk, 32, lane);
+            keys[(c << 6) + lane] = k0;
+            keys[(c << 6) + 32 + lane] = k1;
+        }
+        __syncthreads();
+    }
+}

@@ -307,19 +307,7 @@ __global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
     }
     __syncthreads();
 
-    for (int k = 2; k <= SCAP; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < 3 * SCAP; t += NTH) {
-                const int seg = t / (SCAP / 2), tl = t % (SCAP / 2);
-                const int i = ((tl & ~(j - 1)) << 1) | (tl & (j - 1));
-                u64* K = keys + seg * SCAP;
-                const u64 a = K[i], c = K[i | j];
-                const bool asc = (i & k) == 0;
-                if ((a > c) == asc) { K[i] = c; K[i | j] = a; }
-            }
-            __syncthreads();
-        }
-    }
+    block_bitonic_sort_u64(keys, 6 * SCAP, SCAP);  // six independent ascending sector sorts
     for (int i = 5 + tid; i < n - 6; i += NTH) {
         int j = 0;
 #pragma unroll
@@ -525,7 +513,7 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
     const int min_b0 = (int)floorf(bmn[0] * inv), min_b1 = (int)floorf(bmn[1] * inv), min_b2 = (int)floorf(bmn[2] * inv);
     const int div0 = (int)floorf(bmx[0] * inv) - min_b0 + 1, div1 = (int)floorf(bmx[1] * inv) - min_b1 + 1;
     const int mul1 = div0, mul2 = div0 * div1;
-    int NS = 32;
+    int NS = 64;
     while (NS < m) NS <<= 1;
     {
         int o = off;
@@ -541,17 +529,7 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
         for (int i = m + tid; i < NS; i += NTH) keys[i] = ~0ull;
     }
     __syncthreads();
-    for (int k = 2; k <= NS; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < NS / 2; t += NTH) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const u64 a = keys[i], c = keys[i | j];
-                const bool asc = (i & k) == 0;
-                if ((a > c) == asc) { keys[i] = c; keys[i | j] = a; }
-            }
-            __syncthreads();
-        }
-    }
+    block_bitonic_sort_u64(keys, NS, NS);
     const int p0 = tid * CH, p1 = min(p0 + CH, m);
     int heads = 0;
     for (int p = p0; p < p1; ++p) heads += (p == 0 || (unsigned)(keys[p] >> 32) != (unsigned)(keys[p - 1] >> 32));

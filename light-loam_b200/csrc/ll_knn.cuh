@@ -86,18 +86,31 @@ __device__ __forceinline__ void grid_visit_shell(const GridView& g, int cx, int 
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
         const int excl = incl - cnt;
         const int total = __shfl_sync(LL_FULL_MASK, incl, 31);
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + lane;
-            int lo = 0;
+        // four chunks of 32 candidates per iteration: all four loads are issued before any is consumed (MLP)
+        for (int t0 = 0; t0 < total; t0 += 128) {
+            float4 pv[4];
+            bool ok[4];
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int cand = lo + step;
-                const int pv = __shfl_sync(LL_FULL_MASK, excl, cand & 31);
-                if (cand < 32 && pv <= t) lo = cand;
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u * 32 + lane;
+                ok[u] = false;
+                if (t0 + u * 32 < total) {  // warp-uniform
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int cand = lo + step;
+                        const int pv_ = __shfl_sync(LL_FULL_MASK, excl, cand & 31);
+                        if (cand < 32 && pv_ <= t) lo = cand;
+                    }
+                    const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
+                    const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
+                    ok[u] = t < total;
+                    if (ok[u]) pv[u] = g.sorted[cbeg + (t - cexc)];
+                }
             }
-            const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
-            const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
-            if (t < total) f(g.sorted[cbeg + (t - cexc)]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) f(pv[u]);
         }
     }
 }

@@ -201,55 +201,76 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
             if (!resolved) { k2 = ~0ull; k3 = ~0ull; }
         }
         if (!resolved) {
-        // increasing scan line (LO:504-527 / LO:668-693); lane order inside a chunk = visit order
-        for (int j0 = closest + 1; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            bool brk = false;
-            u64 c2 = ~0ull, c3 = ~0ull;
-            if (j < n) {
-                const float4 t = last[j];
-                const int rj = (int)t.w;
-                brk = (double)rj > (double)cring + 2.5;
-                const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                const u64 key = ((u64)__float_as_uint(d2) << 32) | (unsigned)(j - (closest + 1));
-                if (!brk && (double)d2 < 25.0) {
-                    if (is_corner) {
-                        if (!(rj <= cring)) c2 = key;  // LO:507: same scan line -> continue
-                    } else {
-                        if (rj <= cring) c2 = key;     // LO:682
-                        else c3 = key;                 // LO:688
+        // increasing scan line (LO:504-527 / LO:668-693); lane order inside a chunk = visit order.
+        // Four chunks are fetched per iteration (loads first, then consumed in visit order until the first break).
+        {
+            bool stop = false;
+            for (int j0 = closest + 1; j0 < n && !stop; j0 += 128) {
+                float4 tv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int j = j0 + u * 32 + lane; if (j < n) tv[u] = last[j]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (stop || j0 + u * 32 >= n) continue;  // warp-uniform
+                    const int j = j0 + u * 32 + lane;
+                    bool brk = false;
+                    u64 c2 = ~0ull, c3 = ~0ull;
+                    if (j < n) {
+                        const float4 t = tv[u];
+                        const int rj = (int)t.w;
+                        brk = (double)rj > (double)cring + 2.5;
+                        const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
+                        const u64 key = ((u64)__float_as_uint(d2) << 32) | (unsigned)(j - (closest + 1));
+                        if (!brk && (double)d2 < 25.0) {
+                            if (is_corner) {
+                                if (!(rj <= cring)) c2 = key;  // LO:507: same scan line -> continue
+                            } else {
+                                if (rj <= cring) c2 = key;     // LO:682
+                                else c3 = key;                 // LO:688
+                            }
+                        }
                     }
+                    const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
+                    const int fb = bm ? __ffs(bm) - 1 : 32;
+                    if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
+                    if (bm) stop = true;
                 }
             }
-            const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
-            const int fb = bm ? __ffs(bm) - 1 : 32;
-            if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
-            if (bm) break;
         }
         // decreasing scan line (LO:530-553 / LO:696-721); visit order continues after the up-scan
-        for (int j0 = closest - 1; j0 >= 0; j0 -= 32) {
-            const int j = j0 - lane;
-            bool brk = false;
-            u64 c2 = ~0ull, c3 = ~0ull;
-            if (j >= 0) {
-                const float4 t = last[j];
-                const int rj = (int)t.w;
-                brk = (double)rj < (double)cring - 2.5;
-                const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                const u64 key = ((u64)__float_as_uint(d2) << 32) | (down_base + (unsigned)(closest - 1 - j));
-                if (!brk && (double)d2 < 25.0) {
-                    if (is_corner) {
-                        if (!(rj >= cring)) c2 = key;
-                    } else {
-                        if (rj >= cring) c2 = key;
-                        else c3 = key;
+        {
+            bool stop = false;
+            for (int j0 = closest - 1; j0 >= 0 && !stop; j0 -= 128) {
+                float4 tv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int j = j0 - u * 32 - lane; if (j >= 0) tv[u] = last[j]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (stop || j0 - u * 32 < 0) continue;
+                    const int j = j0 - u * 32 - lane;
+                    bool brk = false;
+                    u64 c2 = ~0ull, c3 = ~0ull;
+                    if (j >= 0) {
+                        const float4 t = tv[u];
+                        const int rj = (int)t.w;
+                        brk = (double)rj < (double)cring - 2.5;
+                        const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
+                        const u64 key = ((u64)__float_as_uint(d2) << 32) | (down_base + (unsigned)(closest - 1 - j));
+                        if (!brk && (double)d2 < 25.0) {
+                            if (is_corner) {
+                                if (!(rj >= cring)) c2 = key;
+                            } else {
+                                if (rj >= cring) c2 = key;
+                                else c3 = key;
+                            }
+                        }
                     }
+                    const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
+                    const int fb = bm ? __ffs(bm) - 1 : 32;
+                    if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
+                    if (bm) stop = true;
                 }
             }
-            const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
-            const int fb = bm ? __ffs(bm) - 1 : 32;
-            if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
-            if (bm) break;
         }
         }  // literal scan loops
         k2 = warp_min_u64(k2);
