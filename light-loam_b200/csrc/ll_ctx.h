@@ -57,8 +57,13 @@ struct LaneState {
     // --- mapping ---
     double map_par[7];               // LM:81 parameters: q_w_curr (xyzw), t_w_curr
     double q_wmap_wodom[4], t_wmap_wodom[3];  // LM:87-88
+    double map_odom[7];              // q_wodom_curr, t_wodom_curr of the frame being mapped (LM:90-91)
     int cen[3];                      // laserCloudCenWidth/Height/Depth LM:42-44
     int map_frame;
+    int map_shift[3];                // this frame's cube shift: new logical index = old + shift (LM:1596-1779)
+    int map_center[3];               // centerCubeI/J/K after shifting
+    int n_valid;                     // laserCloudValidNum (<= 125)
+    int map_ok;                      // LM:1826 guard: map corner > 10 && map surf > 50
     int n_map_corner, n_map_surf, n_stack_corner, n_stack_surf, n_map_corner_corr, n_map_surf_corr;
     int err;                         // sticky device-side error (LL_E_*)
 };

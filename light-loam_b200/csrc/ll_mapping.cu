@@ -1,8 +1,861 @@
-// placeholder — replaced by the scan-to-map implementation
+// Scan-to-map on the device — replaces laserMapping.cpp `process()` LM:1581-2168 for `batch` lanes.
+//
+//   k_map_begin     LM:1581 transformAssociateToMap, LM:1584-1779 centre cube + shifts, LM:1781-1803 valid cubes
+//   voxel grid      LM:1814-1822 (incoming clouds) and LM:2155-2168 (every valid cube): pcl::VoxelGrid restated as
+//                   bbox (atomics) -> voxel id -> stable radix sort of (lane, segment, voxel id) -> run-sum centroids
+//   k_map_gather    LM:1805-1811 concatenation of the 5x5x3 valid cubes into the local map
+//   grid build      kdtree*FromMap->setInputCloud (LM:1830-1831) -> hashed uniform grid, cell 1.05 m (>= the 1 m
+//                   acceptance radius of LM:1884 / LM:1952, so one 27-cell pass is exact)
+//   k_map_assoc     LM:1877-1940 / LM:1943-2055: pointAssociateToMap, exact 5-NN, line fit (3x3 symmetric eigen,
+//                   lambda2 > 3 lambda1) -> LidarEdgeFactor record; plane fit (5x3 pivoted Householder QR, all
+//                   residuals <= 0.2) -> LidarPlaneNormFactor record; one warp per stack point, dense records
+//   k_lm_solve_map  ceres::Solve LM:2079-2087 (shared LM controller, ll_solve.cuh)
+//   k_map_end       LM:2101 transformUpdate
+//   rebuild         LM:2104-2168: insert the stack points into their cubes, voxel-filter every valid cube, and
+//                   re-emit the whole cube array as CSR (cube_off + points) with this frame's shift applied
+//
+// The cube map is stored per lane and cloud type as CSR over the 21 x 21 x 11 logical cube array and rebuilt once per
+// frame (a streaming copy of the map), which makes the reference's pointer-rotation shifts and per-cube filters one
+// pass.  The two sorts / one scan of the voxel filter use CUB (cub::DeviceRadixSort / DeviceScan, shipped with the
+// CUDA toolkit) — library plumbing on the map-maintenance side ("next" row of SURVEY.md §8f); every other step is a
+// hand-written kernel.
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include <cub/cub.cuh>
+
 #include "ll_ctx.h"
-int ll_map_alloc(ll_ctx*) { return LL_OK; }
-void ll_map_free(ll_ctx*) {}
-int ll_launch_mapping(ll_ctx*, int) { return LL_OK; }
+#include "ll_device.cuh"
+#include "ll_knn.cuh"
+#include "ll_solve.cuh"
+
+#define MAP_W 21
+#define MAP_H 21
+#define MAP_D 11
+#define MAP_NUM (MAP_W * MAP_H * MAP_D)  // 4851, LM:45-50
+#define MAP_MAXVALID 128
+
+int ll_build_map_grid(ll_ctx* c, KnnGrid& g, const float4* pts, size_t lane_stride, int which, int n_lanes, int max_pts);
+
+struct MapState {
+    int map_cap = 0;           // points per lane and type over the whole cube array
+    int stack_cap[2] = {0, 0};
+    int in_cap[2] = {0, 0};
+    int E = 0;                 // voxel-filter element capacity per lane = map_cap + max stack
+    int buf = 0;               // current CSR buffer (same for all lanes)
+    float4* map_pts[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int* cube_off[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    float4* in_cloud[2] = {nullptr, nullptr};   // laserCloudCornerLast / SurfLast as received
+    int* in_n = nullptr;                        // [B][2]
+    float4* stack[2] = {nullptr, nullptr};      // laserCloudCornerStack / SurfStack
+    float4* frommap[2] = {nullptr, nullptr};    // laserCloudCornerFromMap / SurfFromMap
+    KnnGrid grid[2];
+    unsigned char* valid_mask = nullptr;        // [B][MAP_NUM]
+    int* valid_ind = nullptr;                   // [B][MAP_MAXVALID]
+    double* pose_in = nullptr;                  // [B][7] q_wodom_curr, t_wodom_curr
+    // voxel filter work space (one filter runs at a time)
+    float4* vg_in = nullptr;   // [B][E]
+    int* vg_seg = nullptr;     // [B][E]
+    int* vg_n = nullptr;       // [B] elements per lane
+    u64* vg_keys[2] = {nullptr, nullptr};
+    int* vg_vals[2] = {nullptr, nullptr};
+    int* vg_head = nullptr;
+    int* vg_scan = nullptr;
+    int* vg_bbox = nullptr;    // [B][nseg][6] ordered-int min xyz / max xyz
+    int* seg_count = nullptr;  // [B][MAP_NUM]
+    int* lane_base = nullptr;  // [B+1]
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    double* blocks = nullptr;  // dense records [B][LL_BLOCK_DOUBLES][nblk_cap]
+    int nblk_cap = 0;
+};
+
+namespace {
+
+__device__ __forceinline__ int f2ord(float f) { const int a = __float_as_int(f); return a >= 0 ? a : a ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7FFFFFFF); }
+
+// LM:125-134 pointAssociateToMap: fp64 rotate + translate, stored fp32
+__device__ __forceinline__ float4 associate_to_map(const float4 p, const double* par)
+{
+    double rx, ry, rz;
+    quat_rotate(par, (double)p.x, (double)p.y, (double)p.z, rx, ry, rz);
+    return make_float4((float)(rx + par[4]), (float)(ry + par[5]), (float)(rz + par[6]), p.w);
+}
+// LM:2109-2118
+__device__ __forceinline__ int cube_index(const float4 p, const int cen[3])
+{
+    int I = (int)(((double)p.x + 25.0) / 50.0) + cen[0];
+    int J = (int)(((double)p.y + 25.0) / 50.0) + cen[1];
+    int K = (int)(((double)p.z + 25.0) / 50.0) + cen[2];
+    if ((double)p.x + 25.0 < 0) I--;
+    if ((double)p.y + 25.0 < 0) J--;
+    if ((double)p.z + 25.0 < 0) K--;
+    if (I >= 0 && I < MAP_W && J >= 0 && J < MAP_H && K >= 0 && K < MAP_D) return I + MAP_W * J + MAP_W * MAP_H * K;
+    return -1;
+}
+
+__global__ void k_map_begin(LaneState* lane, const double* pose_in, unsigned char* valid_mask, int* valid_ind, int from_odom, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_lanes) return;
+    LaneState& L = lane[b];
+    double qo[4], to[3];
+    if (from_odom) {
+        for (int k = 0; k < 4; ++k) qo[k] = L.q_w[k];
+        for (int k = 0; k < 3; ++k) to[k] = L.t_w[k];
+    } else {
+        for (int k = 0; k < 4; ++k) qo[k] = pose_in[b * 7 + k];
+        for (int k = 0; k < 3; ++k) to[k] = pose_in[b * 7 + 4 + k];
+    }
+    // keep the odometry pose for transformUpdate
+    L.map_odom[0] = qo[0]; L.map_odom[1] = qo[1]; L.map_odom[2] = qo[2]; L.map_odom[3] = qo[3];
+    L.map_odom[4] = to[0]; L.map_odom[5] = to[1]; L.map_odom[6] = to[2];
+    // transformAssociateToMap LM:113-117
+    double q[4], rx, ry, rz;
+    quat_mul(L.q_wmap_wodom, qo, q);
+    quat_rotate(L.q_wmap_wodom, to[0], to[1], to[2], rx, ry, rz);
+    for (int k = 0; k < 4; ++k) L.map_par[k] = q[k];
+    L.map_par[4] = rx + L.t_wmap_wodom[0];
+    L.map_par[5] = ry + L.t_wmap_wodom[1];
+    L.map_par[6] = rz + L.t_wmap_wodom[2];
+    // LM:1584-1594
+    int c[3];
+    const int dim[3] = {MAP_W, MAP_H, MAP_D};
+    for (int a = 0; a < 3; ++a) {
+        c[a] = (int)((L.map_par[4 + a] + 25.0) / 50.0) + L.cen[a];
+        if (L.map_par[4 + a] + 25.0 < 0) c[a]--;
+    }
+    // LM:1596-1779: each shift moves every cube one slot and recycles (clears) the slot that falls off
+    for (int a = 0; a < 3; ++a) {
+        int sh = 0;
+        while (c[a] < 3) { c[a]++; L.cen[a]++; sh++; }
+        while (c[a] >= dim[a] - 3) { c[a]--; L.cen[a]--; sh--; }
+        L.map_shift[a] = sh;
+        L.map_center[a] = c[a];
+    }
+    // LM:1781-1803
+    unsigned char* vm = valid_mask + (size_t)b * MAP_NUM;
+    for (int k = 0; k < MAP_NUM; ++k) vm[k] = 0;
+    int nv = 0;
+    for (int i = c[0] - 2; i <= c[0] + 2; i++)
+        for (int j = c[1] - 2; j <= c[1] + 2; j++)
+            for (int k = c[2] - 1; k <= c[2] + 1; k++)
+                if (i >= 0 && i < MAP_W && j >= 0 && j < MAP_H && k >= 0 && k < MAP_D) {
+                    const int id = i + MAP_W * j + MAP_W * MAP_H * k;
+                    valid_ind[b * MAP_MAXVALID + nv++] = id;
+                    vm[id] = 1;
+                }
+    L.n_valid = nv;
+}
+
+// new logical cube id -> old logical cube id under this frame's shift, or -1 (recycled / cleared)
+__device__ __forceinline__ int shifted_source(int id, const int sh[3])
+{
+    const int i = id % MAP_W, j = (id / MAP_W) % MAP_H, k = id / (MAP_W * MAP_H);
+    const int oi = i - sh[0], oj = j - sh[1], ok = k - sh[2];
+    if (oi < 0 || oi >= MAP_W || oj < 0 || oj >= MAP_H || ok < 0 || ok >= MAP_D) return -1;
+    return oi + MAP_W * oj + MAP_W * MAP_H * ok;
+}
+
+// LM:1805-1811: one CTA per (valid cube slot, lane, type)
+__global__ void k_map_gather(LaneState* lane, const int* valid_ind, const float4* map0, const int* off0, float4* out0, const float4* map1,
+                             const int* off1, float4* out1, int map_cap)
+{
+    __shared__ int base_s, src_s, cnt_s;
+    const int v = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    LaneState& L = lane[b];
+    if (v >= L.n_valid) return;
+    const int* off = (t == 0 ? off0 : off1) + (size_t)b * (MAP_NUM + 1);
+    const float4* src = (t == 0 ? map0 : map1) + (size_t)b * map_cap;
+    float4* dst = (t == 0 ? out0 : out1) + (size_t)b * map_cap;
+    if (threadIdx.x == 0) {
+        int base = 0;
+        for (int u = 0; u <= v; ++u) {
+            const int s = shifted_source(valid_ind[b * MAP_MAXVALID + u], L.map_shift);
+            const int cnt = s >= 0 ? off[s + 1] - off[s] : 0;
+            if (u == v) { src_s = s >= 0 ? off[s] : 0; cnt_s = cnt; } else base += cnt;
+        }
+        base_s = base;
+        if (v == L.n_valid - 1) { if (t == 0) L.n_map_corner = base + cnt_s; else L.n_map_surf = base + cnt_s; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt_s; k += blockDim.x) dst[base_s + k] = src[src_s + k];
+}
+
+__global__ void k_map_guard(LaneState* lane, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_lanes) return;
+    LaneState& L = lane[b];
+    if (L.n_valid == 0) { L.n_map_corner = 0; L.n_map_surf = 0; }
+    L.map_ok = (L.n_map_corner > 10 && L.n_map_surf > 50) ? 1 : 0;  // LM:1826
+    L.n_map_corner_corr = 0;
+    L.n_map_surf_corr = 0;
+}
+
+// ---- small dense helpers (fp64), same algorithms as oracle/orc_mapping.cpp ---------------------------------------
+static __device__ void sym_eig3(const double Ain[9], double evals[3], double evecs[9])
+{
+    double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = Ain[i * 3 + j];
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        const double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+            }
+    }
+    int ord[3] = {0, 1, 2};
+    for (int a = 0; a < 2; ++a)
+        for (int c = 0; c < 2 - a; ++c)
+            if (A[ord[c + 1]][ord[c + 1]] < A[ord[c]][ord[c]]) { const int t = ord[c]; ord[c] = ord[c + 1]; ord[c + 1] = t; }
+    for (int c = 0; c < 3; ++c) {
+        evals[c] = A[ord[c]][ord[c]];
+        for (int r = 0; r < 3; ++r) evecs[r * 3 + c] = V[r][ord[c]];
+    }
+}
+
+static __device__ void plane_fit5(const double pts[15], double nrm[3])
+{
+    double A[5][3], b[5];
+    int perm[3] = {0, 1, 2};
+    for (int i = 0; i < 5; ++i) { for (int j = 0; j < 3; ++j) A[i][j] = pts[i * 3 + j]; b[i] = -1.0; }
+    double maxpivot = 0.0, diag[3] = {0, 0, 0};
+    int rank = 3;
+    for (int k = 0; k < 3; ++k) {
+        int piv = k;
+        double best = -1.0;
+        for (int j = k; j < 3; ++j) {
+            double s = 0;
+            for (int i = k; i < 5; ++i) s += A[i][j] * A[i][j];
+            if (s > best) { best = s; piv = j; }
+        }
+        if (piv != k) {
+            for (int i = 0; i < 5; ++i) { const double t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
+            const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        const double nrmk = sqrt(best);
+        if (nrmk == 0.0) { rank = k; break; }
+        const double alpha = A[k][k] > 0 ? -nrmk : nrmk;
+        const double v0 = A[k][k] - alpha;
+        double vtv = v0 * v0;
+        for (int i = k + 1; i < 5; ++i) vtv += A[i][k] * A[i][k];
+        if (vtv > 0.0) {
+            for (int j = k + 1; j < 3; ++j) {
+                double s = v0 * A[k][j];
+                for (int i = k + 1; i < 5; ++i) s += A[i][k] * A[i][j];
+                s = 2.0 * s / vtv;
+                A[k][j] -= s * v0;
+                for (int i = k + 1; i < 5; ++i) A[i][j] -= s * A[i][k];
+            }
+            double s = v0 * b[k];
+            for (int i = k + 1; i < 5; ++i) s += A[i][k] * b[i];
+            s = 2.0 * s / vtv;
+            b[k] -= s * v0;
+            for (int i = k + 1; i < 5; ++i) b[i] -= s * A[i][k];
+        }
+        A[k][k] = alpha;
+        diag[k] = fabs(alpha);
+        if (diag[k] > maxpivot) maxpivot = diag[k];
+    }
+    const double thr = 2.220446049250313e-16 * 3.0 * maxpivot;
+    int r = 0;
+    for (int k = 0; k < rank; ++k) if (diag[k] > thr) ++r;
+    double y[3] = {0, 0, 0};
+    for (int k = r - 1; k >= 0; --k) {
+        double s = b[k];
+        for (int j = k + 1; j < r; ++j) s -= A[k][j] * y[j];
+        y[k] = s / A[k][k];
+    }
+    for (int k = 0; k < 3; ++k) nrm[perm[k]] = y[k];
+}
+
+struct MapAssocParams {
+    LaneState* lane;
+    const float4* stack[2];
+    const float4* frommap[2];
+    int stack_cap[2];
+    int map_cap;
+    KnnGrid g[2];
+    double* blocks;
+    int nblk_cap;
+};
+
+// one warp per stack point; the fit runs on lane 0 (fp64, a few hundred flops)
+__global__ void __launch_bounds__(256) k_map_assoc(MapAssocParams P)
+{
+    const int b = blockIdx.y;
+    LaneState& L = P.lane[b];
+    const int lane = lane_id();
+    const int q = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const int nc = L.n_stack_corner, ns = L.n_stack_surf;
+    if (q >= nc + ns) return;
+    double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    const int cap = P.nblk_cap;
+    if (!L.map_ok) { if (lane == 0) blk[q] = -1.0; return; }
+    const int t = q < nc ? 0 : 1;
+    const int i = t == 0 ? q : q - nc;
+    const float4 pointOri = P.stack[t][(size_t)b * P.stack_cap[t] + i];
+    const float4 pointSel = associate_to_map(pointOri, L.map_par);
+    const KnnGrid& G = P.g[t];
+    GridView gv;
+    gv.start = G.start + (size_t)b * (G.T + 1);
+    gv.sorted = G.sorted + (size_t)b * G.cap;
+    gv.Tmask = G.T - 1;
+    gv.h = G.h;
+    gv.inv_h = G.inv_h;
+    u64 best[5];
+    grid_knn<5>(gv, pointSel.x, pointSel.y, pointSel.z, 1.0f, best);
+    double type = -1.0;
+    if (lane == 0) {
+        // kd-tree semantics: fewer than 5 points in the map cannot happen behind the LM:1826 guard; the 5th
+        // neighbour must exist and satisfy d2 < 1.0 (LM:1884 / LM:1952)
+        if (best[4] != ~0ull && (double)__uint_as_float((unsigned)(best[4] >> 32)) < 1.0) {
+            const float4* mp = P.frommap[t] + (size_t)b * P.map_cap;
+            double pts[15];
+            for (int j = 0; j < 5; ++j) {
+                const float4 m = mp[(int)(unsigned)best[j]];
+                pts[j * 3] = m.x; pts[j * 3 + 1] = m.y; pts[j * 3 + 2] = m.z;
+            }
+            if (t == 0) {  // LM:1886-1921
+                double center[3] = {0, 0, 0};
+                for (int j = 0; j < 5; ++j) for (int a = 0; a < 3; ++a) center[a] = center[a] + pts[j * 3 + a];
+                for (int a = 0; a < 3; ++a) center[a] = center[a] / 5.0;
+                double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < 5; ++j) {
+                    const double zm[3] = {pts[j * 3] - center[0], pts[j * 3 + 1] - center[1], pts[j * 3 + 2] - center[2]};
+                    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cov[r * 3 + c] = cov[r * 3 + c] + zm[r] * zm[c];
+                }
+                double ev[3], evec[9];
+                sym_eig3(cov, ev, evec);
+                if (ev[2] > 3 * ev[1]) {
+                    type = 0.0;
+                    blk[1 * cap + q] = pointOri.x; blk[2 * cap + q] = pointOri.y; blk[3 * cap + q] = pointOri.z;
+                    for (int a = 0; a < 3; ++a) {
+                        blk[(4 + a) * cap + q] = 0.1 * evec[a * 3 + 2] + center[a];
+                        blk[(7 + a) * cap + q] = -0.1 * evec[a * 3 + 2] + center[a];
+                    }
+                    blk[10 * cap + q] = 1.0;
+                    atomicAdd(&L.n_map_corner_corr, 1);
+                }
+            } else {  // LM:1949-2036
+                double nrm[3];
+                plane_fit5(pts, nrm);
+                const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+                const double d = 1 / nn;
+                if (nn * nn > 0.0) for (int a = 0; a < 3; ++a) nrm[a] = nrm[a] / nn;
+                bool ok = true;
+                for (int j = 0; j < 5; ++j) {
+                    const float4 m = mp[(int)(unsigned)best[j]];
+                    if (fabs(nrm[0] * m.x + nrm[1] * m.y + nrm[2] * m.z + d) > 0.2) { ok = false; break; }
+                }
+                if (ok) {
+                    type = 2.0;
+                    blk[1 * cap + q] = pointOri.x; blk[2 * cap + q] = pointOri.y; blk[3 * cap + q] = pointOri.z;
+                    for (int a = 0; a < 3; ++a) { blk[(4 + a) * cap + q] = nrm[a]; blk[(7 + a) * cap + q] = 0.0; }
+                    blk[10 * cap + q] = d;
+                    atomicAdd(&L.n_map_surf_corr, 1);
+                }
+            }
+        }
+        blk[q] = type;
+    }
+}
+
+__global__ void k_map_reset_corr(LaneState* lane, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_lanes) { lane[b].n_map_corner_corr = 0; lane[b].n_map_surf_corr = 0; }
+}
+
+__global__ void __launch_bounds__(LM_THREADS) k_lm_solve_map(LaneState* lane, const double* blocks, int nblk_cap, int iter)
+{
+    const int b = blockIdx.x;
+    LaneState& L = lane[b];
+    const int nb = L.map_ok ? L.n_stack_corner + L.n_stack_surf : 0;
+    lm_solve(blocks + (size_t)b * LL_BLOCK_DOUBLES * nblk_cap, nblk_cap, nb, L.map_par, L.map_par + 4, &L, 3 + iter);
+}
+
+// LM:119-123 transformUpdate + pose output
+__global__ void k_map_end(LaneState* lane, double* pose_out, int n_lanes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_lanes) return;
+    LaneState& L = lane[b];
+    const double* qo = L.map_odom;
+    const double n2 = qo[0] * qo[0] + qo[1] * qo[1] + qo[2] * qo[2] + qo[3] * qo[3];  // Eigen inverse = conjugate / squaredNorm
+    double qi[4] = {0, 0, 0, 0};
+    if (n2 > 0.0) { qi[0] = -qo[0] / n2; qi[1] = -qo[1] / n2; qi[2] = -qo[2] / n2; qi[3] = qo[3] / n2; }
+    double qm[4], rx, ry, rz;
+    quat_mul(L.map_par, qi, qm);
+    quat_rotate(qm, qo[4], qo[5], qo[6], rx, ry, rz);
+    for (int k = 0; k < 4; ++k) L.q_wmap_wodom[k] = qm[k];
+    L.t_wmap_wodom[0] = L.map_par[4] - rx;
+    L.t_wmap_wodom[1] = L.map_par[5] - ry;
+    L.t_wmap_wodom[2] = L.map_par[6] - rz;
+    L.map_frame++;
+    if (pose_out) for (int k = 0; k < 7; ++k) pose_out[(size_t)b * 14 + 7 + k] = L.map_par[k];
+}
+
+// ---- voxel filter (pcl::VoxelGrid) over (lane, segment) groups ------------------------------------------------------
+struct VgParams {
+    LaneState* lane;
+    const float4* in;    // [B][E]
+    const int* seg;      // [B][E] segment id, -1 = dropped
+    const int* n;        // [B]
+    int E, nseg;
+    const unsigned char* ds_mask;  // [B][nseg] 1 = filter the segment, 0 = keep every point; nullptr = filter all
+    int* bbox;           // [B][nseg][6]
+    u64* keys;
+    int* vals;
+    float inv_leaf;
+};
+
+__global__ void k_vg_init(int* bbox, int* seg_count, int nseg_total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg_total) {
+        for (int a = 0; a < 3; ++a) { bbox[i * 6 + a] = INT_MAX; bbox[i * 6 + 3 + a] = INT_MIN; }
+        seg_count[i] = 0;
+    }
+}
+__global__ void k_vg_bbox(VgParams P)
+{
+    const int b = blockIdx.y;
+    const int n = P.n[b];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int s = P.seg[(size_t)b * P.E + e];
+        if (s < 0) continue;
+        const float4 p = P.in[(size_t)b * P.E + e];
+        int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
+        atomicMin(&bb[0], f2ord(p.x)); atomicMin(&bb[1], f2ord(p.y)); atomicMin(&bb[2], f2ord(p.z));
+        atomicMax(&bb[3], f2ord(p.x)); atomicMax(&bb[4], f2ord(p.y)); atomicMax(&bb[5], f2ord(p.z));
+    }
+}
+// key = lane (8 bits) | segment (13) | voxel id or element number (31); ~0 = padding / dropped
+__global__ void k_vg_keys(VgParams P)
+{
+    const int b = blockIdx.y;
+    const int n = P.n[b];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P.E; e += gridDim.x * blockDim.x) {
+        const size_t g = (size_t)b * P.E + e;
+        u64 key = ~0ull;
+        if (e < n) {
+            const int s = P.seg[g];
+            if (s >= 0) {
+                const float4 p = P.in[g];
+                const int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
+                const float inv = P.inv_leaf;
+                const float mn[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])}, mx[3] = {ord2f(bb[3]), ord2f(bb[4]), ord2f(bb[5])};
+                bool ds = P.ds_mask ? P.ds_mask[(size_t)b * P.nseg + s] != 0 : true;
+                const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
+                                dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+                if (dx * dy * dz > (long long)INT_MAX) ds = false;  // PCL: leaf too small -> output = input
+                unsigned v = (unsigned)e;
+                if (ds) {
+                    const int mb0 = (int)floorf(mn[0] * inv), mb1 = (int)floorf(mn[1] * inv), mb2 = (int)floorf(mn[2] * inv);
+                    const int div0 = (int)floorf(mx[0] * inv) - mb0 + 1, div1 = (int)floorf(mx[1] * inv) - mb1 + 1;
+                    const int i0 = (int)(floorf(p.x * inv) - (float)mb0), i1 = (int)(floorf(p.y * inv) - (float)mb1),
+                              i2 = (int)(floorf(p.z * inv) - (float)mb2);
+                    v = (unsigned)(i0 + i1 * div0 + i2 * div0 * div1);
+                }
+                key = ((u64)b << 44) | ((u64)s << 31) | (u64)(v & 0x7FFFFFFFu);
+            }
+        }
+        P.keys[g] = key;
+        P.vals[g] = (int)g;
+    }
+}
+__global__ void k_vg_heads(const u64* keys, int* head, int* seg_count, int nseg, long long total)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const u64 k = keys[p];
+    int h = 0;
+    if (k != ~0ull && (p == 0 || keys[p - 1] != k)) {
+        h = 1;
+        const int b = (int)(k >> 44), s = (int)((k >> 31) & 0x1FFF);
+        atomicAdd(&seg_count[(size_t)b * nseg + s], 1);
+    }
+    head[p] = h;
+}
+// exclusive offsets of the segments inside each lane and the lanes' bases in the flat head ranking
+__global__ void __launch_bounds__(1024) k_vg_offsets(const int* seg_count, int* seg_off, int* lane_base, int nseg, int n_lanes, int* n_out_field0,
+                                                      LaneState* lane, int which)
+{
+    __shared__ int ws[40];
+    const int b = blockIdx.x;
+    const int per = (nseg + 1023) / 1024;
+    const int i0 = threadIdx.x * per, i1 = min(i0 + per, nseg);
+    int s = 0;
+    for (int i = i0; i < i1; ++i) s += seg_count[(size_t)b * nseg + i];
+    int tot = 0;
+    int run = block_exclusive_scan(s, ws, &tot);
+    if (seg_off) {
+        for (int i = i0; i < i1; ++i) { seg_off[(size_t)b * (nseg + 1) + i] = run; run += seg_count[(size_t)b * nseg + i]; }
+        if (threadIdx.x == 0) seg_off[(size_t)b * (nseg + 1) + nseg] = tot;
+    }
+    if (threadIdx.x == 0) {
+        lane_base[b] = tot;  // turned into an exclusive prefix by k_vg_lane_prefix
+        if (which == 0) lane[b].n_stack_corner = tot;
+        else if (which == 1) lane[b].n_stack_surf = tot;
+    }
+    (void)n_out_field0;
+}
+__global__ void k_vg_lane_prefix(int* lane_base, int n_lanes)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < n_lanes; ++b) { const int c = lane_base[b]; lane_base[b] = run; run += c; }
+        lane_base[n_lanes] = run;
+    }
+}
+// centroid of x,y,z,intensity over every run of equal keys, fp32 sums in sorted (= input) order
+__global__ void k_vg_centroid(const u64* keys, const int* vals, const int* head, const int* scan, const int* lane_base, const float4* in,
+                              float4* out, int out_cap, long long total)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total || !head[p]) return;
+    const u64 k = keys[p];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    long long q = p;
+    for (; q < total && keys[q] == k; ++q) {
+        const float4 a = in[vals[q]];
+        sx += a.x; sy += a.y; sz += a.z; si += a.w;
+    }
+    const float cnt = (float)(q - p);
+    const int b = (int)(k >> 44);
+    const int o = scan[p] - lane_base[b];
+    if (o < out_cap) out[(size_t)b * out_cap + o] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+}
+
+// ---- element assembly ------------------------------------------------------------------------------------------------------
+__global__ void k_vg_fill_incoming(const float4* src, int src_cap, const int* in_n, int t, float4* vg_in, int* vg_seg, int* vg_n, int E)
+{
+    const int b = blockIdx.y;
+    const int n = in_n[b * 2 + t];
+    if (blockIdx.x == 0 && threadIdx.x == 0) vg_n[b] = n;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        vg_in[(size_t)b * E + e] = src[(size_t)b * src_cap + e];
+        vg_seg[(size_t)b * E + e] = 0;
+    }
+}
+// LM:2104-2152 + the shift: old map points keep their (shifted) cube, stack points go to the cube of their map-frame position
+__global__ void k_vg_fill_rebuild(LaneState* lane, const float4* map_old, const int* off_old, int map_cap, const float4* stack, int stack_cap, int t,
+                                  float4* vg_in, int* vg_seg, int* vg_n, int E)
+{
+    const int b = blockIdx.y;
+    LaneState& L = lane[b];
+    const int* off = off_old + (size_t)b * (MAP_NUM + 1);
+    const int n_old = off[MAP_NUM];
+    const int n_new = t == 0 ? L.n_stack_corner : L.n_stack_surf;
+    const int n = min(n_old + n_new, E);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { vg_n[b] = n; if (n_old + n_new > E) L.err = LL_E_CAPACITY; }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        float4 p;
+        int seg;
+        if (e < n_old) {
+            p = map_old[(size_t)b * map_cap + e];
+            int lo = 0, hi = MAP_NUM;  // cube whose CSR range contains e: largest c with off[c] <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
+            const int i = lo % MAP_W + L.map_shift[0], j = (lo / MAP_W) % MAP_H + L.map_shift[1], k = lo / (MAP_W * MAP_H) + L.map_shift[2];
+            seg = (i >= 0 && i < MAP_W && j >= 0 && j < MAP_H && k >= 0 && k < MAP_D) ? i + MAP_W * j + MAP_W * MAP_H * k : -1;
+        } else {
+            p = associate_to_map(stack[(size_t)b * stack_cap + (e - n_old)], L.map_par);
+            seg = cube_index(p, L.cen);
+        }
+        vg_in[(size_t)b * E + e] = p;
+        vg_seg[(size_t)b * E + e] = seg;
+    }
+}
+
+__global__ void k_map_copy_odom_clouds(LaneState* lane, const float4* ls0, const float4* ls1, int ls_cap, const float4* lf0, const float4* lf1, int lf_cap,
+                                       float4* in0, int in0_cap, float4* in1, int in1_cap, int* in_n)
+{
+    // fused pipeline: laserOdometry publishes this frame's less-sharp / less-flat clouds as corner_last / surf_last (LO:882-912)
+    const int b = blockIdx.y;
+    LaneState& L = lane[b];
+    const float4* ls = (L.cur == 0 ? ls0 : ls1) + (size_t)b * ls_cap;
+    const float4* lf = (L.cur == 0 ? lf0 : lf1) + (size_t)b * lf_cap;
+    const int nc = min(L.n_less_sharp, in0_cap), ns = min(L.n_less_flat, in1_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { in_n[b * 2] = nc; in_n[b * 2 + 1] = ns; }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nc; e += gridDim.x * blockDim.x) in0[(size_t)b * in0_cap + e] = ls[e];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ns; e += gridDim.x * blockDim.x) in1[(size_t)b * in1_cap + e] = lf[e];
+}
+
+}  // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------------------------------
+static int pow2ceil_i(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+void ll_map_free(ll_ctx* c)
+{
+    MapState* m = c->map;
+    if (!m) return;
+    for (int t = 0; t < 2; ++t) {
+        for (int k = 0; k < 2; ++k) { cudaFree(m->map_pts[t][k]); cudaFree(m->cube_off[t][k]); }
+        cudaFree(m->in_cloud[t]); cudaFree(m->stack[t]); cudaFree(m->frommap[t]);
+        cudaFree(m->grid[t].start); cudaFree(m->grid[t].cursor); cudaFree(m->grid[t].sorted); cudaFree(m->grid[t].partial);
+        cudaFree(m->vg_keys[t]); cudaFree(m->vg_vals[t]);
+    }
+    cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->vg_in); cudaFree(m->vg_seg);
+    cudaFree(m->vg_n); cudaFree(m->vg_head); cudaFree(m->vg_scan); cudaFree(m->vg_bbox); cudaFree(m->seg_count); cudaFree(m->lane_base);
+    cudaFree(m->cub_tmp); cudaFree(m->blocks);
+    delete m;
+    c->map = nullptr;
+}
+
+int ll_map_alloc(ll_ctx* c)
+{
+    if (c->B > 255) { c->last_error = "mapping supports at most 255 lanes"; return LL_E_INVAL; }
+    MapState* m = new MapState();
+    c->map = m;
+    const size_t B = c->B;
+    m->map_cap = c->cfg.map_capacity > 1024 ? c->cfg.map_capacity : 1024;
+    m->in_cap[0] = c->R * LL_LSHARP_PER_RING;
+    m->in_cap[1] = c->Nmax;
+    m->stack_cap[0] = m->in_cap[0];
+    m->stack_cap[1] = m->in_cap[1];
+    m->E = m->map_cap + m->stack_cap[1];
+#define MK(expr)                                                              \
+    do {                                                                      \
+        cudaError_t e__ = (expr);                                             \
+        if (e__ != cudaSuccess) { c->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__); return LL_E_CUDA; } \
+    } while (0)
+    for (int t = 0; t < 2; ++t) {
+        for (int k = 0; k < 2; ++k) {
+            MK(cudaMalloc((void**)&m->map_pts[t][k], sizeof(float4) * B * m->map_cap));
+            MK(cudaMalloc((void**)&m->cube_off[t][k], sizeof(int) * B * (MAP_NUM + 1)));
+            MK(cudaMemsetAsync(m->cube_off[t][k], 0, sizeof(int) * B * (MAP_NUM + 1), c->stream));
+        }
+        MK(cudaMalloc((void**)&m->in_cloud[t], sizeof(float4) * B * m->in_cap[t]));
+        MK(cudaMalloc((void**)&m->stack[t], sizeof(float4) * B * m->stack_cap[t]));
+        MK(cudaMalloc((void**)&m->frommap[t], sizeof(float4) * B * m->map_cap));
+        KnnGrid& g = m->grid[t];
+        g.T = pow2ceil_i(m->map_cap / 2) < 2048 ? 2048 : pow2ceil_i(m->map_cap / 2);
+        g.cap = m->map_cap;
+        g.h = 1.05f;  // one 27-cell pass covers the 1 m acceptance radius (LM:1884 / LM:1952) with margin
+        g.inv_h = 1.0f / g.h;
+        MK(cudaMalloc((void**)&g.start, sizeof(int) * B * (size_t)(g.T + 1)));
+        MK(cudaMalloc((void**)&g.cursor, sizeof(int) * B * (size_t)g.T));
+        MK(cudaMalloc((void**)&g.sorted, sizeof(float4) * B * (size_t)g.cap));
+        MK(cudaMalloc((void**)&g.partial, sizeof(int) * B * (size_t)(g.T / 2048 + 1)));
+    }
+    for (int k = 0; k < 2; ++k) {
+        MK(cudaMalloc((void**)&m->vg_keys[k], sizeof(u64) * B * m->E));
+        MK(cudaMalloc((void**)&m->vg_vals[k], sizeof(int) * B * m->E));
+    }
+    MK(cudaMalloc((void**)&m->in_n, sizeof(int) * B * 2));
+    MK(cudaMalloc((void**)&m->valid_mask, B * MAP_NUM));
+    MK(cudaMalloc((void**)&m->valid_ind, sizeof(int) * B * MAP_MAXVALID));
+    MK(cudaMalloc((void**)&m->pose_in, sizeof(double) * B * 7));
+    MK(cudaMalloc((void**)&m->vg_in, sizeof(float4) * B * m->E));
+    MK(cudaMalloc((void**)&m->vg_seg, sizeof(int) * B * m->E));
+    MK(cudaMalloc((void**)&m->vg_n, sizeof(int) * B));
+    MK(cudaMalloc((void**)&m->vg_head, sizeof(int) * B * m->E));
+    MK(cudaMalloc((void**)&m->vg_scan, sizeof(int) * B * m->E));
+    MK(cudaMalloc((void**)&m->vg_bbox, sizeof(int) * B * MAP_NUM * 6));
+    MK(cudaMalloc((void**)&m->seg_count, sizeof(int) * B * MAP_NUM));
+    MK(cudaMalloc((void**)&m->lane_base, sizeof(int) * (B + 1)));
+    size_t s1 = 0, s2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, s1, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], (long long)B * m->E, 0, 52, c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, s2, m->vg_head, m->vg_scan, (long long)B * m->E, c->stream);
+    m->cub_bytes = s1 > s2 ? s1 : s2;
+    MK(cudaMalloc(&m->cub_tmp, m->cub_bytes));
+    m->nblk_cap = m->stack_cap[0] + m->stack_cap[1];
+    MK(cudaMalloc((void**)&m->blocks, sizeof(double) * B * LL_BLOCK_DOUBLES * (size_t)m->nblk_cap));
+#undef MK
+    return LL_OK;
+}
+
+// pcl::VoxelGrid over the elements currently assembled in vg_in / vg_seg / vg_n. Writes the filtered points to `out`
+// (lane slabs of out_cap) in (segment, voxel id) order; seg_off (optional) receives the CSR offsets; which = 0 / 1
+// additionally stores the lane totals into n_stack_corner / n_stack_surf.
+static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const unsigned char* ds_mask, float leaf, float4* out, int out_cap, int* seg_off, int which)
+{
+    MapState* m = c->map;
+    cudaStream_t s = c->stream;
+    VgParams P;
+    P.lane = c->d_lane; P.in = m->vg_in; P.seg = m->vg_seg; P.n = m->vg_n; P.E = E_used; P.nseg = nseg; P.ds_mask = ds_mask; P.bbox = m->vg_bbox;
+    P.keys = m->vg_keys[0]; P.vals = m->vg_vals[0]; P.inv_leaf = 1.0f / leaf;
+    const long long total = (long long)n_lanes * E_used;
+    const int gx = 296;
+    { LLProf pr(c, "k_vg_init"); k_vg_init<<<(n_lanes * nseg + 255) / 256, 256, 0, s>>>(m->vg_bbox, m->seg_count, n_lanes * nseg); }
+    { LLProf pr(c, "k_vg_bbox"); k_vg_bbox<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
+    { LLProf pr(c, "k_vg_keys"); k_vg_keys<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
+    {
+        LLProf pr(c, "cub_radix_sort");
+        size_t bytes = m->cub_bytes;
+        LL_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], total, 0, 52, s));
+    }
+    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[1], m->vg_head, m->seg_count, nseg, total); }
+    {
+        LLProf pr(c, "cub_scan");
+        size_t bytes = m->cub_bytes;
+        LL_CUDA_CHECK(c, cub::DeviceScan::ExclusiveSum(m->cub_tmp, bytes, m->vg_head, m->vg_scan, total, s));
+    }
+    { LLProf pr(c, "k_vg_offsets"); k_vg_offsets<<<n_lanes, 1024, 0, s>>>(m->seg_count, seg_off, m->lane_base, nseg, n_lanes, nullptr, c->d_lane, which); }
+    { LLProf pr(c, "k_vg_lane_prefix"); k_vg_lane_prefix<<<1, 32, 0, s>>>(m->lane_base, n_lanes); }
+    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[1], m->vg_vals[1], m->vg_head, m->vg_scan, m->lane_base, m->vg_in, out, out_cap, total); }
+    c->launches += 9;
+    LL_CUDA_CHECK(c, cudaGetLastError());
+    return LL_OK;
+}
+
+static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
+{
+    MapState* m = c->map;
+    cudaStream_t s = c->stream;
+    const int cur = m->buf, nxt = m->buf ^ 1;
+    { LLProf pr(c, "k_map_begin"); k_map_begin<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, m->pose_in, m->valid_mask, m->valid_ind, from_odom, n_lanes); }
+    // LM:1814-1822: voxel-filter the incoming clouds
+    const float leaf[2] = {c->cfg.line_res, c->cfg.plane_res};
+    for (int t = 0; t < 2; ++t) {
+        { LLProf pr(c, "k_vg_fill_incoming"); k_vg_fill_incoming<<<dim3(64, n_lanes), 256, 0, s>>>(m->in_cloud[t], m->in_cap[t], m->in_n, t, m->vg_in, m->vg_seg, m->vg_n, m->in_cap[t]); }
+        const int rc = run_voxel_filter(c, n_lanes, m->in_cap[t], 1, nullptr, leaf[t], m->stack[t], m->stack_cap[t], nullptr, t);
+        if (rc) return rc;
+    }
+    // LM:1805-1811 local map, LM:1826 guard, LM:1830-1831 search structures
+    { LLProf pr(c, "k_map_gather"); k_map_gather<<<dim3(MAP_MAXVALID, n_lanes, 2), 256, 0, s>>>(c->d_lane, m->valid_ind, m->map_pts[0][cur], m->cube_off[0][cur], m->frommap[0], m->map_pts[1][cur], m->cube_off[1][cur], m->frommap[1], m->map_cap); }
+    { LLProf pr(c, "k_map_guard"); k_map_guard<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
+    c->launches += 5;
+    for (int t = 0; t < 2; ++t) {
+        const int rc = ll_build_map_grid(c, m->grid[t], m->frommap[t], (size_t)m->map_cap, 2 + t, n_lanes, m->map_cap);
+        if (rc) return rc;
+    }
+    MapAssocParams A;
+    A.lane = c->d_lane; A.stack[0] = m->stack[0]; A.stack[1] = m->stack[1]; A.frommap[0] = m->frommap[0]; A.frommap[1] = m->frommap[1];
+    A.stack_cap[0] = m->stack_cap[0]; A.stack_cap[1] = m->stack_cap[1]; A.map_cap = m->map_cap; A.g[0] = m->grid[0]; A.g[1] = m->grid[1];
+    A.blocks = m->blocks; A.nblk_cap = m->nblk_cap;
+    for (int iter = 0; iter < 2; ++iter) {  // LM:1834
+        { LLProf pr(c, "k_map_reset_corr"); k_map_reset_corr<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
+        { LLProf pr(c, "k_map_assoc"); k_map_assoc<<<dim3((m->nblk_cap + 7) / 8, n_lanes), 256, 0, s>>>(A); }
+        { LLProf pr(c, "k_lm_solve_map"); k_lm_solve_map<<<n_lanes, LM_THREADS, 0, s>>>(c->d_lane, m->blocks, m->nblk_cap, iter); }
+        c->launches += 3;
+    }
+    { LLProf pr(c, "k_map_end"); k_map_end<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
+    c->launches += 1;
+    // LM:2104-2168: insert + per-cube filter + shift, one CSR rebuild per cloud type
+    for (int t = 0; t < 2; ++t) {
+        { LLProf pr(c, "k_vg_fill_rebuild"); k_vg_fill_rebuild<<<dim3(296, n_lanes), 256, 0, s>>>(c->d_lane, m->map_pts[t][cur], m->cube_off[t][cur], m->map_cap, m->stack[t], m->stack_cap[t], t, m->vg_in, m->vg_seg, m->vg_n, m->E); }
+        c->launches += 1;
+        const int rc = run_voxel_filter(c, n_lanes, m->E, MAP_NUM, m->valid_mask, leaf[t], m->map_pts[t][nxt], m->map_cap, m->cube_off[t][nxt], -1);
+        if (rc) return rc;
+    }
+    m->buf = nxt;
+    LL_CUDA_CHECK(c, cudaGetLastError());
+    return LL_OK;
+}
+
+int ll_launch_mapping(ll_ctx* c, int n_lanes)
+{
+    MapState* m = c->map;
+    if (!m) return LL_E_INVAL;
+    {
+        LLProf pr(c, "k_map_copy_odom_clouds");
+        k_map_copy_odom_clouds<<<dim3(64, n_lanes), 256, 0, c->stream>>>(c->d_lane, c->d_lsharp[0], c->d_lsharp[1], c->R * LL_LSHARP_PER_RING, c->d_lflat[0],
+                                                                          c->d_lflat[1], c->Nmax, m->in_cloud[0], m->in_cap[0], m->in_cloud[1], m->in_cap[1], m->in_n);
+    }
+    c->launches += 1;
+    return mapping_frame(c, n_lanes, 1);
+}
+
+static int upload_cloud(ll_ctx* c, const ll_cloud_view& v, float4* dst, int cap)
+{
+    if (v.n < 0 || v.n > cap) return LL_E_CAPACITY;
+    if (v.n == 0) return LL_OK;
+    if (!v.data || v.stride_bytes < 16 || (v.stride_bytes & 3)) return LL_E_INVAL;
+    if (v.stride_bytes == 16) LL_CUDA_CHECK(c, cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
+    else LL_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, 16, v.data, v.stride_bytes, 16, v.n, cudaMemcpyHostToDevice, c->stream));
+    return LL_OK;
+}
+
+extern "C" int ll_mapping_step(ll_ctx* c, ll_cloud_view corner_last, ll_cloud_view surf_last, const double q_wodom_curr[4], const double t_wodom_curr[3],
+                               double q_w_curr[4], double t_w_curr[3])
+{
+    if (!c || !q_wodom_curr || !t_wodom_curr) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    if (!c->map) { const int rc = ll_map_alloc(c); if (rc) return rc; }
+    MapState* m = c->map;
+    if (c->prof) ll_prof_harvest(c);
+    c->launches = 0;
+    int rc;
+    if ((rc = upload_cloud(c, corner_last, m->in_cloud[0], m->in_cap[0]))) return rc;
+    if ((rc = upload_cloud(c, surf_last, m->in_cloud[1], m->in_cap[1]))) return rc;
+    const int hn[2] = {corner_last.n, surf_last.n};
+    double hp[7] = {q_wodom_curr[0], q_wodom_curr[1], q_wodom_curr[2], q_wodom_curr[3], t_wodom_curr[0], t_wodom_curr[1], t_wodom_curr[2]};
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(m->in_n, hn, sizeof(hn), cudaMemcpyHostToDevice, c->stream));
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(m->pose_in, hp, sizeof(hp), cudaMemcpyHostToDevice, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));  // hn / hp live on this stack frame
+    if ((rc = mapping_frame(c, 1, 0))) return rc;
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_lane, c->d_lane, sizeof(LaneState), cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    const LaneState& L = c->h_lane[0];
+    if (q_w_curr) memcpy(q_w_curr, L.map_par, sizeof(double) * 4);
+    if (t_w_curr) memcpy(t_w_curr, L.map_par + 4, sizeof(double) * 3);
+    if (L.err) return L.err;
+    return L.map_ok ? LL_OK : LL_W_FEW_CORRESPONDENCES;  // LM:2097-2100
+}
+
+// Pre-loads map-frame points into lane 0's cube map (benchmark / test helper; no reference equivalent): the points are
+// binned by cube exactly like LM:2104-2152 with the identity pose and stored unfiltered.
+extern "C" int ll_map_insert(ll_ctx* c, ll_cloud_view corner, ll_cloud_view surf)
+{
+    if (!c) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    if (!c->map) { const int rc = ll_map_alloc(c); if (rc) return rc; }
+    MapState* m = c->map;
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_lane, c->d_lane, sizeof(LaneState), cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    const LaneState saved = c->h_lane[0];
+    const ll_cloud_view* v[2] = {&corner, &surf};
+    int done[2] = {0, 0};
+    while (done[0] < corner.n || done[1] < surf.n) {  // chunks of at most one stack buffer per cloud type
+        int nchunk[2];
+        for (int t = 0; t < 2; ++t) {
+            nchunk[t] = v[t]->n - done[t] < m->stack_cap[t] ? v[t]->n - done[t] : m->stack_cap[t];
+            ll_cloud_view part = *v[t];
+            part.data = reinterpret_cast<const float*>(reinterpret_cast<const char*>(v[t]->data) + (size_t)done[t] * v[t]->stride_bytes);
+            part.n = nchunk[t];
+            const int rc = upload_cloud(c, part, m->stack[t], m->stack_cap[t]);
+            if (rc) return rc;
+        }
+        // temporarily: identity map pose, no shift, nothing valid (no filtering), stack counts = this chunk
+        LaneState tmp = saved;
+        tmp.map_par[0] = tmp.map_par[1] = tmp.map_par[2] = 0; tmp.map_par[3] = 1; tmp.map_par[4] = tmp.map_par[5] = tmp.map_par[6] = 0;
+        tmp.map_shift[0] = tmp.map_shift[1] = tmp.map_shift[2] = 0;
+        tmp.n_stack_corner = nchunk[0]; tmp.n_stack_surf = nchunk[1];
+        c->h_lane[0] = tmp;
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_lane, c->h_lane, sizeof(LaneState), cudaMemcpyHostToDevice, c->stream));
+        LL_CUDA_CHECK(c, cudaMemsetAsync(m->valid_mask, 0, MAP_NUM, c->stream));
+        const int cur = m->buf, nxt = m->buf ^ 1;
+        for (int t = 0; t < 2; ++t) {
+            k_vg_fill_rebuild<<<dim3(296, 1), 256, 0, c->stream>>>(c->d_lane, m->map_pts[t][cur], m->cube_off[t][cur], m->map_cap, m->stack[t], m->stack_cap[t], t, m->vg_in, m->vg_seg, m->vg_n, m->E);
+            const int rc = run_voxel_filter(c, 1, m->E, MAP_NUM, m->valid_mask, 1.0f, m->map_pts[t][nxt], m->map_cap, m->cube_off[t][nxt], -1);
+            if (rc) return rc;
+        }
+        m->buf = nxt;
+        LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        done[0] += nchunk[0];
+        done[1] += nchunk[1];
+    }
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_lane, c->d_lane, sizeof(LaneState), cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    const int err = c->h_lane[0].err;
+    c->h_lane[0] = saved;
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_lane, c->h_lane, sizeof(LaneState), cudaMemcpyHostToDevice, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return err ? err : LL_OK;
+}
+
 int ll_map_insert_impl(ll_ctx*, const float*, int, const float*, int) { return LL_E_INVAL; }
-extern "C" int ll_mapping_step(ll_ctx*, ll_cloud_view, ll_cloud_view, const double*, const double*, double*, double*) { return LL_E_INVAL; }
-extern "C" int ll_map_insert(ll_ctx*, ll_cloud_view, ll_cloud_view) { return LL_E_INVAL; }

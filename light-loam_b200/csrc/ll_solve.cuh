@@ -41,6 +41,7 @@ __device__ __forceinline__ void lm_accumulate(const double* blk, int cap, int nb
     for (int k = 0; k < LM_NRED; ++k) acc[k] = 0.0;
     for (int i = threadIdx.x; i < nb; i += LM_THREADS) {
         const int type = (int)blk[i];
+        if (type < 0) continue;  // dense mapping records: slot without a correspondence
         const double cpx = blk[1 * cap + i], cpy = blk[2 * cap + i], cpz = blk[3 * cap + i];
         const double ax = blk[4 * cap + i], ay = blk[5 * cap + i], az = blk[6 * cap + i];
         const double bx = blk[7 * cap + i], by = blk[8 * cap + i], bz = blk[9 * cap + i];
@@ -176,7 +177,7 @@ __device__ __forceinline__ bool chol6_solve(const double* Ap, const double* b, d
 }
 
 // The whole Solve. q_io / t_io point at the parameter blocks (global memory); all threads of the CTA call it.
-__device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot)
+static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot)
 {
     __shared__ LmShared S;
     const int tid = threadIdx.x;
