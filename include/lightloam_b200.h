@@ -112,6 +112,13 @@ int ll_process_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans, doubl
 int ll_stage_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);
 int ll_process_staged(ll_ctx* ctx, int n_scans, double* poses_out);
 
+/* Asynchronous form of ll_process_scans: ll_submit_scans enqueues the H2D copies (copy stream) and the whole pipeline
+ * behind them (compute stream) and returns; ll_collect blocks for the OLDEST outstanding submission, writes its poses
+ * (n x 14 doubles) and returns the number of scans it held.  At most two submissions may be in flight, which lets
+ * the copies of step k+1 overlap the kernels of step k.  Scan buffers must stay valid until the matching collect. */
+int ll_submit_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);
+int ll_collect(ll_ctx* ctx, double* poses_out);
+
 /* Scan pool: upload many scans once (float4 records in HBM), then feed lane i from pooled scan scan_ids[i].
  * Same per-lane semantics as ll_process_scans without the per-call H2D of the points. */
 int ll_pool_upload(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);

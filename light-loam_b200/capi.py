@@ -17,7 +17,7 @@ LL_W_FEW_CORRESPONDENCES = 1
 
 SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
            "ll_extract_features", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
-           "ll_process_staged", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
+           "ll_process_staged", "ll_submit_scans", "ll_collect", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
            "ll_debug_assoc", "ll_cuda_stream"]
 
 
@@ -79,6 +79,8 @@ def lib():
         L.ll_process_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView), ctypes.c_void_p]
         L.ll_stage_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
         L.ll_process_staged.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.ll_submit_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
+        L.ll_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ll_pool_upload.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
         L.ll_process_pool.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.ll_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -202,6 +204,23 @@ class Context:
         poses = np.zeros((n, 14)) if want_poses else None
         self._check(self.L.ll_process_staged(self.h, n, poses.ctypes.data if want_poses else None), "ll_process_staged")
         return poses
+
+    def submit_scans(self, scans):
+        """Asynchronous ll_process_scans: returns after enqueuing; at most two submissions in flight."""
+        arrs = [np.ascontiguousarray(s, dtype=np.float32) for s in scans]
+        views = (LLCloudView * len(arrs))()
+        for i, a in enumerate(arrs):
+            views[i] = _view(a)
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._check(self.L.ll_submit_scans(self.h, len(arrs), views), "ll_submit_scans")
+        self._inflight.append(arrs)      # keep the host buffers alive until collected
+
+    def collect(self):
+        poses = np.zeros((self.B, 14))
+        n = self._check(self.L.ll_collect(self.h, poses.ctypes.data), "ll_collect")
+        self._inflight.pop(0)
+        return poses[:n]
 
     def pool_upload(self, scans):
         """Keeps the scans resident in HBM; lanes are then fed by scan id (process_pool)."""

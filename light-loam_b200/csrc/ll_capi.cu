@@ -153,6 +153,16 @@ void ll_destroy(ll_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     ll_map_free(c);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) {
+        if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
+        if (c->ev_raw_free[k]) cudaEventDestroy(c->ev_raw_free[k]);
+        if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d_raw2) cudaFree(c->d_raw2);
+    if (c->d_hdr2) cudaFree(c->d_hdr2);
+    if (c->h_hdr2) cudaFreeHost(c->h_hdr2);
+    if (c->h_pose2) cudaFreeHost(c->h_pose2);
     if (c->h_ids) cudaFreeHost(c->h_ids);
     void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
@@ -412,6 +422,82 @@ int ll_profile_read(ll_ctx* c, char* names_buf, int buf_len, double* total_ms, i
     if ((int)names.size() + 1 > buf_len) return LL_E_CAPACITY;
     memcpy(names_buf, names.c_str(), names.size() + 1);
     return k;
+}
+
+// ---- asynchronous submit / collect ------------------------------------------------------------------------------
+// ll_submit_scans enqueues the H2D copies of one batch on a copy stream and the whole pipeline behind them on the
+// compute stream, then returns; ll_collect blocks for the OLDEST outstanding submission and returns its poses.
+// Two submissions may be in flight, so the copies of step k+1 overlap the kernels of step k.  The caller's scan
+// buffers must stay valid (and should be pinned) until the matching ll_collect returns.
+static int submit_alloc(ll_ctx* c)
+{
+    if (c->copy_stream) return LL_OK;
+    const size_t B = c->B;
+    LL_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_raw2, sizeof(uint32_t) * B * c->Nmax * 8));
+    LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_hdr2, sizeof(int) * 2 * B * 2));
+    LL_CUDA_CHECK(c, cudaHostAlloc((void**)&c->h_hdr2, sizeof(int) * 2 * B * 2, cudaHostAllocDefault));
+    LL_CUDA_CHECK(c, cudaHostAlloc((void**)&c->h_pose2, sizeof(double) * 2 * B * 14, cudaHostAllocDefault));
+    for (int k = 0; k < 2; ++k) {
+        LL_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
+        LL_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_raw_free[k], cudaEventDisableTiming));
+        LL_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    }
+    return LL_OK;
+}
+
+int ll_submit_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
+{
+    if (!c || !scans || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    int rc = submit_alloc(c);
+    if (rc) return rc;
+    if (c->sub_count >= 2) return LL_E_CAPACITY;  // collect first
+    const int slot = (c->sub_head + c->sub_count) & 1;
+    uint32_t* raw = slot == 0 ? c->d_raw : c->d_raw2;
+    ScanHdr* hdr = reinterpret_cast<ScanHdr*>(c->h_hdr2) + (size_t)slot * c->B;
+    ScanHdr* dhdr = reinterpret_cast<ScanHdr*>(c->d_hdr2) + (size_t)slot * c->B;
+    for (int i = 0; i < n_scans; ++i) {
+        const ll_cloud_view& v = scans[i];
+        if (!v.data || v.n < 1 || v.stride_bytes < 12 || v.stride_bytes > 32 || (v.stride_bytes & 3)) return LL_E_INVAL;
+        if (v.n > c->Nmax) return LL_E_CAPACITY;
+    }
+    // the slab may still be read by the feature kernels of the submission before last (already collected => done)
+    LL_CUDA_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_raw_free[slot], 0));
+    for (int i = 0; i < n_scans; ++i) {
+        const ll_cloud_view& v = scans[i];
+        hdr[i].n_raw = v.n;
+        hdr[i].stride_words = v.stride_bytes / 4;
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(raw + (size_t)i * c->Nmax * 8, v.data, (size_t)v.n * v.stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(dhdr, hdr, sizeof(ScanHdr) * n_scans, cudaMemcpyHostToDevice, c->copy_stream));
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_staged[slot], c->copy_stream));
+    LL_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_staged[slot], 0));
+    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, dhdr, raw, (size_t)c->Nmax * 8, n_scans);
+    if (c->prof) ll_prof_harvest(c);
+    c->launches = 0;
+    if ((rc = ll_launch_features(c, n_scans))) return rc;
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_raw_free[slot], c->stream));
+    if ((rc = ll_launch_odometry(c, n_scans))) return rc;
+    if (c->cfg.enable_mapping && (rc = ll_launch_mapping(c, n_scans))) return rc;
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_pose2 + (size_t)slot * c->B * 14, c->d_pose, sizeof(double) * 14 * n_scans, cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_done[slot], c->stream));
+    c->sub_n[slot] = n_scans;
+    c->sub_count++;
+    return LL_OK;
+}
+
+int ll_collect(ll_ctx* c, double* poses_out)
+{
+    if (!c) return LL_E_INVAL;
+    if (c->sub_count < 1) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    const int slot = c->sub_head;
+    LL_CUDA_CHECK(c, cudaEventSynchronize(c->ev_done[slot]));
+    if (poses_out) memcpy(poses_out, c->h_pose2 + (size_t)slot * c->B * 14, sizeof(double) * 14 * c->sub_n[slot]);
+    c->sub_head ^= 1;
+    c->sub_count--;
+    return c->sub_n[slot];
 }
 
 int ll_last_timings(ll_ctx* c, float ms[4])

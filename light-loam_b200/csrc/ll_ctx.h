@@ -122,6 +122,17 @@ struct ll_ctx {
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;
 
+    // asynchronous submit / collect: a second staging slab + a copy stream so the H2D of step k+1 overlaps the
+    // kernels of step k (ll_submit_scans / ll_collect)
+    cudaStream_t copy_stream = nullptr;
+    uint32_t* d_raw2 = nullptr;        // second staging slab [B][Nmax * 8]
+    int* h_hdr2 = nullptr;             // pinned headers per slot [2][B][2]
+    int* d_hdr2 = nullptr;             // [2][B][2]
+    double* h_pose2 = nullptr;         // pinned poses per slot [2][B][14]
+    cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_raw_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int sub_n[2] = {0, 0};             // scans of the submission occupying each slot
+    int sub_head = 0, sub_count = 0;   // ring of outstanding submissions (at most 2)
+
     // scan pool: scans kept resident in HBM and referenced by id (ll_pool_upload / ll_process_pool)
     uint32_t* d_pool = nullptr;    // [pool_cap][Nmax * 4] words (float4 records)
     int* d_pool_n = nullptr;       // [pool_cap] points per pooled scan

@@ -144,3 +144,23 @@ def test_non_monotone_last_cloud_takes_literal_path(ll, orc):
             got_p = np.array([[i, a, b, c] for i, (a, b, c, _) in enumerate(gp[:len(f["flat"])]) if a >= 0], np.int32).reshape(-1, 4)
             assert np.array_equal(got_c, oc) and np.array_equal(got_p, op), k
     ctx.close()
+
+
+def test_async_submit_collect_equals_sync_call(ll):
+    line, B = 16, 3
+    a = ll.Context(scan_line=line, batch=B)
+    b = ll.Context(scan_line=line, batch=B)
+    seqs = [[ll.synth.scan(line, k + 2 * i) for i in range(B)] for k in range(6)]
+    want = [a.process_scans(s) for s in seqs]
+    got = []
+    b.submit_scans(seqs[0])
+    for k in range(1, 6):
+        b.submit_scans(seqs[k])
+        got.append(b.collect())
+    got.append(b.collect())
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
+    with pytest.raises(ll.LightLoamError):
+        b.collect()                      # nothing outstanding
+    a.close()
+    b.close()
