@@ -167,7 +167,8 @@ void ll_destroy(ll_ctx* c)
     void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted, c->g_corner.partial,
-                    c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
+                    c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
+                    c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_lane) cudaFreeHost(c->h_lane);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -246,6 +247,18 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
         g->h = 1.01f;
         if (const char* e = getenv("LL_GRID_H")) { const float v = (float)atof(e); if (v > 0.05f && v < 10.f) g->h = v; }
         g->inv_h = 1.0f / g->h;
+        CK(dalloc(g->start, B * (size_t)(g->T + 1)));
+        CK(dalloc(g->cursor, B * (size_t)g->T));
+        CK(dalloc(g->partial, B * (size_t)(g->T / 2048 + 1)));
+        CK(dalloc(g->sorted, B * (size_t)g->cap));
+    }
+    // ring x azimuth-bin index (2nd / 3rd neighbour search of LO:504-553 / LO:668-721 without walking whole rings)
+    c->az_bins_corner = 64; c->az_bins_surf = 256;
+    while ((int)R * c->az_bins_corner < 2048) c->az_bins_corner <<= 1;
+    while ((int)R * c->az_bins_surf < 2048) c->az_bins_surf <<= 1;
+    c->a_corner.T = (int)R * c->az_bins_corner; c->a_corner.cap = c->g_corner.cap;
+    c->a_surf.T = (int)R * c->az_bins_surf; c->a_surf.cap = c->g_surf.cap;
+    for (KnnGrid* g : {&c->a_corner, &c->a_surf}) {
         CK(dalloc(g->start, B * (size_t)(g->T + 1)));
         CK(dalloc(g->cursor, B * (size_t)g->T));
         CK(dalloc(g->partial, B * (size_t)(g->T / 2048 + 1)));
@@ -587,6 +600,7 @@ int ll_get_last_stats(ll_ctx* c, ll_stats* o)
         o->map_initial_cost[k] = L.initial_cost[3 + k]; o->map_final_cost[k] = L.final_cost[3 + k];
     }
     o->frame = L.now_frame;
+    if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg: planes resolved by grid %d, by walk %d\n", L.dbg[0], L.dbg[1]);
     o->kernel_launches = c->launches;
     return LL_OK;
 }

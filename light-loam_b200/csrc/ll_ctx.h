@@ -66,6 +66,7 @@ struct LaneState {
     int map_ok;                      // LM:1826 guard: map corner > 10 && map surf > 50
     int n_map_corner, n_map_surf, n_stack_corner, n_stack_surf, n_map_corner_corr, n_map_surf_corr;
     int err;                         // sticky device-side error (LL_E_*)
+    int dbg[8];                      // association statistics (plane queries resolved per shell / by the walk)
 };
 
 struct KnnGrid {
@@ -117,6 +118,8 @@ struct ll_ctx {
     float4* d_lflat[2] = {nullptr, nullptr};   // [B][Nmax]
 
     KnnGrid g_corner, g_surf;      // over last less-sharp / less-flat
+    KnnGrid a_corner, a_surf;      // ring x azimuth-bin index over the same clouds (T = rings * az_bins)
+    int az_bins_corner = 64, az_bins_surf = 256;
     int* d_corner_assoc = nullptr; // [B][R*12][2]
     int* d_plane_assoc = nullptr;  // [B][R*24][4]
     double* d_blocks = nullptr;    // [B][nblk_cap][12]

@@ -155,3 +155,11 @@ __device__ __forceinline__ void block_bitonic_sort_u64(u64* keys, int N, int SEG
         __syncthreads();
     }
 }
+
+// ring x azimuth-bin index: bin of a point / query; NB = bins per ring (power of two)
+__device__ __forceinline__ int azimuth_bin(float x, float y, int NB)
+{
+    const float phi = atan2f(y, x);  // any deterministic function: build and query use the same one
+    int b = (int)floorf((phi + 3.14159265f) * ((float)NB * 0.15915494f));
+    return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+}

@@ -60,8 +60,52 @@ __device__ __forceinline__ void warp_merge_topk(const WarpKnn<K>& loc, u64 out[K
     }
 }
 
+// Streams the points of up to 32 buckets (one per lane, negative = none; duplicates must already be removed) through
+// f(float4 point): bucket ranges are concatenated across the warp and read with coalesced float4 loads, two chunks
+// of 32 candidates in flight per iteration.
+template <typename F>
+__device__ __forceinline__ void grid_stream_buckets(const GridView& g, int bucket, F&& f)
+{
+    const int lane = lane_id();
+    int beg = 0, cnt = 0;
+    if (bucket >= 0) {
+        beg = g.start[bucket];
+        cnt = g.start[bucket + 1] - beg;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+    const int excl = incl - cnt;
+    const int total = __shfl_sync(LL_FULL_MASK, incl, 31);
+    for (int t0 = 0; t0 < total; t0 += 64) {
+        float4 pv[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = t0 + u * 32 + lane;
+            ok[u] = false;
+            if (t0 + u * 32 < total) {  // warp-uniform
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int cand = lo + step;
+                    const int pv_ = __shfl_sync(LL_FULL_MASK, excl, cand & 31);
+                    if (cand < 32 && pv_ <= t) lo = cand;
+                }
+                const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
+                const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
+                ok[u] = t < total;
+                if (ok[u]) pv[u] = g.sorted[cbeg + (t - cexc)];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (ok[u]) f(pv[u]);
+    }
+}
+
 // Streams every point of shell s (cells at Chebyshev distance s from (cx,cy,cz); s == 1 also covers s == 0)
-// through f(float4 point), 32 bucket headers per round, bucket ranges concatenated across the warp.
+// through f(float4 point), 32 bucket headers per round.
 template <typename F>
 __device__ __forceinline__ void grid_visit_shell(const GridView& g, int cx, int cy, int cz, int s, F&& f)
 {
@@ -76,43 +120,37 @@ __device__ __forceinline__ void grid_visit_shell(const GridView& g, int cx, int 
             if (cheb == s || s == 1) bucket = cell_bucket(cx + dx, cy + dy, cz + dz, g.Tmask);
         }
         const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
-        int beg = 0, cnt = 0;
-        if (bucket >= 0 && (__ffs(grp) - 1) == lane) {
-            beg = g.start[bucket];
-            cnt = g.start[bucket + 1] - beg;
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
-        const int excl = incl - cnt;
-        const int total = __shfl_sync(LL_FULL_MASK, incl, 31);
-        // four chunks of 32 candidates per iteration: all four loads are issued before any is consumed (MLP)
-        for (int t0 = 0; t0 < total; t0 += 128) {
-            float4 pv[4];
-            bool ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int t = t0 + u * 32 + lane;
-                ok[u] = false;
-                if (t0 + u * 32 < total) {  // warp-uniform
-                    int lo = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int cand = lo + step;
-                        const int pv_ = __shfl_sync(LL_FULL_MASK, excl, cand & 31);
-                        if (cand < 32 && pv_ <= t) lo = cand;
-                    }
-                    const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
-                    const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
-                    ok[u] = t < total;
-                    if (ok[u]) pv[u] = g.sorted[cbeg + (t - cexc)];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (ok[u]) f(pv[u]);
+        if ((__ffs(grp) - 1) != lane) bucket = -1;
+        grid_stream_buckets(g, bucket, f);
+    }
+}
+
+// Shells 0 + 1 with pruning: the query's own cell first, then only those of the 26 neighbours whose box can still hold
+// a point closer than bound() (a warp-uniform squared distance evaluated after the own cell; INFINITY = keep all).
+// Exact: a skipped cell has every point farther than the bound (1e-3 m slack covers fp32 cell-assignment rounding).
+template <typename F, typename BoundFn>
+__device__ __forceinline__ void grid_visit_near_pruned(const GridView& g, float qx, float qy, float qz, int cx, int cy, int cz, F&& f, BoundFn&& bound)
+{
+    const int lane = lane_id();
+    const int b0 = cell_bucket(cx, cy, cz, g.Tmask);
+    grid_stream_buckets(g, lane == 0 ? b0 : -1, f);
+    const float thr = bound();
+    int bucket = -1 - lane;
+    if (lane < 27 && lane != 13) {
+        const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+        const float lox = (float)(cx + dx) * g.h - 1e-3f, hix = (float)(cx + dx + 1) * g.h + 1e-3f;
+        const float loy = (float)(cy + dy) * g.h - 1e-3f, hiy = (float)(cy + dy + 1) * g.h + 1e-3f;
+        const float loz = (float)(cz + dz) * g.h - 1e-3f, hiz = (float)(cz + dz + 1) * g.h + 1e-3f;
+        const float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix)), ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)),
+                    ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
+        if (ex * ex + ey * ey + ez * ez <= thr) {
+            const int bk = cell_bucket(cx + dx, cy + dy, cz + dz, g.Tmask);
+            if (bk != b0) bucket = bk;
         }
     }
+    const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
+    if ((__ffs(grp) - 1) != lane) bucket = -1;
+    grid_stream_buckets(g, bucket, f);
 }
 
 // Returns (warp-uniform) the K best keys; the caller applies its own d2 cutoff.

@@ -13,6 +13,7 @@
 // All decisions (accept / reject, radius, termination) run on the device: one launch per Solve, no host sync.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "ll_ctx.h"
 #include "ll_device.cuh"
@@ -28,7 +29,16 @@ struct GridSrc {           // where a lane's points and count come from
     const float4* pts[2];  // ping-pong buffers (or both the same)
     size_t lane_stride;    // points per lane
     int which;             // 0: (n_less_sharp, slot cur) 1: (n_less_flat, slot cur) 2: (n_map_corner, slot 0) 3: (n_map_surf, slot 0)
+    int az_bins;           // 0: spatial hash grid; > 0: ring x azimuth-bin index with this many bins per ring
+    int rings;
 };
+__device__ __forceinline__ int src_bucket(const GridSrc& S, const float4 p, int T, float inv_h)
+{
+    if (S.az_bins == 0) return cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
+    int r = (int)p.w;
+    r = r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
+    return r * S.az_bins + azimuth_bin(p.x, p.y, S.az_bins);
+}
 __device__ __forceinline__ int grid_src_count(const GridSrc& S, const LaneState& L)
 {
     switch (S.which) {
@@ -52,11 +62,11 @@ __global__ void k_grid_count(GridSrc S, LaneState* lane, int* cursor, int T, flo
     const float4* pts = grid_src_pts(S, L, b);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
-        const int bk = cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
+        const int bk = src_bucket(S, p, T, inv_h);
         atomicAdd(&cursor[(size_t)b * T + bk], 1);
-        if (S.which < 2) {  // is the cloud ring-monotone? (LO:504-553 assumes it; the fast association path needs it)
+        if (S.which < 2 && S.az_bins == 0) {  // is the cloud ring-monotone? (LO:504-553 assumes it; the fast association path needs it)
             const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
-            if (r0 < 0 || r0 > 255 || r1 < r0) { if (S.which == 0) L.mono_corner = 0; else L.mono_surf = 0; }
+            if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (S.which == 0) L.mono_corner = 0; else L.mono_surf = 0; }
         }
     }
 }
@@ -105,7 +115,7 @@ __global__ void k_grid_scatter(GridSrc S, const LaneState* lane, int* cursor, fl
     const float4* pts = grid_src_pts(S, L, b);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
-        const int bk = cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
+        const int bk = src_bucket(S, p, T, inv_h);
         const int pos = atomicAdd(&cursor[(size_t)b * T + bk], 1);
         int ring = S.which < 2 ? (int)p.w : 0;
         ring = ring < 0 ? 0 : (ring > 255 ? 255 : ring);
@@ -124,6 +134,8 @@ struct OdomParams {
     const float4* lflat[2];
     int Nmax, R;
     KnnGrid gc, gs;
+    KnnGrid ac, as_;       // ring x azimuth-bin indexes
+    int az_bins_corner, az_bins_surf;
     int* corner_assoc;     // [B][R*12][2]
     int* plane_assoc;      // [B][R*24][4]
     double* blocks;        // [B][LL_BLOCK_DOUBLES][nblk_cap]
@@ -131,12 +143,13 @@ struct OdomParams {
     int graph_from_frame;
     float vote_t_min;
     int outer;             // opti_counter
+    int dev_skip;          // development only: bit mask of association stages to skip (timing experiments)
     int plane_shells;      // grid shells tried for the 2nd / 3rd plane neighbour before the literal walk
 };
 
 __device__ __forceinline__ int last_slot(const LaneState& L) { return L.last_slot; }  // previous frame's clouds
 
-__global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
+__global__ void __launch_bounds__(256, 4) k_odom_assoc(OdomParams P)
 {
     const int b = blockIdx.y;
     const LaneState& L = P.lane[b];
@@ -146,6 +159,8 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
     const int ns = L.n_sharp, nf = L.n_flat;
     if (q >= ns + nf) return;
     const bool is_corner = q < ns;
+    if ((P.dev_skip & 2) && is_corner) return;
+    if ((P.dev_skip & 4) && !is_corner) return;
     const int i = is_corner ? q : q - ns;
     const float4 p = is_corner ? P.sharp[(size_t)b * P.R * LL_SHARP_PER_RING + i] : P.flat[(size_t)b * P.R * LL_FLAT_PER_RING + i];
 
@@ -165,40 +180,98 @@ __global__ void __launch_bounds__(256) k_odom_assoc(OdomParams P)
     const float4* last = is_corner ? P.lsharp[slot] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[slot] + (size_t)b * P.Nmax;
     const int n = is_corner ? L.n_last_corner : L.n_last_surf;
 
+    // ---- 1-NN (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656) -----------------------------------
+    const float geps = 1e-3f;
+    const int cx = (int)floorf(qx * gv.inv_h), cy = (int)floorf(qy * gv.inv_h), cz = (int)floorf(qz * gv.inv_h);
+    const int smax = (int)ceilf((5.0f + geps) * gv.inv_h);
     u64 best[1];
     best[0] = ~0ull;
-    if (n > 0) grid_knn<1>(gv, qx, qy, qz, 5.0f, best);
+    if (n > 0) {
+        u64 lb = ~0ull;  // lane-local best (d2 bits << 32 | index)
+        auto upd = [&](const float4 t) {
+            const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
+            const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
+            if (key < lb) lb = key;
+        };
+        grid_visit_near_pruned(gv, qx, qy, qz, cx, cy, cz, upd, [&]() {
+            const u64 m = warp_min_u64(lb);
+            return m == ~0ull ? INFINITY : __uint_as_float((unsigned)(m >> 32));
+        });
+        for (int s = 2;; ++s) {
+            const u64 m = warp_min_u64(lb);
+            const float safe = (float)(s - 1) * gv.h - geps;
+            if ((m != ~0ull && __uint_as_float((unsigned)(m >> 32)) < safe * safe) || s > smax) { best[0] = m; break; }
+            grid_visit_shell(gv, cx, cy, cz, s, upd);
+        }
+    }
     int closest = -1, ind2 = -1, ind3 = -1;
+    if (P.dev_skip & 1) best[0] = ~0ull;
     if (best[0] != ~0ull && (double)__uint_as_float((unsigned)(best[0] >> 32)) < 25.0) {  // LO:497 / LO:659
         closest = (int)(unsigned)best[0];
         const int cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
         u64 k2 = ~0ull, k3 = ~0ull;              // (d2 bits << 32) | visit order  -> strict '<' of the serial loops
         const unsigned down_base = (unsigned)n;
         bool resolved = false;
-        if (!is_corner && L.mono_surf) {
+        if ((is_corner ? L.mono_corner : L.mono_surf) && !(P.dev_skip & 8)) {
             // Ring-monotone cloud (always the case for clouds produced by scanRegistration): the serial loops of
-            // LO:668-721 visit exactly the points whose ring lies in [cring-2, cring+2], so the same minima come out
-            // of a ring-filtered shell search over the grid; ties keep the loops' visit order.  Only the first
-            // `plane_shells` shells are tried: when the 2nd / 3rd neighbour is farther than that (sparse ground
-            // rings) the literal walk below is cheaper, and it yields the same answer by construction.
-            const int cx = (int)floorf(qx * gv.inv_h), cy = (int)floorf(qy * gv.inv_h), cz = (int)floorf(qz * gv.inv_h);
-            for (int s = 1; s <= P.plane_shells && !resolved; ++s) {
-                grid_visit_shell(gv, cx, cy, cz, s, [&](const float4 t) {
-                    const unsigned bits = (unsigned)__float_as_int(t.w);
-                    const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
-                    const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                    if (!((double)d2 < 25.0) || j == closest || rj < cring - 2 || rj > cring + 2) return;
-                    const unsigned rank = j > closest ? (unsigned)(j - (closest + 1)) : down_base + (unsigned)(closest - 1 - j);
-                    const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
-                    if (rj == cring) { if (key < k2) k2 = key; }
-                    else if (key < k3) k3 = key;
-                });
-                const u64 m2 = warp_min_u64(k2), m3 = warp_min_u64(k3);
-                const float safe = (float)s * gv.h - 1e-3f, safe2 = safe * safe;
-                resolved = m2 != ~0ull && __uint_as_float((unsigned)(m2 >> 32)) < safe2 && m3 != ~0ull &&
-                           __uint_as_float((unsigned)(m3 >> 32)) < safe2;
+            // LO:504-553 / LO:668-721 visit exactly the points whose ring lies in [cring-2, cring+2].  Those rings
+            // are searched through the ring x azimuth-bin index: a point whose azimuth differs from the query's by
+            // D lies at least rho * sin(D) away (rho = horizontal range of the query), so bins are visited outward
+            // from the query's azimuth until that bound exceeds the best distances found (or 5 m, LO:29).
+            // Ties keep the loops' visit order through the rank in the key.
+            const KnnGrid& A = is_corner ? P.ac : P.as_;
+            const int NB = is_corner ? P.az_bins_corner : P.az_bins_surf;
+            GridView av;
+            av.start = A.start + (size_t)b * (A.T + 1);
+            av.sorted = A.sorted + (size_t)b * A.cap;
+            av.Tmask = A.T - 1;
+            av.h = 0.f; av.inv_h = 0.f;
+            auto consider = [&](const float4 t) {
+                const unsigned bits = (unsigned)__float_as_int(t.w);
+                const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
+                const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
+                if (!((double)d2 < 25.0) || j == closest) return;
+                const unsigned rank = j > closest ? (unsigned)(j - (closest + 1)) : down_base + (unsigned)(closest - 1 - j);
+                const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
+                if (rj == cring) { if (!is_corner && key < k2) k2 = key; }
+                else if (is_corner) { if (key < k2) k2 = key; }
+                else if (key < k3) k3 = key;
+            };
+            const float rho = sqrtf(qx * qx + qy * qy);
+            const int b0 = azimuth_bin(qx, qy, NB);
+            const float wbin = 6.2831853f / (float)NB;
+            // lane -> (ring slot 0..4 = cring-2..cring+2, bin slot 0..5); 30 lanes per round
+            const int rslot = lane / 6, bslot = lane % 6;
+            const int ring = cring - 2 + rslot;
+            const bool ring_ok = lane < 30 && ring >= 0 && ring < P.R && !(is_corner && ring == cring);
+            int done = -1;  // offsets |k| <= done have been visited
+            for (int round = 0;; ++round) {
+                // round 0: offsets -2..+2 (bslot 0..4); round r >= 1: offsets +-(3r .. 3r+2)
+                int off = 0;
+                bool use = ring_ok;
+                if (round == 0) { use = use && bslot < 5; off = bslot - 2; }
+                else { const int mag = 3 * round + (bslot % 3); off = bslot < 3 ? mag : -mag; }
+                const int reach = round == 0 ? 2 : 3 * round + 2;
+                if (2 * reach + 1 > NB) {  // wrapped all the way round: keep each bin once
+                    if (abs(off) > NB / 2 || (off == -(NB / 2))) use = false;
+                }
+                int bucket = -1 - lane;
+                if (use && abs(off) <= NB / 2) bucket = ring * NB + ((b0 + off) % NB + NB) % NB;
+                const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
+                if ((__ffs(grp) - 1) != lane) bucket = -1;
+                grid_stream_buckets(av, bucket, consider);
+                done = reach;
+                const u64 m2 = warp_min_u64(k2), m3 = is_corner ? 0ull : warp_min_u64(k3);
+                // every unvisited bin is at least done * wbin away in azimuth
+                const float dmin = (float)done * wbin - 1e-4f;
+                const float lb = (dmin >= 1.5707963f ? rho : rho * sinf(fmaxf(dmin, 0.f))) - 1e-3f;
+                const float lb2 = lb > 0.f ? lb * lb : 0.f;
+                const bool ok2 = m2 != ~0ull && __uint_as_float((unsigned)(m2 >> 32)) < lb2;
+                const bool ok3 = is_corner || (m3 != ~0ull && __uint_as_float((unsigned)(m3 >> 32)) < lb2);
+                if ((ok2 && ok3) || lb2 >= 25.0f || 2 * done + 1 >= NB) break;
             }
-            if (!resolved) { k2 = ~0ull; k3 = ~0ull; }
+            resolved = true;
+            if (lane == 0 && P.outer == 2) atomicAdd(&P.lane[b].dbg[0], 1);
         }
         if (!resolved) {
         // increasing scan line (LO:504-527 / LO:668-693); lane order inside a chunk = visit order.
@@ -468,10 +541,10 @@ __global__ void k_odom_finalize(LaneState* lane, double* pose_out, int n_lanes)
 
 }  // namespace
 
-static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1, size_t lane_stride, int which, int n_lanes, int max_pts)
+static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1, size_t lane_stride, int which, int n_lanes, int max_pts, int az_bins = 0)
 {
     GridSrc S;
-    S.pts[0] = p0; S.pts[1] = p1; S.lane_stride = lane_stride; S.which = which;
+    S.pts[0] = p0; S.pts[1] = p1; S.lane_stride = lane_stride; S.which = which; S.az_bins = az_bins; S.rings = c->R;
     cudaStream_t s = c->stream;
     LL_CUDA_CHECK(c, cudaMemsetAsync(g.cursor, 0, sizeof(int) * (size_t)g.T * n_lanes, s));
     const int gx = (max_pts + 255) / 256 > 0 ? (max_pts + 255) / 256 : 1;
@@ -488,9 +561,9 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     OdomParams P;
     P.lane = c->d_lane; P.sharp = c->d_sharp; P.flat = c->d_flat;
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
-    P.Nmax = c->Nmax; P.R = c->R; P.gc = c->g_corner; P.gs = c->g_surf;
+    P.Nmax = c->Nmax; P.R = c->R; P.gc = c->g_corner; P.gs = c->g_surf; P.ac = c->a_corner; P.as_ = c->a_surf; P.az_bins_corner = c->az_bins_corner; P.az_bins_surf = c->az_bins_surf;
     P.corner_assoc = c->d_corner_assoc; P.plane_assoc = c->d_plane_assoc; P.blocks = c->d_blocks; P.nblk_cap = c->nblk_cap;
-    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.plane_shells = c->plane_shells;
+    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.plane_shells = c->plane_shells; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
     cudaStream_t s = c->stream;
     const int nq = c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     const size_t prep_smem = (size_t)c->R * LL_FLAT_PER_RING * 8 * 4;
@@ -508,6 +581,10 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     int rc = build_grid(c, c->g_corner, c->d_lsharp[0], c->d_lsharp[1], (size_t)c->R * LL_LSHARP_PER_RING, 0, n_lanes, c->R * LL_LSHARP_PER_RING);
     if (rc) return rc;
     rc = build_grid(c, c->g_surf, c->d_lflat[0], c->d_lflat[1], (size_t)c->Nmax, 1, n_lanes, c->Nmax / 2);
+    if (rc) return rc;
+    rc = build_grid(c, c->a_corner, c->d_lsharp[0], c->d_lsharp[1], (size_t)c->R * LL_LSHARP_PER_RING, 0, n_lanes, c->R * LL_LSHARP_PER_RING, c->az_bins_corner);
+    if (rc) return rc;
+    rc = build_grid(c, c->a_surf, c->d_lflat[0], c->d_lflat[1], (size_t)c->Nmax, 1, n_lanes, c->Nmax / 2, c->az_bins_surf);
     if (rc) return rc;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
