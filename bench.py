@@ -306,7 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "64")), help="scan streams (lanes) per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "128")), help="scan streams (lanes) per GPU")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -164,7 +164,7 @@ void ll_destroy(ll_ctx* c)
     if (c->h_hdr2) cudaFreeHost(c->h_hdr2);
     if (c->h_pose2) cudaFreeHost(c->h_pose2);
     if (c->h_ids) cudaFreeHost(c->h_ids);
-    void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_lf_tmp,
+    void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted, c->g_corner.partial,
                     c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
@@ -225,6 +225,7 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_curv, B * N));
     CK(dalloc(c->d_label, B * N));
     CK(dalloc(c->d_sorted16, B * N));
+    CK(dalloc(c->d_brk, B * R * (size_t)((c->RCAP + 31) / 32)));
     CK(dalloc(c->d_lf_tmp, B * N));
     CK(dalloc(c->d_ring_lists, B * R * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING)));
     CK(dalloc(c->d_ring_counts, B * R * 4));

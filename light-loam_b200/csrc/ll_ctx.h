@@ -105,6 +105,7 @@ struct ll_ctx {
     float4* d_full = nullptr;      // [B][Nmax]
     float* d_curv = nullptr;       // [B][Nmax]
     int8_t* d_label = nullptr;     // [B][Nmax] cloudLabel (SR:40)
+    unsigned* d_brk = nullptr;     // [B][R][(RCAP+31)/32] consecutive-gap break bits (SR:290-293)
     uint16_t* d_sorted16 = nullptr;// [B][Nmax] per-sector sorted local index | curvature class bits
     float4* d_lf_tmp = nullptr;    // [B][Nmax] per-ring voxel-DS output parked at the ring's own offset
     int* d_ring_lists = nullptr;   // [B][R][12 + 120 + 24]

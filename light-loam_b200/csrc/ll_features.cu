@@ -30,6 +30,8 @@ struct FeatParams {
     float* curv;
     int8_t* label;       // [B][Nmax] SR:234/272/278/324
     uint16_t* sorted16;  // [B][Nmax] per-sector sorted order + curvature class bits
+    unsigned* brk;       // [B][R][brk_words] consecutive-gap break bits per ring
+    int brk_words;
     float4* lf_tmp;
     int* ring_lists;
     int* ring_counts;
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
     float* gcurv = P.curv + (size_t)b * P.Nmax;
     int8_t* glabel = P.label + (size_t)b * P.Nmax;
     uint16_t* gsorted = P.sorted16 + (size_t)b * P.Nmax;
+    unsigned* gbrk = P.brk + ((size_t)b * P.R + r) * P.brk_words;
 
     auto global_curv = [&](int g) {  // the reference's stencil runs over ring joins (global index)
         float c = 0.f;
@@ -308,6 +311,18 @@ __global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
     __syncthreads();
 
     block_bitonic_sort_u64(keys, 6 * SCAP, SCAP);  // six independent ascending sector sorts
+    // consecutive-gap break bits for the +-5 suppression (SR:290-293): bit i = |p[i] - p[i-1]|^2 > 0.05;
+    // each warp covers 32 consecutive points, the ballot is the bitmask word
+    for (int i0 = (tid & ~31); i0 < P.brk_words * 32; i0 += NTH) {
+        const int i = i0 + (tid & 31);
+        bool brk = false;
+        if (i >= 1 && i < n) {
+            const float4 a = pts[i], c = pts[i - 1];
+            brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
+        }
+        const unsigned bits = __ballot_sync(LL_FULL_MASK, brk);
+        if ((tid & 31) == 0) gbrk[i0 >> 5] = bits;
+    }
     for (int i = 5 + tid; i < n - 6; i += NTH) {
         int j = 0;
 #pragma unroll
@@ -318,43 +333,50 @@ __global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
     }
 }
 
-// SR:288-311: +-5 neighbour suppression with the 0.05 m^2 consecutive-gap break. Called by one warp with the
-// picked local index `ind` (warp-uniform). Lanes 0..4 test l = +1..+5, lanes 8..12 test l = -1..-5.
-__device__ __forceinline__ void suppress_neighbours(const float4* pts, unsigned* picked, int ind, int lane)
+// 64-bit window of a bit array held in 32-bit words
+__device__ __forceinline__ u64 bits_at(const unsigned* words, int pos)
 {
-    bool brk = false;
-    int tgt = -1;
-    if (lane < 5) {
-        const int l = lane + 1;
-        const float4 a = pts[ind + l], c = pts[ind + l - 1];
-        brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
-        tgt = ind + l;
-    } else if (lane >= 8 && lane < 13) {
-        const int l = -(lane - 7);
-        const float4 a = pts[ind + l], c = pts[ind + l + 1];
-        brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
-        tgt = ind + l;
+    const int w = pos >> 5;
+    return (((u64)words[w + 1] << 32) | words[w]) >> (pos & 31);
+}
+// SR:288-311: +-5 neighbour suppression with the consecutive-gap break bits; one thread, bit operations only.
+__device__ __forceinline__ void suppress_neighbours(const unsigned* brk, unsigned* picked, int ind)
+{
+    // forward: l = 1..5 stops at the first i = ind + l with brk[i]
+    const unsigned f = (unsigned)bits_at(brk, ind + 1) & 0x1Fu;
+    const int nf = f ? __ffs(f) - 1 : 5;
+    // backward: l = -1..-5 tests gap(ind + l, ind + l + 1) = brk[ind + l + 1] -> brk[ind], brk[ind-1], ...
+    const unsigned back = (unsigned)bits_at(brk, ind - 4) & 0x1Fu;   // bits: brk[ind-4 .. ind]
+    const unsigned rev = __brev(back) >> 27;                          // bit k = brk[ind - k]
+    const int nr = rev ? __ffs(rev) - 1 : 5;
+    // the suppressed points form one contiguous range [ind - nr, ind + nf] (<= 11 bits, at most two words)
+    const int lo = ind - nr, hi = ind + nf;
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    const unsigned m_lo = 0xFFFFFFFFu << (lo & 31), m_hi = 0xFFFFFFFFu >> (31 - (hi & 31));
+    if (w0 == w1) {
+        picked[w0] |= m_lo & m_hi;
+    } else {
+        picked[w0] |= m_lo;
+        picked[w1] |= m_hi;
     }
-    const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
-    const unsigned f = bm & 0x1Fu, r = (bm >> 8) & 0x1Fu;
-    const int nf = f ? __ffs(f) - 1 : 5, nr = r ? __ffs(r) - 1 : 5;
-    if ((lane < 5 && lane < nf) || (lane >= 8 && lane < 13 && (lane - 8) < nr)) atomicOr(&picked[tgt >> 5], 1u << (tgt & 31));
-    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // k_ring_pick: the greedy, order-dependent part of SR:251-359, one WARP per (ring, lane) so that thousands of
-// rings run concurrently.  State per warp: a picked bitmask in shared memory; sorted candidates (u16) and
-// the ring's points are read through L2.  Each ballot examines 32 sorted candidates at once.
+// rings run concurrently.  Per warp, shared memory holds the sorted candidates (u16), the gap-break bits and the
+// picked bitmask, so the serial chain only touches shared memory; each ballot examines 32 sorted candidates.
 // ---------------------------------------------------------------------------------------------------------
 #define PICK_WARPS 4
 template <int SCAP>
 __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int n_lanes)
 {
     constexpr int RCAP = 6 * SCAP + 16;
-    constexpr int WORDS = (RCAP + 31) / 32;
-    __shared__ unsigned picked_all[PICK_WARPS][WORDS];
+    constexpr int WORDS = (RCAP + 31) / 32 + 2;
+    extern __shared__ __align__(16) unsigned char smem_pick[];
     const int lane = lane_id(), wid = warp_id();
+    unsigned* picked = reinterpret_cast<unsigned*>(smem_pick) + (size_t)wid * (2 * WORDS + RCAP / 2);
+    unsigned* brk = picked + WORDS;
+    uint16_t* sorted = reinterpret_cast<uint16_t*>(brk + WORDS);
     const int ring_lane = blockIdx.x * PICK_WARPS + wid;
     if (ring_lane >= P.R * n_lanes) return;
     const int b = ring_lane / P.R, r = ring_lane % P.R;
@@ -366,11 +388,11 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
         if (lane == 0) { my_counts[0] = my_counts[1] = my_counts[2] = 0; }
         return;
     }
-    unsigned* picked = picked_all[wid];
-    for (int i = lane; i < WORDS; i += 32) picked[i] = 0;
+    const unsigned* gbrk = P.brk + ((size_t)b * P.R + r) * P.brk_words;
+    const uint16_t* gsorted = P.sorted16 + (size_t)b * P.Nmax + base;
+    for (int i = lane; i < WORDS; i += 32) { picked[i] = 0; brk[i] = i < P.brk_words ? gbrk[i] : 0u; }
+    for (int i = lane; i < n; i += 32) sorted[i] = (i >= 5 && i < n - 6) ? gsorted[i] : (uint16_t)0;
     __syncwarp();
-    const float4* pts = P.full + (size_t)b * P.Nmax + base;
-    const uint16_t* sorted = P.sorted16 + (size_t)b * P.Nmax + base;
     int8_t* label = P.label + (size_t)b * P.Nmax + base;
     const int len = n - 11;
     int n_sharp = 0, n_lsharp = 0, n_flat = 0;
@@ -401,11 +423,11 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
                 if (npick <= 2) my_lists[n_sharp] = base + ind;
                 my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
                 picked[ind >> 5] |= 1u << (ind & 31);
+                suppress_neighbours(brk, picked, ind);
             }
             if (npick <= 2) ++n_sharp;
             ++n_lsharp;
             __syncwarp();
-            suppress_neighbours(pts, picked, ind, lane);
             pos -= f + 1;
         }
         // flats: from the smallest curvature up (SR:316-359)
@@ -433,9 +455,11 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
             ++n_flat;
             ++nsm;
             if (nsm >= 4) break;  // SR:328-331: before picked / suppression
-            if (lane == 0) picked[ind >> 5] |= 1u << (ind & 31);
+            if (lane == 0) {
+                picked[ind >> 5] |= 1u << (ind & 31);
+                suppress_neighbours(brk, picked, ind);
+            }
             __syncwarp();
-            suppress_neighbours(pts, picked, ind, lane);
             pos += f + 1;
         }
         __syncwarp();
@@ -629,7 +653,7 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
 {
     FeatParams P;
     P.lane = c->d_lane; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.ori = c->d_ori; P.tile_hist = c->d_tile_hist;
-    P.full = c->d_full; P.curv = c->d_curv; P.label = c->d_label; P.sorted16 = c->d_sorted16; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
+    P.full = c->d_full; P.curv = c->d_curv; P.label = c->d_label; P.sorted16 = c->d_sorted16; P.brk = c->d_brk; P.brk_words = (c->RCAP + 31) / 32; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
     P.sharp = c->d_sharp; P.flat = c->d_flat; P.sharp_idx = c->d_sharp_idx; P.lsharp_idx = c->d_lsharp_idx; P.flat_idx = c->d_flat_idx;
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
     P.Nmax = c->Nmax; P.NT = c->NT; P.R = c->R; P.scan_line = c->cfg.scan_line;
@@ -645,19 +669,22 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     { LLProf pr(c, "k_scatter"); k_scatter<<<tiles, LL_TILE, 0, s>>>(P); }
     const size_t smem_sort = ll_feature_smem_bytes(c->SCAP);
     const size_t smem_lf = ll_lessflat_smem_bytes(c->SCAP);
+    const size_t smem_pick = (size_t)PICK_WARPS * (2 * ((c->RCAP + 31) / 32 + 2) + c->RCAP / 2) * 4;
     const dim3 rings(c->R, n_lanes);
     const int pick_blocks = (c->R * n_lanes + PICK_WARPS - 1) / PICK_WARPS;
     if (c->SCAP == 512) {
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
         { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, 512, smem_sort, s>>>(P); }
-        { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, 0, s>>>(P, n_lanes); }
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick));
+        { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, smem_pick, s>>>(P, n_lanes); }
         { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512><<<rings, 512, smem_lf, s>>>(P); }
     } else {
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
         { LLProf pr(c, "k_ring_sort"); k_ring_sort<1024><<<rings, 512, smem_sort, s>>>(P); }
-        { LLProf pr(c, "k_ring_pick"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, 0, s>>>(P, n_lanes); }
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick));
+        { LLProf pr(c, "k_ring_pick"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, smem_pick, s>>>(P, n_lanes); }
         { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<1024><<<rings, 512, smem_lf, s>>>(P); }
     }
     { LLProf pr(c, "k_compact"); k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P); }
