@@ -149,7 +149,7 @@ struct OdomParams {
 
 __device__ __forceinline__ int last_slot(const LaneState& L) { return L.last_slot; }  // previous frame's clouds
 
-__global__ void __launch_bounds__(256, 4) k_odom_assoc(OdomParams P)
+__global__ void __launch_bounds__(256, 6) k_odom_assoc(OdomParams P)
 {
     const int b = blockIdx.y;
     const LaneState& L = P.lane[b];
