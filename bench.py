@@ -91,8 +91,8 @@ def algorithmic_bytes(counts):
         "k_ring_lessflat": 2 * 16 * P + 1 * P + 16 * nlf,      # two passes over the ring (bbox, keys), labels, DS output
         "k_compact": 2 * (16 * nlf) + 2 * feats,
         "k_odom_assoc": 3 * 0 + 16 * (ns + nf) + 16 * (nls + nlf) + 8 * ns + 16 * nf,  # upper bound 16 (Q + M) per launch
-        "k_grid_count": 16 * (nls + nlf),
-        "k_grid_scatter": 32 * (nls + nlf),
+        "k_index_count": 16 * (nls + nlf),
+        "k_index_scatter": 16 * (nls + nlf) + 2 * 16 * (nls + nlf),   # read once, write the spatial and the ring-azimuth copy
     }
 
 

@@ -123,6 +123,103 @@ __global__ void k_grid_scatter(GridSrc S, const LaneState* lane, int* cursor, fl
     }
 }
 
+// ---- fused build of the four odometry indexes (corner / surf x spatial hash / ring-azimuth) -------------------
+struct IndexSet {
+    const float4* pts[2][2];   // [cloud][ping-pong slot]
+    size_t lane_stride[2];
+    int* cursor[4];            // table = cloud + 2 * kind   (kind 0 spatial, 1 ring-azimuth)
+    int* start[4];
+    int* partial[4];
+    float4* sorted[4];
+    int T[4], cap[4];
+    int chunk_begin[5];        // prefix of T / GRID_CHUNK over the tables
+    float inv_h;
+    int az_bins[2];
+    int rings;
+};
+__device__ __forceinline__ int index_bucket(const IndexSet& S, int cloud, int kind, const float4 p)
+{
+    if (kind == 0) return cell_bucket((int)floorf(p.x * S.inv_h), (int)floorf(p.y * S.inv_h), (int)floorf(p.z * S.inv_h), S.T[cloud] - 1);
+    int r = (int)p.w;
+    r = r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
+    return r * S.az_bins[cloud] + azimuth_bin(p.x, p.y, S.az_bins[cloud]);
+}
+__global__ void k_index_count(IndexSet S, LaneState* lane)
+{
+    const int b = blockIdx.y, cloud = blockIdx.z;
+    LaneState& L = lane[b];
+    const int n = cloud == 0 ? L.n_less_sharp : L.n_less_flat;
+    const float4* pts = S.pts[cloud][L.cur] + (size_t)b * S.lane_stride[cloud];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, 0, p)], 1);
+        atomicAdd(&S.cursor[cloud + 2][(size_t)b * S.T[cloud + 2] + index_bucket(S, cloud, 1, p)], 1);
+        // is the cloud ring-monotone? (LO:504-553 assumes it; the ring-azimuth search needs it)
+        const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
+        if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (cloud == 0) L.mono_corner = 0; else L.mono_surf = 0; }
+    }
+}
+__global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
+{
+    __shared__ int ws[40];
+    const int b = blockIdx.y;
+    int t = 0;
+    while (t < 3 && (int)blockIdx.x >= S.chunk_begin[t + 1]) ++t;
+    const int chunk = blockIdx.x - S.chunk_begin[t], nchunk = S.T[t] / GRID_CHUNK;
+    const int* cur = S.cursor[t] + (size_t)b * S.T[t] + (size_t)chunk * GRID_CHUNK;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < GRID_CHUNK / 256; ++k) s += cur[threadIdx.x * (GRID_CHUNK / 256) + k];
+    int tot = 0;
+    block_exclusive_scan(s, ws, &tot);
+    if (threadIdx.x == 0) S.partial[t][(size_t)b * (nchunk + 1) + chunk] = tot;
+}
+__global__ void __launch_bounds__(256) k_index_scan(IndexSet S)
+{
+    __shared__ int ws[40];
+    __shared__ int base_s;
+    const int b = blockIdx.y;
+    int t = 0;
+    while (t < 3 && (int)blockIdx.x >= S.chunk_begin[t + 1]) ++t;
+    const int chunk = blockIdx.x - S.chunk_begin[t], nchunk = S.T[t] / GRID_CHUNK, T = S.T[t];
+    if (threadIdx.x < 32) {
+        int v = 0;
+        for (int q = threadIdx.x; q < chunk; q += 32) v += S.partial[t][(size_t)b * (nchunk + 1) + q];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(LL_FULL_MASK, v, d);
+        if (threadIdx.x == 0) base_s = v;
+    }
+    int* cur = S.cursor[t] + (size_t)b * T + (size_t)chunk * GRID_CHUNK;
+    int* st = S.start[t] + (size_t)b * (T + 1) + (size_t)chunk * GRID_CHUNK;
+    const int per = GRID_CHUNK / 256, i0 = threadIdx.x * per;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) s += cur[i0 + k];
+    int tot = 0;
+    int run = block_exclusive_scan(s, ws, &tot) + base_s;
+#pragma unroll
+    for (int k = 0; k < per; ++k) { const int c = cur[i0 + k]; st[i0 + k] = run; cur[i0 + k] = run; run += c; }
+    if (chunk == nchunk - 1 && threadIdx.x == 255) S.start[t][(size_t)b * (T + 1) + T] = run;
+}
+__global__ void k_index_scatter(IndexSet S, const LaneState* lane)
+{
+    const int b = blockIdx.y, cloud = blockIdx.z;
+    const LaneState& L = lane[b];
+    const int n = cloud == 0 ? L.n_less_sharp : L.n_less_flat;
+    const float4* pts = S.pts[cloud][L.cur] + (size_t)b * S.lane_stride[cloud];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        int ring = (int)p.w;
+        ring = ring < 0 ? 0 : (ring > 255 ? 255 : ring);
+        const float4 rec = make_float4(p.x, p.y, p.z, __int_as_float((i & 0xFFFFFF) | (ring << 24)));
+#pragma unroll
+        for (int kind = 0; kind < 2; ++kind) {
+            const int t = cloud + 2 * kind;
+            const int pos = atomicAdd(&S.cursor[t][(size_t)b * S.T[t] + index_bucket(S, cloud, kind, p)], 1);
+            S.sorted[t][(size_t)b * S.cap[t] + pos] = rec;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // association
 // ------------------------------------------------------------------------------------------------------
@@ -577,15 +674,28 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     }
     { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
     c->launches += 1;
-    // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud on this frame's less-sharp / less-flat (LO:895-896)
-    int rc = build_grid(c, c->g_corner, c->d_lsharp[0], c->d_lsharp[1], (size_t)c->R * LL_LSHARP_PER_RING, 0, n_lanes, c->R * LL_LSHARP_PER_RING);
-    if (rc) return rc;
-    rc = build_grid(c, c->g_surf, c->d_lflat[0], c->d_lflat[1], (size_t)c->Nmax, 1, n_lanes, c->Nmax / 2);
-    if (rc) return rc;
-    rc = build_grid(c, c->a_corner, c->d_lsharp[0], c->d_lsharp[1], (size_t)c->R * LL_LSHARP_PER_RING, 0, n_lanes, c->R * LL_LSHARP_PER_RING, c->az_bins_corner);
-    if (rc) return rc;
-    rc = build_grid(c, c->a_surf, c->d_lflat[0], c->d_lflat[1], (size_t)c->Nmax, 1, n_lanes, c->Nmax / 2, c->az_bins_surf);
-    if (rc) return rc;
+    // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud on this frame's less-sharp / less-flat (LO:895-896):
+    // the spatial hash grids and the ring x azimuth indexes of both clouds are built together, 4 launches
+    {
+        IndexSet S;
+        KnnGrid* tab[4] = {&c->g_corner, &c->g_surf, &c->a_corner, &c->a_surf};
+        S.pts[0][0] = c->d_lsharp[0]; S.pts[0][1] = c->d_lsharp[1]; S.pts[1][0] = c->d_lflat[0]; S.pts[1][1] = c->d_lflat[1];
+        S.lane_stride[0] = (size_t)c->R * LL_LSHARP_PER_RING; S.lane_stride[1] = (size_t)c->Nmax;
+        S.chunk_begin[0] = 0;
+        for (int t = 0; t < 4; ++t) {
+            S.cursor[t] = tab[t]->cursor; S.start[t] = tab[t]->start; S.partial[t] = tab[t]->partial; S.sorted[t] = tab[t]->sorted;
+            S.T[t] = tab[t]->T; S.cap[t] = tab[t]->cap;
+            S.chunk_begin[t + 1] = S.chunk_begin[t] + tab[t]->T / GRID_CHUNK;
+            LL_CUDA_CHECK(c, cudaMemsetAsync(tab[t]->cursor, 0, sizeof(int) * (size_t)tab[t]->T * n_lanes, s));
+        }
+        S.inv_h = c->g_corner.inv_h; S.az_bins[0] = c->az_bins_corner; S.az_bins[1] = c->az_bins_surf; S.rings = c->R;
+        const int gx = (c->Nmax / 2 + 255) / 256 < 148 ? (c->Nmax / 2 + 255) / 256 : 148;
+        { LLProf pr(c, "k_index_count"); k_index_count<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
+        { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[4], n_lanes), 256, 0, s>>>(S); }
+        { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[4], n_lanes), 256, 0, s>>>(S); }
+        { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
+        c->launches += 4;
+    }
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }
