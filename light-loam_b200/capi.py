@@ -216,6 +216,18 @@ class Context:
         self._check(self.L.ll_submit_scans(self.h, len(arrs), views), "ll_submit_scans")
         self._inflight.append(arrs)      # keep the host buffers alive until collected
 
+    def make_views(self, arrays):
+        """Pre-builds the ll_cloud_view records of float32 (n, k) arrays (kept alive by the caller)."""
+        return [_view(a) for a in arrays]
+
+    def submit_views(self, views):
+        """ll_submit_scans on pre-built views (no per-call array conversion); buffers must outlive the collect."""
+        arr = (LLCloudView * len(views))(*views)
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._check(self.L.ll_submit_scans(self.h, len(views), arr), "ll_submit_scans")
+        self._inflight.append(arr)
+
     def collect(self):
         poses = np.zeros((self.B, 14))
         n = self._check(self.L.ll_collect(self.h, poses.ctypes.data), "ll_collect")

@@ -25,11 +25,14 @@ __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
     int hi = __shfl_xor_sync(LL_FULL_MASK, (int)(unsigned)(v >> 32), m);
     return ((u64)(unsigned)hi << 32) | (unsigned)lo;
 }
+// warp-wide minimum of 64-bit keys with the hardware reduction (REDUX): first the high words, then the low words
+// among the lanes that hold the minimal high word
 __device__ __forceinline__ u64 warp_min_u64(u64 v)
 {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) { u64 o = shfl_xor_u64(v, m); v = o < v ? o : v; }
-    return v;
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mhi = __reduce_min_sync(LL_FULL_MASK, hi);
+    const unsigned mlo = __reduce_min_sync(LL_FULL_MASK, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((u64)mhi << 32) | mlo;
 }
 __device__ __forceinline__ double shfl_xor_f64(double v, int m)
 {

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, 6) k_odom_assoc(OdomParams P)
                 const unsigned bits = (unsigned)__float_as_int(t.w);
                 const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
                 const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                if (!((double)d2 < 25.0) || j == closest) return;
+                if (!(d2 < 25.0f) || j == closest) return;  // 25 is exact in fp32: same decision as the fp64 compare of LO:521
                 const unsigned rank = j > closest ? (unsigned)(j - (closest + 1)) : down_base + (unsigned)(closest - 1 - j);
                 const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
                 if (rj == cring) { if (!is_corner && key < k2) k2 = key; }
@@ -388,10 +388,10 @@ __global__ void __launch_bounds__(256, 6) k_odom_assoc(OdomParams P)
                     if (j < n) {
                         const float4 t = tv[u];
                         const int rj = (int)t.w;
-                        brk = (double)rj > (double)cring + 2.5;
+                        brk = rj > cring + 2;   // int ring vs cring + 2.5 (LO:511)
                         const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
                         const u64 key = ((u64)__float_as_uint(d2) << 32) | (unsigned)(j - (closest + 1));
-                        if (!brk && (double)d2 < 25.0) {
+                        if (!brk && d2 < 25.0f) {
                             if (is_corner) {
                                 if (!(rj <= cring)) c2 = key;  // LO:507: same scan line -> continue
                             } else {
@@ -423,10 +423,10 @@ __global__ void __launch_bounds__(256, 6) k_odom_assoc(OdomParams P)
                     if (j >= 0) {
                         const float4 t = tv[u];
                         const int rj = (int)t.w;
-                        brk = (double)rj < (double)cring - 2.5;
+                        brk = rj < cring - 2;   // LO:537
                         const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
                         const u64 key = ((u64)__float_as_uint(d2) << 32) | (down_base + (unsigned)(closest - 1 - j));
-                        if (!brk && (double)d2 < 25.0) {
+                        if (!brk && d2 < 25.0f) {
                             if (is_corner) {
                                 if (!(rj >= cring)) c2 = key;
                             } else {
