@@ -209,8 +209,15 @@ def run_ours(args, rank, world, local_rank):
                             "alg_gbs": round(bytes_launch / (avg_ms * 1e-3) / 1e9, 1) if bytes_launch else None}
     dom_ms = prof[dom][0] / prof[dom][1]
     achieved = ab.get(dom, 0.0) * B / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("batch") == B and dom in tj.get("kernels", {}):
+            traffic = tj["kernels"][dom]   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at this batch
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": int(ab.get(dom, 0.0) * B),
+                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": int(ab.get(dom, 0.0) * B),
                 "ms_per_launch": round(dom_ms, 4), "share_of_step": round(prof[dom][0] / total_prof, 4), "kernels": per_kernel}
 
     # ---- CPU baseline: the oracle port of the same path on one host core, bounded sample (rank 0, N = 1) ---------

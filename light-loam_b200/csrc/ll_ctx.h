@@ -192,9 +192,6 @@ void ll_prof_harvest(ll_ctx* c);  // folds the in-flight event pairs into prof_a
 // kernel-group entry points (defined in the .cu files) ---------------------------------------------------
 int ll_launch_features(ll_ctx* c, int n_lanes);                 // SR:100-377 on lanes [0, n_lanes)
 int ll_launch_odometry(ll_ctx* c, int n_lanes);                 // LO:425-896
-int ll_launch_grid_build(ll_ctx* c, KnnGrid& g, const float4* pts, size_t lane_stride, const int* n_per_lane_field_dev,
-                         int field_offset_bytes, int n_lanes);
 int ll_map_alloc(ll_ctx* c);
 void ll_map_free(ll_ctx* c);
 int ll_launch_mapping(ll_ctx* c, int n_lanes);                  // LM:1581-2168
-int ll_map_insert_impl(ll_ctx* c, const float* corner, int nc, const float* surf, int ns);

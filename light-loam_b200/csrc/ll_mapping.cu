@@ -858,4 +858,3 @@ extern "C" int ll_map_insert(ll_ctx* c, ll_cloud_view corner, ll_cloud_view surf
     return err ? err : LL_OK;
 }
 
-int ll_map_insert_impl(ll_ctx*, const float*, int, const float*, int) { return LL_E_INVAL; }
