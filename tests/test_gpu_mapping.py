@@ -72,3 +72,68 @@ def test_map_preload_and_cube_shift(ll, orc):
         st = ctx.stats()
         assert (st.map_corner, st.map_surf) == (int(mo["info"][1]), int(mo["info"][2])), (k, st.map_corner, st.map_surf, mo["info"])
     ctx.close()
+
+
+def test_cpp_host_driver_matches_python_path(ll, tmp_path):
+    """host/ll_run (C++ over the C ABI, KITTI-format trajectory file of LM:2284-2325) vs the same run through ctypes."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(ll.capi.LIB_PATH), "host", "ll_run")
+    out = tmp_path / "traj.txt"
+    subprocess.check_call([exe, "--lines", "16", "--scans", "6", "--mapping", "--out", str(out)])
+    rows = np.loadtxt(out)
+    assert rows.shape == (6, 12)
+    ctx = ll.Context(scan_line=16, enable_mapping=1, map_capacity=1 << 20)
+    H0 = None
+    for k in range(6):
+        p = ctx.process_scans([ll.synth.scan(16, k)])[0]
+        x, y, z, w = p[7:11]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        H = np.eye(4)
+        H[:3, :3], H[:3, 3] = R, p[11:14]
+        if H0 is None:
+            H0 = H
+        rel = (np.linalg.inv(H0) @ H)[:3, :].reshape(-1)
+        assert np.abs(rel - rows[k]).max() < 5e-5          # fp32 matrices + 7 significant digits in the file
+    ctx.close()
+
+
+def test_config3_large_map_scan_to_map(ll, orc):
+    """BASELINE.json configs[2] in small: HDL-64 scan against a large voxelised local map (here ~0.45 M points
+    preloaded in the 5 x 5 x 3 cubes), graph vote off (the reference's mapping call site is commented out, LM:2057-2072)."""
+    line = 64
+    ocfg = orc.config(line, voxel_stable=1)
+    rng = np.random.default_rng(3)
+    n_s, n_c = 400000, 40000
+    # ground + four walls of the synthetic room, jittered, then random vertical edges as corner map
+    surf = np.zeros((n_s, 4), np.float32)
+    u = rng.uniform(-1, 1, (n_s, 2))
+    which = rng.integers(0, 5, n_s)
+    surf[:, 0] = np.where(which == 1, 60, np.where(which == 2, -60, u[:, 0] * 60))
+    surf[:, 1] = np.where(which == 3, 40, np.where(which == 4, -40, u[:, 1] * 40))
+    surf[:, 2] = np.where(which == 0, -1.73, rng.uniform(-1.73, 13, n_s))
+    surf[:, :3] += rng.normal(0, 0.01, (n_s, 3))
+    corner = np.zeros((n_c, 4), np.float32)
+    poles = rng.uniform(-55, 55, (200, 2))
+    pid = rng.integers(0, 200, n_c)
+    corner[:, 0], corner[:, 1] = poles[pid, 0], poles[pid, 1] * 0.7
+    corner[:, 2] = rng.uniform(-1.7, 8, n_c)
+    corner[:, :3] += rng.normal(0, 0.01, (n_c, 3))
+    ctx = ll.Context(scan_line=line, map_capacity=1 << 20)
+    omap = orc.Mapping(ocfg)
+    ctx.map_insert(corner, surf)
+    omap.insert(corner, surf)
+    f = orc.extract_features(ll.synth.scan(line, 0, mode=1), ocfg)      # sensor at (25, 0), heading +y
+    q0 = np.array([0, 0, np.sin(np.pi / 4), np.cos(np.pi / 4)])
+    t0 = np.array([25.0, 0.0, 0.0])
+    for k in range(2):
+        mo = omap.step(f["less_sharp"], f["less_flat"], q0, t0)
+        mg = ctx.mapping_step(f["less_sharp"], f["less_flat"], q0, t0)
+        st = ctx.stats()
+        assert (st.map_corner, st.map_surf) == (int(mo["info"][1]), int(mo["info"][2]))
+        assert st.map_surf > 300000 or k > 0      # the first frame sees the whole preloaded map, then it is voxel-filtered
+        assert np.abs(mg["t"] - mo["t"]).max() < 1e-6 and np.abs(mg["q"] - mo["q"]).max() < 1e-6, (k, mg, mo)
+        assert (st.map_corner_corr, st.map_surf_corr) == (int(mo["info"][5]), int(mo["info"][6]))
+    ctx.close()
