@@ -168,7 +168,7 @@ void ll_destroy(ll_ctx* c)
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted, c->g_corner.partial,
                     c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
-                    c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks};
+                    c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_lane) cudaFreeHost(c->h_lane);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -238,14 +238,14 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
         CK(dalloc(c->d_lsharp[k], B * R * LL_LSHARP_PER_RING));
         CK(dalloc(c->d_lflat[k], B * N));
     }
-    // hashed grids over the previous frame's less-sharp / less-flat clouds; cell 1.01 m so that the 5 m
-    // acceptance radius (LO:29) is covered by at most 5 shells
+    // hashed grids over the previous frame's less-sharp / less-flat clouds; the 5 m acceptance radius (LO:29) is
+    // covered by ceil(5 / h) shells
     c->g_corner.T = pow2ceil(2 * (int)R * LL_LSHARP_PER_RING) < 2048 ? 2048 : pow2ceil(2 * (int)R * LL_LSHARP_PER_RING);
     c->g_corner.cap = (int)R * LL_LSHARP_PER_RING;
     c->g_surf.T = pow2ceil((int)N / 2) < 2048 ? 2048 : pow2ceil((int)N / 2);
     c->g_surf.cap = (int)N;
     for (KnnGrid* g : {&c->g_corner, &c->g_surf}) {
-        g->h = 1.01f;
+        g->h = 1.3f;   // tuned on B200: a larger cell hands fewer queries to the warp pass, a smaller one costs fewer candidates
         if (const char* e = getenv("LL_GRID_H")) { const float v = (float)atof(e); if (v > 0.05f && v < 10.f) g->h = v; }
         g->inv_h = 1.0f / g->h;
         CK(dalloc(g->start, B * (size_t)(g->T + 1)));
@@ -267,6 +267,10 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     }
     CK(dalloc(c->d_corner_assoc, B * R * LL_SHARP_PER_RING * 2));
     CK(dalloc(c->d_plane_assoc, B * R * LL_FLAT_PER_RING * 4));
+    c->assoc_queue_cap = (int)(B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING));
+    CK(dalloc(c->d_assoc_queue, (size_t)c->assoc_queue_cap));
+    CK(dalloc(c->d_assoc_queue_n, 8));
+    CK(cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, c->stream));
     c->nblk_cap = (int)R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     CK(dalloc(c->d_blocks, B * (size_t)LL_BLOCK_DOUBLES * c->nblk_cap));
     CK(cudaMemsetAsync(c->d_raw, 0, sizeof(uint32_t) * B * N * 8, c->stream));
@@ -601,7 +605,7 @@ int ll_get_last_stats(ll_ctx* c, ll_stats* o)
         o->map_initial_cost[k] = L.initial_cost[3 + k]; o->map_final_cost[k] = L.final_cost[3 + k];
     }
     o->frame = L.now_frame;
-    if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg: planes resolved by grid %d, by walk %d\n", L.dbg[0], L.dbg[1]);
+    if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg (all lanes, cumulative): - %d, queued with the 1-NN open %d, queued for the ring window %d\n", L.dbg[0], L.dbg[1], L.dbg[2]);
     o->kernel_launches = c->launches;
     return LL_OK;
 }

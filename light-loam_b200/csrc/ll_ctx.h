@@ -123,6 +123,9 @@ struct ll_ctx {
     int az_bins_corner = 64, az_bins_surf = 256;
     int* d_corner_assoc = nullptr; // [B][R*12][2]
     int* d_plane_assoc = nullptr;  // [B][R*24][4]
+    int4* d_assoc_queue = nullptr; // [B * R * 36] queries handed to the warp pass of the association
+    int* d_assoc_queue_n = nullptr;// [8] queue lengths [0..2] and pop cursors [4..6] per outer iteration
+    int assoc_queue_cap = 0;
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;
 

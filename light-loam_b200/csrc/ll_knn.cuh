@@ -64,14 +64,22 @@ __device__ __forceinline__ void warp_merge_topk(const WarpKnn<K>& loc, u64 out[K
 // f(float4 point): bucket ranges are concatenated across the warp and read with coalesced float4 loads, two chunks
 // of 32 candidates in flight per iteration.
 template <typename F>
+__device__ __forceinline__ void grid_stream_ranges(const float4* __restrict__ sorted, int beg, int cnt, F&& f);
+template <typename F>
 __device__ __forceinline__ void grid_stream_buckets(const GridView& g, int bucket, F&& f)
 {
-    const int lane = lane_id();
     int beg = 0, cnt = 0;
     if (bucket >= 0) {
         beg = g.start[bucket];
         cnt = g.start[bucket + 1] - beg;
     }
+    grid_stream_ranges(g.sorted, beg, cnt, f);
+}
+// The same for explicit ranges: lane l contributes sorted[beg, beg + cnt) (cnt may be 0).
+template <typename F>
+__device__ __forceinline__ void grid_stream_ranges(const float4* __restrict__ sorted, int beg, int cnt, F&& f)
+{
+    const int lane = lane_id();
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
@@ -95,7 +103,7 @@ __device__ __forceinline__ void grid_stream_buckets(const GridView& g, int bucke
                 const int cbeg = __shfl_sync(LL_FULL_MASK, beg, lo);
                 const int cexc = __shfl_sync(LL_FULL_MASK, excl, lo);
                 ok[u] = t < total;
-                if (ok[u]) pv[u] = g.sorted[cbeg + (t - cexc)];
+                if (ok[u]) pv[u] = sorted[cbeg + (t - cexc)];
             }
         }
 #pragma unroll

@@ -37,7 +37,7 @@ __device__ __forceinline__ int src_bucket(const GridSrc& S, const float4 p, int 
     if (S.az_bins == 0) return cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
     int r = (int)p.w;
     r = r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
-    return r * S.az_bins + azimuth_bin(p.x, p.y, S.az_bins);
+    return azimuth_bin(p.x, p.y, S.az_bins) * S.rings + r;  // bin-major: the rings of one bin are consecutive buckets
 }
 __device__ __forceinline__ int grid_src_count(const GridSrc& S, const LaneState& L)
 {
@@ -142,14 +142,14 @@ __device__ __forceinline__ int index_bucket(const IndexSet& S, int cloud, int ki
     if (kind == 0) return cell_bucket((int)floorf(p.x * S.inv_h), (int)floorf(p.y * S.inv_h), (int)floorf(p.z * S.inv_h), S.T[cloud] - 1);
     int r = (int)p.w;
     r = r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
-    return r * S.az_bins[cloud] + azimuth_bin(p.x, p.y, S.az_bins[cloud]);
+    return azimuth_bin(p.x, p.y, S.az_bins[cloud]) * S.rings + r;  // bin-major: the rings of one bin are consecutive buckets
 }
 __global__ void k_index_count(IndexSet S, LaneState* lane)
 {
     const int b = blockIdx.y, cloud = blockIdx.z;
     LaneState& L = lane[b];
-    const int n = cloud == 0 ? L.n_less_sharp : L.n_less_flat;
-    const float4* pts = S.pts[cloud][L.cur] + (size_t)b * S.lane_stride[cloud];
+    const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
+    const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
         atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, 0, p)], 1);
@@ -204,8 +204,8 @@ __global__ void k_index_scatter(IndexSet S, const LaneState* lane)
 {
     const int b = blockIdx.y, cloud = blockIdx.z;
     const LaneState& L = lane[b];
-    const int n = cloud == 0 ? L.n_less_sharp : L.n_less_flat;
-    const float4* pts = S.pts[cloud][L.cur] + (size_t)b * S.lane_stride[cloud];
+    const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
+    const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
         int ring = (int)p.w;
@@ -242,230 +242,437 @@ struct OdomParams {
     int outer;             // opti_counter
     int dev_skip;          // development only: bit mask of association stages to skip (timing experiments)
     int plane_shells;      // grid shells tried for the 2nd / 3rd plane neighbour before the literal walk
+    int4* queue;           // queries handed from the per-thread pass to the warp pass (k_odom_assoc_heavy)
+    int* queue_n;          // [3] entries queued per outer iteration
+    int queue_cap;
 };
 
 __device__ __forceinline__ int last_slot(const LaneState& L) { return L.last_slot; }  // previous frame's clouds
 
-__global__ void __launch_bounds__(256, 6) k_odom_assoc(OdomParams P)
+// ------------------------------------------------------------------------------------------------------
+// k_odom_assoc: one THREAD per feature point for the common case, the WARP for the rare long searches.
+//
+// A query normally sees a few dozen candidates (its grid cell, the neighbour cells that can still beat the running
+// best, a handful of azimuth bins on five rings) — far too few to feed a warp, so every lane runs its own query.
+// Searches that do not resolve inside that budget (nearest neighbour farther than one cell, 2nd / 3rd point not
+// bounded after a few azimuth bins, clouds that are not ring-sorted) would make one lane walk hundreds of buckets
+// while 31 wait; those are handed to the whole warp, one query at a time, 32 buckets / candidates per step.
+// Decisions are the ones of LO:491-556 / LO:653-723: the minima are taken over total orders ((d2 bits, target
+// index) for the 1-NN, (d2 bits, visit rank of the serial loops) for the 2nd / 3rd point), so the visiting order
+// and the thread / warp split are free.
+// ------------------------------------------------------------------------------------------------------
+#define ASSOC_THREADS 128
+// Read-only 16-byte load that asks L2 to bring in the whole 128-byte line (8 bucket-sorted points): the following
+// candidates of the same bucket then hit L2 instead of paying another DRAM round trip.
+__device__ __forceinline__ float4 ld_point(const float4* p)
 {
-    const int b = blockIdx.y;
-    const LaneState& L = P.lane[b];
-    if (!L.inited) return;
+    float4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// Per-thread candidate loop with four loads in flight.  Indices past the end are clamped to the last element: a
+// candidate met twice changes nothing because every consumer keeps a minimum over a total order.
+template <typename F>
+__device__ __forceinline__ void for_range4(const float4* __restrict__ sorted, int s, int e, F&& f)
+{
+#pragma unroll 1
+    for (int k = s; k < e; k += 4) {
+        const float4 t0 = ld_point(sorted + k), t1 = ld_point(sorted + min(k + 1, e - 1)), t2 = ld_point(sorted + min(k + 2, e - 1)),
+                     t3 = ld_point(sorted + min(k + 3, e - 1));
+        f(t0); f(t1); f(t2); f(t3);
+    }
+}
+struct AssocQuery {
+    float qx, qy, qz;
+    int closest, cring, n;
+    u64 k2, k3;
+};
+template <bool CORNER>
+__device__ __forceinline__ void assoc_consider(AssocQuery& Q, const float4 t)
+{
+    const unsigned bits = (unsigned)__float_as_int(t.w);
+    const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
+    const float d2 = sqdist3(t.x, t.y, t.z, Q.qx, Q.qy, Q.qz);
+    if (!(d2 < 25.0f) || j == Q.closest) return;  // 25 is exact in fp32: same decision as the fp64 compare of LO:521
+    const unsigned rank = j > Q.closest ? (unsigned)(j - (Q.closest + 1)) : (unsigned)Q.n + (unsigned)(Q.closest - 1 - j);
+    const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
+    if (CORNER) { if (rj != Q.cring && key < Q.k2) Q.k2 = key; }  // same scan line -> continue (LO:507 / LO:533)
+    else if (rj == Q.cring) { if (key < Q.k2) Q.k2 = key; }  // LO:682 / LO:710 on a ring-monotone cloud
+    else if (key < Q.k3) Q.k3 = key;                         // LO:688 / LO:716
+}
+// every bin at azimuth offset > done from the query's bin holds only points at least this far away (squared)
+__device__ __forceinline__ float assoc_az_bound2(float rho, float wbin, int done)
+{
+    const float dmin = (float)done * wbin - 1e-4f;
+    const float lb = (dmin >= 1.5707963f ? rho : rho * __sinf(fmaxf(dmin, 0.f))) - 1e-3f;  // |__sinf error| * rho << 1e-3
+    return lb > 0.f ? lb * lb : 0.f;
+}
+template <bool CORNER>
+__device__ __forceinline__ bool assoc_window_done(const AssocQuery& Q, float lb2, int done, int NB)
+{
+    const bool ok2 = Q.k2 != ~0ull && __uint_as_float((unsigned)(Q.k2 >> 32)) < lb2;
+    const bool ok3 = CORNER || (Q.k3 != ~0ull && __uint_as_float((unsigned)(Q.k3 >> 32)) < lb2);
+    return (ok2 && ok3) || lb2 >= 25.0f || 2 * done + 1 >= NB;
+}
+// Ring-monotone *Last cloud: the serial loops of LO:504-553 / LO:668-721 visit exactly the points whose ring lies
+// in [cring-2, cring+2].  Those rings are searched through the ring x azimuth-bin index: a point whose azimuth
+// differs from the query's by D lies at least rho * sin(D) away (rho = horizontal range of the query), so bins
+// are visited outward from the query's bin until that bound exceeds the best distances found (or 5 m, LO:29).
+// The index is bin-major (bucket = bin * R + ring): the five rings of one bin are ONE contiguous span of the
+// bucket-sorted array, two header loads and a linear read.
+// Per-thread part: offsets up to dmax.  Returns the offset reached, negative once the search is resolved.
+template <bool CORNER>
+__device__ __forceinline__ int assoc_ring_window(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int dmax)
+{
+    const float rho = sqrtf(Q.qx * Q.qx + Q.qy * Q.qy);
+    const int b0 = azimuth_bin(Q.qx, Q.qy, NB);
+    const float wbin = 6.2831853f / (float)NB;
+    const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
+    auto header = [&](int off, int& s, int& e) {
+        const int bin = (b0 + off) & (NB - 1);  // NB is a power of two
+        s = __ldg(start + bin * R + r_lo);
+        e = __ldg(start + bin * R + r_lo + r_n);
+    };
+    int s0, e0, s1, e1, s2, e2;
+    header(-1, s0, e0); header(0, s1, e1); header(1, s2, e2);
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+        const int s = t == 0 ? s0 : (t == 1 ? s1 : s2), e = t == 0 ? e0 : (t == 1 ? e1 : e2);
+        for_range4(sorted, s, e, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
+    }
+    int done = 1;  // offsets |k| <= done have been visited
+    for (;;) {
+        if (assoc_window_done<CORNER>(Q, assoc_az_bound2(rho, wbin, done), done, NB)) return -1;
+        if (done >= dmax) return done;
+        ++done;
+        header(-done, s0, e0); header(done, s1, e1);
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+            const int s = t == 0 ? s0 : s1, e = t == 0 ? e0 : e1;
+            for_range4(sorted, s, e, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
+        }
+    }
+}
+// Warp part: continues one query's ring window from offset `done`, 32 bins (16 per side, five rings each) per step.
+template <bool CORNER>
+__device__ __forceinline__ void assoc_ring_window_warp(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int done)
+{
     const int lane = lane_id();
-    const int q = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    const int ns = L.n_sharp, nf = L.n_flat;
-    if (q >= ns + nf) return;
-    const bool is_corner = q < ns;
-    if ((P.dev_skip & 2) && is_corner) return;
-    if ((P.dev_skip & 4) && !is_corner) return;
-    const int i = is_corner ? q : q - ns;
-    const float4 p = is_corner ? P.sharp[(size_t)b * P.R * LL_SHARP_PER_RING + i] : P.flat[(size_t)b * P.R * LL_FLAT_PER_RING + i];
-
-    // TransformToStart, LO:77-95 with DISTORTION 0: slerp(1, q) = +-q, same rotation bit for bit
-    double sx, sy, sz;
-    quat_rotate(L.para_q, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
-    const float qx = (float)(sx + L.para_t[0]), qy = (float)(sy + L.para_t[1]), qz = (float)(sz + L.para_t[2]);
-
-    const int slot = last_slot(L);
-    const KnnGrid& G = is_corner ? P.gc : P.gs;
+    const float rho = sqrtf(Q.qx * Q.qx + Q.qy * Q.qy);
+    const int b0 = azimuth_bin(Q.qx, Q.qy, NB);
+    const float wbin = 6.2831853f / (float)NB;
+    const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
+    for (;;) {
+        const int mag = done + 1 + (lane >> 1);
+        const int off = (lane & 1) ? -mag : mag;
+        int beg = 0, cnt = 0;
+        if (mag <= NB / 2 && !(off == -(NB / 2))) {  // all the way round: keep each bin once
+            const int bin = (b0 + off) & (NB - 1);
+            beg = __ldg(start + bin * R + r_lo);
+            cnt = __ldg(start + bin * R + r_lo + r_n) - beg;
+        }
+        grid_stream_ranges(sorted, beg, cnt, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
+        done += 16;
+        Q.k2 = warp_min_u64(Q.k2);
+        if (!CORNER) Q.k3 = warp_min_u64(Q.k3);
+        if (assoc_window_done<CORNER>(Q, assoc_az_bound2(rho, wbin, done), done, NB)) break;
+    }
+}
+// The literal scan loops (LO:504-553 / LO:668-721) for clouds that are not ring-sorted (legal on the topic, never
+// produced by scanRegistration); the warp evaluates 32 candidates per ballot, lane order = visit order.
+template <bool CORNER>
+__device__ __forceinline__ void assoc_literal_walk_warp(AssocQuery& Q, const float4* __restrict__ last)
+{
+    const int lane = lane_id();
+    const int closest = Q.closest, cring = Q.cring, n = Q.n;
+    bool stop = false;
+    for (int j0 = closest + 1; j0 < n && !stop; j0 += 32) {  // increasing scan line
+        const int j = j0 + lane;
+        bool brk = false;
+        u64 c2 = ~0ull, c3 = ~0ull;
+        if (j < n) {
+            const float4 t = last[j];
+            const int rj = (int)t.w;
+            brk = rj > cring + 2;   // int ring vs cring + 2.5 (LO:511)
+            const float d2 = sqdist3(t.x, t.y, t.z, Q.qx, Q.qy, Q.qz);
+            const u64 key = ((u64)__float_as_uint(d2) << 32) | (unsigned)(j - (closest + 1));
+            if (!brk && d2 < 25.0f) {
+                if (CORNER) { if (!(rj <= cring)) c2 = key; }  // LO:507: same scan line -> continue
+                else if (rj <= cring) c2 = key;                // LO:682
+                else c3 = key;                                 // LO:688
+            }
+        }
+        const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
+        const int fb = bm ? __ffs(bm) - 1 : 32;
+        if (lane < fb) { if (c2 < Q.k2) Q.k2 = c2; if (c3 < Q.k3) Q.k3 = c3; }
+        if (bm) stop = true;
+    }
+    stop = false;
+    for (int j0 = closest - 1; j0 >= 0 && !stop; j0 -= 32) {  // decreasing scan line; visit order continues after the up-scan
+        const int j = j0 - lane;
+        bool brk = false;
+        u64 c2 = ~0ull, c3 = ~0ull;
+        if (j >= 0) {
+            const float4 t = last[j];
+            const int rj = (int)t.w;
+            brk = rj < cring - 2;   // LO:537
+            const float d2 = sqdist3(t.x, t.y, t.z, Q.qx, Q.qy, Q.qz);
+            const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)n + (unsigned)(closest - 1 - j));
+            if (!brk && d2 < 25.0f) {
+                if (CORNER) { if (!(rj >= cring)) c2 = key; }
+                else if (rj >= cring) c2 = key;
+                else c3 = key;
+            }
+        }
+        const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
+        const int fb = bm ? __ffs(bm) - 1 : 32;
+        if (lane < fb) { if (c2 < Q.k2) Q.k2 = c2; if (c3 < Q.k3) Q.k3 = c3; }
+        if (bm) stop = true;
+    }
+    Q.k2 = warp_min_u64(Q.k2);
+    Q.k3 = warp_min_u64(Q.k3);
+}
+// Exact 1-NN over the hashed grid (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656), per-thread part:
+// own cell, then the neighbour cells whose box can still hold a closer (or equally close, lower-index) point.
+// Returns (d2 bits << 32) | target index, ~0 if none; the caller continues with further shells when the best is not
+// provably inside the 27 cells.
+__device__ __forceinline__ u64 assoc_nearest27(const int* __restrict__ start, const float4* __restrict__ sorted, int Tmask, float h, float inv_h,
+                                               float qx, float qy, float qz)
+{
+    const float geps = 1e-3f;
+    const int cx = (int)floorf(qx * inv_h), cy = (int)floorf(qy * inv_h), cz = (int)floorf(qz * inv_h);
+    u64 best = ~0ull;
+    float bd2 = INFINITY;
+    auto bucket = [&](int bk) {
+        const int s = __ldg(start + bk), e = __ldg(start + bk + 1);
+        for_range4(sorted, s, e, [&](const float4 t) {
+            const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
+            const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
+            if (key < best) { best = key; bd2 = d2; }
+        });
+    };
+    const int b0 = cell_bucket(cx, cy, cz, Tmask);
+    bucket(b0);
+    // squared distance from the query to the slab of cells at offset d along one axis (1e-3 m slack covers the fp32
+    // rounding of the cell assignment)
+    auto axis = [&](float q, int c, int d) {
+        const float e = d < 0 ? (q - (float)c * h) - geps : (d > 0 ? ((float)(c + 1) * h - q) - geps : 0.f);
+        return e > 0.f ? e * e : 0.f;
+    };
+    for (int dz = -1; dz <= 1; ++dz) {
+        const float ez = axis(qz, cz, dz);
+        if (ez > bd2) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const float eyz = ez + axis(qy, cy, dy);
+            if (eyz > bd2) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                if ((dx | dy | dz) == 0 || eyz + axis(qx, cx, dx) > bd2) continue;
+                const int bk = cell_bucket(cx + dx, cy + dy, cz + dz, Tmask);
+                if (bk != b0) bucket(bk);   // a bucket met twice (hash collision) changes nothing: min is idempotent
+            }
+        }
+    }
+    return best;
+}
+// views of one lane's spatial grid / ring-azimuth index
+__device__ __forceinline__ GridView assoc_view(const KnnGrid& G, int b)
+{
     GridView gv;
     gv.start = G.start + (size_t)b * (G.T + 1);
     gv.sorted = G.sorted + (size_t)b * G.cap;
     gv.Tmask = G.T - 1;
     gv.h = G.h;
     gv.inv_h = G.inv_h;
-    const float4* last = is_corner ? P.lsharp[slot] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[slot] + (size_t)b * P.Nmax;
-    const int n = is_corner ? L.n_last_corner : L.n_last_surf;
+    return gv;
+}
+template <bool CORNER>
+__device__ __forceinline__ void assoc_store(const OdomParams& P, int b, int i, const AssocQuery& Q)
+{
+    auto decode = [&](u64 k) -> int {
+        if (k == ~0ull) return -1;
+        const unsigned rk = (unsigned)k;
+        return rk >= (unsigned)Q.n ? Q.closest - 1 - (int)(rk - (unsigned)Q.n) : Q.closest + 1 + (int)rk;
+    };
+    const int ind2 = Q.closest >= 0 ? decode(Q.k2) : -1, ind3 = Q.closest >= 0 ? decode(Q.k3) : -1;
+    if (CORNER) {
+        int* o = P.corner_assoc + ((size_t)b * P.R * LL_SHARP_PER_RING + i) * 2;
+        *reinterpret_cast<int2*>(o) = make_int2(ind2 >= 0 ? Q.closest : -1, ind2);  // LO:556
+    } else {
+        int* o = P.plane_assoc + ((size_t)b * P.R * LL_FLAT_PER_RING + i) * 4;
+        const bool ok = ind2 >= 0 && ind3 >= 0;  // LO:723
+        *reinterpret_cast<int4*>(o) = ok ? make_int4(Q.closest, ind2, ind3, 0) : make_int4(-1, -1, -1, 0);
+    }
+}
+template <bool CORNER>
+__device__ __forceinline__ void assoc_query_init(const OdomParams& P, const LaneState& L, int b, int i, AssocQuery& Q)
+{
+    const float4 p = CORNER ? P.sharp[(size_t)b * P.R * LL_SHARP_PER_RING + i] : P.flat[(size_t)b * P.R * LL_FLAT_PER_RING + i];
+    // TransformToStart, LO:77-95 with DISTORTION 0: slerp(1, q) = +-q, same rotation bit for bit
+    double sx, sy, sz;
+    quat_rotate(L.para_q, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
+    Q.qx = (float)(sx + L.para_t[0]); Q.qy = (float)(sy + L.para_t[1]); Q.qz = (float)(sz + L.para_t[2]);
+    Q.k2 = ~0ull; Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0;
+    Q.n = CORNER ? L.n_last_corner : L.n_last_surf;
+}
+// queue entry of a query the per-thread pass did not finish: x = lane, y = feature index | plane << 30 | open << 29;
+// open (nearest neighbour not yet proven): z, w = best key so far (d2 bits, index; ~0 = none)
+// otherwise: z = closest point, w = -1 (ring window, restarted by the warp) or -2 (literal walk)
+#define ASSOC_PLANE_BIT (1 << 30)
+#define ASSOC_OPEN_BIT (1 << 29)
 
-    // ---- 1-NN (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656) -----------------------------------
+// Per-thread pass.  Writes the correspondences of the queries it resolves, queues the others for k_odom_assoc_heavy.
+template <bool CORNER>
+__device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const LaneState& L, int b, int i, bool active, int dmax)
+{
+    const int lane = lane_id();
     const float geps = 1e-3f;
-    const int cx = (int)floorf(qx * gv.inv_h), cy = (int)floorf(qy * gv.inv_h), cz = (int)floorf(qz * gv.inv_h);
-    const int smax = (int)ceilf((5.0f + geps) * gv.inv_h);
-    u64 best[1];
-    best[0] = ~0ull;
-    if (n > 0) {
-        u64 lb = ~0ull;  // lane-local best (d2 bits << 32 | index)
-        auto upd = [&](const float4 t) {
-            const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
-            const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
-            if (key < lb) lb = key;
+    AssocQuery Q;
+    Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0;
+    int4 entry = make_int4(b, CORNER ? i : (i | ASSOC_PLANE_BIT), -1, -1);
+    bool heavy = false;
+    if (active) {
+        assoc_query_init<CORNER>(P, L, b, i, Q);
+        const GridView gv = assoc_view(CORNER ? P.gc : P.gs, b);
+        u64 best = ~0ull;
+        if (Q.n > 0) {
+            best = assoc_nearest27(gv.start, gv.sorted, gv.Tmask, gv.h, gv.inv_h, Q.qx, Q.qy, Q.qz);
+            const float safe = gv.h - geps;
+            // not provably inside the 27 cells searched: the further shells are a job for a whole warp
+            heavy = !(best != ~0ull && __uint_as_float((unsigned)(best >> 32)) < safe * safe);
+            if (heavy) { entry.y |= ASSOC_OPEN_BIT; entry.z = (int)(unsigned)(best >> 32); entry.w = (int)(unsigned)best; }
+        }
+        if (!heavy && best != ~0ull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // LO:497 / LO:659
+            const float4* last = CORNER ? P.lsharp[last_slot(L)] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[last_slot(L)] + (size_t)b * P.Nmax;
+            Q.closest = (int)(unsigned)best;
+            Q.cring = (int)last[Q.closest].w;  // int(intensity), LO:500 / LO:664
+            int pending = -2;                  // clouds that are not ring-sorted: literal walk
+            if (CORNER ? L.mono_corner : L.mono_surf) {
+                const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
+                pending = assoc_ring_window<CORNER>(Q, av.start, av.sorted, CORNER ? P.az_bins_corner : P.az_bins_surf, P.R, dmax);
+                heavy = pending >= 0;
+            } else {
+                heavy = true;
+            }
+            entry.z = Q.closest;
+            entry.w = pending >= 0 ? -1 : pending;
+        }
+        if (!heavy) assoc_store<CORNER>(P, b, i, Q);
+    }
+    const unsigned hm = __ballot_sync(LL_FULL_MASK, heavy);
+    if (hm) {
+        const int leader = __ffs(hm) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(P.queue_n + P.outer, __popc(hm));
+        base = __shfl_sync(LL_FULL_MASK, base, leader);
+        const int pos = base + __popc(hm & ((1u << lane) - 1u));
+        if (heavy && pos < P.queue_cap) P.queue[pos] = entry;
+    }
+}
+// grid: (ceil(R*12 / T) + ceil(R*24 / T), B): corner queries and plane queries never share a block
+__global__ void __launch_bounds__(ASSOC_THREADS, 6) k_odom_assoc(OdomParams P, int corner_blocks, int dmax)
+{
+    const int b = blockIdx.y;
+    const LaneState& L = P.lane[b];
+    if (!L.inited) return;
+    if ((int)blockIdx.x < corner_blocks) {
+        const int i = blockIdx.x * ASSOC_THREADS + threadIdx.x;
+        if ((i & ~31) >= L.n_sharp) return;   // whole warp idle
+        assoc_thread_pass<true>(P, L, b, i, i < L.n_sharp, dmax);
+    } else {
+        const int i = (blockIdx.x - corner_blocks) * ASSOC_THREADS + threadIdx.x;
+        if ((i & ~31) >= L.n_flat) return;
+        assoc_thread_pass<false>(P, L, b, i, i < L.n_flat, dmax);
+    }
+}
+
+// One WARP per queued query, the queue spread over a fixed grid: the long searches (nearest neighbour farther than
+// one cell, wide ring windows, literal walks) run side by side instead of serialising inside the warp that met them.
+template <bool CORNER>
+__device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int i, bool open, int ez, int ew)
+{
+    const LaneState& L = P.lane[b];
+    const int lane = lane_id();
+    const float geps = 1e-3f;
+    AssocQuery Q;
+    assoc_query_init<CORNER>(P, L, b, i, Q);
+    const float4* last = CORNER ? P.lsharp[last_slot(L)] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[last_slot(L)] + (size_t)b * P.Nmax;
+    int closest = open ? -1 : ez, mode = open ? -1 : ew;
+    if (open) {
+        // 1-NN (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656) beyond the 27 cells the thread pass
+        // searched: shell by shell.  The lanes share out the cells of a shell, skip those whose box cannot beat the
+        // warp's best, and keep eight bucket headers in flight each, so a whole shell costs about two memory round
+        // trips (these queries live in sparse regions: a shell holds few points).
+        const GridView gv = assoc_view(CORNER ? P.gc : P.gs, b);
+        const int cx = (int)floorf(Q.qx * gv.inv_h), cy = (int)floorf(Q.qy * gv.inv_h), cz = (int)floorf(Q.qz * gv.inv_h);
+        const int smax = (int)ceilf((5.0f + geps) * gv.inv_h);
+        u64 best = ((u64)(unsigned)ez << 32) | (unsigned)ew;  // the thread pass's best over the 27 cells (~0: none)
+        u64 lb = best;
+        auto axis = [&](float q, int c, int d) {
+            const float e = d < 0 ? (q - (float)(c + d + 1) * gv.h) - geps : (d > 0 ? ((float)(c + d) * gv.h - q) - geps : 0.f);
+            return e > 0.f ? e * e : 0.f;
         };
-        grid_visit_near_pruned(gv, qx, qy, qz, cx, cy, cz, upd, [&]() {
-            const u64 m = warp_min_u64(lb);
-            return m == ~0ull ? INFINITY : __uint_as_float((unsigned)(m >> 32));
-        });
-        for (int s = 2;; ++s) {
-            const u64 m = warp_min_u64(lb);
+        for (int s = 2; s <= smax; ++s) {
             const float safe = (float)(s - 1) * gv.h - geps;
-            if ((m != ~0ull && __uint_as_float((unsigned)(m >> 32)) < safe * safe) || s > smax) { best[0] = m; break; }
-            grid_visit_shell(gv, cx, cy, cz, s, upd);
-        }
-    }
-    int closest = -1, ind2 = -1, ind3 = -1;
-    if (P.dev_skip & 1) best[0] = ~0ull;
-    if (best[0] != ~0ull && (double)__uint_as_float((unsigned)(best[0] >> 32)) < 25.0) {  // LO:497 / LO:659
-        closest = (int)(unsigned)best[0];
-        const int cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
-        u64 k2 = ~0ull, k3 = ~0ull;              // (d2 bits << 32) | visit order  -> strict '<' of the serial loops
-        const unsigned down_base = (unsigned)n;
-        bool resolved = false;
-        if ((is_corner ? L.mono_corner : L.mono_surf) && !(P.dev_skip & 8)) {
-            // Ring-monotone cloud (always the case for clouds produced by scanRegistration): the serial loops of
-            // LO:504-553 / LO:668-721 visit exactly the points whose ring lies in [cring-2, cring+2].  Those rings
-            // are searched through the ring x azimuth-bin index: a point whose azimuth differs from the query's by
-            // D lies at least rho * sin(D) away (rho = horizontal range of the query), so bins are visited outward
-            // from the query's azimuth until that bound exceeds the best distances found (or 5 m, LO:29).
-            // Ties keep the loops' visit order through the rank in the key.
-            const KnnGrid& A = is_corner ? P.ac : P.as_;
-            const int NB = is_corner ? P.az_bins_corner : P.az_bins_surf;
-            GridView av;
-            av.start = A.start + (size_t)b * (A.T + 1);
-            av.sorted = A.sorted + (size_t)b * A.cap;
-            av.Tmask = A.T - 1;
-            av.h = 0.f; av.inv_h = 0.f;
-            auto consider = [&](const float4 t) {
-                const unsigned bits = (unsigned)__float_as_int(t.w);
-                const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
-                const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                if (!(d2 < 25.0f) || j == closest) return;  // 25 is exact in fp32: same decision as the fp64 compare of LO:521
-                const unsigned rank = j > closest ? (unsigned)(j - (closest + 1)) : down_base + (unsigned)(closest - 1 - j);
-                const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
-                if (rj == cring) { if (!is_corner && key < k2) k2 = key; }
-                else if (is_corner) { if (key < k2) k2 = key; }
-                else if (key < k3) k3 = key;
-            };
-            const float rho = sqrtf(qx * qx + qy * qy);
-            const int b0 = azimuth_bin(qx, qy, NB);
-            const float wbin = 6.2831853f / (float)NB;
-            // lane -> (ring slot 0..4 = cring-2..cring+2, bin slot 0..5); 30 lanes per round
-            const int rslot = lane / 6, bslot = lane % 6;
-            const int ring = cring - 2 + rslot;
-            const bool ring_ok = lane < 30 && ring >= 0 && ring < P.R && !(is_corner && ring == cring);
-            int done = -1;  // offsets |k| <= done have been visited
-            for (int round = 0;; ++round) {
-                // round 0: offsets -2..+2 (bslot 0..4); round r >= 1: offsets +-(3r .. 3r+2)
-                int off = 0;
-                bool use = ring_ok;
-                if (round == 0) { use = use && bslot < 5; off = bslot - 2; }
-                else { const int mag = 3 * round + (bslot % 3); off = bslot < 3 ? mag : -mag; }
-                const int reach = round == 0 ? 2 : 3 * round + 2;
-                if (2 * reach + 1 > NB) {  // wrapped all the way round: keep each bin once
-                    if (abs(off) > NB / 2 || (off == -(NB / 2))) use = false;
-                }
-                int bucket = -1 - lane;
-                if (use && abs(off) <= NB / 2) bucket = ring * NB + ((b0 + off) % NB + NB) % NB;
-                const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
-                if ((__ffs(grp) - 1) != lane) bucket = -1;
-                grid_stream_buckets(av, bucket, consider);
-                done = reach;
-                const u64 m2 = warp_min_u64(k2), m3 = is_corner ? 0ull : warp_min_u64(k3);
-                // every unvisited bin is at least done * wbin away in azimuth
-                const float dmin = (float)done * wbin - 1e-4f;
-                const float lb = (dmin >= 1.5707963f ? rho : rho * sinf(fmaxf(dmin, 0.f))) - 1e-3f;
-                const float lb2 = lb > 0.f ? lb * lb : 0.f;
-                const bool ok2 = m2 != ~0ull && __uint_as_float((unsigned)(m2 >> 32)) < lb2;
-                const bool ok3 = is_corner || (m3 != ~0ull && __uint_as_float((unsigned)(m3 >> 32)) < lb2);
-                if ((ok2 && ok3) || lb2 >= 25.0f || 2 * done + 1 >= NB) break;
-            }
-            resolved = true;
-            if (lane == 0 && P.outer == 2) atomicAdd(&P.lane[b].dbg[0], 1);
-        }
-        if (!resolved) {
-        // increasing scan line (LO:504-527 / LO:668-693); lane order inside a chunk = visit order.
-        // Four chunks are fetched per iteration (loads first, then consumed in visit order until the first break).
-        {
-            bool stop = false;
-            for (int j0 = closest + 1; j0 < n && !stop; j0 += 128) {
-                float4 tv[4];
+            const float bd2 = best != ~0ull ? __uint_as_float((unsigned)(best >> 32)) : INFINITY;
+            if (bd2 < safe * safe) break;
+            const int w = 2 * s + 1, ncell = w * w * w;
+            for (int e0 = 0; e0 < ncell; e0 += 256) {
+                int beg[8], end[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int j = j0 + u * 32 + lane; if (j < n) tv[u] = last[j]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (stop || j0 + u * 32 >= n) continue;  // warp-uniform
-                    const int j = j0 + u * 32 + lane;
-                    bool brk = false;
-                    u64 c2 = ~0ull, c3 = ~0ull;
-                    if (j < n) {
-                        const float4 t = tv[u];
-                        const int rj = (int)t.w;
-                        brk = rj > cring + 2;   // int ring vs cring + 2.5 (LO:511)
-                        const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                        const u64 key = ((u64)__float_as_uint(d2) << 32) | (unsigned)(j - (closest + 1));
-                        if (!brk && d2 < 25.0f) {
-                            if (is_corner) {
-                                if (!(rj <= cring)) c2 = key;  // LO:507: same scan line -> continue
-                            } else {
-                                if (rj <= cring) c2 = key;     // LO:682
-                                else c3 = key;                 // LO:688
-                            }
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * 32 + lane;
+                    beg[u] = 0; end[u] = 0;
+                    if (e < ncell) {
+                        const int dx = e % w - s, dy = (e / w) % w - s, dz = e / (w * w) - s;
+                        if (max(abs(dx), max(abs(dy), abs(dz))) == s && axis(Q.qx, cx, dx) + axis(Q.qy, cy, dy) + axis(Q.qz, cz, dz) <= bd2) {
+                            const int bk = cell_bucket(cx + dx, cy + dy, cz + dz, gv.Tmask);
+                            beg[u] = __ldg(gv.start + bk);
+                            end[u] = __ldg(gv.start + bk + 1);
                         }
                     }
-                    const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
-                    const int fb = bm ? __ffs(bm) - 1 : 32;
-                    if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
-                    if (bm) stop = true;
                 }
-            }
-        }
-        // decreasing scan line (LO:530-553 / LO:696-721); visit order continues after the up-scan
-        {
-            bool stop = false;
-            for (int j0 = closest - 1; j0 >= 0 && !stop; j0 -= 128) {
-                float4 tv[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int j = j0 - u * 32 - lane; if (j >= 0) tv[u] = last[j]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (stop || j0 - u * 32 < 0) continue;
-                    const int j = j0 - u * 32 - lane;
-                    bool brk = false;
-                    u64 c2 = ~0ull, c3 = ~0ull;
-                    if (j >= 0) {
-                        const float4 t = tv[u];
-                        const int rj = (int)t.w;
-                        brk = rj < cring - 2;   // LO:537
-                        const float d2 = sqdist3(t.x, t.y, t.z, qx, qy, qz);
-                        const u64 key = ((u64)__float_as_uint(d2) << 32) | (down_base + (unsigned)(closest - 1 - j));
-                        if (!brk && d2 < 25.0f) {
-                            if (is_corner) {
-                                if (!(rj >= cring)) c2 = key;
-                            } else {
-                                if (rj >= cring) c2 = key;
-                                else c3 = key;
-                            }
-                        }
-                    }
-                    const unsigned bm = __ballot_sync(LL_FULL_MASK, brk);
-                    const int fb = bm ? __ffs(bm) - 1 : 32;
-                    if (lane < fb) { if (c2 < k2) k2 = c2; if (c3 < k3) k3 = c3; }
-                    if (bm) stop = true;
-                }
+                for (int u = 0; u < 8; ++u)
+                    for_range4(gv.sorted, beg[u], end[u], [&](const float4 t) {
+                        const float d2 = sqdist3(Q.qx, Q.qy, Q.qz, t.x, t.y, t.z);
+                        const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
+                        if (key < lb) lb = key;
+                    });
             }
+            best = warp_min_u64(lb);
         }
-        }  // literal scan loops
-        k2 = warp_min_u64(k2);
-        k3 = warp_min_u64(k3);
-        auto decode = [&](u64 k) -> int {
-            if (k == ~0ull) return -1;
-            const unsigned rk = (unsigned)k;
-            return rk >= down_base ? closest - 1 - (int)(rk - down_base) : closest + 1 + (int)rk;
-        };
-        ind2 = decode(k2);
-        ind3 = decode(k3);
+        if (best != ~0ull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // LO:497 / LO:659
+            closest = (int)(unsigned)best;
+            mode = (CORNER ? L.mono_corner : L.mono_surf) ? -1 : -2;
+        }
     }
-    if (lane == 0) {
-        if (is_corner) {
-            int* o = P.corner_assoc + ((size_t)b * P.R * LL_SHARP_PER_RING + i) * 2;
-            o[0] = ind2 >= 0 ? closest : -1;  // LO:556
-            o[1] = ind2;
+    if (closest >= 0) {
+        Q.closest = closest;
+        Q.cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
+        if (mode == -2) {
+            assoc_literal_walk_warp<CORNER>(Q, last);
         } else {
-            int* o = P.plane_assoc + ((size_t)b * P.R * LL_FLAT_PER_RING + i) * 4;
-            const bool ok = ind2 >= 0 && ind3 >= 0;  // LO:723
-            o[0] = ok ? closest : -1;
-            o[1] = ok ? ind2 : -1;
-            o[2] = ok ? ind3 : -1;
-            o[3] = 0;
+            const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
+            assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, CORNER ? P.az_bins_corner : P.az_bins_surf, P.R, -1);
         }
+    }
+    if (lane == 0) assoc_store<CORNER>(P, b, i, Q);
+}
+__global__ void __launch_bounds__(256, 4) k_odom_assoc_heavy(OdomParams P)
+{
+    const int n = min(P.queue_n[P.outer], P.queue_cap);
+    int* head = P.queue_n + 4 + P.outer;  // entries are popped one at a time: their costs differ by orders of magnitude
+    for (;;) {
+        int e = 0;
+        if (lane_id() == 0) e = atomicAdd(head, 1);
+        e = __shfl_sync(LL_FULL_MASK, e, 0);
+        if (e >= n) break;
+        const int4 en = P.queue[e];
+        const int i = en.y & ~(ASSOC_PLANE_BIT | ASSOC_OPEN_BIT);
+        const bool open = (en.y & ASSOC_OPEN_BIT) != 0;
+        if (P.dev_skip & 16) { if (lane_id() == 0) atomicAdd(&P.lane[0].dbg[open ? 1 : 2], 1); }
+        if (en.y & ASSOC_PLANE_BIT) assoc_warp_query<false>(P, en.x, i, open, en.z, en.w);
+        else assoc_warp_query<true>(P, en.x, i, open, en.z, en.w);
     }
 }
 
@@ -661,21 +868,17 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     P.Nmax = c->Nmax; P.R = c->R; P.gc = c->g_corner; P.gs = c->g_surf; P.ac = c->a_corner; P.as_ = c->a_surf; P.az_bins_corner = c->az_bins_corner; P.az_bins_surf = c->az_bins_surf;
     P.corner_assoc = c->d_corner_assoc; P.plane_assoc = c->d_plane_assoc; P.blocks = c->d_blocks; P.nblk_cap = c->nblk_cap;
     P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.plane_shells = c->plane_shells; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
+    P.queue = c->d_assoc_queue; P.queue_n = c->d_assoc_queue_n; P.queue_cap = c->assoc_queue_cap;
     cudaStream_t s = c->stream;
-    const int nq = c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
+    const int cblocks = (c->R * LL_SHARP_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS, pblocks = (c->R * LL_FLAT_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS;
+    LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, s));
+    const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
+    const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;
     const size_t prep_smem = (size_t)c->R * LL_FLAT_PER_RING * 8 * 4;
     LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-    for (int outer = 0; outer < 3; ++outer) {  // LO:439
-        P.outer = outer;
-        { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3((nq + 7) / 8, n_lanes), 256, 0, s>>>(P); }
-        { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, prep_smem, s>>>(P); }
-        { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, LM_THREADS, 0, s>>>(P); }
-        c->launches += 3;
-    }
-    { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
-    c->launches += 1;
-    // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud on this frame's less-sharp / less-flat (LO:895-896):
-    // the spatial hash grids and the ring x azimuth indexes of both clouds are built together, 4 launches
+    // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
+    // the spatial hash grids and the ring x azimuth indexes of the two *Last clouds are built together (4 launches)
+    // right before the association, so the tables are still in L2 when the queries walk them
     {
         IndexSet S;
         KnnGrid* tab[4] = {&c->g_corner, &c->g_surf, &c->a_corner, &c->a_surf};
@@ -696,6 +899,16 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
         c->launches += 4;
     }
+    for (int outer = 0; outer < 3; ++outer) {  // LO:439
+        P.outer = outer;
+        { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3(cblocks + pblocks, n_lanes), ASSOC_THREADS, 0, s>>>(P, cblocks, dmax); }
+        { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
+        { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, prep_smem, s>>>(P); }
+        { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, LM_THREADS, 0, s>>>(P); }
+        c->launches += 4;
+    }
+    { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
+    c->launches += 1;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }
