@@ -429,17 +429,41 @@ __global__ void k_vg_init(int* bbox, int* seg_count, int nseg_total)
         seg_count[i] = 0;
     }
 }
+// Elements arrive grouped by segment (CSR order of the old map, then the stack), so a warp's 32 elements nearly
+// always share one segment: reduce in the warp and issue six atomics per warp instead of six per point.
 __global__ void k_vg_bbox(VgParams P)
 {
     const int b = blockIdx.y;
     const int n = P.n[b];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int s = P.seg[(size_t)b * P.E + e];
-        if (s < 0) continue;
-        const float4 p = P.in[(size_t)b * P.E + e];
-        int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
-        atomicMin(&bb[0], f2ord(p.x)); atomicMin(&bb[1], f2ord(p.y)); atomicMin(&bb[2], f2ord(p.z));
-        atomicMax(&bb[3], f2ord(p.x)); atomicMax(&bb[4], f2ord(p.y)); atomicMax(&bb[5], f2ord(p.z));
+    const int lane = lane_id();
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += gridDim.x * blockDim.x) {
+        const int e = base + lane;
+        int s = -1;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n) {
+            s = P.seg[(size_t)b * P.E + e];
+            if (s >= 0) p = P.in[(size_t)b * P.E + e];
+        }
+        const unsigned have = __ballot_sync(LL_FULL_MASK, s >= 0);
+        if (!have) continue;
+        const int s0 = __shfl_sync(LL_FULL_MASK, s, __ffs(have) - 1);
+        const bool uniform = __all_sync(LL_FULL_MASK, s < 0 || s == s0);
+        if (uniform) {
+            const bool v = s >= 0;
+            const int lo0 = __reduce_min_sync(LL_FULL_MASK, v ? f2ord(p.x) : INT_MAX), lo1 = __reduce_min_sync(LL_FULL_MASK, v ? f2ord(p.y) : INT_MAX),
+                      lo2 = __reduce_min_sync(LL_FULL_MASK, v ? f2ord(p.z) : INT_MAX);
+            const int hi0 = __reduce_max_sync(LL_FULL_MASK, v ? f2ord(p.x) : INT_MIN), hi1 = __reduce_max_sync(LL_FULL_MASK, v ? f2ord(p.y) : INT_MIN),
+                      hi2 = __reduce_max_sync(LL_FULL_MASK, v ? f2ord(p.z) : INT_MIN);
+            if (lane == 0) {
+                int* bb = P.bbox + ((size_t)b * P.nseg + s0) * 6;
+                atomicMin(&bb[0], lo0); atomicMin(&bb[1], lo1); atomicMin(&bb[2], lo2);
+                atomicMax(&bb[3], hi0); atomicMax(&bb[4], hi1); atomicMax(&bb[5], hi2);
+            }
+        } else if (s >= 0) {
+            int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
+            atomicMin(&bb[0], f2ord(p.x)); atomicMin(&bb[1], f2ord(p.y)); atomicMin(&bb[2], f2ord(p.z));
+            atomicMax(&bb[3], f2ord(p.x)); atomicMax(&bb[4], f2ord(p.y)); atomicMax(&bb[5], f2ord(p.z));
+        }
     }
 }
 // key = lane (8 bits) | segment (13) | voxel id or element number (31); ~0 = padding / dropped

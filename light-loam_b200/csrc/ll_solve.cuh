@@ -23,12 +23,73 @@
 #define LM_THREADS 512
 #define LM_NRED 28
 
+#define LM_MAX_WORLD 8
+#define LM_MBOX_DOUBLES 32   // 28 used; one mailbox slot = 32 doubles
+
+// Multi-GPU solve (BASELINE config 5): each rank evaluates its own residual blocks, the 28 doubles are
+// all-reduced INSIDE the solve kernel over peer memory (NVLink P2P stores into every peer's mailbox, a sequence flag,
+// a spin on the local flags), then every rank sums the contributions in rank order — identical bits everywhere, so all
+// ranks take the identical LM step and no host round trip or separate collective launch sits between evaluations.
+// Mailbox of one context: mbox[lane][parity][rank][32] doubles + flag[lane][rank] (last sequence number written).
+struct LmComm {
+    double* mbox[LM_MAX_WORLD];                 // peer mailboxes (own included), device pointers valid on this GPU
+    unsigned long long* flag[LM_MAX_WORLD];
+    int rank, world;
+    unsigned long long timeout_ns;              // a peer that never shows up must not hang the GPU
+};
+
 struct LmShared {
     double x[7], cand[7];
     double red[LM_THREADS / 32][LM_NRED];
     double out[LM_NRED];
     int go;
+    int comm_dead;
 };
+__device__ __forceinline__ unsigned long long lm_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// One-shot all-reduce (sum) of S.out[first..28) across the ranks of `comm` for problem `b`; seq is this problem's
+// evaluation counter (identical on all ranks).  Two mailbox slots (seq parity) suffice: a peer can run at most one
+// evaluation ahead, because it needs this rank's contribution to finish the next one.
+__device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b, unsigned long long seq, int first, LaneState* L)
+{
+    const int tid = threadIdx.x, W = C.world;
+    const size_t slot = ((size_t)b * 2 + (seq & 1)) * LM_MAX_WORLD * LM_MBOX_DOUBLES;
+    if (tid < LM_NRED && tid >= first) {
+        const double v = S.out[tid];
+        for (int p = 0; p < W; ++p) {
+            volatile double* dst = C.mbox[p] + slot + (size_t)C.rank * LM_MBOX_DOUBLES;
+            dst[tid] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < W) {
+        __threadfence_system();
+        volatile unsigned long long* f = C.flag[tid] + (size_t)b * LM_MAX_WORLD + C.rank;
+        *f = seq;
+        // wait for rank `tid`'s contribution to arrive in OUR mailbox
+        volatile unsigned long long* mine = C.flag[C.rank] + (size_t)b * LM_MAX_WORLD + tid;
+        if (!S.comm_dead) {
+            const unsigned long long t0 = lm_globaltimer();
+            while (*mine < seq) {
+                if (lm_globaltimer() - t0 > C.timeout_ns) { S.comm_dead = 1; if (L) L->err = LL_E_NCCL; break; }
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < LM_NRED && tid >= first) {
+        volatile const double* src = C.mbox[C.rank] + slot;
+        double v = 0.0;
+        for (int r = 0; r < W; ++r) v += src[(size_t)r * LM_MBOX_DOUBLES + tid];  // rank order: same bits on every rank
+        S.out[tid] = v;
+    }
+    __syncthreads();
+}
 
 // residual-block record (SoA, stride = cap): [0] type, [1..3] cp, [4..6] p0, [7..9] p1, [10] w
 //   type 0 EDGE        p0 = a, p1 = b
@@ -177,15 +238,28 @@ __device__ __forceinline__ bool chol6_solve(const double* Ap, const double* b, d
 }
 
 // The whole Solve. q_io / t_io point at the parameter blocks (global memory); all threads of the CTA call it.
-static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot)
+static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot,
+                                             const LmComm* comm = nullptr, int comm_b = 0, unsigned long long* comm_seq = nullptr)
 {
     __shared__ LmShared S;
     const int tid = threadIdx.x;
+    const bool dist = comm != nullptr && comm->world > 1;
+    unsigned long long seq = dist ? *comm_seq : 0ull;   // every thread keeps its own copy; thread 0 stores it back at the end
+    if (tid == 0) S.comm_dead = 0;
     if (tid < 4) S.x[tid] = q_io[tid];
     if (tid >= 4 && tid < 7) S.x[tid] = t_io[tid - 4];
     __syncthreads();
-    if (nb <= 0) {  // nothing to minimise: parameters untouched
+    if (dist) {  // the ranks agree on the problem size first: "nothing to minimise" must be a collective decision
+        if (tid < LM_NRED) S.out[tid] = tid == 27 ? (double)(nb > 0 ? nb : 0) : 0.0;
+        __syncthreads();
+        lm_allreduce(S, *comm, comm_b, ++seq, 27, L);
+        const int nb_all = (int)S.out[27];
+        __syncthreads();
+        if (nb_all <= 0) nb = 0; else if (nb <= 0) nb = -1;  // -1: this rank owns no block but takes part in every reduction
+    }
+    if (nb == 0) {  // nothing to minimise: parameters untouched
         if (tid == 0 && L) { L->initial_cost[slot] = 0; L->final_cost[slot] = 0; L->jac_evals[slot] = 0; L->cost_evals[slot] = 0; L->termination[slot] = -1; }
+        if (tid == 0 && dist) *comm_seq = seq;
         return;
     }
     double acc[LM_NRED];
@@ -201,6 +275,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     // IterationZero: cost, gradient, Jacobian (as JtJ) at x
     lm_accumulate<true>(blk, cap, nb, S.x, acc);
     lm_reduce<true>(S, acc);
+    if (dist) lm_allreduce(S, *comm, comm_b, ++seq, 0, L);
     if (tid == 0) {
         for (int k = 0; k < 21; ++k) H[k] = S.out[k];
         for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
@@ -272,6 +347,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         // ---- all threads: cost at the candidate --------------------------------------------------------
         lm_accumulate<false>(blk, cap, nb, S.cand, acc);
         lm_reduce<false>(S, acc);
+        if (dist) lm_allreduce(S, *comm, comm_b, ++seq, 27, L);
         if (tid == 0) {
             const double cand_cost = S.out[27];
             ++cost_evals;
@@ -309,6 +385,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         if (go == 2) {
             lm_accumulate<true>(blk, cap, nb, S.x, acc);
             lm_reduce<true>(S, acc);
+            if (dist) lm_allreduce(S, *comm, comm_b, ++seq, 0, L);
             if (tid == 0) {
                 for (int k = 0; k < 21; ++k) H[k] = S.out[k];
                 for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
@@ -326,6 +403,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) q_io[i] = S.x[i];
         for (int i = 0; i < 3; ++i) t_io[i] = S.x[4 + i];
+        if (dist) *comm_seq = seq;
         if (L) {
             L->initial_cost[slot] = initial_cost;
             L->final_cost[slot] = x_cost;
