@@ -102,6 +102,21 @@ int ll_mapping_step(ll_ctx* ctx, ll_cloud_view corner_last, ll_cloud_view surf_l
 /* Pre-loads map-frame points into lane 0's cube map (config-3 style benchmarks; no reference equivalent). */
 int ll_map_insert(ll_ctx* ctx, ll_cloud_view corner, ll_cloud_view surf);
 
+/* Multi-GPU scan-to-map (BASELINE.json configs[4]: map in spatial slabs, per-GPU JtJ, all-reduce of the 6x6 normal
+ * equations; no reference equivalent — the reference is single-process).  One context per GPU / process.  Every rank
+ * calls ll_mapping_step with the SAME clouds and odometry pose; rank r only associates the stack points whose
+ * map-frame x lies in its slab [x_lo, x_hi) (LM:1877-2055 for those points), and the LM kernel all-reduces the 28
+ * doubles (21 JtJ + 6 Jtr + cost) of every linearisation over peer memory inside the kernel, so all ranks take the
+ * identical step and return the identical pose.  ll_comm_export / ll_comm_attach(kind 0) connect processes through
+ * CUDA IPC handles (exchange them with any host-side all-gather); kind 1 connects contexts of one process through
+ * ll_comm_local_ptr.  Attach right after ll_create (all ranks at the same point of identical call sequences). */
+#define LL_COMM_HANDLE_BYTES 64
+int   ll_comm_export(ll_ctx* ctx, void* handle_out /* LL_COMM_HANDLE_BYTES */);
+void* ll_comm_local_ptr(ll_ctx* ctx);
+int   ll_comm_attach(ll_ctx* ctx, int rank, int world, const void* peers /* world entries */, int kind);
+int   ll_comm_detach(ll_ctx* ctx);
+int   ll_map_set_slab(ll_ctx* ctx, double x_lo, double x_hi);
+
 /* Fused device pipeline: scan i of the call feeds lane i (n_scans <= batch).  Per lane the call is
  * SR:100-377 -> LO:425-896 (-> LM:1581-2168 when enable_mapping), with features handed over in HBM.
  * poses_out: n_scans x 14 doubles = odometry q_w_curr[4], t_w_curr[3], mapped q_w_curr[4], t_w_curr[3]

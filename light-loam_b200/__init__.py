@@ -2,5 +2,5 @@
 
 The directory name carries a hyphen; import it with importlib:  importlib.import_module("light-loam_b200").
 """
-from . import capi, synth  # noqa: F401
+from . import capi, multigpu, synth  # noqa: F401
 from .capi import Context, LightLoamError, default_config  # noqa: F401

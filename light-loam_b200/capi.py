@@ -18,7 +18,7 @@ LL_W_FEW_CORRESPONDENCES = 1
 SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
            "ll_extract_features", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
            "ll_process_staged", "ll_submit_scans", "ll_collect", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
-           "ll_debug_assoc", "ll_cuda_stream"]
+           "ll_debug_assoc", "ll_cuda_stream", "ll_comm_export", "ll_comm_local_ptr", "ll_comm_attach", "ll_comm_detach", "ll_map_set_slab"]
 
 
 class LLConfig(ctypes.Structure):
@@ -87,6 +87,12 @@ def lib():
         L.ll_profile_read.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.ll_last_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ll_debug_assoc.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.ll_comm_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ll_comm_local_ptr.restype = ctypes.c_void_p
+        L.ll_comm_local_ptr.argtypes = [ctypes.c_void_p]
+        L.ll_comm_attach.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.ll_comm_detach.argtypes = [ctypes.c_void_p]
+        L.ll_map_set_slab.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]
         _LIB = L
     return _LIB
 
@@ -273,6 +279,32 @@ class Context:
         p = np.zeros((self.R * 24, 4), np.int32)
         self._check(self.L.ll_debug_assoc(self.h, lane, c.ctypes.data, c.shape[0], p.ctypes.data, p.shape[0]), "ll_debug_assoc")
         return c, p
+
+    # ---- multi-GPU scan-to-map (configs[4]): slab-sharded queries + in-kernel all-reduce over peer memory ----------
+    def comm_export(self):
+        """64-byte CUDA IPC handle of this context's mailbox (send it to the other ranks)."""
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.L.ll_comm_export(self.h, buf), "ll_comm_export")
+        return buf.raw
+
+    def comm_local_ptr(self):
+        return self.L.ll_comm_local_ptr(self.h)
+
+    def comm_attach(self, rank, world, peers):
+        """peers: list of `world` 64-byte handles (other processes) or of `world` ints (pointers of contexts in this process)."""
+        if isinstance(peers[0], (bytes, bytearray)):
+            blob = b"".join(bytes(p) for p in peers)
+            assert len(blob) == 64 * world
+            self._check(self.L.ll_comm_attach(self.h, rank, world, blob, 0), "ll_comm_attach")
+        else:
+            arr = (ctypes.c_void_p * world)(*[int(p) for p in peers])
+            self._check(self.L.ll_comm_attach(self.h, rank, world, arr, 1), "ll_comm_attach")
+
+    def comm_detach(self):
+        self._check(self.L.ll_comm_detach(self.h), "ll_comm_detach")
+
+    def map_set_slab(self, x_lo, x_hi):
+        self._check(self.L.ll_map_set_slab(self.h, float(x_lo), float(x_hi)), "ll_map_set_slab")
 
     def cuda_stream(self):
         return self.L.ll_cuda_stream(self.h)

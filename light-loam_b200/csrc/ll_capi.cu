@@ -291,7 +291,7 @@ int ll_reset(ll_ctx* c)
     if (!c) return LL_E_INVAL;
     LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
     k_init_lanes<<<(c->B + 63) / 64, 64, 0, c->stream>>>(c->d_lane, c->B);
-    if (c->map) { ll_map_free(c); const int rc = ll_map_alloc(c); if (rc) return rc; }
+    if (c->map) ll_map_clear(c);  // empties the cube map in place: buffers (and the mailbox other ranks may hold) stay put
     LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return LL_OK;
 }

@@ -197,4 +197,5 @@ int ll_launch_features(ll_ctx* c, int n_lanes);                 // SR:100-377 on
 int ll_launch_odometry(ll_ctx* c, int n_lanes);                 // LO:425-896
 int ll_map_alloc(ll_ctx* c);
 void ll_map_free(ll_ctx* c);
+void ll_map_clear(ll_ctx* c);                                   // forget the map contents, keep the allocations
 int ll_launch_mapping(ll_ctx* c, int n_lanes);                  // LM:1581-2168

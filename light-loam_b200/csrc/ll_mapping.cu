@@ -69,6 +69,16 @@ struct MapState {
     size_t cub_bytes = 0;
     double* blocks = nullptr;  // dense records [B][LL_BLOCK_DOUBLES][nblk_cap]
     int nblk_cap = 0;
+    // split / multi-GPU solve (LmComm, ll_solve.cuh)
+    void* comm_buf = nullptr;          // this context's mailbox: mbox doubles followed by the flags
+    size_t comm_mbox_bytes = 0, comm_bytes = 0;
+    unsigned long long* comm_seq[2] = {nullptr, nullptr};  // [B] collective counters, alternated per solve launch
+    int comm_flip = 0;
+    int grank = 0, gworld = 1;
+    void* peer_buf[LM_MAX_GPUS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool peer_ipc[LM_MAX_GPUS] = {false, false, false, false, false, false, false, false};
+    double slab_lo = -INFINITY, slab_hi = INFINITY;   // this rank associates stack points with slab_lo <= pointSel.x < slab_hi
+    unsigned long long timeout_ns = 2000000000ull;
 };
 
 namespace {
@@ -289,6 +299,7 @@ struct MapAssocParams {
     KnnGrid g[2];
     double* blocks;
     int nblk_cap;
+    float slab_lo, slab_hi;   // multi-GPU: only the stack points whose map-frame x lies in [slab_lo, slab_hi) are this rank's
 };
 
 // one warp per stack point; the fit runs on lane 0 (fp64, a few hundred flops)
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(256) k_map_assoc(MapAssocParams P)
     const int i = t == 0 ? q : q - nc;
     const float4 pointOri = P.stack[t][(size_t)b * P.stack_cap[t] + i];
     const float4 pointSel = associate_to_map(pointOri, L.map_par);
+    if (!(pointSel.x >= P.slab_lo && pointSel.x < P.slab_hi)) { if (lane == 0) blk[q] = -1.0; return; }  // another rank's query
     const KnnGrid& G = P.g[t];
     GridView gv;
     gv.start = G.start + (size_t)b * (G.T + 1);
@@ -378,12 +390,15 @@ __global__ void k_map_reset_corr(LaneState* lane, int n_lanes)
     if (b < n_lanes) { lane[b].n_map_corner_corr = 0; lane[b].n_map_surf_corr = 0; }
 }
 
-__global__ void __launch_bounds__(LM_THREADS) k_lm_solve_map(LaneState* lane, const double* blocks, int nblk_cap, int iter)
+// grid (lanes, parts): `parts` CTAs share one lane's residual blocks and all-reduce inside the kernel (LmComm)
+__global__ void __launch_bounds__(LM_THREADS) k_lm_solve_map(LaneState* lane, const double* blocks, int nblk_cap, int iter, LmComm comm, int n_all_lanes)
 {
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, part = blockIdx.y;
     LaneState& L = lane[b];
     const int nb = L.map_ok ? L.n_stack_corner + L.n_stack_surf : 0;
-    lm_solve(blocks + (size_t)b * LL_BLOCK_DOUBLES * nblk_cap, nblk_cap, nb, L.map_par, L.map_par + 4, &L, 3 + iter);
+    if (comm.gworld * comm.nparts > 1 && b == 0 && part == 0)   // lanes outside this launch keep their collective counters
+        for (int i = gridDim.x + threadIdx.x; i < n_all_lanes; i += LM_THREADS) comm.seq_out[i] = comm.seq_in[i];
+    lm_solve(blocks + (size_t)b * LL_BLOCK_DOUBLES * nblk_cap, nblk_cap, nb, L.map_par, L.map_par + 4, &L, 3 + iter, &comm, b, part);
 }
 
 // LM:119-123 transformUpdate + pose output
@@ -635,8 +650,19 @@ void ll_map_free(ll_ctx* c)
     cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->vg_in); cudaFree(m->vg_seg);
     cudaFree(m->vg_n); cudaFree(m->vg_head); cudaFree(m->vg_scan); cudaFree(m->vg_bbox); cudaFree(m->seg_count); cudaFree(m->lane_base);
     cudaFree(m->cub_tmp); cudaFree(m->blocks);
+    for (int g = 0; g < LM_MAX_GPUS; ++g) if (m->peer_ipc[g] && m->peer_buf[g]) cudaIpcCloseMemHandle(m->peer_buf[g]);
+    cudaFree(m->comm_buf); cudaFree(m->comm_seq[0]); cudaFree(m->comm_seq[1]);
     delete m;
     c->map = nullptr;
+}
+
+void ll_map_clear(ll_ctx* c)
+{
+    MapState* m = c->map;
+    if (!m) return;
+    for (int t = 0; t < 2; ++t)
+        for (int k = 0; k < 2; ++k) cudaMemsetAsync(m->cube_off[t][k], 0, sizeof(int) * (size_t)c->B * (MAP_NUM + 1), c->stream);
+    m->buf = 0;
 }
 
 int ll_map_alloc(ll_ctx* c)
@@ -698,6 +724,15 @@ int ll_map_alloc(ll_ctx* c)
     MK(cudaMalloc(&m->cub_tmp, m->cub_bytes));
     m->nblk_cap = m->stack_cap[0] + m->stack_cap[1];
     MK(cudaMalloc((void**)&m->blocks, sizeof(double) * B * LL_BLOCK_DOUBLES * (size_t)m->nblk_cap));
+    m->comm_mbox_bytes = sizeof(double) * B * 2 * LM_MAX_WORLD * LM_MBOX_DOUBLES;
+    m->comm_bytes = m->comm_mbox_bytes + sizeof(unsigned long long) * B * LM_MAX_WORLD;
+    MK(cudaMalloc(&m->comm_buf, m->comm_bytes));
+    MK(cudaMemsetAsync(m->comm_buf, 0, m->comm_bytes, c->stream));
+    for (int k = 0; k < 2; ++k) {
+        MK(cudaMalloc((void**)&m->comm_seq[k], sizeof(unsigned long long) * B));
+        MK(cudaMemsetAsync(m->comm_seq[k], 0, sizeof(unsigned long long) * B, c->stream));
+    }
+    if (const char* e = getenv("LL_COMM_TIMEOUT_MS")) m->timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
 #undef MK
     return LL_OK;
 }
@@ -760,11 +795,25 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     MapAssocParams A;
     A.lane = c->d_lane; A.stack[0] = m->stack[0]; A.stack[1] = m->stack[1]; A.frommap[0] = m->frommap[0]; A.frommap[1] = m->frommap[1];
     A.stack_cap[0] = m->stack_cap[0]; A.stack_cap[1] = m->stack_cap[1]; A.map_cap = m->map_cap; A.g[0] = m->grid[0]; A.g[1] = m->grid[1];
-    A.blocks = m->blocks; A.nblk_cap = m->nblk_cap;
+    A.blocks = m->blocks; A.nblk_cap = m->nblk_cap; A.slab_lo = (float)m->slab_lo; A.slab_hi = (float)m->slab_hi;
+    // solve split: `parts` CTAs per lane on this GPU (all co-resident: lanes x parts <= SM count) x the attached GPUs
+    int parts = 148 / n_lanes;
+    parts = parts < 1 ? 1 : (parts > LM_MAX_PARTS ? LM_MAX_PARTS : parts);
+    if (const char* e = getenv("LL_LM_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= LM_MAX_PARTS && v * n_lanes <= 148) parts = v; }
+    LmComm comm;
+    for (int g = 0; g < LM_MAX_GPUS; ++g) {
+        char* base = reinterpret_cast<char*>(g == m->grank ? m->comm_buf : m->peer_buf[g]);
+        comm.mbox[g] = reinterpret_cast<double*>(base);
+        comm.flag[g] = base ? reinterpret_cast<unsigned long long*>(base + m->comm_mbox_bytes) : nullptr;
+    }
+    comm.grank = m->grank; comm.gworld = m->gworld; comm.nparts = parts; comm.timeout_ns = m->timeout_ns;
+    const bool dist = comm.gworld * comm.nparts > 1;
     for (int iter = 0; iter < 2; ++iter) {  // LM:1834
         { LLProf pr(c, "k_map_reset_corr"); k_map_reset_corr<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
         { LLProf pr(c, "k_map_assoc"); k_map_assoc<<<dim3((m->nblk_cap + 7) / 8, n_lanes), 256, 0, s>>>(A); }
-        { LLProf pr(c, "k_lm_solve_map"); k_lm_solve_map<<<n_lanes, LM_THREADS, 0, s>>>(c->d_lane, m->blocks, m->nblk_cap, iter); }
+        comm.seq_in = m->comm_seq[m->comm_flip]; comm.seq_out = m->comm_seq[m->comm_flip ^ (dist ? 1 : 0)];
+        { LLProf pr(c, "k_lm_solve_map"); k_lm_solve_map<<<dim3(n_lanes, parts), LM_THREADS, 0, s>>>(c->d_lane, m->blocks, m->nblk_cap, iter, comm, c->B); }
+        if (dist) m->comm_flip ^= 1;
         c->launches += 3;
     }
     { LLProf pr(c, "k_map_end"); k_map_end<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
@@ -882,3 +931,84 @@ extern "C" int ll_map_insert(ll_ctx* c, ll_cloud_view corner, ll_cloud_view surf
     return err ? err : LL_OK;
 }
 
+
+// ---- multi-GPU scan-to-map (BASELINE config 5) -------------------------------------------------------------------------------
+// Every rank (one context per GPU / process) calls ll_mapping_step with the SAME clouds and odometry pose; the stack
+// points are shared out by map-frame x slab (ll_map_set_slab), each rank fits and accumulates only its own, and the
+// LM kernel all-reduces the 28 doubles over peer memory (ll_solve.cuh), so all ranks end with the identical pose.
+extern "C" int ll_comm_export(ll_ctx* c, void* handle_out)
+{
+    if (!c || !handle_out) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    if (!c->map) { const int rc = ll_map_alloc(c); if (rc) return rc; }
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));  // the mailbox is zeroed before anybody can learn its address
+    cudaIpcMemHandle_t h;
+    LL_CUDA_CHECK(c, cudaIpcGetMemHandle(&h, c->map->comm_buf));
+    static_assert(sizeof(h) == LL_COMM_HANDLE_BYTES, "handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    return LL_OK;
+}
+extern "C" void* ll_comm_local_ptr(ll_ctx* c)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->dev);
+    if (!c->map && ll_map_alloc(c) != LL_OK) return nullptr;
+    cudaStreamSynchronize(c->stream);
+    return c->map->comm_buf;
+}
+extern "C" int ll_comm_detach(ll_ctx* c)
+{
+    if (!c || !c->map) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    MapState* m = c->map;
+    for (int g = 0; g < LM_MAX_GPUS; ++g) {
+        if (m->peer_ipc[g] && m->peer_buf[g]) cudaIpcCloseMemHandle(m->peer_buf[g]);
+        m->peer_buf[g] = nullptr; m->peer_ipc[g] = false;
+    }
+    m->grank = 0; m->gworld = 1;
+    return LL_OK;
+}
+// kind 0: `peers` = world x 64-byte handles from ll_comm_export (other processes); kind 1: world x void* from
+// ll_comm_local_ptr (contexts of this process).  The own entry is ignored.  The collective counters keep running, so
+// all ranks must attach at the same point of identical call sequences (normally: right after ll_create).
+extern "C" int ll_comm_attach(ll_ctx* c, int rank, int world, const void* peers, int kind)
+{
+    if (!c || !peers || world < 1 || world > LM_MAX_GPUS || rank < 0 || rank >= world || (kind != 0 && kind != 1)) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    if (!c->map) { const int rc = ll_map_alloc(c); if (rc) return rc; }
+    int rc = ll_comm_detach(c);
+    if (rc) return rc;
+    MapState* m = c->map;
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) continue;
+        if (kind == 0) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, reinterpret_cast<const char*>(peers) + (size_t)g * LL_COMM_HANDLE_BYTES, sizeof(h));
+            void* p = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { c->last_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); ll_comm_detach(c); return LL_E_NCCL; }
+            m->peer_buf[g] = p; m->peer_ipc[g] = true;
+        } else {
+            void* p = reinterpret_cast<void* const*>(peers)[g];
+            if (!p) { ll_comm_detach(c); return LL_E_INVAL; }
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.device != c->dev) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->last_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); ll_comm_detach(c); return LL_E_NCCL; }
+                cudaGetLastError();
+            }
+            m->peer_buf[g] = p; m->peer_ipc[g] = false;
+        }
+    }
+    m->grank = rank; m->gworld = world;
+    // the local mailbox is NOT cleared here: a faster peer may already be writing into it (flags only grow)
+    return LL_OK;
+}
+extern "C" int ll_map_set_slab(ll_ctx* c, double x_lo, double x_hi)
+{
+    if (!c || !(x_lo < x_hi)) return LL_E_INVAL;
+    if (!c->map) { const int rc = ll_map_alloc(c); if (rc) return rc; }
+    c->map->slab_lo = x_lo; c->map->slab_hi = x_hi;
+    return LL_OK;
+}

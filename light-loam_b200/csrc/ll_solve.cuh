@@ -12,8 +12,8 @@
 // scaling from the first Jacobian, HuberLoss(0.1) with the rho'' <= 0 corrector, radius 1e4, accept if
 // rho > 1e-3, max 4 iterations, function / gradient / parameter tolerances 1e-6 / 1e-10 / 1e-8.
 //
-// One CTA per problem; LM_THREADS threads stride over the residual blocks; the reduction order is fixed
-// (lane tree, then warps in order), so results are run-to-run deterministic.
+// One CTA per problem (or several, see LmComm); LM_THREADS threads stride over the residual blocks; the reduction
+// order is fixed (lane tree, then warps in order, then CTAs in rank order), so results are run-to-run deterministic.
 #pragma once
 #include <float.h>
 
@@ -23,18 +23,24 @@
 #define LM_THREADS 512
 #define LM_NRED 28
 
-#define LM_MAX_WORLD 8
+#define LM_MAX_GPUS 8
+#define LM_MAX_PARTS 16
+#define LM_MAX_WORLD (LM_MAX_GPUS * LM_MAX_PARTS)
 #define LM_MBOX_DOUBLES 32   // 28 used; one mailbox slot = 32 doubles
 
-// Multi-GPU solve (BASELINE config 5): each rank evaluates its own residual blocks, the 28 doubles are
-// all-reduced INSIDE the solve kernel over peer memory (NVLink P2P stores into every peer's mailbox, a sequence flag,
-// a spin on the local flags), then every rank sums the contributions in rank order — identical bits everywhere, so all
-// ranks take the identical LM step and no host round trip or separate collective launch sits between evaluations.
-// Mailbox of one context: mbox[lane][parity][rank][32] doubles + flag[lane][rank] (last sequence number written).
+// Split solve.  One problem can be evaluated by several CTAs — `nparts` CTAs of this GPU and the CTAs of `gworld`
+// GPUs (BASELINE config 5) — each owning a share of the residual blocks.  The 28 doubles are
+// all-reduced INSIDE the solve kernel: every CTA stores its partial sums into the mailbox of every GPU (local stores
+// or NVLink P2P stores), publishes a sequence flag, spins on the flags of its own GPU's mailbox and sums the
+// contributions in rank order — identical bits in every CTA, so all of them take the identical LM step, and neither a
+// host round trip nor a separate collective launch sits between two evaluations.
+// Mailbox of one context: mbox[lane][parity][LM_MAX_WORLD][32] doubles + flag[lane][LM_MAX_WORLD] (sequence numbers).
 struct LmComm {
-    double* mbox[LM_MAX_WORLD];                 // peer mailboxes (own included), device pointers valid on this GPU
-    unsigned long long* flag[LM_MAX_WORLD];
-    int rank, world;
+    double* mbox[LM_MAX_GPUS];                  // mailboxes of all GPUs (own included), device pointers valid on this GPU
+    unsigned long long* flag[LM_MAX_GPUS];
+    const unsigned long long* seq_in;           // [B] collectives executed so far per problem (same on every rank)
+    unsigned long long* seq_out;                // [B] written by part 0 of this launch (the host alternates the two arrays)
+    int grank, gworld, nparts;
     unsigned long long timeout_ns;              // a peer that never shows up must not hang the GPU
 };
 
@@ -51,41 +57,42 @@ __device__ __forceinline__ unsigned long long lm_globaltimer()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// One-shot all-reduce (sum) of S.out[first..28) across the ranks of `comm` for problem `b`; seq is this problem's
-// evaluation counter (identical on all ranks).  Two mailbox slots (seq parity) suffice: a peer can run at most one
-// evaluation ahead, because it needs this rank's contribution to finish the next one.
-__device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b, unsigned long long seq, int first, LaneState* L)
+// One-shot all-reduce (sum) of S.out[first..28) over all CTAs working on problem `b`.  Two mailbox slots (parity of
+// the collective counter) suffice: a peer can be at most one collective ahead, because it needs this CTA's
+// contribution to complete the next one.
+__device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b, int part, unsigned long long seq, int first, LaneState* L)
 {
-    const int tid = threadIdx.x, W = C.world;
+    const int tid = threadIdx.x, W = C.gworld * C.nparts, me = C.grank * C.nparts + part;
     const size_t slot = ((size_t)b * 2 + (seq & 1)) * LM_MAX_WORLD * LM_MBOX_DOUBLES;
     if (tid < LM_NRED && tid >= first) {
         const double v = S.out[tid];
-        for (int p = 0; p < W; ++p) {
-            volatile double* dst = C.mbox[p] + slot + (size_t)C.rank * LM_MBOX_DOUBLES;
+        for (int g = 0; g < C.gworld; ++g) {
+            volatile double* dst = C.mbox[g] + slot + (size_t)me * LM_MBOX_DOUBLES;
             dst[tid] = v;
         }
     }
     __syncthreads();
-    if (tid < W) {
+    if (tid < C.gworld) {  // publish: one thread per destination GPU
         __threadfence_system();
-        volatile unsigned long long* f = C.flag[tid] + (size_t)b * LM_MAX_WORLD + C.rank;
+        volatile unsigned long long* f = C.flag[tid] + (size_t)b * LM_MAX_WORLD + me;
         *f = seq;
-        // wait for rank `tid`'s contribution to arrive in OUR mailbox
-        volatile unsigned long long* mine = C.flag[C.rank] + (size_t)b * LM_MAX_WORLD + tid;
+    }
+    if (tid < W) {         // wait for contribution `tid` to arrive in THIS GPU's mailbox
+        volatile unsigned long long* mine = C.flag[C.grank] + (size_t)b * LM_MAX_WORLD + tid;
         if (!S.comm_dead) {
             const unsigned long long t0 = lm_globaltimer();
             while (*mine < seq) {
                 if (lm_globaltimer() - t0 > C.timeout_ns) { S.comm_dead = 1; if (L) L->err = LL_E_NCCL; break; }
-                __nanosleep(64);
+                __nanosleep(32);
             }
         }
         __threadfence_system();
     }
     __syncthreads();
     if (tid < LM_NRED && tid >= first) {
-        volatile const double* src = C.mbox[C.rank] + slot;
+        volatile const double* src = C.mbox[C.grank] + slot;
         double v = 0.0;
-        for (int r = 0; r < W; ++r) v += src[(size_t)r * LM_MBOX_DOUBLES + tid];  // rank order: same bits on every rank
+        for (int r = 0; r < W; ++r) v += src[(size_t)r * LM_MBOX_DOUBLES + tid];  // rank order: same bits in every CTA
         S.out[tid] = v;
     }
     __syncthreads();
@@ -96,11 +103,11 @@ __device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b
 //   type 1 PLANE_MODIFY p0 = j, p1 = ljm_norm, w = weight
 //   type 2 PLANE_NORM   p0 = unit normal, w = negative_OA_dot_norm
 template <bool FULL>
-__device__ __forceinline__ void lm_accumulate(const double* blk, int cap, int nb, const double* x, double acc[LM_NRED])
+__device__ __forceinline__ void lm_accumulate(const double* blk, int cap, int nb, const double* x, double acc[LM_NRED], int part = 0, int nparts = 1)
 {
 #pragma unroll
     for (int k = 0; k < LM_NRED; ++k) acc[k] = 0.0;
-    for (int i = threadIdx.x; i < nb; i += LM_THREADS) {
+    for (int i = part * LM_THREADS + threadIdx.x; i < nb; i += LM_THREADS * nparts) {
         const int type = (int)blk[i];
         if (type < 0) continue;  // dense mapping records: slot without a correspondence
         const double cpx = blk[1 * cap + i], cpy = blk[2 * cap + i], cpz = blk[3 * cap + i];
@@ -239,27 +246,28 @@ __device__ __forceinline__ bool chol6_solve(const double* Ap, const double* b, d
 
 // The whole Solve. q_io / t_io point at the parameter blocks (global memory); all threads of the CTA call it.
 static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot,
-                                             const LmComm* comm = nullptr, int comm_b = 0, unsigned long long* comm_seq = nullptr)
+                                             const LmComm* comm = nullptr, int comm_b = 0, int part = 0)
 {
     __shared__ LmShared S;
     const int tid = threadIdx.x;
-    const bool dist = comm != nullptr && comm->world > 1;
-    unsigned long long seq = dist ? *comm_seq : 0ull;   // every thread keeps its own copy; thread 0 stores it back at the end
+    const bool dist = comm != nullptr && comm->gworld * comm->nparts > 1;
+    const int nparts = dist ? comm->nparts : 1;
+    unsigned long long seq = dist ? comm->seq_in[comm_b] : 0ull;   // collectives so far; every thread keeps its own copy
     if (tid == 0) S.comm_dead = 0;
     if (tid < 4) S.x[tid] = q_io[tid];
     if (tid >= 4 && tid < 7) S.x[tid] = t_io[tid - 4];
     __syncthreads();
     if (dist) {  // the ranks agree on the problem size first: "nothing to minimise" must be a collective decision
-        if (tid < LM_NRED) S.out[tid] = tid == 27 ? (double)(nb > 0 ? nb : 0) : 0.0;
+        if (tid < LM_NRED) S.out[tid] = tid == 27 ? (double)(nb > 0 && part == 0 ? nb : 0) : 0.0;
         __syncthreads();
-        lm_allreduce(S, *comm, comm_b, ++seq, 27, L);
+        lm_allreduce(S, *comm, comm_b, part, ++seq, 27, L);
         const int nb_all = (int)S.out[27];
         __syncthreads();
-        if (nb_all <= 0) nb = 0; else if (nb <= 0) nb = -1;  // -1: this rank owns no block but takes part in every reduction
+        if (nb_all <= 0) nb = 0; else if (nb <= 0) nb = -1;  // -1: this GPU owns no block but takes part in every reduction
     }
-    if (nb == 0) {  // nothing to minimise: parameters untouched
+    if (nb == 0 || (!dist && nb < 0)) {  // nothing to minimise: parameters untouched
         if (tid == 0 && L) { L->initial_cost[slot] = 0; L->final_cost[slot] = 0; L->jac_evals[slot] = 0; L->cost_evals[slot] = 0; L->termination[slot] = -1; }
-        if (tid == 0 && dist) *comm_seq = seq;
+        if (tid == 0 && dist && part == 0) comm->seq_out[comm_b] = seq;
         return;
     }
     double acc[LM_NRED];
@@ -273,9 +281,9 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     auto norm7 = [](const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); };
 
     // IterationZero: cost, gradient, Jacobian (as JtJ) at x
-    lm_accumulate<true>(blk, cap, nb, S.x, acc);
+    lm_accumulate<true>(blk, cap, nb, S.x, acc, part, nparts);
     lm_reduce<true>(S, acc);
-    if (dist) lm_allreduce(S, *comm, comm_b, ++seq, 0, L);
+    if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
     if (tid == 0) {
         for (int k = 0; k < 21; ++k) H[k] = S.out[k];
         for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
@@ -345,9 +353,9 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         __syncthreads();
         if (!S.go) break;
         // ---- all threads: cost at the candidate --------------------------------------------------------
-        lm_accumulate<false>(blk, cap, nb, S.cand, acc);
+        lm_accumulate<false>(blk, cap, nb, S.cand, acc, part, nparts);
         lm_reduce<false>(S, acc);
-        if (dist) lm_allreduce(S, *comm, comm_b, ++seq, 27, L);
+        if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 27, L);
         if (tid == 0) {
             const double cand_cost = S.out[27];
             ++cost_evals;
@@ -383,9 +391,9 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         const int go = S.go;
         if (go == 0) break;
         if (go == 2) {
-            lm_accumulate<true>(blk, cap, nb, S.x, acc);
+            lm_accumulate<true>(blk, cap, nb, S.x, acc, part, nparts);
             lm_reduce<true>(S, acc);
-            if (dist) lm_allreduce(S, *comm, comm_b, ++seq, 0, L);
+            if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
             if (tid == 0) {
                 for (int k = 0; k < 21; ++k) H[k] = S.out[k];
                 for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
@@ -400,10 +408,10 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         }
         __syncthreads();
     }
-    if (tid == 0) {
+    if (tid == 0 && part == 0) {  // every part holds the same result; one writes it
         for (int i = 0; i < 4; ++i) q_io[i] = S.x[i];
         for (int i = 0; i < 3; ++i) t_io[i] = S.x[4 + i];
-        if (dist) *comm_seq = seq;
+        if (dist) comm->seq_out[comm_b] = seq;
         if (L) {
             L->initial_cost[slot] = initial_cost;
             L->final_cost[slot] = x_cost;

@@ -77,3 +77,46 @@ print("ok", r)
                           "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_slab_bounds_partition_the_line(ll):
+    mg = ll.multigpu
+    for world in (1, 2, 3, 8):
+        b = [mg.slab_bounds(r, world, -60.0, 60.0) for r in range(world)]
+        assert b[0][0] == -np.inf and b[-1][1] == np.inf
+        for r in range(world - 1):
+            assert b[r][1] == b[r + 1][0]           # half-open slabs: every x has exactly one owner
+    pts = np.random.default_rng(0).uniform(-60, 60, (1000, 4)).astype(np.float32)
+    lo, hi = mg.slab_bounds(1, 4, -60.0, 60.0)
+    sub = mg.slab_with_halo(pts, lo, hi, halo=1.0)
+    assert sub[:, 0].min() >= lo - 1.0 and sub[:, 0].max() < hi + 1.0
+    assert len(sub) == int(((pts[:, 0] >= lo - 1) & (pts[:, 0] < hi + 1)).sum())
+
+
+def test_two_rank_gloo_handle_exchange(tmp_path):
+    """The host-side plumbing of the multi-GPU scan-to-map mode under gloo, world_size 2: every rank ends up with all
+    mailbox handles in rank order and with its own slab (a stub stands in for the CUDA context)."""
+    code = r"""
+import importlib, sys, torch.distributed as dist
+sys.path.insert(0, %r)
+mg = importlib.import_module("light-loam_b200.multigpu")
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+class Stub:
+    def comm_export(self): return bytes([r]) * 64
+    def comm_attach(self, rank, world, handles): self.got = (rank, world, handles)
+    def map_set_slab(self, lo, hi): self.slab = (lo, hi)
+s = Stub()
+lo, hi = mg.attach_all(s, dist, -60.0, 60.0)
+assert s.got[0] == r and s.got[1] == w and [h[0] for h in s.got[2]] == list(range(w)) and all(len(h) == 64 for h in s.got[2])
+assert s.slab == (lo, hi) and ((r == 0 and hi == 0.0) or (r == 1 and lo == 0.0))
+dist.destroy_process_group()
+print("ok", r)
+""" % ROOT
+    script = tmp_path / "gloo_handles.py"
+    script.write_text(code)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29618", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2

@@ -137,3 +137,98 @@ def test_config3_large_map_scan_to_map(ll, orc):
         assert np.abs(mg["t"] - mo["t"]).max() < 1e-6 and np.abs(mg["q"] - mo["q"]).max() < 1e-6, (k, mg, mo)
         assert (st.map_corner_corr, st.map_surf_corr) == (int(mo["info"][5]), int(mo["info"][6]))
     ctx.close()
+
+
+def _config5_inputs(ll, line=32):
+    """BASELINE.json configs[4] in small: an HDL-32 scan against a preloaded map."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("prof_map", os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "prof_map.py"))
+    pm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pm)
+    corner, surf = pm.config3_map(n_s=300000, n_c=30000, seed=7)
+    return corner, surf
+
+
+def test_split_solve_matches_single_cta(ll, monkeypatch):
+    """The LM solve split over 16 CTAs (in-kernel all-reduce through the mailbox) vs one CTA: same pose to fp64
+    summation-order noise, same iteration counts and termination."""
+    corner, surf = _config5_inputs(ll)
+    q0 = np.array([0, 0, np.sin(np.pi / 4), np.cos(np.pi / 4)])
+    t0 = np.array([25.0, 0.0, 0.0])
+    res = {}
+    for parts in (1, 16, 5):
+        monkeypatch.setenv("LL_LM_PARTS", str(parts))
+        ctx = ll.Context(scan_line=32, map_capacity=1 << 19)
+        f = ctx.extract_features(ll.synth.scan(32, 0, mode=1))
+        ctx.map_insert(corner, surf)
+        out = []
+        for k in range(2):
+            m = ctx.mapping_step(f["less_sharp"], f["less_flat"], q0, t0)
+            st = ctx.stats()
+            out.append((m["q"].copy(), m["t"].copy(), list(st.map_jacobian_evals), list(st.map_termination), st.map_corner_corr, st.map_surf_corr))
+        res[parts] = out
+        ctx.close()
+    for parts in (16, 5):
+        for a, b in zip(res[1], res[parts]):
+            assert np.abs(a[0] - b[0]).max() < 1e-11 and np.abs(a[1] - b[1]).max() < 1e-10, (parts, a, b)
+            assert a[2:] == b[2:], (parts, a[2:], b[2:])
+    assert res[1][0][5] > 1000
+
+
+def test_two_contexts_slab_sharded_allreduce(ll):
+    """Config 5 on one GPU: two contexts (= two ranks) with the same map, the stack points shared out by x slab, the 28
+    doubles all-reduced inside the LM kernels through each other's mailboxes.  Both ranks must return bit-identical
+    poses, equal to the single-context result to fp64 summation-order noise; every correspondence has one owner."""
+    import threading
+    corner, surf = _config5_inputs(ll)
+    q0 = np.array([0, 0, np.sin(np.pi / 4), np.cos(np.pi / 4)])
+    t0 = np.array([25.0, 0.0, 0.0])
+    single = ll.Context(scan_line=32, map_capacity=1 << 19)
+    f = single.extract_features(ll.synth.scan(32, 0, mode=1))
+    single.map_insert(corner, surf)
+    want = single.mapping_step(f["less_sharp"], f["less_flat"], q0, t0)
+    st1 = single.stats()
+    ranks = [ll.Context(scan_line=32, map_capacity=1 << 19) for _ in range(2)]
+    ptrs = [c.comm_local_ptr() for c in ranks]
+    for r, c in enumerate(ranks):
+        c.comm_attach(r, 2, ptrs)
+        c.map_set_slab(*ll.multigpu.slab_bounds(r, 2, 10.0, 40.0))     # the sensor sits at x = 25: both slabs get work
+        c.map_insert(corner, surf)
+    got = [None, None]
+
+    def run(r):
+        got[r] = ranks[r].mapping_step(f["less_sharp"], f["less_flat"], q0, t0)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert got[0] is not None and got[1] is not None
+    assert got[0]["rc"] == 0 and got[1]["rc"] == 0
+    assert np.array_equal(got[0]["q"], got[1]["q"]) and np.array_equal(got[0]["t"], got[1]["t"])
+    assert np.abs(got[0]["t"] - want["t"]).max() < 1e-10 and np.abs(got[0]["q"] - want["q"]).max() < 1e-11
+    s = [c.stats() for c in ranks]
+    assert s[0].map_surf_corr > 100 and s[1].map_surf_corr > 100
+    assert s[0].map_surf_corr + s[1].map_surf_corr == st1.map_surf_corr
+    assert s[0].map_corner_corr + s[1].map_corner_corr == st1.map_corner_corr
+    assert list(s[0].map_jacobian_evals) == list(st1.map_jacobian_evals) == list(s[1].map_jacobian_evals)
+    for c in ranks + [single]:
+        c.close()
+
+
+def test_multi_process_config5_when_two_gpus(ll, tmp_path):
+    """The same through CUDA IPC between processes, one GPU each (skipped on a 1-GPU box; run with gpurun --gpus 2)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29655", os.path.join(root, "scripts", "bench_config5.py"), "--check", "--small"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert "config5 ok" in out.stdout
