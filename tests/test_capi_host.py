@@ -120,3 +120,44 @@ print("ok", r)
                           "--master-port", "29618", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_two_rank_gloo_segment_chaining(tmp_path):
+    """configs[3] exchange step under gloo, world_size 2: a stream of relative motions cut into two segments, each
+    rank chaining its own increments from identity; after the 7-double all-gather + prefix product the global poses equal
+    the single-process chain."""
+    code = r"""
+import importlib, sys, numpy as np, torch.distributed as dist
+sys.path.insert(0, %r)
+mg = importlib.import_module("light-loam_b200.multigpu")
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(11)
+n = 21
+inc = []
+for k in range(n):
+    ax = rng.normal(0, 0.02, 3); ang = np.linalg.norm(ax)
+    q = list(np.sin(ang / 2) * ax / ang) + [np.cos(ang / 2)]
+    inc.append((q, list(rng.normal([1, 0, 0], 0.05))))
+def chain(incs):
+    q, t, out = [0, 0, 0, 1.0], [0, 0, 0.0], []
+    for (dq, dt) in incs:                      # LO:830-831
+        rt = mg.quat_rotate(q, dt); t = [t[i] + rt[i] for i in range(3)]; q = mg.quat_mul(q, dq)
+        out.append(q + t)
+    return np.array(out)
+full = chain(inc)
+b, e = mg.segment_ranges(n, w)[r]
+assert mg.segment_ranges(n, w)[0][0] == 0 and mg.segment_ranges(n, w)[-1][1] == n
+local = chain(inc[b:e])
+glob = mg.chain_segments(local, dist)
+assert np.abs(glob - full[b:e]).max() < 1e-12, np.abs(glob - full[b:e]).max()
+dist.destroy_process_group()
+print("ok", r)
+""" % ROOT
+    script = tmp_path / "gloo_chain.py"
+    script.write_text(code)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29619", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
