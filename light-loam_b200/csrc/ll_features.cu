@@ -5,7 +5,7 @@
 //   k_ring_scan      SR:215-221 (ring offsets = stable counting sort by ring)
 //   k_scatter        SR:194-209 (relTime, intensity) + scatter into the ring-major cloud
 //   k_ring_sort      SR:225-257: one CTA per (ring, lane): TMA bulk load of the ring into shared memory,
-//                    11-tap curvature, six in-smem sector sorts -> u16 sorted order per point
+//                    11-tap curvature, six sector sorts in registers (one warp each) -> u16 sorted order per point
 //   k_ring_pick      SR:251-359: greedy pick with +-5 suppression, one warp per ring (order-dependent part)
 //   k_ring_lessflat  SR:361-376: less-flat collection and pcl::VoxelGrid(0.2) per ring
 //   k_compact        concatenation of the per-ring outputs in the reference's publish order (SR:273-376)
@@ -234,23 +234,66 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_ring_sort: one CTA per (ring, lane).  TMA bulk load of the ring slab into shared memory, 11-tap curvature
-// (SR:225-235), six concurrent bitonic sector sorts on (curvature bits, index) keys (SR:257), then the sorted
-// order is written back as one u16 per point: local index | over(c > 0.1) << 14 | under(c < 0.1) << 15 —
+// k_ring_sort: one CTA per (ring, lane), one WARP per sector.  TMA bulk load of the ring slab into shared memory,
+// 11-tap curvature (SR:225-235), then each warp sorts its sector (SR:257) entirely in registers: SCAP / 32 keys per
+// lane, element e = r * 32 + lane, so compare-exchange distances >= 32 are register-to-register and the rest are
+// shuffles — no shared-memory passes and no block barriers inside the sort.
+// Keys are ONE 32-bit word: the high (32 - log2 SCAP) bits of the curvature's fp32 pattern (monotone for c >= 0) and
+// the position inside the sector.  Curvatures that collide in the truncated bits end up adjacent (ordered by
+// position); a fix-up pass re-sorts each such group (a handful per sector, two or three elements) on the full
+// (curvature, position) key, which restores exactly the total order (curvature bits, index) of a 64-bit sort.
+// The sorted order is written back as one u16 per point: local index | over(c > 0.1) << 14 | under(c < 0.1) << 15 —
 // everything the greedy pick needs to know about the curvature.
 // ---------------------------------------------------------------------------------------------------------
+template <int NREG>
+__device__ __forceinline__ void warp_bitonic_sort_regs(unsigned (&k)[NREG], int lane)
+{
+    constexpr int N = NREG * 32;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {  // partner lives in the same lane: registers r and r ^ (j / 32)
+#pragma unroll
+                for (int r = 0; r < NREG; ++r) {
+                    if ((r & (j >> 5)) == 0) {
+                        const bool asc = (((r * 32) & kk) == 0) || kk == N;  // kk >= 64 here: the direction depends on r only
+                        const unsigned a = k[r], c = k[r | (j >> 5)];
+                        const unsigned lo = min(a, c), hi = max(a, c);
+                        k[r] = asc ? lo : hi;
+                        k[r | (j >> 5)] = asc ? hi : lo;
+                    }
+                }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < NREG; ++r) {
+                    const unsigned o = __shfl_xor_sync(LL_FULL_MASK, k[r], j);
+                    const bool asc = kk == N ? true : (((r * 32) | lane) & kk) == 0;  // direction of element e = r * 32 + lane
+                    k[r] = (lower == asc) ? min(k[r], o) : max(k[r], o);
+                }
+            }
+        }
+    }
+}
+
+#define SORT_THREADS 192   // six sectors, one warp each
 template <int SCAP>
-__global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
+__global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
 {
     constexpr int RCAP = 6 * SCAP + 16;
-    constexpr int NTH = 512;
+    constexpr int NTH = SORT_THREADS;
+    constexpr int NREG = SCAP / 32;
+    constexpr int IDXBITS = SCAP == 512 ? 9 : 10;
+    constexpr unsigned IDXMASK = (1u << IDXBITS) - 1u;
     extern __shared__ __align__(128) unsigned char smem[];
     float4* pts = reinterpret_cast<float4*>(smem);
-    u64* keys = reinterpret_cast<u64*>(smem + (size_t)RCAP * 16);
+    float* curv_s = reinterpret_cast<float*>(smem + (size_t)RCAP * 16);
+    unsigned* keys = reinterpret_cast<unsigned*>(curv_s + RCAP);
     int* sp = reinterpret_cast<int*>(keys + 6 * SCAP);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sp + 8);
 
-    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     LaneState& L = P.lane[b];
     const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base, ntot = L.n_full;
     const float4* gfull = P.full + (size_t)b * P.Nmax;
@@ -280,7 +323,6 @@ __global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) tma_bulk_g2s(pts, gfull + base, (uint32_t)n * 16u, bar);
-    for (int i = tid; i < 6 * SCAP; i += NTH) keys[i] = ~0ull;
     const int len = n - 11;
     if (tid <= 6) sp[tid] = 5 + len * tid / 6;  // SR:253-254 with ring-local indices
     mbar_wait(bar, 0);
@@ -296,40 +338,71 @@ __global__ void __launch_bounds__(512) k_ring_sort(FeatParams P)
 #pragma unroll
             for (int k = 1; k <= 5; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
             c = dx * dx + dy * dy + dz * dz;
-            if (i < n - 6) {  // sectors tile [5, n-6)
-                int j = 0;
-#pragma unroll
-                for (int q = 1; q < 6; ++q) j += (i >= sp[q]);
-                keys[j * SCAP + (i - sp[j])] = ((u64)__float_as_uint(c) << 32) | (unsigned)i;
-            }
         } else {
             c = global_curv(base + i);
         }
+        curv_s[i] = c;
         gcurv[base + i] = c;
         glabel[base + i] = 0;
     }
-    __syncthreads();
-
-    block_bitonic_sort_u64(keys, 6 * SCAP, SCAP);  // six independent ascending sector sorts
     // consecutive-gap break bits for the +-5 suppression (SR:290-293): bit i = |p[i] - p[i-1]|^2 > 0.05;
     // each warp covers 32 consecutive points, the ballot is the bitmask word
     for (int i0 = (tid & ~31); i0 < P.brk_words * 32; i0 += NTH) {
-        const int i = i0 + (tid & 31);
+        const int i = i0 + lane;
         bool brk = false;
         if (i >= 1 && i < n) {
             const float4 a = pts[i], c = pts[i - 1];
             brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
         }
         const unsigned bits = __ballot_sync(LL_FULL_MASK, brk);
-        if ((tid & 31) == 0) gbrk[i0 >> 5] = bits;
+        if (lane == 0) gbrk[i0 >> 5] = bits;
     }
-    for (int i = 5 + tid; i < n - 6; i += NTH) {
-        int j = 0;
+    __syncthreads();
+
+    // ---- one warp per sector (sectors tile [5, n-6)) ---------------------------------------------------------------
+    const int j = wid, s0 = sp[j], slen = sp[j + 1] - s0;
+    unsigned k[NREG];
 #pragma unroll
-        for (int q = 1; q < 6; ++q) j += (i >= sp[q]);
-        const u64 key = keys[j * SCAP + (i - sp[j])];
-        const float c = __uint_as_float((unsigned)(key >> 32));
-        gsorted[base + i] = (uint16_t)((unsigned)key | ((double)c > 0.1 ? 0x4000u : 0u) | ((double)c < 0.1 ? 0x8000u : 0u));
+    for (int q = 0; q < NREG; ++q) {
+        const int e = q * 32 + lane;
+        k[q] = e < slen ? ((__float_as_uint(curv_s[s0 + e]) >> IDXBITS) << IDXBITS) | (unsigned)e : 0xFFFFFFFFu;
+    }
+    warp_bitonic_sort_regs<NREG>(k, lane);
+    unsigned* sk = keys + j * SCAP;
+#pragma unroll
+    for (int q = 0; q < NREG; ++q) sk[q * 32 + lane] = k[q];
+    __syncwarp();
+    // fix-up: groups of equal truncated curvature are re-sorted on (full curvature bits, position)
+#pragma unroll 1
+    for (int q = 0; q < NREG; ++q) {
+        const int e = q * 32 + lane;
+        if (e + 1 < slen) {
+            const unsigned me = sk[e], nx = sk[e + 1];
+            const bool head = (me >> IDXBITS) == (nx >> IDXBITS) && (e == 0 || (sk[e - 1] >> IDXBITS) != (me >> IDXBITS));
+            if (head) {
+                int g = 2;
+                while (e + g < slen && (sk[e + g] >> IDXBITS) == (me >> IDXBITS)) ++g;
+                for (int a = 1; a < g; ++a) {  // insertion sort of sk[e .. e+g)
+                    const unsigned ka = sk[e + a];
+                    const u64 fa = ((u64)__float_as_uint(curv_s[s0 + (int)(ka & IDXMASK)]) << 32) | (ka & IDXMASK);
+                    int c = a - 1;
+                    while (c >= 0) {
+                        const unsigned kc = sk[e + c];
+                        const u64 fc = ((u64)__float_as_uint(curv_s[s0 + (int)(kc & IDXMASK)]) << 32) | (kc & IDXMASK);
+                        if (fc <= fa) break;
+                        sk[e + c + 1] = kc;
+                        --c;
+                    }
+                    sk[e + c + 1] = ka;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < slen; e += 32) {
+        const int idx = s0 + (int)(sk[e] & IDXMASK);
+        const float c = curv_s[idx];
+        gsorted[base + s0 + e] = (uint16_t)((unsigned)idx | ((double)c > 0.1 ? 0x4000u : 0u) | ((double)c < 0.1 ? 0x8000u : 0u));
     }
 }
 
@@ -469,8 +542,11 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
 
 // ---------------------------------------------------------------------------------------------------------
 // k_ring_lessflat: less-flat = every sector point with label <= 0 (SR:361-367), then pcl::VoxelGrid(0.2) on
-// the ring (SR:370-376): bbox -> voxel id -> bitonic sort of (voxel id, index) -> run-sum centroids in
-// sorted (= input) order, fp32.  Points and labels are read through L2; only the sort keys live in smem.
+// the ring (SR:370-376): bbox -> voxel id -> groups of equal voxel id -> fp32 centroids accumulated in input order,
+// emitted in ascending voxel id.  Along a ring consecutive points mostly fall into the same voxel, so the sort is
+// done over RUNS of consecutive equal voxel ids (about a third of the points): keys (voxel id, run number), and the
+// thread that owns a voxel walks its runs in order — the summation order stays the input order.
+// Points and labels are read through L2; voxel ids, run starts and the sort keys live in shared memory.
 // ---------------------------------------------------------------------------------------------------------
 template <int SCAP>
 __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
@@ -480,8 +556,11 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
     constexpr int NTH = 512;
     constexpr int CH = (RCAP + NTH - 1) / NTH;
     extern __shared__ __align__(128) unsigned char smem[];
-    u64* keys = reinterpret_cast<u64*>(smem);
-    int* ws = reinterpret_cast<int*>(keys + KCAP);
+    u64* keys = reinterpret_cast<u64*>(smem);                       // [KCAP] (voxel id << 32) | run number
+    int* vid = reinterpret_cast<int*>(keys + KCAP);                 // [RCAP] voxel id per less-flat point (compacted order)
+    uint16_t* pidx = reinterpret_cast<uint16_t*>(vid + RCAP);       // [RCAP] ring-local index of that point
+    uint16_t* run_start = pidx + RCAP;                              // [RCAP + 1] first compacted position of every run
+    int* ws = reinterpret_cast<int*>(run_start + RCAP + 2);
     float* red = reinterpret_cast<float*>(ws + 40);
 
     const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
@@ -537,8 +616,6 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
     const int min_b0 = (int)floorf(bmn[0] * inv), min_b1 = (int)floorf(bmn[1] * inv), min_b2 = (int)floorf(bmn[2] * inv);
     const int div0 = (int)floorf(bmx[0] * inv) - min_b0 + 1, div1 = (int)floorf(bmx[1] * inv) - min_b1 + 1;
     const int mul1 = div0, mul2 = div0 * div1;
-    int NS = 64;
-    while (NS < m) NS <<= 1;
     {
         int o = off;
         for (int i = c0; i < c1; ++i)
@@ -547,29 +624,54 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
                 const int i0 = (int)(floorf(q.x * inv) - (float)min_b0);
                 const int i1 = (int)(floorf(q.y * inv) - (float)min_b1);
                 const int i2 = (int)(floorf(q.z * inv) - (float)min_b2);
-                const int vidx = i0 + i1 * mul1 + i2 * mul2;
-                keys[o++] = ((u64)(unsigned)vidx << 32) | (unsigned)i;
+                vid[o] = i0 + i1 * mul1 + i2 * mul2;
+                pidx[o] = (uint16_t)i;
+                ++o;
             }
-        for (int i = m + tid; i < NS; i += NTH) keys[i] = ~0ull;
     }
     __syncthreads();
-    block_bitonic_sort_u64(keys, NS, NS);
-    const int p0 = tid * CH, p1 = min(p0 + CH, m);
+    // runs of consecutive equal voxel ids (threads own consecutive chunks of the compacted positions)
+    const int MCH = (m + NTH - 1) / NTH;
+    const int p0 = min(tid * MCH, m), p1 = min(p0 + MCH, m);
     int heads = 0;
-    for (int p = p0; p < p1; ++p) heads += (p == 0 || (unsigned)(keys[p] >> 32) != (unsigned)(keys[p - 1] >> 32));
+    for (int p = p0; p < p1; ++p) heads += (p == 0 || vid[p] != vid[p - 1]);
+    int R = 0;
+    int ro = block_exclusive_scan(heads, ws, &R);
+    int NS = 64;
+    while (NS < R) NS <<= 1;
+    for (int p = p0; p < p1; ++p)
+        if (p == 0 || vid[p] != vid[p - 1]) {
+            keys[ro] = ((u64)(unsigned)vid[p] << 32) | (unsigned)ro;
+            run_start[ro] = (uint16_t)p;
+            ++ro;
+        }
+    if (tid == 0) run_start[R] = (uint16_t)m;
+    for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort_u64(keys, NS, NS);
+    // voxels = groups of equal voxel id among the sorted runs; the group's first run's thread accumulates the centroid
+    const int RCH = (R + NTH - 1) / NTH;
+    const int s0 = min(tid * RCH, R), s1 = min(s0 + RCH, R);
+    int vheads = 0;
+    for (int q = s0; q < s1; ++q) vheads += (q == 0 || (unsigned)(keys[q] >> 32) != (unsigned)(keys[q - 1] >> 32));
     int nvox = 0;
-    int o = block_exclusive_scan(heads, ws, &nvox);
-    for (int p = p0; p < p1; ++p) {
-        const unsigned v = (unsigned)(keys[p] >> 32);
-        if (p == 0 || v != (unsigned)(keys[p - 1] >> 32)) {
+    int o = block_exclusive_scan(vheads, ws, &nvox);
+    for (int q = s0; q < s1; ++q) {
+        const unsigned v = (unsigned)(keys[q] >> 32);
+        if (q == 0 || v != (unsigned)(keys[q - 1] >> 32)) {
             float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-            int q = p;
-            for (; q < m && (unsigned)(keys[q] >> 32) == v; ++q) {
-                const float4 a = pts[(int)(unsigned)keys[q]];
-                sx += a.x; sy += a.y; sz += a.z; si += a.w;
+            int cnt = 0;
+            for (int g = q; g < R && (unsigned)(keys[g] >> 32) == v; ++g) {  // runs in ascending run number = input order
+                const int run = (int)(unsigned)keys[g];
+                const int e0 = run_start[run], e1 = run_start[run + 1];
+                for (int p = e0; p < e1; ++p) {
+                    const float4 a = pts[pidx[p]];
+                    sx += a.x; sy += a.y; sz += a.z; si += a.w;
+                }
+                cnt += e1 - e0;
             }
-            const float cnt = (float)(q - p);
-            gout[o++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+            const float fc = (float)cnt;
+            gout[o++] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
         }
     }
     if (tid == 0) my_counts[3] = nvox;
@@ -638,15 +740,15 @@ __global__ void k_reset_scan_state(LaneState* lane, int n_lanes)
 
 }  // namespace
 
-size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + six sector key arrays + sector starts + mbarrier
+size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + curvature + six sector key arrays + sector starts + mbarrier
 {
     const int RCAP = 6 * SCAP + 16;
-    return (size_t)RCAP * 16 + (size_t)6 * SCAP * 8 + 8 * 4 + 16;
+    return (size_t)RCAP * 16 + (size_t)RCAP * 4 + (size_t)6 * SCAP * 4 + 8 * 4 + 16;
 }
-size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: voxel sort keys + scan / reduction scratch
+size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxel ids, point indices, run starts, scratch
 {
     const int RCAP = 6 * SCAP + 16, KCAP = RCAP <= 4096 ? 4096 : 8192;
-    return (size_t)KCAP * 8 + 40 * 4 + 112 * 4;
+    return (size_t)KCAP * 8 + (size_t)RCAP * 4 + (size_t)RCAP * 2 + (size_t)(RCAP + 2) * 2 + 40 * 4 + 112 * 4;
 }
 
 int ll_launch_features(ll_ctx* c, int n_lanes)
@@ -675,14 +777,14 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     if (c->SCAP == 512) {
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
-        { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, 512, smem_sort, s>>>(P); }
+        { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, SORT_THREADS, smem_sort, s>>>(P); }
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick));
         { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, smem_pick, s>>>(P, n_lanes); }
         { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512><<<rings, 512, smem_lf, s>>>(P); }
     } else {
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
-        { LLProf pr(c, "k_ring_sort"); k_ring_sort<1024><<<rings, 512, smem_sort, s>>>(P); }
+        { LLProf pr(c, "k_ring_sort"); k_ring_sort<1024><<<rings, SORT_THREADS, smem_sort, s>>>(P); }
         LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick));
         { LLProf pr(c, "k_ring_pick"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, smem_pick, s>>>(P, n_lanes); }
         { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<1024><<<rings, 512, smem_lf, s>>>(P); }
