@@ -83,8 +83,7 @@ def algorithmic_bytes(counts):
     Nr, P, nlf, nls, ns, nf = counts["n_raw"], counts["n_full"], counts["n_less_flat"], counts["n_less_sharp"], counts["n_sharp"], counts["n_flat"]
     feats = 16 * (ns + nls + nf) + 4 * (ns + nls + nf)
     return {
-        "k_classify": 16 * Nr + 5 * Nr,                      # read raw, write ring id (1 B) + azimuth (4 B)
-        "k_halfpass_hist": 5 * Nr + 1 * Nr + 4 * 64 * (Nr / 256.0),
+        "k_classify": 16 * Nr + 6 * Nr + 4 * 64 * (Nr / 256.0),   # read raw, write ring id (1 B) + azimuth (4 B) + rank (1 B) + tile histogram
         "k_scatter": 16 * Nr + 6 * Nr + 16 * P,              # read raw + ring/ori/rank, write ring-sorted cloud
         "k_ring_sort": 16 * P + 4 * P + 1 * P + 2 * P,         # read ring slabs (TMA), write curvature, label, sorted order
         "k_ring_pick": 2 * P + feats,                          # read sorted order (+ a few points), write picks

@@ -1,8 +1,8 @@
 // Feature extraction on the device — replaces scanRegistration.cpp:100-377 (`laserCloudHandler` body).
 //
-//   k_classify       SR:109-110 (NaN / range filter), SR:139-169 (ring id), SR:177 (-atan2)     coalesced, 1 thread / point
-//   k_halfpass_hist  SR:178-193 (which point flips halfPassed) + per-tile ring histogram / ranks
-//   k_ring_scan      SR:215-221 (ring offsets = stable counting sort by ring)
+//   k_classify       SR:109-110 (NaN / range filter), SR:139-169 (ring id), SR:177 (-atan2), per-tile ring histogram
+//                    and stable ranks; coalesced, 1 thread / point
+//   k_ring_scan      SR:215-221 (ring offsets = stable counting sort by ring), SR:178-193 (which point flips halfPassed)
 //   k_scatter        SR:194-209 (relTime, intensity) + scatter into the ring-major cloud
 //   k_ring_sort      SR:225-257: one CTA per (ring, lane): TMA bulk load of the ring into shared memory,
 //                    11-tap curvature, six sector sorts in registers (one warp each) -> u16 sorted order per point
@@ -61,6 +61,9 @@ __device__ __forceinline__ float end_ori_of(float last_ori, float startOri)
 
 __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
 {
+    __shared__ int cnt[LL_TILE / 32][LL_MAX_RINGS];
+    for (int k = threadIdx.x; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0])[k] = 0;
+    __syncthreads();
     const int b = blockIdx.y;
     LaneState& L = P.lane[b];
     const int n = L.n_raw, sw = L.stride_words;
@@ -97,40 +100,14 @@ __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
         P.ring8[(size_t)b * P.Nmax + i] = (int8_t)ring;
         P.ori[(size_t)b * P.Nmax + i] = ori;
     }
+    const int w = warp_id(), lane = lane_id();
     const int lo = __reduce_min_sync(LL_FULL_MASK, valid ? i : INT_MAX);
     const int hi = __reduce_max_sync(LL_FULL_MASK, valid ? i : -1);
-    if (lane_id() == 0) {
+    if (lane == 0) {
         if (lo != INT_MAX) atomicMin(&L.first_valid, lo);
         if (hi >= 0) atomicMax(&L.last_valid, hi);
     }
-}
-
-__global__ void __launch_bounds__(LL_TILE) k_halfpass_hist(FeatParams P)
-{
-    __shared__ int cnt[LL_TILE / 32][LL_MAX_RINGS];
-    const int b = blockIdx.y;
-    LaneState& L = P.lane[b];
-    const int i = blockIdx.x * LL_TILE + threadIdx.x;
-    const int w = warp_id(), lane = lane_id();
-    for (int k = threadIdx.x; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0])[k] = 0;
-    __syncthreads();
-    int ring = -1;
-    if (i < L.n_raw) ring = P.ring8[(size_t)b * P.Nmax + i];
-    bool flag = false;
-    if (ring >= 0 && L.first_valid != INT_MAX) {
-        const float startOri = P.ori[(size_t)b * P.Nmax + L.first_valid];
-        float ori = P.ori[(size_t)b * P.Nmax + i];
-        // SR:180-192 in the !halfPassed state
-        if ((double)ori < (double)startOri - LL_PI / 2)
-            ori = (float)((double)ori + 2 * LL_PI);
-        else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
-            ori = (float)((double)ori - 2 * LL_PI);
-        flag = (double)(ori - startOri) > LL_PI;
-    }
-    const int fi = __reduce_min_sync(LL_FULL_MASK, flag ? i : INT_MAX);
-    if (lane == 0 && fi != INT_MAX) atomicMin(&L.half_idx, fi);
-
-    // stable rank inside the tile: warp match on the ring id, then prefix over the tile's warps
+    // stable rank inside the tile (SR:209 push_back order): warp match on the ring id, then prefix over the tile's warps
     const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
     const int rank_in_warp = __popc(m & ((1u << lane) - 1u));
     if (ring >= 0 && rank_in_warp == 0) cnt[w][ring] = __popc(m);
@@ -145,12 +122,46 @@ __global__ void __launch_bounds__(LL_TILE) k_halfpass_hist(FeatParams P)
 }
 
 // one CTA per lane: tile_hist[t][r] -> exclusive offset of tile t inside ring r; ring_begin[]; n_full
+// ... and the point that flips halfPassed (SR:178-193): the first valid point whose adjusted azimuth is more than pi past
+// startOri.  The scan walks the azimuths in chunks of 8192 and stops at the first chunk that holds such a point.
 __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
 {
     __shared__ int tot[LL_MAX_RINGS];
+    __shared__ int half_s;
     const int b = blockIdx.x;
     LaneState& L = P.lane[b];
     const int w = warp_id(), lane = lane_id();
+    if (threadIdx.x == 0) half_s = INT_MAX;
+    __syncthreads();
+    if (L.first_valid != INT_MAX) {
+        const float startOri = P.ori[(size_t)b * P.Nmax + L.first_valid];
+        const int n_raw = L.n_raw;
+        for (int i0 = 0; i0 < n_raw; i0 += 8192) {  // eight independent loads per thread and barrier
+            bool any = false;
+            int first = INT_MAX;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 1024 + threadIdx.x;
+                bool flag = false;
+                if (i < n_raw && P.ring8[(size_t)b * P.Nmax + i] >= 0) {
+                    float ori = P.ori[(size_t)b * P.Nmax + i];
+                    // SR:180-192 in the !halfPassed state
+                    if ((double)ori < (double)startOri - LL_PI / 2)
+                        ori = (float)((double)ori + 2 * LL_PI);
+                    else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
+                        ori = (float)((double)ori - 2 * LL_PI);
+                    flag = (double)(ori - startOri) > LL_PI;
+                }
+                if (flag && i < first) first = i;
+                any |= flag;
+            }
+            const int fi = __reduce_min_sync(LL_FULL_MASK, first);
+            if (lane == 0 && fi != INT_MAX) atomicMin(&half_s, fi);
+            if (__syncthreads_or(any)) break;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) L.half_idx = half_s;
     const int ntiles = (L.n_raw + LL_TILE - 1) / LL_TILE;
     const int per = (ntiles + 31) / 32;
     for (int r = w; r < P.R; r += 32) {
@@ -766,7 +777,6 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     const dim3 tiles(c->NT, n_lanes);
     { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<(n_lanes + 127) / 128, 128, 0, s>>>(c->d_lane, n_lanes); }
     { LLProf pr(c, "k_classify"); k_classify<<<tiles, LL_TILE, 0, s>>>(P); }
-    { LLProf pr(c, "k_halfpass_hist"); k_halfpass_hist<<<tiles, LL_TILE, 0, s>>>(P); }
     { LLProf pr(c, "k_ring_scan"); k_ring_scan<<<n_lanes, 1024, 0, s>>>(P); }
     { LLProf pr(c, "k_scatter"); k_scatter<<<tiles, LL_TILE, 0, s>>>(P); }
     const size_t smem_sort = ll_feature_smem_bytes(c->SCAP);
@@ -790,7 +800,7 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<1024><<<rings, 512, smem_lf, s>>>(P); }
     }
     { LLProf pr(c, "k_compact"); k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P); }
-    c->launches += 9;
+    c->launches += 8;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }
