@@ -168,7 +168,7 @@ void ll_destroy(ll_ctx* c)
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted, c->g_corner.partial,
                     c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
-                    c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n};
+                    c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n, c->d_vote_src, c->d_vote_tgt};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_lane) cudaFreeHost(c->h_lane);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -267,6 +267,8 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     }
     CK(dalloc(c->d_corner_assoc, B * R * LL_SHARP_PER_RING * 2));
     CK(dalloc(c->d_plane_assoc, B * R * LL_FLAT_PER_RING * 4));
+    CK(dalloc(c->d_vote_src, B * R * LL_FLAT_PER_RING));
+    CK(dalloc(c->d_vote_tgt, B * R * LL_FLAT_PER_RING));
     c->assoc_queue_cap = (int)(B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING));
     CK(dalloc(c->d_assoc_queue, (size_t)c->assoc_queue_cap));
     CK(dalloc(c->d_assoc_queue_n, 8));

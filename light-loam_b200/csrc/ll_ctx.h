@@ -123,6 +123,8 @@ struct ll_ctx {
     int az_bins_corner = 64, az_bins_surf = 256;
     int* d_corner_assoc = nullptr; // [B][R*12][2]
     int* d_plane_assoc = nullptr;  // [B][R*24][4]
+    float4* d_vote_src = nullptr;  // [B][R*24] compacted plane matches for the graph vote (current point, w = feature index)
+    float4* d_vote_tgt = nullptr;  // [B][R*24] ... and their closest points
     int4* d_assoc_queue = nullptr; // [B * R * 36] queries handed to the warp pass of the association
     int* d_assoc_queue_n = nullptr;// [8] queue lengths [0..2] and pop cursors [4..6] per outer iteration
     int assoc_queue_cap = 0;

@@ -3,8 +3,8 @@
 //   k_grid_count / k_grid_scan / k_grid_scatter   kdtree*Last->setInputCloud (LO:895-896) -> hashed grid
 //   k_odom_assoc     LO:491-556 + LO:653-723: TransformToStart, 1-NN (d2 < 25), ring-window 2nd / 3rd point;
 //                    one warp per feature point, literal scan-loop semantics evaluated 32 candidates at a time
-//   k_odom_prep      order-preserving compaction of the matches, graph_based_correspondence_vote_simple
-//                    (LO:165-342) for planes when now_frame > 5, residual-block records (LF ctor maths)
+//   k_odom_prep      order-preserving compaction of the matches, residual-block records (LF ctor maths)
+//   k_odom_vote      graph_based_correspondence_vote_simple (LO:165-342) for planes when now_frame > 5, one CTA per region
 //   k_lm_solve       ceres::Solve as configured at LO:819-825 / LM:2079-2087: Levenberg-Marquardt on the
 //                    6-dim tangent space with Huber(0.1); residual + analytic Jacobian + JtJ / Jtr / cost in one
 //                    pass (fixed-order warp-shuffle + smem reduction of 28 doubles), LM controller on-device
@@ -242,6 +242,8 @@ struct OdomParams {
     int outer;             // opti_counter
     int dev_skip;          // development only: bit mask of association stages to skip (timing experiments)
     int plane_shells;      // grid shells tried for the 2nd / 3rd plane neighbour before the literal walk
+    float4* vote_src;      // [B][R*24] compacted plane matches: current point (w = feature index) / closest point
+    float4* vote_tgt;
     int4* queue;           // queries handed from the per-thread pass to the warp pass (k_odom_assoc_heavy)
     int* queue_n;          // [3] entries queued per outer iteration
     int queue_cap;
@@ -680,21 +682,15 @@ __global__ void __launch_bounds__(256, 4) k_odom_assoc_heavy(OdomParams P)
 // compaction + graph vote + residual-block records; one CTA per lane
 // ------------------------------------------------------------------------------------------------------
 #define PREP_THREADS 1024
+// Compaction of the matches in feature order and the residual-block records.  Corners: LidarEdgeFactor records
+// (LO:556-618).  Planes: every match gets its LidarPlaneFactor_modify record (LF:210-211 normal) at slot
+// ncorner + k with weight 1 (LO:781-787); when the graph vote is on (now_frame > 5) k_odom_vote then overwrites
+// the weights and disables the rejected matches (record type -1), so the block order stays the reference's
+// selected_idx order with gaps.
 __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // src / tgt xyz of the compacted plane matches, their feature index and votes
-    const int maxp = P.R * LL_FLAT_PER_RING;
-    float* srcx = reinterpret_cast<float*>(smem_raw);
-    float* srcy = srcx + maxp;
-    float* srcz = srcy + maxp;
-    float* tgtx = srcz + maxp;
-    float* tgty = tgtx + maxp;
-    float* tgtz = tgty + maxp;
-    int* fidx = reinterpret_cast<int*>(tgtz + maxp);
-    float* wsel = reinterpret_cast<float*>(fidx + maxp);
     __shared__ int ws[40];
-
+    const int maxp = P.R * LL_FLAT_PER_RING;
     const int b = blockIdx.x, tid = threadIdx.x;
     LaneState& L = P.lane[b];
     if (!L.inited) { if (tid == 0) L.n_blocks = 0; return; }
@@ -706,6 +702,8 @@ __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
     const int* ca = P.corner_assoc + (size_t)b * P.R * LL_SHARP_PER_RING * 2;
     int* pa = P.plane_assoc + (size_t)b * P.R * LL_FLAT_PER_RING * 4;
     double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    float4* vsrc = P.vote_src + (size_t)b * maxp;
+    float4* vtgt = P.vote_tgt + (size_t)b * maxp;
     const int cap = P.nblk_cap;
 
     // ---- corners: compaction in feature order, LidarEdgeFactor records (LO:556-618) -------------------
@@ -731,77 +729,113 @@ __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
     int nplane = 0;
     int pos = block_exclusive_scan(mine, ws, &nplane);
     for (int i = i0; i < i1; ++i) {
-        if (pa[i * 4] >= 0) {
-            const float4 s = flat[i], t = lasts[pa[i * 4]];  // Corre_Match src / tgt, LO:753-754
-            srcx[pos] = s.x; srcy[pos] = s.y; srcz[pos] = s.z;
-            tgtx[pos] = t.x; tgty[pos] = t.y; tgtz[pos] = t.z;
-            fidx[pos] = i;
-            ++pos;
-        }
-    }
-    __syncthreads();
-    // ---- graph_based_correspondence_vote_simple, plane case: 10 contiguous regions (LO:184-252) ----------
-    const bool vote = L.now_frame > P.graph_from_frame;  // LO:781 / LO:794
-    const int region_len = nplane / 10;
-    for (int k = tid; k < nplane; k += PREP_THREADS) {
-        float w = 1.0f;  // LO:783: weight 1 while now_frame <= 5
-        if (vote) {
-            int reg = region_len > 0 ? k / region_len : 9;
-            if (reg > 9) reg = 9;
-            const int r0 = region_len * reg, r1 = reg == 9 ? nplane : region_len * (reg + 1);
-            const float ax = srcx[k], ay = srcy[k], az = srcz[k], bx = tgtx[k], by = tgty[k], bz = tgtz[k];
-            int votes = 0;
-            for (int j = r0; j < r1; ++j) {
-                if (j == k) continue;
-                // Distance() LO:153-162 is symmetric bit for bit, so each unordered pair is evaluated from both ends
-                const float s1 = sqrtf(sqdist3(ax, ay, az, srcx[j], srcy[j], srcz[j]));
-                const float s2 = sqrtf(sqdist3(bx, by, bz, tgtx[j], tgty[j], tgtz[j]));
-                const float gap = fabsf(s1 - s2);
-                // score = expf(-(gap*gap)/(1*1)) < 0.96f  <=>  gap*gap >= t_min (host-calibrated on glibc expf)
-                votes += (gap * gap >= P.vote_t_min);
-            }
-            const float num_selected = 0.90f * (float)(r1 - r0);  // LO:299-300
-            if ((float)votes > num_selected) w = 0.f;             // LO:312-316: this and all worse are dropped
-            else if ((float)votes <= 50.f) w = 5.0f;              // LO:317-318
-            else w = 1.0f;
-        }
-        wsel[k] = w;
-        pa[fidx[k] * 4 + 3] = (int)(w * 1000.f);
-    }
-    __syncthreads();
-    // ---- LidarPlaneFactor_modify records for the selected matches (LO:797-808 / LO:781-787) ---------------
-    const int k0 = tid * per, k1 = min(k0 + per, nplane);
-    int sel = 0;
-    for (int k = k0; k < k1; ++k) sel += wsel[k] > 0.f;
-    int nsel = 0;
-    int o = ncorner + block_exclusive_scan(sel, ws, &nsel);
-    for (int k = k0; k < k1; ++k) {
-        if (wsel[k] > 0.f) {
-            const int i = fidx[k];
-            const float4 cp = flat[i], pj = lasts[pa[i * 4]], pl = lasts[pa[i * 4 + 1]], pm = lasts[pa[i * 4 + 2]];
+        const int4 m = *reinterpret_cast<const int4*>(pa + i * 4);
+        if (m.x >= 0) {
+            const float4 cp = flat[i], pj = lasts[m.x], pl = lasts[m.y], pm = lasts[m.z];
+            vsrc[pos] = make_float4(cp.x, cp.y, cp.z, __int_as_float(i));  // Corre_Match src / tgt, LO:753-754 (+ the feature index)
+            vtgt[pos] = pj;
             // LF:210-211  ljm_norm = (j - l).cross(j - m); normalize()
             const double ax = (double)pj.x - (double)pl.x, ay = (double)pj.y - (double)pl.y, az = (double)pj.z - (double)pl.z;
             const double bx = (double)pj.x - (double)pm.x, by = (double)pj.y - (double)pm.y, bz = (double)pj.z - (double)pm.z;
             double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
             const double z = nx * nx + ny * ny + nz * nz;
             if (z > 0.0) { const double nn = sqrt(z); nx = nx / nn; ny = ny / nn; nz = nz / nn; }
+            const int o = ncorner + pos;
             blk[0 * cap + o] = 1.0;
             blk[1 * cap + o] = cp.x; blk[2 * cap + o] = cp.y; blk[3 * cap + o] = cp.z;
             blk[4 * cap + o] = pj.x; blk[5 * cap + o] = pj.y; blk[6 * cap + o] = pj.z;
             blk[7 * cap + o] = nx; blk[8 * cap + o] = ny; blk[9 * cap + o] = nz;
-            blk[10 * cap + o] = (double)wsel[k];
-            ++o;
+            blk[10 * cap + o] = 1.0;             // LO:783: weight 1 while now_frame <= 5
+            pa[i * 4 + 3] = 1000;
+            ++pos;
         }
     }
     if (tid == 0) {
-        L.n_blocks = ncorner + nsel;
+        const bool vote = L.now_frame > P.graph_from_frame;  // LO:781 / LO:794
+        L.n_blocks = ncorner + nplane;
         L.n_corner_corr = ncorner;
         L.n_plane_corr = nplane;
-        L.n_plane_sel = nsel;
+        L.n_plane_sel = vote ? 0 : nplane;       // k_odom_vote adds the selected ones
         L.corner_corr[P.outer] = ncorner;
         L.plane_corr[P.outer] = nplane;
-        L.plane_sel[P.outer] = nsel;
+        L.plane_sel[P.outer] = vote ? 0 : nplane;
     }
+}
+
+// graph_based_correspondence_vote_simple, plane case (LO:165-342): 10 contiguous regions, one CTA per (region, lane).
+// Every unordered pair of the region is evaluated once (Distance() LO:153-162 is symmetric bit for bit).  The
+// reference's test  expf(-(gap*gap)) < 0.96f  is  gap*gap >= t_min  with t_min calibrated on the host's glibc expf;
+// gap = |sqrtf(d_src) - sqrtf(d_tgt)| is first estimated with the fast reciprocal square root, and only pairs whose
+// estimate lies within 1e-3 of the threshold take the IEEE square roots that decide them exactly.
+#define VOTE_THREADS 256
+__global__ void __launch_bounds__(VOTE_THREADS) k_odom_vote(OdomParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.y, reg = blockIdx.x, tid = threadIdx.x;
+    LaneState& L = P.lane[b];
+    if (!L.inited || !(L.now_frame > P.graph_from_frame)) return;  // LO:781 / LO:794
+    const int nplane = L.n_plane_corr, ncorner = L.n_corner_corr;
+    const int region_len = nplane / 10;                              // LO:202-215
+    const int r0 = region_len * reg, r1 = reg == 9 ? nplane : region_len * (reg + 1);
+    const int m = r1 - r0;
+    if (m <= 0) return;
+    const int maxp = P.R * LL_FLAT_PER_RING;
+    const int mcap = maxp / 10 + 16;
+    float4* src = reinterpret_cast<float4*>(smem_raw);
+    float4* tgt = src + mcap;
+    int* votes = reinterpret_cast<int*>(tgt + mcap);
+    __shared__ int nsel_s;
+    for (int k = tid; k < m; k += VOTE_THREADS) {
+        src[k] = P.vote_src[(size_t)b * maxp + r0 + k];
+        tgt[k] = P.vote_tgt[(size_t)b * maxp + r0 + k];
+        votes[k] = 0;
+    }
+    if (tid == 0) nsel_s = 0;
+    __syncthreads();
+    const float t_min = P.vote_t_min;
+    const float g_mid = sqrtf(t_min);
+    // rows k and m-1-k together hold m-1 pairs: every row pair is the same amount of work; four threads share one
+    for (int k = tid >> 2; k < (m + 1) / 2; k += VOTE_THREADS / 4) {
+        const int q = tid & 3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int row = half == 0 ? k : m - 1 - k;
+            if (half == 1 && row == k) break;
+            const float4 a = src[row], c = tgt[row];
+            int mine = 0;
+            for (int j = row + 1 + q; j < m; j += 4) {
+                const float4 sj = src[j], tj = tgt[j];
+                const float d1 = sqdist3(a.x, a.y, a.z, sj.x, sj.y, sj.z), d2 = sqdist3(c.x, c.y, c.z, tj.x, tj.y, tj.z);
+                const float ge = fabsf(d1 * rsqrtf(fmaxf(d1, 1e-30f)) - d2 * rsqrtf(fmaxf(d2, 1e-30f)));
+                bool v = ge > g_mid;
+                if (fabsf(ge - g_mid) < 1e-3f) {  // too close to call with the approximation: LO:236-242 to the letter
+                    const float gap = fabsf(sqrtf(d1) - sqrtf(d2));
+                    v = gap * gap >= t_min;
+                }
+                if (v) { ++mine; atomicAdd(&votes[j], 1); }
+            }
+            if (mine) atomicAdd(&votes[row], mine);
+        }
+    }
+    __syncthreads();
+    double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    int* pa = P.plane_assoc + (size_t)b * P.R * LL_FLAT_PER_RING * 4;
+    const float num_selected = 0.90f * (float)m;                    // LO:299-300
+    int sel = 0;
+    for (int k = tid; k < m; k += VOTE_THREADS) {
+        const float fv = (float)votes[k];
+        float w;
+        if (fv > num_selected) w = 0.f;                              // LO:312-316: this and all worse are dropped
+        else if (fv <= 50.f) w = 5.0f;                               // LO:317-318
+        else w = 1.0f;
+        const int o = ncorner + r0 + k;
+        if (w > 0.f) { blk[10 * P.nblk_cap + o] = (double)w; ++sel; }
+        else blk[o] = -1.0;                                          // not selected: no residual block (LO:797-808)
+        pa[__float_as_int(src[k].w) * 4 + 3] = (int)(w * 1000.f);
+    }
+    if (sel) atomicAdd(&nsel_s, sel);
+    __syncthreads();
+    if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
 }
 
 __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P)
@@ -868,14 +902,14 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     P.Nmax = c->Nmax; P.R = c->R; P.gc = c->g_corner; P.gs = c->g_surf; P.ac = c->a_corner; P.as_ = c->a_surf; P.az_bins_corner = c->az_bins_corner; P.az_bins_surf = c->az_bins_surf;
     P.corner_assoc = c->d_corner_assoc; P.plane_assoc = c->d_plane_assoc; P.blocks = c->d_blocks; P.nblk_cap = c->nblk_cap;
     P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.plane_shells = c->plane_shells; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
+    P.vote_src = c->d_vote_src; P.vote_tgt = c->d_vote_tgt;
     P.queue = c->d_assoc_queue; P.queue_n = c->d_assoc_queue_n; P.queue_cap = c->assoc_queue_cap;
     cudaStream_t s = c->stream;
     const int cblocks = (c->R * LL_SHARP_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS, pblocks = (c->R * LL_FLAT_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS;
     LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, s));
     const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
     const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;
-    const size_t prep_smem = (size_t)c->R * LL_FLAT_PER_RING * 8 * 4;
-    LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    const size_t vote_smem = (size_t)(c->R * LL_FLAT_PER_RING / 10 + 16) * (2 * sizeof(float4) + sizeof(int));
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
     // the spatial hash grids and the ring x azimuth indexes of the two *Last clouds are built together (4 launches)
     // right before the association, so the tables are still in L2 when the queries walk them
@@ -897,15 +931,16 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[4], n_lanes), 256, 0, s>>>(S); }
         { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[4], n_lanes), 256, 0, s>>>(S); }
         { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
-        c->launches += 4;
+        c->launches += 5;
     }
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
         { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3(cblocks + pblocks, n_lanes), ASSOC_THREADS, 0, s>>>(P, cblocks, dmax); }
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
-        { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, prep_smem, s>>>(P); }
+        { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
+        { LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P); }
         { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, LM_THREADS, 0, s>>>(P); }
-        c->launches += 4;
+        c->launches += 5;
     }
     { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
     c->launches += 1;
