@@ -62,7 +62,6 @@ __global__ void k_set_feature_counts(LaneState* lane, int ns, int nls, int nf, i
     L.err = 0;
 }
 
-int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <typename T>
 cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, n * sizeof(T)); }
@@ -166,8 +165,7 @@ void ll_destroy(ll_ctx* c)
     if (c->h_ids) cudaFreeHost(c->h_ids);
     void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
-                    c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->g_corner.start, c->g_corner.cursor, c->g_corner.sorted, c->g_corner.partial,
-                    c->g_surf.start, c->g_surf.cursor, c->g_surf.sorted, c->g_surf.partial, c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
+                    c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->d_ebound[0], c->d_ebound[1], c->d_bands[0], c->d_bands[1], c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
                     c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n, c->d_vote_src, c->d_vote_tgt};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_lane) cudaFreeHost(c->h_lane);
@@ -196,7 +194,6 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     c->RCAP = 6 * c->SCAP + 16;
     c->dev = cfg->device;
     c->vote_t_min = calibrate_vote_threshold();
-    if (const char* e = getenv("LL_PLANE_SHELLS")) c->plane_shells = atoi(e);
 #define CK(expr)                                                                     \
     do {                                                                             \
         cudaError_t e__ = (expr);                                                    \
@@ -238,33 +235,22 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
         CK(dalloc(c->d_lsharp[k], B * R * LL_LSHARP_PER_RING));
         CK(dalloc(c->d_lflat[k], B * N));
     }
-    // hashed grids over the previous frame's less-sharp / less-flat clouds; the 5 m acceptance radius (LO:29) is
-    // covered by ceil(5 / h) shells
-    c->g_corner.T = pow2ceil(2 * (int)R * LL_LSHARP_PER_RING) < 2048 ? 2048 : pow2ceil(2 * (int)R * LL_LSHARP_PER_RING);
-    c->g_corner.cap = (int)R * LL_LSHARP_PER_RING;
-    c->g_surf.T = pow2ceil((int)N / 2) < 2048 ? 2048 : pow2ceil((int)N / 2);
-    c->g_surf.cap = (int)N;
-    for (KnnGrid* g : {&c->g_corner, &c->g_surf}) {
-        g->h = 1.3f;   // tuned on B200: a larger cell hands fewer queries to the warp pass, a smaller one costs fewer candidates
-        if (const char* e = getenv("LL_GRID_H")) { const float v = (float)atof(e); if (v > 0.05f && v < 10.f) g->h = v; }
-        g->inv_h = 1.0f / g->h;
-        CK(dalloc(g->start, B * (size_t)(g->T + 1)));
-        CK(dalloc(g->cursor, B * (size_t)g->T));
-        CK(dalloc(g->partial, B * (size_t)(g->T / 2048 + 1)));
-        CK(dalloc(g->sorted, B * (size_t)g->cap));
-    }
-    // ring x azimuth-bin index (2nd / 3rd neighbour search of LO:504-553 / LO:668-721 without walking whole rings)
+    // polar index over the previous frame's less-sharp / less-flat clouds: bucket = azimuth bin * R + ring.  It serves
+    // both the exact 1-NN (kdtree*Last, LO:494 / LO:656) and the ring-window search of LO:504-553 / LO:668-721.
     c->az_bins_corner = 64; c->az_bins_surf = 256;
+    if (const char* e = getenv("LL_AZ_CORNER")) { const int v = atoi(e); if (v >= 8 && v <= 4096 && (v & (v - 1)) == 0) c->az_bins_corner = v; }
+    if (const char* e = getenv("LL_AZ_SURF")) { const int v = atoi(e); if (v >= 8 && v <= 4096 && (v & (v - 1)) == 0) c->az_bins_surf = v; }
     while ((int)R * c->az_bins_corner < 2048) c->az_bins_corner <<= 1;
     while ((int)R * c->az_bins_surf < 2048) c->az_bins_surf <<= 1;
-    c->a_corner.T = (int)R * c->az_bins_corner; c->a_corner.cap = c->g_corner.cap;
-    c->a_surf.T = (int)R * c->az_bins_surf; c->a_surf.cap = c->g_surf.cap;
+    c->a_corner.T = (int)R * c->az_bins_corner; c->a_corner.cap = (int)R * LL_LSHARP_PER_RING;
+    c->a_surf.T = (int)R * c->az_bins_surf; c->a_surf.cap = (int)N;
     for (KnnGrid* g : {&c->a_corner, &c->a_surf}) {
         CK(dalloc(g->start, B * (size_t)(g->T + 1)));
         CK(dalloc(g->cursor, B * (size_t)g->T));
         CK(dalloc(g->partial, B * (size_t)(g->T / 2048 + 1)));
         CK(dalloc(g->sorted, B * (size_t)g->cap));
     }
+    for (int k = 0; k < 2; ++k) { CK(dalloc(c->d_ebound[k], B * R * 2)); CK(dalloc(c->d_bands[k], B * (2 * LL_MAX_RINGS + 4))); }
     CK(dalloc(c->d_corner_assoc, B * R * LL_SHARP_PER_RING * 2));
     CK(dalloc(c->d_plane_assoc, B * R * LL_FLAT_PER_RING * 4));
     CK(dalloc(c->d_vote_src, B * R * LL_FLAT_PER_RING));

@@ -87,7 +87,6 @@ struct ll_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     int launches = 0;
-    int plane_shells = 2;     // see k_odom_assoc (env LL_PLANE_SHELLS)
     float vote_t_min = 0.f;   // smallest fp32 t with expf(-t) < 0.96f on this host's libm (LO:239-242)
 
     LaneState* d_lane = nullptr;
@@ -118,8 +117,9 @@ struct ll_ctx {
     float4* d_lsharp[2] = {nullptr, nullptr};  // [B][R*120]
     float4* d_lflat[2] = {nullptr, nullptr};   // [B][Nmax]
 
-    KnnGrid g_corner, g_surf;      // over last less-sharp / less-flat
-    KnnGrid a_corner, a_surf;      // ring x azimuth-bin index over the same clouds (T = rings * az_bins)
+    KnnGrid a_corner, a_surf;      // polar (azimuth bin x ring) index over last less-sharp / less-flat (T = rings * az_bins)
+    unsigned* d_ebound[2] = {nullptr, nullptr};  // [B][R][2] per-ring elevation band of the indexed cloud (order-preserving encodings)
+    float* d_bands[2] = {nullptr, nullptr};      // [B][2 * LL_MAX_RINGS + 4] the same decoded (k_index_partial)
     int az_bins_corner = 64, az_bins_surf = 256;
     int* d_corner_assoc = nullptr; // [B][R*12][2]
     int* d_plane_assoc = nullptr;  // [B][R*24][4]

@@ -29,15 +29,10 @@ struct GridSrc {           // where a lane's points and count come from
     const float4* pts[2];  // ping-pong buffers (or both the same)
     size_t lane_stride;    // points per lane
     int which;             // 0: (n_less_sharp, slot cur) 1: (n_less_flat, slot cur) 2: (n_map_corner, slot 0) 3: (n_map_surf, slot 0)
-    int az_bins;           // 0: spatial hash grid; > 0: ring x azimuth-bin index with this many bins per ring
-    int rings;
 };
 __device__ __forceinline__ int src_bucket(const GridSrc& S, const float4 p, int T, float inv_h)
 {
-    if (S.az_bins == 0) return cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
-    int r = (int)p.w;
-    r = r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
-    return azimuth_bin(p.x, p.y, S.az_bins) * S.rings + r;  // bin-major: the rings of one bin are consecutive buckets
+    return cell_bucket((int)floorf(p.x * inv_h), (int)floorf(p.y * inv_h), (int)floorf(p.z * inv_h), T - 1);
 }
 __device__ __forceinline__ int grid_src_count(const GridSrc& S, const LaneState& L)
 {
@@ -64,10 +59,6 @@ __global__ void k_grid_count(GridSrc S, LaneState* lane, int* cursor, int T, flo
         const float4 p = pts[i];
         const int bk = src_bucket(S, p, T, inv_h);
         atomicAdd(&cursor[(size_t)b * T + bk], 1);
-        if (S.which < 2 && S.az_bins == 0) {  // is the cloud ring-monotone? (LO:504-553 assumes it; the fast association path needs it)
-            const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
-            if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (S.which == 0) L.mono_corner = 0; else L.mono_surf = 0; }
-        }
     }
 }
 // two-level exclusive scan of the bucket counts: chunk sums, then per-chunk scan with its base
@@ -123,26 +114,39 @@ __global__ void k_grid_scatter(GridSrc S, const LaneState* lane, int* cursor, fl
     }
 }
 
-// ---- fused build of the four odometry indexes (corner / surf x spatial hash / ring-azimuth) -------------------
+// ---- fused build of the two odometry indexes (corner / surf: ring x azimuth-bin tables) ---------------------------
+// The index is polar, in the frame the *Last cloud was measured in: bucket = azimuth bin * R + ring (bin-major, so
+// the rings of one bin are consecutive buckets and any ring range of a bin is ONE contiguous span of the sorted
+// array).  Next to the buckets the build records, per ring, the smallest and largest elevation angle of the ring's
+// points; a query at elevation e is at least |q| sin(gap) away from every point of a ring whose elevation band lies
+// `gap` away from e, and at least rho sin(D) away from every point whose azimuth differs by D — the two bounds that
+// make the search exact (k_odom_assoc).
 struct IndexSet {
     const float4* pts[2][2];   // [cloud][ping-pong slot]
     size_t lane_stride[2];
-    int* cursor[4];            // table = cloud + 2 * kind   (kind 0 spatial, 1 ring-azimuth)
-    int* start[4];
-    int* partial[4];
-    float4* sorted[4];
-    int T[4], cap[4];
-    int chunk_begin[5];        // prefix of T / GRID_CHUNK over the tables
-    float inv_h;
+    int* cursor[2];            // table = cloud (0 corner, 1 surf)
+    int* start[2];
+    int* partial[2];
+    float4* sorted[2];
+    unsigned* ebound[2];       // [B][R][2] order-preserving encodings: max of ~enc(elevation), max of enc(elevation); 0 = empty
+    float* bands[2];           // [B][BAND_STRIDE] decoded: elo[R], ehi[R] (empty rings filled in), then the "bands are ordered" flag
+    int T[2], cap[2];
+    int chunk_begin[3];        // prefix of T / GRID_CHUNK over the tables
     int az_bins[2];
     int rings;
 };
-__device__ __forceinline__ int index_bucket(const IndexSet& S, int cloud, int kind, const float4 p)
+#define BAND_STRIDE (2 * LL_MAX_RINGS + 4)
+__device__ __forceinline__ unsigned enc_f32(float f) { const unsigned b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float dec_f32(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+__device__ __forceinline__ float elevation_of(float x, float y, float z) { return atan2f(z, sqrtf(x * x + y * y)); }
+__device__ __forceinline__ int index_ring(const IndexSet& S, const float4 p)
 {
-    if (kind == 0) return cell_bucket((int)floorf(p.x * S.inv_h), (int)floorf(p.y * S.inv_h), (int)floorf(p.z * S.inv_h), S.T[cloud] - 1);
     int r = (int)p.w;
-    r = r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
-    return azimuth_bin(p.x, p.y, S.az_bins[cloud]) * S.rings + r;  // bin-major: the rings of one bin are consecutive buckets
+    return r < 0 ? 0 : (r >= S.rings ? S.rings - 1 : r);
+}
+__device__ __forceinline__ int index_bucket(const IndexSet& S, int cloud, const float4 p)
+{
+    return azimuth_bin(p.x, p.y, S.az_bins[cloud]) * S.rings + index_ring(S, p);
 }
 __global__ void k_index_count(IndexSet S, LaneState* lane)
 {
@@ -150,21 +154,38 @@ __global__ void k_index_count(IndexSet S, LaneState* lane)
     LaneState& L = lane[b];
     const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = pts[i];
-        atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, 0, p)], 1);
-        atomicAdd(&S.cursor[cloud + 2][(size_t)b * S.T[cloud + 2] + index_bucket(S, cloud, 1, p)], 1);
-        // is the cloud ring-monotone? (LO:504-553 assumes it; the ring-azimuth search needs it)
-        const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
-        if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (cloud == 0) L.mono_corner = 0; else L.mono_surf = 0; }
+    unsigned* eb = S.ebound[cloud] + (size_t)b * S.rings * 2;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + (threadIdx.x & 31);
+        int ring = -1;
+        unsigned elo = 0u, ehi = 0u;
+        if (i < n) {
+            const float4 p = pts[i];
+            atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, p)], 1);
+            // is the cloud ring-monotone? (LO:504-553 assumes it; the ring-window search needs it)
+            const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
+            if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (cloud == 0) L.mono_corner = 0; else L.mono_surf = 0; }
+            ring = index_ring(S, p);
+            const unsigned e = enc_f32(elevation_of(p.x, p.y, p.z));
+            elo = ~e; ehi = e;
+        }
+        // a warp's 32 consecutive points nearly always share the ring: one pair of atomics per warp
+        const unsigned have = __ballot_sync(LL_FULL_MASK, ring >= 0);
+        if (!have) continue;
+        const int ring0 = __shfl_sync(LL_FULL_MASK, ring, __ffs(have) - 1);
+        if (__all_sync(LL_FULL_MASK, ring < 0 || ring == ring0)) {
+            const unsigned mlo = __reduce_max_sync(LL_FULL_MASK, elo), mhi = __reduce_max_sync(LL_FULL_MASK, ehi);
+            if ((threadIdx.x & 31) == 0) { atomicMax(&eb[ring0 * 2], mlo); atomicMax(&eb[ring0 * 2 + 1], mhi); }
+        } else if (ring >= 0) {
+            atomicMax(&eb[ring * 2], elo); atomicMax(&eb[ring * 2 + 1], ehi);
+        }
     }
 }
 __global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
 {
     __shared__ int ws[40];
     const int b = blockIdx.y;
-    int t = 0;
-    while (t < 3 && (int)blockIdx.x >= S.chunk_begin[t + 1]) ++t;
+    const int t = (int)blockIdx.x >= S.chunk_begin[1] ? 1 : 0;
     const int chunk = blockIdx.x - S.chunk_begin[t], nchunk = S.T[t] / GRID_CHUNK;
     const int* cur = S.cursor[t] + (size_t)b * S.T[t] + (size_t)chunk * GRID_CHUNK;
     int s = 0;
@@ -173,14 +194,32 @@ __global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
     int tot = 0;
     block_exclusive_scan(s, ws, &tot);
     if (threadIdx.x == 0) S.partial[t][(size_t)b * (nchunk + 1) + chunk] = tot;
+    // the first chunk of each table also decodes the ring elevation bands (complete since k_index_count).  An empty
+    // ring gets an empty band at its predecessor's upper edge, so ordered bands stay ordered through the gaps.
+    if (chunk == 0 && threadIdx.x == 32) {
+        const unsigned* eb = S.ebound[t] + (size_t)b * S.rings * 2;
+        float* bd = S.bands[t] + (size_t)b * BAND_STRIDE;
+        float plo = -INFINITY, phi = -INFINITY;
+        int ordered = 1;
+        for (int r = 0; r < S.rings; ++r) {
+            const unsigned lo = eb[r * 2], hi = eb[r * 2 + 1];
+            float elo = phi, ehi = phi;
+            if (hi != 0u) {
+                elo = dec_f32(~lo); ehi = dec_f32(hi);
+                if (elo < plo || ehi < phi) ordered = 0;
+                plo = elo; phi = ehi;
+            }
+            bd[r] = elo; bd[LL_MAX_RINGS + r] = ehi;
+        }
+        reinterpret_cast<int*>(bd)[2 * LL_MAX_RINGS] = ordered;
+    }
 }
 __global__ void __launch_bounds__(256) k_index_scan(IndexSet S)
 {
     __shared__ int ws[40];
     __shared__ int base_s;
     const int b = blockIdx.y;
-    int t = 0;
-    while (t < 3 && (int)blockIdx.x >= S.chunk_begin[t + 1]) ++t;
+    const int t = (int)blockIdx.x >= S.chunk_begin[1] ? 1 : 0;
     const int chunk = blockIdx.x - S.chunk_begin[t], nchunk = S.T[t] / GRID_CHUNK, T = S.T[t];
     if (threadIdx.x < 32) {
         int v = 0;
@@ -204,19 +243,13 @@ __global__ void k_index_scatter(IndexSet S, const LaneState* lane)
 {
     const int b = blockIdx.y, cloud = blockIdx.z;
     const LaneState& L = lane[b];
-    const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
+    const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
-        int ring = (int)p.w;
-        ring = ring < 0 ? 0 : (ring > 255 ? 255 : ring);
-        const float4 rec = make_float4(p.x, p.y, p.z, __int_as_float((i & 0xFFFFFF) | (ring << 24)));
-#pragma unroll
-        for (int kind = 0; kind < 2; ++kind) {
-            const int t = cloud + 2 * kind;
-            const int pos = atomicAdd(&S.cursor[t][(size_t)b * S.T[t] + index_bucket(S, cloud, kind, p)], 1);
-            S.sorted[t][(size_t)b * S.cap[t] + pos] = rec;
-        }
+        const int ring = index_ring(S, p);
+        const int pos = atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, p)], 1);
+        S.sorted[cloud][(size_t)b * S.cap[cloud] + pos] = make_float4(p.x, p.y, p.z, __int_as_float((i & 0xFFFFFF) | (ring << 24)));
     }
 }
 
@@ -230,8 +263,8 @@ struct OdomParams {
     const float4* lsharp[2];
     const float4* lflat[2];
     int Nmax, R;
-    KnnGrid gc, gs;
-    KnnGrid ac, as_;       // ring x azimuth-bin indexes
+    KnnGrid ac, as_;       // polar (azimuth bin x ring) indexes of the corner / surf *Last clouds
+    const float* bands[2]; // [B][BAND_STRIDE] ring elevation bands of the two indexed clouds
     int az_bins_corner, az_bins_surf;
     int* corner_assoc;     // [B][R*12][2]
     int* plane_assoc;      // [B][R*24][4]
@@ -241,7 +274,6 @@ struct OdomParams {
     float vote_t_min;
     int outer;             // opti_counter
     int dev_skip;          // development only: bit mask of association stages to skip (timing experiments)
-    int plane_shells;      // grid shells tried for the 2nd / 3rd plane neighbour before the literal walk
     float4* vote_src;      // [B][R*24] compacted plane matches: current point (w = feature index) / closest point
     float4* vote_tgt;
     int4* queue;           // queries handed from the per-thread pass to the warp pass (k_odom_assoc_heavy)
@@ -254,11 +286,18 @@ __device__ __forceinline__ int last_slot(const LaneState& L) { return L.last_slo
 // ------------------------------------------------------------------------------------------------------
 // k_odom_assoc: one THREAD per feature point for the common case, the WARP for the rare long searches.
 //
-// A query normally sees a few dozen candidates (its grid cell, the neighbour cells that can still beat the running
-// best, a handful of azimuth bins on five rings) — far too few to feed a warp, so every lane runs its own query.
-// Searches that do not resolve inside that budget (nearest neighbour farther than one cell, 2nd / 3rd point not
-// bounded after a few azimuth bins, clouds that are not ring-sorted) would make one lane walk hundreds of buckets
-// while 31 wait; those are handed to the whole warp, one query at a time, 32 buckets / candidates per step.
+// Both searches of a query run over ONE polar index of the *Last cloud (bucket = azimuth bin * R + ring, built in the
+// frame the cloud was measured in, so points are spread evenly over the buckets at every range):
+//   * the exact nearest neighbour (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656; accepted when
+//     d2 < 25): a target whose direction is an angle g away from the query's lies at least |q| sin g away, and
+//     g >= |elevation difference| as well as (for the horizontal projections) >= |azimuth difference|.  With the
+//     per-ring elevation bands recorded by the index build this bounds, for the best distance found so far, the rings
+//     and the azimuth bins that can still hold something closer; the search starts at the query's own bucket and stops
+//     when nothing remains inside those bounds.
+//   * the ring window of LO:504-553 / LO:668-721 (rings c-2 .. c+2 around the closest point's ring c).
+// A query normally sees a few dozen candidates - far too few to feed a warp, so every lane runs its own query.
+// Searches that do not resolve inside that budget (no target nearby, 2nd / 3rd point not bounded after a few bins,
+// clouds that are not ring-sorted) are handed to the whole warp, one query at a time (k_odom_assoc_heavy).
 // Decisions are the ones of LO:491-556 / LO:653-723: the minima are taken over total orders ((d2 bits, target
 // index) for the 1-NN, (d2 bits, visit rank of the serial loops) for the 2nd / 3rd point), so the visiting order
 // and the thread / warp split are free.
@@ -434,49 +473,165 @@ __device__ __forceinline__ void assoc_literal_walk_warp(AssocQuery& Q, const flo
     Q.k2 = warp_min_u64(Q.k2);
     Q.k3 = warp_min_u64(Q.k3);
 }
-// Exact 1-NN over the hashed grid (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656), per-thread part:
-// own cell, then the neighbour cells whose box can still hold a closer (or equally close, lower-index) point.
-// Returns (d2 bits << 32) | target index, ~0 if none; the caller continues with further shells when the best is not
-// provably inside the 27 cells.
-__device__ __forceinline__ u64 assoc_nearest27(const int* __restrict__ start, const float4* __restrict__ sorted, int Tmask, float h, float inv_h,
-                                               float qx, float qy, float qz)
+// ---- exact 1-NN over the polar index ---------------------------------------------------------------------------
+struct RingBands { float elo[LL_MAX_RINGS], ehi[LL_MAX_RINGS]; int ordered; };
+struct PolarQuery {
+    float rho, qn, eq, frac, inv_w;  // horizontal range, range, elevation, position inside the own azimuth bin [0,1], bins per radian
+    int b0, r0;                      // own azimuth bin; first ring whose band ends at or above the query's elevation
+};
+struct PolarReach { int ra, rb, kl, kr; };  // rings [ra, rb]; azimuth bins b0-kl .. b0+kr
+#define NN_NONE ((u64)0x41C80000u << 32)    // (bits of 25.0f, index 0): only d2 < 25 beats it (LO:497 / LO:659)
+__device__ __forceinline__ int azimuth_bin_frac(float x, float y, int NB, float& frac)
 {
-    const float geps = 1e-3f;
-    const int cx = (int)floorf(qx * inv_h), cy = (int)floorf(qy * inv_h), cz = (int)floorf(qz * inv_h);
-    u64 best = ~0ull;
-    float bd2 = INFINITY;
-    auto bucket = [&](int bk) {
-        const int s = __ldg(start + bk), e = __ldg(start + bk + 1);
-        for_range4(sorted, s, e, [&](const float4 t) {
-            const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
-            const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
-            if (key < best) { best = key; bd2 = d2; }
-        });
+    const float phi = atan2f(y, x);  // same arithmetic as azimuth_bin()
+    const float fb = (phi + 3.14159265f) * ((float)NB * 0.15915494f);
+    int b = (int)floorf(fb);
+    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+    frac = fminf(fmaxf(fb - (float)b, 0.f), 1.f);
+    return b;
+}
+// Largest angle (+ slack) between the query's direction and that of a point closer than bd, for a query `range` away
+// from the apex: asin(bd / range), over-estimated by 1.0472 x (x <= 0.5) or (pi/2) x; 4 (> pi) = anywhere.
+__device__ __forceinline__ float reach_angle(float bd, float range)
+{
+    const float x = __fdividef(bd, range);
+    if (!(x < 1.f)) return 4.f;
+    return x * (x < 0.5f ? 1.0472f : 1.5708f) + 2e-4f;
+}
+__device__ __forceinline__ void polar_query_init(PolarQuery& pq, float qx, float qy, float qz, int NB)
+{
+    pq.rho = sqrtf(qx * qx + qy * qy);
+    pq.qn = sqrtf(pq.rho * pq.rho + qz * qz);
+    pq.eq = atan2f(qz, pq.rho);   // = elevation_of()
+    pq.b0 = azimuth_bin_frac(qx, qy, NB, pq.frac);
+    pq.inv_w = (float)NB * 0.15915494f;
+}
+// azimuth part of the reach: bins at left offset k begin (frac + k - 1) bins away, at right offset k (k - frac) bins
+__device__ __forceinline__ void polar_reach_bins(const PolarQuery& pq, int NB, float bd, int& kl, int& kr)
+{
+    const float ab = reach_angle(bd, pq.rho) * pq.inv_w;
+    kl = ab >= (float)NB ? NB : (int)floorf(ab - pq.frac + 1.f);
+    kr = ab >= (float)NB ? NB : (int)floorf(ab + pq.frac);
+    kl = max(0, min(kl, NB / 2 - 1));   // all the way round: every bin once
+    kr = max(0, min(kr, NB / 2));
+}
+__device__ __forceinline__ float best_dist(u64 best) { return sqrtf(__uint_as_float((unsigned)(best >> 32))) + 2e-3f; }
+// per-thread version, bands in shared memory
+__device__ __forceinline__ PolarReach polar_reach(const RingBands& S, const PolarQuery& pq, int NB, int R, u64 best)
+{
+    const float bd = best_dist(best);
+    PolarReach W;
+    const float g = reach_angle(bd, pq.qn);
+    int ra = pq.r0, rb = pq.r0;
+    if (!S.ordered) { ra = 0; rb = R - 1; }
+    else {
+        while (ra > 0 && pq.eq - S.ehi[ra - 1] <= g) --ra;
+        while (rb < R - 1 && S.elo[rb + 1] - pq.eq <= g) ++rb;
+    }
+    W.ra = ra; W.rb = rb;
+    polar_reach_bins(pq, NB, bd, W.kl, W.kr);
+    return W;
+}
+__device__ __forceinline__ void nn_consider(u64& best, float qx, float qy, float qz, const float4 t)
+{
+    const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
+    const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
+    if (key < best) best = key;   // NaN distances have bits above 25.0f's and never win
+}
+// Per-thread search.  Returns true when `best` is final; false = too wide for one thread (best = what was found so
+// far, the warp pass restarts from it).
+__device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R,
+                                                     float qx, float qy, float qz, int kmax, u64& best)
+{
+    PolarQuery pq;
+    polar_query_init(pq, qx, qy, qz, NB);
+    {
+        int lo = 0, hi = R;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.ehi[mid] < pq.eq) lo = mid + 1; else hi = mid; }
+        pq.r0 = min(lo, R - 1);
+    }
+    auto visit = [&](int s, int e) { for_range4(sorted, s, e, [&](const float4 t) { nn_consider(best, qx, qy, qz, t); }); };
+    auto span = [&](int off, int ra, int rb, int& s, int& e) {
+        const int* h = start + ((pq.b0 + off) & (NB - 1)) * R;   // NB is a power of two
+        s = __ldg(h + ra); e = __ldg(h + rb + 1);
     };
-    const int b0 = cell_bucket(cx, cy, cz, Tmask);
-    bucket(b0);
-    // squared distance from the query to the slab of cells at offset d along one axis (1e-3 m slack covers the fp32
-    // rounding of the cell assignment)
-    auto axis = [&](float q, int c, int d) {
-        const float e = d < 0 ? (q - (float)c * h) - geps : (d > 0 ? ((float)(c + 1) * h - q) - geps : 0.f);
-        return e > 0.f ? e * e : 0.f;
-    };
-    for (int dz = -1; dz <= 1; ++dz) {
-        const float ez = axis(qz, cz, dz);
-        if (ez > bd2) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const float eyz = ez + axis(qy, cy, dy);
-            if (eyz > bd2) continue;
-            for (int dx = -1; dx <= 1; ++dx) {
-                if ((dx | dy | dz) == 0 || eyz + axis(qx, cx, dx) > bd2) continue;
-                const int bk = cell_bucket(cx + dx, cy + dy, cz + dz, Tmask);
-                if (bk != b0) bucket(bk);   // a bucket met twice (hash collision) changes nothing: min is idempotent
-            }
+    // seed: rings r0-1 .. r0+1 of the own bin and of the nearer neighbour bin
+    const int sa = max(pq.r0 - 1, 0), sb = min(pq.r0 + 1, R - 1);
+    const int near = pq.frac < 0.5f ? -1 : 1;
+    int s0, e0, s1, e1;
+    span(0, sa, sb, s0, e0); span(near, sa, sb, s1, e1);
+    visit(s0, e0); visit(s1, e1);
+    PolarReach W = polar_reach(S, pq, NB, R, best);
+    u64 seen = best;
+    if (W.rb - W.ra > 16 || max(W.kl, W.kr) > kmax) return false;
+    // the remaining rings of the two seeded bins
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+        const int off = t == 0 ? 0 : near;
+        if (t == 1 && (near < 0 ? W.kl : W.kr) < 1) break;
+        if (W.ra < sa) { span(off, W.ra, sa - 1, s0, e0); visit(s0, e0); }
+        if (W.rb > sb) { span(off, sb + 1, W.rb, s1, e1); visit(s1, e1); }
+    }
+    // outward; the reach only shrinks as the best improves
+#pragma unroll 1
+    for (int k = 1;; ++k) {
+        if (best != seen) { W = polar_reach(S, pq, NB, R, best); seen = best; }
+        const bool l = k <= W.kl && !(k == 1 && near < 0), r = k <= W.kr && !(k == 1 && near > 0);
+        if (k > W.kl && k > W.kr) return true;
+        s0 = e0 = s1 = e1 = 0;
+        if (l) span(-k, W.ra, W.rb, s0, e0);
+        if (r) span(k, W.ra, W.rb, s1, e1);
+        visit(s0, e0); visit(s1, e1);
+    }
+}
+// Warp version (one query per warp; bands read from global memory): every step streams the rings in reach of up to
+// 16 bins per side.  `best` (warp-uniform) may carry what the thread pass found.
+__device__ __forceinline__ u64 polar_nearest_warp(const float* __restrict__ bands, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R,
+                                                  float qx, float qy, float qz, u64 best)
+{
+    const int lane = lane_id();
+    PolarQuery pq;
+    polar_query_init(pq, qx, qy, qz, NB);
+    // this lane's two rings
+    const float elo0 = lane < R ? __ldg(bands + lane) : INFINITY, ehi0 = lane < R ? __ldg(bands + LL_MAX_RINGS + lane) : INFINITY;
+    const float elo1 = lane + 32 < R ? __ldg(bands + lane + 32) : INFINITY, ehi1 = lane + 32 < R ? __ldg(bands + LL_MAX_RINGS + lane + 32) : INFINITY;
+    const int ordered = __ldg(reinterpret_cast<const int*>(bands) + 2 * LL_MAX_RINGS);
+    pq.r0 = min(__popc(__ballot_sync(LL_FULL_MASK, ehi0 < pq.eq)) + __popc(__ballot_sync(LL_FULL_MASK, ehi1 < pq.eq)), R - 1);
+    u64 lb = best;
+    int doneL = 0, doneR = -1;   // left offsets 1..doneL and right offsets 0..doneR have been visited
+    for (;;) {
+        const float bd = best_dist(best);
+        const float g = reach_angle(bd, pq.qn);
+        int ra = 0, rb = R - 1, kl, kr;
+        if (ordered) {
+            // ring r is in reach when its band comes within g of the query's elevation; ordered bands: a contiguous range
+            const bool in0 = lane < R && (lane >= pq.r0 ? elo0 - pq.eq <= g : pq.eq - ehi0 <= g);
+            const bool in1 = lane + 32 < R && (lane + 32 >= pq.r0 ? elo1 - pq.eq <= g : pq.eq - ehi1 <= g);
+            const unsigned m0 = __ballot_sync(LL_FULL_MASK, in0 || lane == pq.r0), m1 = __ballot_sync(LL_FULL_MASK, in1 || lane + 32 == pq.r0);
+            // contiguous run around r0
+            ra = pq.r0; rb = pq.r0;
+            const u64 m = ((u64)m1 << 32) | m0;
+            while (ra > 0 && ((m >> (ra - 1)) & 1ull)) --ra;
+            while (rb < R - 1 && ((m >> (rb + 1)) & 1ull)) ++rb;
         }
+        polar_reach_bins(pq, NB, bd, kl, kr);
+        if (doneL >= kl && doneR >= kr) break;
+        const int idx = lane >> 1;
+        int beg = 0, cnt = 0, k = -1, off = 0;
+        if (lane & 1) { k = doneL + 1 + idx; if (k <= kl) off = -k; else k = -1; }
+        else { k = doneR + 1 + idx; if (k <= kr) off = k; else k = -1; }
+        if (k >= 0) {
+            const int* h = start + ((pq.b0 + off) & (NB - 1)) * R;
+            beg = __ldg(h + ra);
+            cnt = __ldg(h + rb + 1) - beg;
+        }
+        grid_stream_ranges(sorted, beg, cnt, [&](const float4 t) { nn_consider(lb, qx, qy, qz, t); });
+        doneL += 16; doneR += 16;
+        best = warp_min_u64(lb);
     }
     return best;
 }
-// views of one lane's spatial grid / ring-azimuth index
+// view of one lane's polar index
 __device__ __forceinline__ GridView assoc_view(const KnnGrid& G, int b)
 {
     GridView gv;
@@ -517,40 +672,36 @@ __device__ __forceinline__ void assoc_query_init(const OdomParams& P, const Lane
     Q.n = CORNER ? L.n_last_corner : L.n_last_surf;
 }
 // queue entry of a query the per-thread pass did not finish: x = lane, y = feature index | plane << 30 | open << 29;
-// open (nearest neighbour not yet proven): z, w = best key so far (d2 bits, index; ~0 = none)
+// open (nearest neighbour not final): z, w = best key so far (d2 bits, index; NN_NONE = nothing within 5 m yet)
 // otherwise: z = closest point, w = -1 (ring window, restarted by the warp) or -2 (literal walk)
 #define ASSOC_PLANE_BIT (1 << 30)
 #define ASSOC_OPEN_BIT (1 << 29)
 
 // Per-thread pass.  Writes the correspondences of the queries it resolves, queues the others for k_odom_assoc_heavy.
 template <bool CORNER>
-__device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const LaneState& L, int b, int i, bool active, int dmax)
+__device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const RingBands& S, const LaneState& L, int b, int i, bool active, int dmax, int kmax)
 {
     const int lane = lane_id();
-    const float geps = 1e-3f;
     AssocQuery Q;
     Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0;
     int4 entry = make_int4(b, CORNER ? i : (i | ASSOC_PLANE_BIT), -1, -1);
     bool heavy = false;
     if (active) {
         assoc_query_init<CORNER>(P, L, b, i, Q);
-        const GridView gv = assoc_view(CORNER ? P.gc : P.gs, b);
-        u64 best = ~0ull;
+        const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
+        const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
+        u64 best = NN_NONE;
         if (Q.n > 0) {
-            best = assoc_nearest27(gv.start, gv.sorted, gv.Tmask, gv.h, gv.inv_h, Q.qx, Q.qy, Q.qz);
-            const float safe = gv.h - geps;
-            // not provably inside the 27 cells searched: the further shells are a job for a whole warp
-            heavy = !(best != ~0ull && __uint_as_float((unsigned)(best >> 32)) < safe * safe);
+            heavy = !polar_nearest_thread(S, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, best);
             if (heavy) { entry.y |= ASSOC_OPEN_BIT; entry.z = (int)(unsigned)(best >> 32); entry.w = (int)(unsigned)best; }
         }
-        if (!heavy && best != ~0ull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // LO:497 / LO:659
+        if (!heavy && best != NN_NONE) {  // d2 < 25: LO:497 / LO:659
             const float4* last = CORNER ? P.lsharp[last_slot(L)] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[last_slot(L)] + (size_t)b * P.Nmax;
             Q.closest = (int)(unsigned)best;
             Q.cring = (int)last[Q.closest].w;  // int(intensity), LO:500 / LO:664
             int pending = -2;                  // clouds that are not ring-sorted: literal walk
             if (CORNER ? L.mono_corner : L.mono_surf) {
-                const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
-                pending = assoc_ring_window<CORNER>(Q, av.start, av.sorted, CORNER ? P.az_bins_corner : P.az_bins_surf, P.R, dmax);
+                pending = assoc_ring_window<CORNER>(Q, av.start, av.sorted, NB, P.R, dmax);
                 heavy = pending >= 0;
             } else {
                 heavy = true;
@@ -571,79 +722,45 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Lan
     }
 }
 // grid: (ceil(R*12 / T) + ceil(R*24 / T), B): corner queries and plane queries never share a block
-__global__ void __launch_bounds__(ASSOC_THREADS, 6) k_odom_assoc(OdomParams P, int corner_blocks, int dmax)
+__global__ void __launch_bounds__(ASSOC_THREADS, 6) k_odom_assoc(OdomParams P, int corner_blocks, int dmax, int kmax)
 {
+    __shared__ RingBands S;
     const int b = blockIdx.y;
     const LaneState& L = P.lane[b];
     if (!L.inited) return;
-    if ((int)blockIdx.x < corner_blocks) {
-        const int i = blockIdx.x * ASSOC_THREADS + threadIdx.x;
-        if ((i & ~31) >= L.n_sharp) return;   // whole warp idle
-        assoc_thread_pass<true>(P, L, b, i, i < L.n_sharp, dmax);
-    } else {
-        const int i = (blockIdx.x - corner_blocks) * ASSOC_THREADS + threadIdx.x;
-        if ((i & ~31) >= L.n_flat) return;
-        assoc_thread_pass<false>(P, L, b, i, i < L.n_flat, dmax);
+    const bool corner = (int)blockIdx.x < corner_blocks;
+    const int i = (corner ? blockIdx.x : blockIdx.x - corner_blocks) * ASSOC_THREADS + threadIdx.x;
+    const int n = corner ? L.n_sharp : L.n_flat;
+    if ((int)(i - threadIdx.x) >= n) return;   // whole block idle
+    {
+        const float* bd = P.bands[corner ? 0 : 1] + (size_t)b * BAND_STRIDE;
+        if (threadIdx.x < P.R) { S.elo[threadIdx.x] = __ldg(bd + threadIdx.x); S.ehi[threadIdx.x] = __ldg(bd + LL_MAX_RINGS + threadIdx.x); }
+        if (threadIdx.x == 0) S.ordered = __ldg(reinterpret_cast<const int*>(bd) + 2 * LL_MAX_RINGS);
+        __syncthreads();
     }
+    if ((i & ~31) >= n) return;   // whole warp idle
+    if (corner) assoc_thread_pass<true>(P, S, L, b, i, i < n, dmax, kmax);
+    else assoc_thread_pass<false>(P, S, L, b, i, i < n, dmax, kmax);
 }
 
-// One WARP per queued query, the queue spread over a fixed grid: the long searches (nearest neighbour farther than
-// one cell, wide ring windows, literal walks) run side by side instead of serialising inside the warp that met them.
+// One WARP per queued query, the queue spread over a fixed grid: the long searches (no target nearby, wide ring
+// windows, literal walks) run side by side instead of serialising inside the warp that met them.
 template <bool CORNER>
 __device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int i, bool open, int ez, int ew)
 {
     const LaneState& L = P.lane[b];
     const int lane = lane_id();
-    const float geps = 1e-3f;
     AssocQuery Q;
     assoc_query_init<CORNER>(P, L, b, i, Q);
     const float4* last = CORNER ? P.lsharp[last_slot(L)] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[last_slot(L)] + (size_t)b * P.Nmax;
+    const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
+    const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
     int closest = open ? -1 : ez, mode = open ? -1 : ew;
     if (open) {
-        // 1-NN (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656) beyond the 27 cells the thread pass
-        // searched: shell by shell.  The lanes share out the cells of a shell, skip those whose box cannot beat the
-        // warp's best, and keep eight bucket headers in flight each, so a whole shell costs about two memory round
-        // trips (these queries live in sparse regions: a shell holds few points).
-        const GridView gv = assoc_view(CORNER ? P.gc : P.gs, b);
-        const int cx = (int)floorf(Q.qx * gv.inv_h), cy = (int)floorf(Q.qy * gv.inv_h), cz = (int)floorf(Q.qz * gv.inv_h);
-        const int smax = (int)ceilf((5.0f + geps) * gv.inv_h);
-        u64 best = ((u64)(unsigned)ez << 32) | (unsigned)ew;  // the thread pass's best over the 27 cells (~0: none)
-        u64 lb = best;
-        auto axis = [&](float q, int c, int d) {
-            const float e = d < 0 ? (q - (float)(c + d + 1) * gv.h) - geps : (d > 0 ? ((float)(c + d) * gv.h - q) - geps : 0.f);
-            return e > 0.f ? e * e : 0.f;
-        };
-        for (int s = 2; s <= smax; ++s) {
-            const float safe = (float)(s - 1) * gv.h - geps;
-            const float bd2 = best != ~0ull ? __uint_as_float((unsigned)(best >> 32)) : INFINITY;
-            if (bd2 < safe * safe) break;
-            const int w = 2 * s + 1, ncell = w * w * w;
-            for (int e0 = 0; e0 < ncell; e0 += 256) {
-                int beg[8], end[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e = e0 + u * 32 + lane;
-                    beg[u] = 0; end[u] = 0;
-                    if (e < ncell) {
-                        const int dx = e % w - s, dy = (e / w) % w - s, dz = e / (w * w) - s;
-                        if (max(abs(dx), max(abs(dy), abs(dz))) == s && axis(Q.qx, cx, dx) + axis(Q.qy, cy, dy) + axis(Q.qz, cz, dz) <= bd2) {
-                            const int bk = cell_bucket(cx + dx, cy + dy, cz + dz, gv.Tmask);
-                            beg[u] = __ldg(gv.start + bk);
-                            end[u] = __ldg(gv.start + bk + 1);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    for_range4(gv.sorted, beg[u], end[u], [&](const float4 t) {
-                        const float d2 = sqdist3(Q.qx, Q.qy, Q.qz, t.x, t.y, t.z);
-                        const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
-                        if (key < lb) lb = key;
-                    });
-            }
-            best = warp_min_u64(lb);
-        }
-        if (best != ~0ull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // LO:497 / LO:659
+        // 1-NN (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656) continued from the thread pass's best
+        const u64 best = polar_nearest_warp(P.bands[CORNER ? 0 : 1] + (size_t)b * BAND_STRIDE, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz,
+                                            ((u64)(unsigned)ez << 32) | (unsigned)ew);
+        if (best != NN_NONE) {  // d2 < 25: LO:497 / LO:659
             closest = (int)(unsigned)best;
             mode = (CORNER ? L.mono_corner : L.mono_surf) ? -1 : -2;
         }
@@ -651,12 +768,8 @@ __device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int
     if (closest >= 0) {
         Q.closest = closest;
         Q.cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
-        if (mode == -2) {
-            assoc_literal_walk_warp<CORNER>(Q, last);
-        } else {
-            const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
-            assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, CORNER ? P.az_bins_corner : P.az_bins_surf, P.R, -1);
-        }
+        if (mode == -2) assoc_literal_walk_warp<CORNER>(Q, last);
+        else assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, NB, P.R, -1);
     }
     if (lane == 0) assoc_store<CORNER>(P, b, i, Q);
 }
@@ -879,10 +992,10 @@ __global__ void k_odom_finalize(LaneState* lane, double* pose_out, int n_lanes)
 
 }  // namespace
 
-static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1, size_t lane_stride, int which, int n_lanes, int max_pts, int az_bins = 0)
+static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1, size_t lane_stride, int which, int n_lanes, int max_pts)
 {
     GridSrc S;
-    S.pts[0] = p0; S.pts[1] = p1; S.lane_stride = lane_stride; S.which = which; S.az_bins = az_bins; S.rings = c->R;
+    S.pts[0] = p0; S.pts[1] = p1; S.lane_stride = lane_stride; S.which = which;
     cudaStream_t s = c->stream;
     LL_CUDA_CHECK(c, cudaMemsetAsync(g.cursor, 0, sizeof(int) * (size_t)g.T * n_lanes, s));
     const int gx = (max_pts + 255) / 256 > 0 ? (max_pts + 255) / 256 : 1;
@@ -899,43 +1012,46 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     OdomParams P;
     P.lane = c->d_lane; P.sharp = c->d_sharp; P.flat = c->d_flat;
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
-    P.Nmax = c->Nmax; P.R = c->R; P.gc = c->g_corner; P.gs = c->g_surf; P.ac = c->a_corner; P.as_ = c->a_surf; P.az_bins_corner = c->az_bins_corner; P.az_bins_surf = c->az_bins_surf;
+    P.Nmax = c->Nmax; P.R = c->R; P.ac = c->a_corner; P.as_ = c->a_surf; P.bands[0] = c->d_bands[0]; P.bands[1] = c->d_bands[1]; P.az_bins_corner = c->az_bins_corner; P.az_bins_surf = c->az_bins_surf;
     P.corner_assoc = c->d_corner_assoc; P.plane_assoc = c->d_plane_assoc; P.blocks = c->d_blocks; P.nblk_cap = c->nblk_cap;
-    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.plane_shells = c->plane_shells; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
+    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
     P.vote_src = c->d_vote_src; P.vote_tgt = c->d_vote_tgt;
     P.queue = c->d_assoc_queue; P.queue_n = c->d_assoc_queue_n; P.queue_cap = c->assoc_queue_cap;
     cudaStream_t s = c->stream;
     const int cblocks = (c->R * LL_SHARP_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS, pblocks = (c->R * LL_FLAT_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS;
     LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, s));
     const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
-    const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;
+    const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;   // ring-window bins per side a thread walks
+    const int kmax = getenv("LL_ASSOC_KMAX") ? atoi(getenv("LL_ASSOC_KMAX")) : 3;   // 1-NN bins per side a thread walks
     const size_t vote_smem = (size_t)(c->R * LL_FLAT_PER_RING / 10 + 16) * (2 * sizeof(float4) + sizeof(int));
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
-    // the spatial hash grids and the ring x azimuth indexes of the two *Last clouds are built together (4 launches)
-    // right before the association, so the tables are still in L2 when the queries walk them
+    // the polar indexes of the two *Last clouds are built together (4 launches) right before the association, so the
+    // tables are still in L2 when the queries walk them
     {
         IndexSet S;
-        KnnGrid* tab[4] = {&c->g_corner, &c->g_surf, &c->a_corner, &c->a_surf};
+        KnnGrid* tab[2] = {&c->a_corner, &c->a_surf};
         S.pts[0][0] = c->d_lsharp[0]; S.pts[0][1] = c->d_lsharp[1]; S.pts[1][0] = c->d_lflat[0]; S.pts[1][1] = c->d_lflat[1];
         S.lane_stride[0] = (size_t)c->R * LL_LSHARP_PER_RING; S.lane_stride[1] = (size_t)c->Nmax;
         S.chunk_begin[0] = 0;
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 2; ++t) {
             S.cursor[t] = tab[t]->cursor; S.start[t] = tab[t]->start; S.partial[t] = tab[t]->partial; S.sorted[t] = tab[t]->sorted;
+            S.ebound[t] = c->d_ebound[t]; S.bands[t] = c->d_bands[t];
             S.T[t] = tab[t]->T; S.cap[t] = tab[t]->cap;
             S.chunk_begin[t + 1] = S.chunk_begin[t] + tab[t]->T / GRID_CHUNK;
             LL_CUDA_CHECK(c, cudaMemsetAsync(tab[t]->cursor, 0, sizeof(int) * (size_t)tab[t]->T * n_lanes, s));
+            LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_ebound[t], 0, sizeof(unsigned) * (size_t)c->R * 2 * n_lanes, s));
         }
-        S.inv_h = c->g_corner.inv_h; S.az_bins[0] = c->az_bins_corner; S.az_bins[1] = c->az_bins_surf; S.rings = c->R;
+        S.az_bins[0] = c->az_bins_corner; S.az_bins[1] = c->az_bins_surf; S.rings = c->R;
         const int gx = (c->Nmax / 2 + 255) / 256 < 148 ? (c->Nmax / 2 + 255) / 256 : 148;
         { LLProf pr(c, "k_index_count"); k_index_count<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
-        { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[4], n_lanes), 256, 0, s>>>(S); }
-        { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[4], n_lanes), 256, 0, s>>>(S); }
+        { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
+        { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
         { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
-        c->launches += 5;
+        c->launches += 4;
     }
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
-        { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3(cblocks + pblocks, n_lanes), ASSOC_THREADS, 0, s>>>(P, cblocks, dmax); }
+        { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3(cblocks + pblocks, n_lanes), ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax); }
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P); }
