@@ -593,7 +593,7 @@ int ll_get_last_stats(ll_ctx* c, ll_stats* o)
         o->map_initial_cost[k] = L.initial_cost[3 + k]; o->map_final_cost[k] = L.final_cost[3 + k];
     }
     o->frame = L.now_frame;
-    if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg (all lanes, cumulative): - %d, queued with the 1-NN open %d, queued for the ring window %d\n", L.dbg[0], L.dbg[1], L.dbg[2]);
+    if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg (all lanes, cumulative): queued with the 1-NN open %d (kcycles %d, longest %d cycles), queued for the ring window %d (kcycles %d, longest %d cycles)\n", L.dbg[1], L.dbg[3], L.dbg[5] * 16, L.dbg[2], L.dbg[4], L.dbg[6] * 16);
     o->kernel_launches = c->launches;
     return LL_OK;
 }

@@ -59,38 +59,59 @@ __device__ __forceinline__ float end_ori_of(float last_ori, float startOri)
     return endOri;
 }
 
+__device__ __forceinline__ bool point_valid(float x, float y, float z, float thres)
+{
+    return isfinite(x) && isfinite(y) && isfinite(z) && !(x * x + y * y + z * z < thres * thres);  // SR:109 / SR:72
+}
 __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
 {
     __shared__ int cnt[LL_TILE / 32][LL_MAX_RINGS];
+    __shared__ int flip_s;
     for (int k = threadIdx.x; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0])[k] = 0;
+    if (threadIdx.x == 0) flip_s = INT_MAX;
     __syncthreads();
     const int b = blockIdx.y;
     LaneState& L = P.lane[b];
     const int n = L.n_raw, sw = L.stride_words;
+    const float startOri = L.start_ori;                  // found by k_reset_scan_state
+    const int half_seen = *(volatile int*)&L.half_idx;   // filter for the atomic below; a stale (larger) value only costs an atomic
+    const int w = warp_id(), lane = lane_id();
     const int i = blockIdx.x * LL_TILE + threadIdx.x;
     bool valid = false;
     int ring = -1;
     float ori = 0.f;
     if (i < n) {
         const uint32_t* p = L.raw + (size_t)i * sw;
-        const float x = __uint_as_float(p[0]), y = __uint_as_float(p[1]), z = __uint_as_float(p[2]);
-        valid = isfinite(x) && isfinite(y) && isfinite(z) && !(x * x + y * y + z * z < P.thres * P.thres);  // SR:72
+        float x, y, z;
+        if (sw == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); x = v.x; y = v.y; z = v.z; }  // slabs and the pool are 16-byte aligned
+        else { x = __uint_as_float(p[0]); y = __uint_as_float(p[1]); z = __uint_as_float(p[2]); }
+        valid = point_valid(x, y, z, P.thres);
         if (valid) {
-            // SR:139: float atan / sqrt, * 180 in fp32, / M_PI in fp64, stored as float.
-            // atanf / atan2f are evaluated in fp64 and rounded once (correctly rounded fp32 result).
+            // SR:139: float atan / sqrt, * 180 in fp32, / M_PI in fp64, stored as float; SR:142-169 ring formula.
+            // Only the integer scanID survives, so it is first computed in plain fp32 (error << 1e-3 of a ring); the
+            // literal sequence (atanf evaluated in fp64 and rounded once, double division) runs only when that value
+            // lies within 2e-3 of a truncation boundary, where the roundings of the reference decide.
             const float t = z / sqrtf(x * x + y * y);
-            const float a = (float)atan((double)t);
-            const float angle = (float)((double)(a * 180.0f) / LL_PI);
+            const float angf = atanf(t) * 57.29578f;
+            const float vf = P.scan_line == 16 ? (angf + 15.0f) * 0.5f + 0.5f : (P.scan_line == 32 ? (angf + 30.666666f) * 0.75f : (angf - P.lower_bound) * P.factor + 0.5f);
+            const float fr = vf - floorf(vf);
             int scanID;
-            if (P.scan_line == 16) {
-                scanID = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
-                if (scanID > 15 || scanID < 0) scanID = -2;
-            } else if (P.scan_line == 32) {
-                scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
-                if (scanID > 31 || scanID < 0) scanID = -2;
+            if (vf > 1e-3f && fr > 2e-3f && fr < 1.0f - 2e-3f) {
+                scanID = (int)vf;
+                if (scanID >= P.scan_line) scanID = -2;
             } else {
-                scanID = (int)((double)((angle - P.lower_bound) * P.factor) + 0.5);
-                if (scanID >= 64 || scanID < 0) scanID = -2;
+                const float a = (float)atan((double)t);
+                const float angle = (float)((double)(a * 180.0f) / LL_PI);
+                if (P.scan_line == 16) {
+                    scanID = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
+                    if (scanID > 15 || scanID < 0) scanID = -2;
+                } else if (P.scan_line == 32) {
+                    scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+                    if (scanID > 31 || scanID < 0) scanID = -2;
+                } else {
+                    scanID = (int)((double)((angle - P.lower_bound) * P.factor) + 0.5);
+                    if (scanID >= 64 || scanID < 0) scanID = -2;
+                }
             }
             ring = scanID;
             ori = -(float)atan2((double)y, (double)x);  // SR:177
@@ -100,18 +121,27 @@ __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
         P.ring8[(size_t)b * P.Nmax + i] = (int8_t)ring;
         P.ori[(size_t)b * P.Nmax + i] = ori;
     }
-    const int w = warp_id(), lane = lane_id();
-    const int lo = __reduce_min_sync(LL_FULL_MASK, valid ? i : INT_MAX);
     const int hi = __reduce_max_sync(LL_FULL_MASK, valid ? i : -1);
-    if (lane == 0) {
-        if (lo != INT_MAX) atomicMin(&L.first_valid, lo);
-        if (hi >= 0) atomicMax(&L.last_valid, hi);
-    }
+    if (lane == 0 && hi >= 0) atomicMax(&L.last_valid, hi);
     // stable rank inside the tile (SR:209 push_back order): warp match on the ring id, then prefix over the tile's warps
     const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
     const int rank_in_warp = __popc(m & ((1u << lane) - 1u));
     if (ring >= 0 && rank_in_warp == 0) cnt[w][ring] = __popc(m);
     __syncthreads();
+    {
+        // SR:180-192 in the !halfPassed state: the first point for which this holds flips halfPassed
+        bool flip = false;
+        if (ring >= 0) {
+            float o = ori;
+            if ((double)o < (double)startOri - LL_PI / 2)
+                o = (float)((double)o + 2 * LL_PI);
+            else if ((double)o > (double)startOri + LL_PI * 3 / 2)
+                o = (float)((double)o - 2 * LL_PI);
+            flip = (double)(o - startOri) > LL_PI;
+        }
+        const int fl = __reduce_min_sync(LL_FULL_MASK, flip ? i : INT_MAX);
+        if (lane == 0 && fl != INT_MAX) atomicMin(&flip_s, fl);
+    }
     if (threadIdx.x < P.R) {
         int run = 0;
         for (int ww = 0; ww < LL_TILE / 32; ++ww) { const int c = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += c; }
@@ -119,75 +149,88 @@ __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
     }
     __syncthreads();
     if (i < P.Nmax) P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(cnt[w][ring] + rank_in_warp) : 0;
+    // about half of all tiles see a flip: one filtered atomic per tile
+    if (threadIdx.x == 0 && flip_s < half_seen) atomicMin(&L.half_idx, flip_s);
 }
 
-// one CTA per lane: tile_hist[t][r] -> exclusive offset of tile t inside ring r; ring_begin[]; n_full
-// ... and the point that flips halfPassed (SR:178-193): the first valid point whose adjusted azimuth is more than pi past
-// startOri.  The scan walks the azimuths in chunks of 8192 and stops at the first chunk that holds such a point.
+// one CTA per lane, one warp per ring at a time: tile_hist[r][t] -> exclusive offset of tile t inside ring r;
+// ring_begin[]; n_full.  Each lane owns four consecutive tiles per 128-tile chunk (one int4), all chunks of a ring
+// are loaded before the first is scanned.
+#define SCAN_MAX_CHUNKS 8   // 8 x 128 tiles x 256 points = 262144 points per scan on the vector path
 __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
 {
     __shared__ int tot[LL_MAX_RINGS];
-    __shared__ int half_s;
     const int b = blockIdx.x;
     LaneState& L = P.lane[b];
     const int w = warp_id(), lane = lane_id();
-    if (threadIdx.x == 0) half_s = INT_MAX;
-    __syncthreads();
-    if (L.first_valid != INT_MAX) {
-        const float startOri = P.ori[(size_t)b * P.Nmax + L.first_valid];
-        const int n_raw = L.n_raw;
-        for (int i0 = 0; i0 < n_raw; i0 += 8192) {  // eight independent loads per thread and barrier
-            bool any = false;
-            int first = INT_MAX;
+    const int ntiles = (L.n_raw + LL_TILE - 1) / LL_TILE;
+    const int nchunk = (ntiles + 127) / 128;
+    for (int r = w; r < P.R; r += 32) {
+        int* col = P.tile_hist + ((size_t)b * P.R + r) * P.NT;
+        if (nchunk <= SCAN_MAX_CHUNKS && (P.NT & 3) == 0) {
+            int4 v[SCAN_MAX_CHUNKS];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * 1024 + threadIdx.x;
-                bool flag = false;
-                if (i < n_raw && P.ring8[(size_t)b * P.Nmax + i] >= 0) {
-                    float ori = P.ori[(size_t)b * P.Nmax + i];
-                    // SR:180-192 in the !halfPassed state
-                    if ((double)ori < (double)startOri - LL_PI / 2)
-                        ori = (float)((double)ori + 2 * LL_PI);
-                    else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
-                        ori = (float)((double)ori - 2 * LL_PI);
-                    flag = (double)(ori - startOri) > LL_PI;
-                }
-                if (flag && i < first) first = i;
-                any |= flag;
+            for (int c = 0; c < SCAN_MAX_CHUNKS; ++c) {
+                const int t = c * 128 + lane * 4;
+                v[c] = make_int4(0, 0, 0, 0);
+                if (c < nchunk && t < P.NT) v[c] = *reinterpret_cast<const int4*>(col + t);
+                if (t + 0 >= ntiles) v[c].x = 0;
+                if (t + 1 >= ntiles) v[c].y = 0;
+                if (t + 2 >= ntiles) v[c].z = 0;
+                if (t + 3 >= ntiles) v[c].w = 0;
             }
-            const int fi = __reduce_min_sync(LL_FULL_MASK, first);
-            if (lane == 0 && fi != INT_MAX) atomicMin(&half_s, fi);
-            if (__syncthreads_or(any)) break;
+            int carry = 0;
+#pragma unroll
+            for (int c = 0; c < SCAN_MAX_CHUNKS; ++c) {
+                if (c < nchunk) {
+                    const int s = v[c].x + v[c].y + v[c].z + v[c].w;
+                    int incl = s;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+                    int run = carry + incl - s;
+                    int4 o;
+                    o.x = run; run += v[c].x; o.y = run; run += v[c].y; o.z = run; run += v[c].z; o.w = run;
+                    const int t = c * 128 + lane * 4;
+                    if (t < P.NT) *reinterpret_cast<int4*>(col + t) = o;
+                    carry += __shfl_sync(LL_FULL_MASK, incl, 31);
+                }
+            }
+            if (lane == 0) tot[r] = carry;
+        } else {
+            const int per = (ntiles + 31) / 32;
+            const int t0 = lane * per, t1 = min(t0 + per, ntiles);
+            int s = 0;
+            for (int t = t0; t < t1; ++t) s += col[t];
+            int incl = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+            int run = incl - s;
+            for (int t = t0; t < t1; ++t) { const int c = col[t]; col[t] = run; run += c; }
+            if (lane == 31) tot[r] = incl;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) L.half_idx = half_s;
-    const int ntiles = (L.n_raw + LL_TILE - 1) / LL_TILE;
-    const int per = (ntiles + 31) / 32;
-    for (int r = w; r < P.R; r += 32) {
-        int* col = P.tile_hist + ((size_t)b * P.R + r) * P.NT;
-        const int t0 = lane * per, t1 = min(t0 + per, ntiles);
-        int s = 0;
-        for (int t = t0; t < t1; ++t) s += col[t];
-        int incl = s;
+    if (threadIdx.x < 32) {  // ring_begin = exclusive scan of the ring totals
+        const int a0 = lane < P.R ? tot[lane] : 0, a1 = lane + 32 < P.R ? tot[lane + 32] : 0;
+        int i0 = a0, i1 = a1;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
-        int run = incl - s;
-        for (int t = t0; t < t1; ++t) { const int c = col[t]; col[t] = run; run += c; }
-        if (lane == 31) tot[r] = incl;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int r = 0; r < P.R; ++r) { L.ring_begin[r] = run; run += tot[r]; }
-        L.ring_begin[P.R] = run;
-        L.n_full = run;
-        L.cur = L.last_slot ^ 1;  // this frame's less-sharp / less-flat go to the slot not holding the *Last clouds
-        if (L.first_valid != INT_MAX) {
-            L.start_ori = P.ori[(size_t)b * P.Nmax + L.first_valid];
-            L.end_ori = end_ori_of(P.ori[(size_t)b * P.Nmax + L.last_valid], L.start_ori);
-        } else {
-            L.err = LL_E_EMPTY;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o0 = __shfl_up_sync(LL_FULL_MASK, i0, d), o1 = __shfl_up_sync(LL_FULL_MASK, i1, d);
+            if (lane >= d) { i0 += o0; i1 += o1; }
+        }
+        const int t0 = __shfl_sync(LL_FULL_MASK, i0, 31), t1 = __shfl_sync(LL_FULL_MASK, i1, 31);
+        if (lane < P.R) L.ring_begin[lane] = i0 - a0;
+        if (lane + 32 < P.R) L.ring_begin[lane + 32] = t0 + i1 - a1;
+        if (lane == 0) {
+            const int run = t0 + t1;
+            L.ring_begin[P.R] = run;
+            L.n_full = run;
+            L.cur = L.last_slot ^ 1;  // this frame's less-sharp / less-flat go to the slot not holding the *Last clouds
+            if (L.first_valid != INT_MAX) {
+                L.end_ori = end_ori_of(P.ori[(size_t)b * P.Nmax + L.last_valid], L.start_ori);
+            } else {
+                L.err = LL_E_EMPTY;
+            }
         }
     }
 }
@@ -218,7 +261,11 @@ __global__ void __launch_bounds__(LL_TILE) k_scatter(FeatParams P)
     const float intensity = (float)((double)ring + 0.1 * (double)relTime);  // SR:208
     const int pos = L.ring_begin[ring] + P.tile_hist[((size_t)b * P.R + ring) * P.NT + blockIdx.x] + P.rank8[(size_t)b * P.Nmax + i];
     const uint32_t* p = L.raw + (size_t)i * L.stride_words;
-    P.full[(size_t)b * P.Nmax + pos] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), intensity);
+    float4 o;
+    if (L.stride_words == 4) o = __ldg(reinterpret_cast<const float4*>(p));
+    else o = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), 0.f);
+    o.w = intensity;
+    P.full[(size_t)b * P.Nmax + pos] = o;
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------------------------
@@ -739,13 +786,33 @@ __global__ void __launch_bounds__(256) k_compact(FeatParams P)
     }
 }
 
-__global__ void k_reset_scan_state(LaneState* lane, int n_lanes)
+// one warp per lane: per-scan state, and startOri (SR:114) = azimuth of the first point that survives the filters
+// (nearly always point 0) so that k_classify can decide where halfPassed flips (SR:178-193) in its single pass
+__global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_lanes) {
-        lane[b].first_valid = INT_MAX;
-        lane[b].last_valid = -1;
-        lane[b].half_idx = INT_MAX;
+    const int b = blockIdx.x, ln = lane_id();
+    if (b >= n_lanes) return;
+    LaneState& L = lane[b];
+    const int n = L.n_raw, sw = L.stride_words;
+    int fv = -1;
+    float sx = 0.f, sy = 0.f;
+    for (int j0 = 0; j0 < n && fv < 0; j0 += 32) {
+        const int j = j0 + ln;
+        bool v = false;
+        float x = 0.f, y = 0.f;
+        if (j < n) {
+            const uint32_t* p = L.raw + (size_t)j * sw;
+            x = __uint_as_float(p[0]); y = __uint_as_float(p[1]);
+            v = point_valid(x, y, __uint_as_float(p[2]), thres);
+        }
+        const unsigned m = __ballot_sync(LL_FULL_MASK, v);
+        if (m) { fv = j0 + __ffs(m) - 1; sx = __shfl_sync(LL_FULL_MASK, x, __ffs(m) - 1); sy = __shfl_sync(LL_FULL_MASK, y, __ffs(m) - 1); }
+    }
+    if (ln == 0) {
+        L.first_valid = fv >= 0 ? fv : INT_MAX;
+        L.start_ori = fv >= 0 ? -(float)atan2((double)sy, (double)sx) : 0.f;   // = the ori k_classify stores for that point
+        L.last_valid = -1;
+        L.half_idx = INT_MAX;
     }
 }
 
@@ -775,7 +842,7 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     P.inv_leaf = 1.0f / 0.2f;
     cudaStream_t s = c->stream;
     const dim3 tiles(c->NT, n_lanes);
-    { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<(n_lanes + 127) / 128, 128, 0, s>>>(c->d_lane, n_lanes); }
+    { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<n_lanes, 32, 0, s>>>(c->d_lane, n_lanes, P.thres); }
     { LLProf pr(c, "k_classify"); k_classify<<<tiles, LL_TILE, 0, s>>>(P); }
     { LLProf pr(c, "k_ring_scan"); k_ring_scan<<<n_lanes, 1024, 0, s>>>(P); }
     { LLProf pr(c, "k_scatter"); k_scatter<<<tiles, LL_TILE, 0, s>>>(P); }

@@ -323,100 +323,159 @@ __device__ __forceinline__ void for_range4(const float4* __restrict__ sorted, in
         f(t0); f(t1); f(t2); f(t3);
     }
 }
+// Up to three spans as ONE candidate stream (four loads in flight across span boundaries): the spans of neighbouring
+// azimuth bins cost one memory round trip together instead of one each.
+template <typename F>
+__device__ __forceinline__ void for_spans3(const float4* __restrict__ sorted, int s0, int e0, int s1, int e1, int s2, int e2, F&& f)
+{
+    const int n0 = e0 - s0, n01 = n0 + (e1 - s1), tot = n01 + (e2 - s2);
+    auto at = [&](int k) { k = min(k, tot - 1); return sorted + (k < n0 ? s0 + k : (k < n01 ? s1 + (k - n0) : s2 + (k - n01))); };
+#pragma unroll 1
+    for (int k = 0; k < tot; k += 4) {
+        const float4 t0 = ld_point(at(k)), t1 = ld_point(at(k + 1)), t2 = ld_point(at(k + 2)), t3 = ld_point(at(k + 3));
+        f(t0); f(t1); f(t2); f(t3);
+    }
+}
 struct AssocQuery {
     float qx, qy, qz;
     int closest, cring, n;
     u64 k2, k3;
+    unsigned cut;   // d2 bit patterns above this cannot improve k2 / k3 (and 25.0f and above never count, LO:521)
 };
+#define D2_BITS_25 0x41C80000u   // 25.0f; for d2 >= 0 the bit patterns order like the values, NaNs sort above
+template <bool CORNER>
+__device__ __forceinline__ void assoc_update_cut(AssocQuery& Q)
+{
+    const unsigned h2 = (unsigned)(Q.k2 >> 32), h3 = (unsigned)(Q.k3 >> 32);
+    Q.cut = min(D2_BITS_25 - 1u, CORNER ? h2 : max(h2, h3));
+}
 template <bool CORNER>
 __device__ __forceinline__ void assoc_consider(AssocQuery& Q, const float4 t)
 {
+    const float d2 = sqdist3(t.x, t.y, t.z, Q.qx, Q.qy, Q.qz);
+    if (__float_as_uint(d2) > Q.cut) return;   // most candidates: farther than what is already held (or >= 25, LO:521)
     const unsigned bits = (unsigned)__float_as_int(t.w);
     const int j = (int)(bits & 0xFFFFFFu), rj = (int)(bits >> 24);
-    const float d2 = sqdist3(t.x, t.y, t.z, Q.qx, Q.qy, Q.qz);
-    if (!(d2 < 25.0f) || j == Q.closest) return;  // 25 is exact in fp32: same decision as the fp64 compare of LO:521
+    if (j == Q.closest) return;
     const unsigned rank = j > Q.closest ? (unsigned)(j - (Q.closest + 1)) : (unsigned)Q.n + (unsigned)(Q.closest - 1 - j);
     const u64 key = ((u64)__float_as_uint(d2) << 32) | rank;
-    if (CORNER) { if (rj != Q.cring && key < Q.k2) Q.k2 = key; }  // same scan line -> continue (LO:507 / LO:533)
-    else if (rj == Q.cring) { if (key < Q.k2) Q.k2 = key; }  // LO:682 / LO:710 on a ring-monotone cloud
-    else if (key < Q.k3) Q.k3 = key;                         // LO:688 / LO:716
+    if (CORNER) { if (rj != Q.cring && key < Q.k2) { Q.k2 = key; assoc_update_cut<CORNER>(Q); } }  // same scan line -> continue (LO:507 / LO:533)
+    else if (rj == Q.cring) { if (key < Q.k2) { Q.k2 = key; assoc_update_cut<CORNER>(Q); } }  // LO:682 / LO:710 on a ring-monotone cloud
+    else if (key < Q.k3) { Q.k3 = key; assoc_update_cut<CORNER>(Q); }                         // LO:688 / LO:716
 }
-// every bin at azimuth offset > done from the query's bin holds only points at least this far away (squared)
-__device__ __forceinline__ float assoc_az_bound2(float rho, float wbin, int done)
+// ---- polar index primitives shared by the two searches ------------------------------------------------------------
+struct RingBands { float elo[LL_MAX_RINGS], ehi[LL_MAX_RINGS]; int ordered; };
+struct PolarQuery {
+    float rho, qn, eq, frac, inv_w;  // horizontal range, range, elevation, position inside the own azimuth bin [0,1], bins per radian
+    int b0, r0;                      // own azimuth bin; first ring whose band ends at or above the query's elevation
+};
+struct PolarReach { int ra, rb, kl, kr; };  // rings [ra, rb]; azimuth bins b0-kl .. b0+kr
+#define NN_NONE ((u64)0x41C80000u << 32)    // (bits of 25.0f, index 0): only d2 < 25 beats it (LO:497 / LO:659)
+__device__ __forceinline__ int azimuth_bin_frac(float x, float y, int NB, float& frac)
 {
-    const float dmin = (float)done * wbin - 1e-4f;
-    const float lb = (dmin >= 1.5707963f ? rho : rho * __sinf(fmaxf(dmin, 0.f))) - 1e-3f;  // |__sinf error| * rho << 1e-3
-    return lb > 0.f ? lb * lb : 0.f;
+    const float phi = atan2f(y, x);  // same arithmetic as azimuth_bin()
+    const float fb = (phi + 3.14159265f) * ((float)NB * 0.15915494f);
+    int b = (int)floorf(fb);
+    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+    frac = fminf(fmaxf(fb - (float)b, 0.f), 1.f);
+    return b;
 }
-template <bool CORNER>
-__device__ __forceinline__ bool assoc_window_done(const AssocQuery& Q, float lb2, int done, int NB)
+// Largest angle (+ slack) between the query's direction and that of a point closer than bd, for a query `range` away
+// from the apex: asin(bd / range), over-estimated by 1.0472 x (x <= 0.5) or (pi/2) x; 4 (> pi) = anywhere.
+__device__ __forceinline__ float reach_angle(float bd, float range)
 {
-    const bool ok2 = Q.k2 != ~0ull && __uint_as_float((unsigned)(Q.k2 >> 32)) < lb2;
-    const bool ok3 = CORNER || (Q.k3 != ~0ull && __uint_as_float((unsigned)(Q.k3 >> 32)) < lb2);
-    return (ok2 && ok3) || lb2 >= 25.0f || 2 * done + 1 >= NB;
+    const float x = __fdividef(bd, range);
+    if (!(x < 1.f)) return 4.f;
+    return x * (x < 0.5f ? 1.0472f : 1.5708f) + 2e-4f;
 }
+__device__ __forceinline__ void polar_query_init(PolarQuery& pq, float qx, float qy, float qz, int NB)
+{
+    pq.rho = sqrtf(qx * qx + qy * qy);
+    pq.qn = sqrtf(pq.rho * pq.rho + qz * qz);
+    pq.eq = atan2f(qz, pq.rho);   // = elevation_of()
+    pq.b0 = azimuth_bin_frac(qx, qy, NB, pq.frac);
+    pq.inv_w = (float)NB * 0.15915494f;
+}
+// azimuth part of the reach: bins at left offset k begin (frac + k - 1) bins away, at right offset k (k - frac) bins
+__device__ __forceinline__ void polar_reach_bins(const PolarQuery& pq, int NB, float bd, int& kl, int& kr)
+{
+    const float ab = reach_angle(bd, pq.rho) * pq.inv_w;
+    kl = ab >= (float)NB ? NB : (int)floorf(ab - pq.frac + 1.f);
+    kr = ab >= (float)NB ? NB : (int)floorf(ab + pq.frac);
+    kl = max(0, min(kl, NB / 2 - 1));   // all the way round: every bin once
+    kr = max(0, min(kr, NB / 2));
+}
+__device__ __forceinline__ float best_dist(u64 best) { return sqrtf(__uint_as_float((unsigned)(best >> 32))) + 2e-3f; }
+// ---- ring window ---------------------------------------------------------------------------------------------
 // Ring-monotone *Last cloud: the serial loops of LO:504-553 / LO:668-721 visit exactly the points whose ring lies
-// in [cring-2, cring+2].  Those rings are searched through the ring x azimuth-bin index: a point whose azimuth
-// differs from the query's by D lies at least rho * sin(D) away (rho = horizontal range of the query), so bins
-// are visited outward from the query's bin until that bound exceeds the best distances found (or 5 m, LO:29).
-// The index is bin-major (bucket = bin * R + ring): the five rings of one bin are ONE contiguous span of the
-// bucket-sorted array, two header loads and a linear read.
-// Per-thread part: offsets up to dmax.  Returns the offset reached, negative once the search is resolved.
+// in [cring-2, cring+2].  Those rings are searched through the polar index: a point whose azimuth differs from the
+// query's by D lies at least rho * sin(D) away (rho = horizontal range of the query), so bins are visited outward from
+// the query's position inside its own bin until that bound exceeds the distances held (or 5 m, LO:29).  The index is
+// bin-major (bucket = bin * R + ring): the five rings of one bin are ONE contiguous span of the sorted array.
+// distance within which the window still has to look: the farther of the 2nd / 3rd point held, 5 m while one is open
 template <bool CORNER>
-__device__ __forceinline__ int assoc_ring_window(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int dmax)
+__device__ __forceinline__ float assoc_window_dist(const AssocQuery& Q)
 {
-    const float rho = sqrtf(Q.qx * Q.qx + Q.qy * Q.qy);
-    const int b0 = azimuth_bin(Q.qx, Q.qy, NB);
-    const float wbin = 6.2831853f / (float)NB;
+    const unsigned h2 = (unsigned)(Q.k2 >> 32), h3 = CORNER ? 0u : (unsigned)(Q.k3 >> 32);
+    const unsigned h = min(max(h2, h3), D2_BITS_25);
+    return sqrtf(__uint_as_float(h)) + 2e-3f;
+}
+// Per-thread part: up to dmax bins per side.  Returns false when the window needs more than that (the warp pass
+// restarts it).
+template <bool CORNER>
+__device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuery& pq, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int dmax)
+{
     const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
     auto header = [&](int off, int& s, int& e) {
-        const int bin = (b0 + off) & (NB - 1);  // NB is a power of two
-        s = __ldg(start + bin * R + r_lo);
-        e = __ldg(start + bin * R + r_lo + r_n);
+        const int* h = start + ((pq.b0 + off) & (NB - 1)) * R + r_lo;  // NB is a power of two
+        s = __ldg(h); e = __ldg(h + r_n);
     };
-    int s0, e0, s1, e1, s2, e2;
-    header(-1, s0, e0); header(0, s1, e1); header(1, s2, e2);
+    auto consider = [&](const float4 t) { assoc_consider<CORNER>(Q, t); };
+    const int near = pq.frac < 0.5f ? -1 : 1;
+    int s0, e0, s1, e1;
+    header(0, s0, e0); header(near, s1, e1);
+    for_spans3(sorted, s0, e0, s1, e1, 0, 0, consider);
+    int kl, kr;
 #pragma unroll 1
-    for (int t = 0; t < 3; ++t) {
-        const int s = t == 0 ? s0 : (t == 1 ? s1 : s2), e = t == 0 ? e0 : (t == 1 ? e1 : e2);
-        for_range4(sorted, s, e, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
-    }
-    int done = 1;  // offsets |k| <= done have been visited
-    for (;;) {
-        if (assoc_window_done<CORNER>(Q, assoc_az_bound2(rho, wbin, done), done, NB)) return -1;
-        if (done >= dmax) return done;
-        ++done;
-        header(-done, s0, e0); header(done, s1, e1);
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-            const int s = t == 0 ? s0 : s1, e = t == 0 ? e0 : e1;
-            for_range4(sorted, s, e, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
-        }
+    for (int k = 1;; ++k) {
+        polar_reach_bins(pq, NB, assoc_window_dist<CORNER>(Q), kl, kr);
+        if (k > kl && k > kr) return true;
+        if (k > dmax) return false;
+        s0 = e0 = s1 = e1 = 0;
+        if (k <= kl && !(k == 1 && near < 0)) header(-k, s0, e0);
+        if (k <= kr && !(k == 1 && near > 0)) header(k, s1, e1);
+        for_spans3(sorted, s0, e0, s1, e1, 0, 0, consider);
     }
 }
-// Warp part: continues one query's ring window from offset `done`, 32 bins (16 per side, five rings each) per step.
+// Warp part: one query's whole ring window, the bins in reach shared out over the lanes (at most 16 per side and
+// round, the reach being re-evaluated between rounds).
 template <bool CORNER>
-__device__ __forceinline__ void assoc_ring_window_warp(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int done)
+__device__ __forceinline__ void assoc_ring_window_warp(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R)
 {
     const int lane = lane_id();
-    const float rho = sqrtf(Q.qx * Q.qx + Q.qy * Q.qy);
-    const int b0 = azimuth_bin(Q.qx, Q.qy, NB);
-    const float wbin = 6.2831853f / (float)NB;
+    PolarQuery pq;
+    polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
     const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
+    int doneL = 0, doneR = -1;   // left offsets 1..doneL and right offsets 0..doneR have been visited
     for (;;) {
-        const int mag = done + 1 + (lane >> 1);
-        const int off = (lane & 1) ? -mag : mag;
-        int beg = 0, cnt = 0;
-        if (mag <= NB / 2 && !(off == -(NB / 2))) {  // all the way round: keep each bin once
-            const int bin = (b0 + off) & (NB - 1);
-            beg = __ldg(start + bin * R + r_lo);
-            cnt = __ldg(start + bin * R + r_lo + r_n) - beg;
+        int kl, kr;
+        polar_reach_bins(pq, NB, assoc_window_dist<CORNER>(Q), kl, kr);
+        if (doneL >= kl && doneR >= kr) break;
+        const int idx = lane >> 1;
+        int beg = 0, cnt = 0, off = 0;
+        bool on = false;
+        if (lane & 1) { const int k = doneL + 1 + idx; on = k <= kl; off = -k; }
+        else { const int k = doneR + 1 + idx; on = k <= kr; off = k; }
+        if (on) {
+            const int* h = start + ((pq.b0 + off) & (NB - 1)) * R + r_lo;
+            beg = __ldg(h);
+            cnt = __ldg(h + r_n) - beg;
         }
         grid_stream_ranges(sorted, beg, cnt, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
-        done += 16;
+        doneL += 16; doneR += 16;
         Q.k2 = warp_min_u64(Q.k2);
         if (!CORNER) Q.k3 = warp_min_u64(Q.k3);
-        if (assoc_window_done<CORNER>(Q, assoc_az_bound2(rho, wbin, done), done, NB)) break;
+        assoc_update_cut<CORNER>(Q);
     }
 }
 // The literal scan loops (LO:504-553 / LO:668-721) for clouds that are not ring-sorted (legal on the topic, never
@@ -474,48 +533,6 @@ __device__ __forceinline__ void assoc_literal_walk_warp(AssocQuery& Q, const flo
     Q.k3 = warp_min_u64(Q.k3);
 }
 // ---- exact 1-NN over the polar index ---------------------------------------------------------------------------
-struct RingBands { float elo[LL_MAX_RINGS], ehi[LL_MAX_RINGS]; int ordered; };
-struct PolarQuery {
-    float rho, qn, eq, frac, inv_w;  // horizontal range, range, elevation, position inside the own azimuth bin [0,1], bins per radian
-    int b0, r0;                      // own azimuth bin; first ring whose band ends at or above the query's elevation
-};
-struct PolarReach { int ra, rb, kl, kr; };  // rings [ra, rb]; azimuth bins b0-kl .. b0+kr
-#define NN_NONE ((u64)0x41C80000u << 32)    // (bits of 25.0f, index 0): only d2 < 25 beats it (LO:497 / LO:659)
-__device__ __forceinline__ int azimuth_bin_frac(float x, float y, int NB, float& frac)
-{
-    const float phi = atan2f(y, x);  // same arithmetic as azimuth_bin()
-    const float fb = (phi + 3.14159265f) * ((float)NB * 0.15915494f);
-    int b = (int)floorf(fb);
-    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-    frac = fminf(fmaxf(fb - (float)b, 0.f), 1.f);
-    return b;
-}
-// Largest angle (+ slack) between the query's direction and that of a point closer than bd, for a query `range` away
-// from the apex: asin(bd / range), over-estimated by 1.0472 x (x <= 0.5) or (pi/2) x; 4 (> pi) = anywhere.
-__device__ __forceinline__ float reach_angle(float bd, float range)
-{
-    const float x = __fdividef(bd, range);
-    if (!(x < 1.f)) return 4.f;
-    return x * (x < 0.5f ? 1.0472f : 1.5708f) + 2e-4f;
-}
-__device__ __forceinline__ void polar_query_init(PolarQuery& pq, float qx, float qy, float qz, int NB)
-{
-    pq.rho = sqrtf(qx * qx + qy * qy);
-    pq.qn = sqrtf(pq.rho * pq.rho + qz * qz);
-    pq.eq = atan2f(qz, pq.rho);   // = elevation_of()
-    pq.b0 = azimuth_bin_frac(qx, qy, NB, pq.frac);
-    pq.inv_w = (float)NB * 0.15915494f;
-}
-// azimuth part of the reach: bins at left offset k begin (frac + k - 1) bins away, at right offset k (k - frac) bins
-__device__ __forceinline__ void polar_reach_bins(const PolarQuery& pq, int NB, float bd, int& kl, int& kr)
-{
-    const float ab = reach_angle(bd, pq.rho) * pq.inv_w;
-    kl = ab >= (float)NB ? NB : (int)floorf(ab - pq.frac + 1.f);
-    kr = ab >= (float)NB ? NB : (int)floorf(ab + pq.frac);
-    kl = max(0, min(kl, NB / 2 - 1));   // all the way round: every bin once
-    kr = max(0, min(kr, NB / 2));
-}
-__device__ __forceinline__ float best_dist(u64 best) { return sqrtf(__uint_as_float((unsigned)(best >> 32))) + 2e-3f; }
 // per-thread version, bands in shared memory
 __device__ __forceinline__ PolarReach polar_reach(const RingBands& S, const PolarQuery& pq, int NB, int R, u64 best)
 {
@@ -541,47 +558,37 @@ __device__ __forceinline__ void nn_consider(u64& best, float qx, float qy, float
 // Per-thread search.  Returns true when `best` is final; false = too wide for one thread (best = what was found so
 // far, the warp pass restarts from it).
 __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R,
-                                                     float qx, float qy, float qz, int kmax, u64& best)
+                                                     float qx, float qy, float qz, int kmax, PolarQuery& pq, u64& best)
 {
-    PolarQuery pq;
-    polar_query_init(pq, qx, qy, qz, NB);
     {
         int lo = 0, hi = R;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.ehi[mid] < pq.eq) lo = mid + 1; else hi = mid; }
         pq.r0 = min(lo, R - 1);
     }
-    auto visit = [&](int s, int e) { for_range4(sorted, s, e, [&](const float4 t) { nn_consider(best, qx, qy, qz, t); }); };
+    auto consider = [&](const float4 t) { nn_consider(best, qx, qy, qz, t); };
     auto span = [&](int off, int ra, int rb, int& s, int& e) {
         const int* h = start + ((pq.b0 + off) & (NB - 1)) * R;   // NB is a power of two
         s = __ldg(h + ra); e = __ldg(h + rb + 1);
     };
-    // seed: rings r0-1 .. r0+1 of the own bin and of the nearer neighbour bin
+    // seed: rings r0-1 .. r0+1 of the own bin and its two neighbours, one stream
     const int sa = max(pq.r0 - 1, 0), sb = min(pq.r0 + 1, R - 1);
-    const int near = pq.frac < 0.5f ? -1 : 1;
-    int s0, e0, s1, e1;
-    span(0, sa, sb, s0, e0); span(near, sa, sb, s1, e1);
-    visit(s0, e0); visit(s1, e1);
+    int s0, e0, s1, e1, s2, e2;
+    span(0, sa, sb, s0, e0); span(-1, sa, sb, s1, e1); span(1, sa, sb, s2, e2);
+    for_spans3(sorted, s0, e0, s1, e1, s2, e2, consider);
     PolarReach W = polar_reach(S, pq, NB, R, best);
-    u64 seen = best;
+    if (W.ra >= sa && W.rb <= sb && W.kl <= 1 && W.kr <= 1) return true;   // nothing closer can lie outside the seed
     if (W.rb - W.ra > 16 || max(W.kl, W.kr) > kmax) return false;
-    // the remaining rings of the two seeded bins
+    // outward from the own bin over the rings in reach (buckets of the seed are met again: a minimum does not mind);
+    // the reach only shrinks as the best improves
+    u64 seen = best;
 #pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-        const int off = t == 0 ? 0 : near;
-        if (t == 1 && (near < 0 ? W.kl : W.kr) < 1) break;
-        if (W.ra < sa) { span(off, W.ra, sa - 1, s0, e0); visit(s0, e0); }
-        if (W.rb > sb) { span(off, sb + 1, W.rb, s1, e1); visit(s1, e1); }
-    }
-    // outward; the reach only shrinks as the best improves
-#pragma unroll 1
-    for (int k = 1;; ++k) {
+    for (int k = 0;; ++k) {
         if (best != seen) { W = polar_reach(S, pq, NB, R, best); seen = best; }
-        const bool l = k <= W.kl && !(k == 1 && near < 0), r = k <= W.kr && !(k == 1 && near > 0);
         if (k > W.kl && k > W.kr) return true;
         s0 = e0 = s1 = e1 = 0;
-        if (l) span(-k, W.ra, W.rb, s0, e0);
-        if (r) span(k, W.ra, W.rb, s1, e1);
-        visit(s0, e0); visit(s1, e1);
+        if (k >= 1 && k <= W.kl) span(-k, W.ra, W.rb, s0, e0);
+        if (k <= W.kr) span(k, W.ra, W.rb, s1, e1);
+        for_spans3(sorted, s0, e0, s1, e1, 0, 0, consider);
     }
 }
 // Warp version (one query per warp; bands read from global memory): every step streams the rings in reach of up to
@@ -598,7 +605,10 @@ __device__ __forceinline__ u64 polar_nearest_warp(const float* __restrict__ band
     const int ordered = __ldg(reinterpret_cast<const int*>(bands) + 2 * LL_MAX_RINGS);
     pq.r0 = min(__popc(__ballot_sync(LL_FULL_MASK, ehi0 < pq.eq)) + __popc(__ballot_sync(LL_FULL_MASK, ehi1 < pq.eq)), R - 1);
     u64 lb = best;
-    int doneL = 0, doneR = -1;   // left offsets 1..doneL and right offsets 0..doneR have been visited
+    // The window (bins b0-wk .. b0+wk, rings r0-wr .. r0+wr) doubles every round and is clipped to the reach of the best
+    // found so far; the search ends when a round's window covered the whole reach it was clipped to.  The cost is
+    // that of the final window (the earlier ones add a third), not that of the 5 m reach a query starts with.
+    int wk = 8, wr = 16;   // what the thread pass hands over nearly always resolves inside this first window
     for (;;) {
         const float bd = best_dist(best);
         const float g = reach_angle(bd, pq.qn);
@@ -607,27 +617,29 @@ __device__ __forceinline__ u64 polar_nearest_warp(const float* __restrict__ band
             // ring r is in reach when its band comes within g of the query's elevation; ordered bands: a contiguous range
             const bool in0 = lane < R && (lane >= pq.r0 ? elo0 - pq.eq <= g : pq.eq - ehi0 <= g);
             const bool in1 = lane + 32 < R && (lane + 32 >= pq.r0 ? elo1 - pq.eq <= g : pq.eq - ehi1 <= g);
-            const unsigned m0 = __ballot_sync(LL_FULL_MASK, in0 || lane == pq.r0), m1 = __ballot_sync(LL_FULL_MASK, in1 || lane + 32 == pq.r0);
-            // contiguous run around r0
-            ra = pq.r0; rb = pq.r0;
-            const u64 m = ((u64)m1 << 32) | m0;
-            while (ra > 0 && ((m >> (ra - 1)) & 1ull)) --ra;
-            while (rb < R - 1 && ((m >> (rb + 1)) & 1ull)) ++rb;
+            const u64 m = ((u64)__ballot_sync(LL_FULL_MASK, in1) << 32) | __ballot_sync(LL_FULL_MASK, in0);
+            // the run of set bits around r0
+            const u64 below = ~m & ((1ull << pq.r0) - 1ull);              // rings < r0 out of reach
+            ra = below ? 64 - __clzll(below) : 0;
+            const u64 above = pq.r0 >= 63 ? 0ull : (~m >> (pq.r0 + 1));   // rings > r0 out of reach, bit 0 = r0 + 1
+            rb = above ? pq.r0 + __ffsll(above) - 1 : 63;
+            rb = min(rb, R - 1);
         }
         polar_reach_bins(pq, NB, bd, kl, kr);
-        if (doneL >= kl && doneR >= kr) break;
-        const int idx = lane >> 1;
-        int beg = 0, cnt = 0, k = -1, off = 0;
-        if (lane & 1) { k = doneL + 1 + idx; if (k <= kl) off = -k; else k = -1; }
-        else { k = doneR + 1 + idx; if (k <= kr) off = k; else k = -1; }
-        if (k >= 0) {
-            const int* h = start + ((pq.b0 + off) & (NB - 1)) * R;
-            beg = __ldg(h + ra);
-            cnt = __ldg(h + rb + 1) - beg;
+        const int cra = max(ra, pq.r0 - wr), crb = min(rb, pq.r0 + wr), ckl = min(kl, wk), ckr = min(kr, wk);
+        for (int o0 = -ckl; o0 <= ckr; o0 += 32) {
+            const int off = o0 + lane;
+            int beg = 0, cnt = 0;
+            if (off <= ckr) {
+                const int* h = start + ((pq.b0 + off) & (NB - 1)) * R;
+                beg = __ldg(h + cra);
+                cnt = __ldg(h + crb + 1) - beg;
+            }
+            grid_stream_ranges(sorted, beg, cnt, [&](const float4 t) { nn_consider(lb, qx, qy, qz, t); });
         }
-        grid_stream_ranges(sorted, beg, cnt, [&](const float4 t) { nn_consider(lb, qx, qy, qz, t); });
-        doneL += 16; doneR += 16;
         best = warp_min_u64(lb);
+        if (cra == ra && crb == rb && ckl == kl && ckr == kr) break;   // the reach only shrinks from here
+        wk <<= 1; wr <<= 1;
     }
     return best;
 }
@@ -668,7 +680,7 @@ __device__ __forceinline__ void assoc_query_init(const OdomParams& P, const Lane
     double sx, sy, sz;
     quat_rotate(L.para_q, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
     Q.qx = (float)(sx + L.para_t[0]); Q.qy = (float)(sy + L.para_t[1]); Q.qz = (float)(sz + L.para_t[2]);
-    Q.k2 = ~0ull; Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0;
+    Q.k2 = ~0ull; Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.cut = D2_BITS_25 - 1u;
     Q.n = CORNER ? L.n_last_corner : L.n_last_surf;
 }
 // queue entry of a query the per-thread pass did not finish: x = lane, y = feature index | plane << 30 | open << 29;
@@ -683,7 +695,7 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
 {
     const int lane = lane_id();
     AssocQuery Q;
-    Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0;
+    Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0; Q.cut = D2_BITS_25 - 1u;
     int4 entry = make_int4(b, CORNER ? i : (i | ASSOC_PLANE_BIT), -1, -1);
     bool heavy = false;
     if (active) {
@@ -691,8 +703,10 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
         const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
         const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
         u64 best = NN_NONE;
+        PolarQuery pq;
+        polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
         if (Q.n > 0) {
-            heavy = !polar_nearest_thread(S, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, best);
+            heavy = !polar_nearest_thread(S, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best);
             if (heavy) { entry.y |= ASSOC_OPEN_BIT; entry.z = (int)(unsigned)(best >> 32); entry.w = (int)(unsigned)best; }
         }
         if (!heavy && best != NN_NONE) {  // d2 < 25: LO:497 / LO:659
@@ -701,13 +715,13 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
             Q.cring = (int)last[Q.closest].w;  // int(intensity), LO:500 / LO:664
             int pending = -2;                  // clouds that are not ring-sorted: literal walk
             if (CORNER ? L.mono_corner : L.mono_surf) {
-                pending = assoc_ring_window<CORNER>(Q, av.start, av.sorted, NB, P.R, dmax);
-                heavy = pending >= 0;
+                pending = assoc_ring_window<CORNER>(Q, pq, av.start, av.sorted, NB, P.R, dmax) ? -3 : -1;
+                heavy = pending == -1;
             } else {
                 heavy = true;
             }
             entry.z = Q.closest;
-            entry.w = pending >= 0 ? -1 : pending;
+            entry.w = pending;
         }
         if (!heavy) assoc_store<CORNER>(P, b, i, Q);
     }
@@ -722,7 +736,8 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
     }
 }
 // grid: (ceil(R*12 / T) + ceil(R*24 / T), B): corner queries and plane queries never share a block
-__global__ void __launch_bounds__(ASSOC_THREADS, 6) k_odom_assoc(OdomParams P, int corner_blocks, int dmax, int kmax)
+template <int MINB>
+__global__ void __launch_bounds__(ASSOC_THREADS, MINB) k_odom_assoc(OdomParams P, int corner_blocks, int dmax, int kmax)
 {
     __shared__ RingBands S;
     const int b = blockIdx.y;
@@ -769,7 +784,7 @@ __device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int
         Q.closest = closest;
         Q.cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
         if (mode == -2) assoc_literal_walk_warp<CORNER>(Q, last);
-        else assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, NB, P.R, -1);
+        else assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, NB, P.R);
     }
     if (lane == 0) assoc_store<CORNER>(P, b, i, Q);
 }
@@ -785,9 +800,15 @@ __global__ void __launch_bounds__(256, 4) k_odom_assoc_heavy(OdomParams P)
         const int4 en = P.queue[e];
         const int i = en.y & ~(ASSOC_PLANE_BIT | ASSOC_OPEN_BIT);
         const bool open = (en.y & ASSOC_OPEN_BIT) != 0;
-        if (P.dev_skip & 16) { if (lane_id() == 0) atomicAdd(&P.lane[0].dbg[open ? 1 : 2], 1); }
+        const long long t0 = (P.dev_skip & 16) ? clock64() : 0;
         if (en.y & ASSOC_PLANE_BIT) assoc_warp_query<false>(P, en.x, i, open, en.z, en.w);
         else assoc_warp_query<true>(P, en.x, i, open, en.z, en.w);
+        if ((P.dev_skip & 16) && lane_id() == 0) {  // development statistics: entries, cycles and longest entry per kind
+            const int dt = (int)((clock64() - t0) >> 4), kind = open ? 0 : 1;
+            atomicAdd(&P.lane[0].dbg[1 + kind], 1);
+            atomicAdd(&P.lane[0].dbg[3 + kind], dt >> 6);
+            atomicMax(&P.lane[0].dbg[5 + kind], dt);
+        }
     }
 }
 
@@ -1022,7 +1043,8 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, s));
     const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
     const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;   // ring-window bins per side a thread walks
-    const int kmax = getenv("LL_ASSOC_KMAX") ? atoi(getenv("LL_ASSOC_KMAX")) : 3;   // 1-NN bins per side a thread walks
+    const int minb = getenv("LL_ASSOC_MINB") ? atoi(getenv("LL_ASSOC_MINB")) : 8;   // resident blocks per SM the thread pass is compiled for
+    const int kmax = getenv("LL_ASSOC_KMAX") ? atoi(getenv("LL_ASSOC_KMAX")) : 2;   // 1-NN bins per side a thread walks
     const size_t vote_smem = (size_t)(c->R * LL_FLAT_PER_RING / 10 + 16) * (2 * sizeof(float4) + sizeof(int));
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
     // the polar indexes of the two *Last clouds are built together (4 launches) right before the association, so the
@@ -1051,7 +1073,14 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     }
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
-        { LLProf pr(c, "k_odom_assoc"); k_odom_assoc<<<dim3(cblocks + pblocks, n_lanes), ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax); }
+        {
+            LLProf pr(c, "k_odom_assoc");
+            const dim3 g(cblocks + pblocks, n_lanes);
+            if (minb >= 12) k_odom_assoc<12><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
+            else if (minb >= 10) k_odom_assoc<10><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
+            else if (minb >= 8) k_odom_assoc<8><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
+            else k_odom_assoc<6><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
+        }
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P); }
