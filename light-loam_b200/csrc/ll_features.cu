@@ -63,93 +63,118 @@ __device__ __forceinline__ bool point_valid(float x, float y, float z, float thr
 {
     return isfinite(x) && isfinite(y) && isfinite(z) && !(x * x + y * y + z * z < thres * thres);  // SR:109 / SR:72
 }
+// SR:139 + SR:142-169: ring id of a valid point (-2 = outside the sensor's rings)
+__device__ __forceinline__ int ring_of(const FeatParams& P, float x, float y, float z)
+{
+    // float atan / sqrt, * 180 in fp32, / M_PI in fp64, stored as float; then the ring formula.
+    // Only the integer scanID survives, so it is first computed in plain fp32 (error << 1e-3 of a ring); the
+    // literal sequence (atanf evaluated in fp64 and rounded once, double division) runs only when that value
+    // lies within 2e-3 of a truncation boundary, where the roundings of the reference decide.
+    const float t = z / sqrtf(x * x + y * y);
+    const float angf = atanf(t) * 57.29578f;
+    const float vf = P.scan_line == 16 ? (angf + 15.0f) * 0.5f + 0.5f : (P.scan_line == 32 ? (angf + 30.666666f) * 0.75f : (angf - P.lower_bound) * P.factor + 0.5f);
+    const float fr = vf - floorf(vf);
+    int scanID;
+    if (vf > 1e-3f && fr > 2e-3f && fr < 1.0f - 2e-3f) {
+        scanID = (int)vf;
+        if (scanID >= P.scan_line) scanID = -2;
+    } else {
+        const float a = (float)atan((double)t);
+        const float angle = (float)((double)(a * 180.0f) / LL_PI);
+        if (P.scan_line == 16) {
+            scanID = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
+            if (scanID > 15 || scanID < 0) scanID = -2;
+        } else if (P.scan_line == 32) {
+            scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+            if (scanID > 31 || scanID < 0) scanID = -2;
+        } else {
+            scanID = (int)((double)((angle - P.lower_bound) * P.factor) + 0.5);
+            if (scanID >= 64 || scanID < 0) scanID = -2;
+        }
+    }
+    return scanID;
+}
+// One CTA classifies CLS_TPB consecutive 256-point tiles of a lane: the points of all its tiles are requested before
+// the first is used, so the dependent chain (lane state -> raw pointer -> point) is paid once per CTA, not per tile.
+#define CLS_TPB 4
 __global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
 {
-    __shared__ int cnt[LL_TILE / 32][LL_MAX_RINGS];
+    __shared__ int cnt[2][LL_TILE / 32][LL_MAX_RINGS];   // per-warp ring counts of a tile, double-buffered over the tiles
     __shared__ int flip_s;
-    for (int k = threadIdx.x; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0])[k] = 0;
+    for (int k = threadIdx.x; k < 2 * (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0][0])[k] = 0;
     if (threadIdx.x == 0) flip_s = INT_MAX;
-    __syncthreads();
     const int b = blockIdx.y;
     LaneState& L = P.lane[b];
     const int n = L.n_raw, sw = L.stride_words;
     const float startOri = L.start_ori;                  // found by k_reset_scan_state
     const int half_seen = *(volatile int*)&L.half_idx;   // filter for the atomic below; a stale (larger) value only costs an atomic
     const int w = warp_id(), lane = lane_id();
-    const int i = blockIdx.x * LL_TILE + threadIdx.x;
-    bool valid = false;
-    int ring = -1;
-    float ori = 0.f;
-    if (i < n) {
-        const uint32_t* p = L.raw + (size_t)i * sw;
-        float x, y, z;
-        if (sw == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); x = v.x; y = v.y; z = v.z; }  // slabs and the pool are 16-byte aligned
-        else { x = __uint_as_float(p[0]); y = __uint_as_float(p[1]); z = __uint_as_float(p[2]); }
-        valid = point_valid(x, y, z, P.thres);
-        if (valid) {
-            // SR:139: float atan / sqrt, * 180 in fp32, / M_PI in fp64, stored as float; SR:142-169 ring formula.
-            // Only the integer scanID survives, so it is first computed in plain fp32 (error << 1e-3 of a ring); the
-            // literal sequence (atanf evaluated in fp64 and rounded once, double division) runs only when that value
-            // lies within 2e-3 of a truncation boundary, where the roundings of the reference decide.
-            const float t = z / sqrtf(x * x + y * y);
-            const float angf = atanf(t) * 57.29578f;
-            const float vf = P.scan_line == 16 ? (angf + 15.0f) * 0.5f + 0.5f : (P.scan_line == 32 ? (angf + 30.666666f) * 0.75f : (angf - P.lower_bound) * P.factor + 0.5f);
-            const float fr = vf - floorf(vf);
-            int scanID;
-            if (vf > 1e-3f && fr > 2e-3f && fr < 1.0f - 2e-3f) {
-                scanID = (int)vf;
-                if (scanID >= P.scan_line) scanID = -2;
-            } else {
-                const float a = (float)atan((double)t);
-                const float angle = (float)((double)(a * 180.0f) / LL_PI);
-                if (P.scan_line == 16) {
-                    scanID = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
-                    if (scanID > 15 || scanID < 0) scanID = -2;
-                } else if (P.scan_line == 32) {
-                    scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
-                    if (scanID > 31 || scanID < 0) scanID = -2;
-                } else {
-                    scanID = (int)((double)((angle - P.lower_bound) * P.factor) + 0.5);
-                    if (scanID >= 64 || scanID < 0) scanID = -2;
-                }
-            }
-            ring = scanID;
-            ori = -(float)atan2((double)y, (double)x);  // SR:177
+    const int tile0 = blockIdx.x * CLS_TPB;
+    float px[CLS_TPB], py[CLS_TPB], pz[CLS_TPB];
+#pragma unroll
+    for (int t = 0; t < CLS_TPB; ++t) {
+        const int i = (tile0 + t) * LL_TILE + threadIdx.x;
+        px[t] = py[t] = pz[t] = 0.f;
+        if (i < n) {
+            const uint32_t* p = L.raw + (size_t)i * sw;
+            if (sw == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); px[t] = v.x; py[t] = v.y; pz[t] = v.z; }  // slabs and the pool are 16-byte aligned
+            else { px[t] = __uint_as_float(p[0]); py[t] = __uint_as_float(p[1]); pz[t] = __uint_as_float(p[2]); }
         }
     }
-    if (i < P.Nmax) {
+    __syncthreads();
+    int hi_max = -1, fl_min = INT_MAX;
+#pragma unroll
+    for (int t = 0; t < CLS_TPB; ++t) {
+        const int tile = tile0 + t;
+        if (tile >= P.NT) break;
+        int (*c)[LL_MAX_RINGS] = cnt[t & 1];
+        const int i = tile * LL_TILE + threadIdx.x;
+        const float x = px[t], y = py[t], z = pz[t];
+        const bool valid = i < n && point_valid(x, y, z, P.thres);
+        int ring = -1;
+        float ori = 0.f;
+        bool flip = false;
+        if (valid) {
+            ring = ring_of(P, x, y, z);
+            ori = -(float)atan2((double)y, (double)x);  // SR:177
+            if (ring >= 0) {
+                // SR:180-192 in the !halfPassed state: the first point for which this holds flips halfPassed
+                float o = ori;
+                if ((double)o < (double)startOri - LL_PI / 2)
+                    o = (float)((double)o + 2 * LL_PI);
+                else if ((double)o > (double)startOri + LL_PI * 3 / 2)
+                    o = (float)((double)o - 2 * LL_PI);
+                flip = (double)(o - startOri) > LL_PI;
+            }
+        }
         P.ring8[(size_t)b * P.Nmax + i] = (int8_t)ring;
         P.ori[(size_t)b * P.Nmax + i] = ori;
-    }
-    const int hi = __reduce_max_sync(LL_FULL_MASK, valid ? i : -1);
-    if (lane == 0 && hi >= 0) atomicMax(&L.last_valid, hi);
-    // stable rank inside the tile (SR:209 push_back order): warp match on the ring id, then prefix over the tile's warps
-    const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
-    const int rank_in_warp = __popc(m & ((1u << lane) - 1u));
-    if (ring >= 0 && rank_in_warp == 0) cnt[w][ring] = __popc(m);
-    __syncthreads();
-    {
-        // SR:180-192 in the !halfPassed state: the first point for which this holds flips halfPassed
-        bool flip = false;
-        if (ring >= 0) {
-            float o = ori;
-            if ((double)o < (double)startOri - LL_PI / 2)
-                o = (float)((double)o + 2 * LL_PI);
-            else if ((double)o > (double)startOri + LL_PI * 3 / 2)
-                o = (float)((double)o - 2 * LL_PI);
-            flip = (double)(o - startOri) > LL_PI;
+        hi_max = max(hi_max, valid ? i : -1);
+        if (flip) fl_min = min(fl_min, i);
+        // stable rank inside the tile (SR:209 push_back order): warp match on the ring id, then prefix over the tile's warps
+        const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
+        const int rank_in_warp = __popc(m & ((1u << lane) - 1u));
+        if (ring >= 0 && rank_in_warp == 0) c[w][ring] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x < P.R) {
+            int run = 0;
+            for (int ww = 0; ww < LL_TILE / 32; ++ww) { const int v = c[ww][threadIdx.x]; c[ww][threadIdx.x] = run; run += v; }
+            P.tile_hist[((size_t)b * P.R + threadIdx.x) * P.NT + tile] = run;  // [lane][ring][tile]: scans run along tiles
+        } else {
+            // the other buffer (read last by the previous tile's rank write, before the barrier above) is cleared for the next tile
+            for (int k = threadIdx.x - P.R; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE - P.R) (&cnt[(t + 1) & 1][0][0])[k] = 0;
         }
-        const int fl = __reduce_min_sync(LL_FULL_MASK, flip ? i : INT_MAX);
-        if (lane == 0 && fl != INT_MAX) atomicMin(&flip_s, fl);
+        __syncthreads();
+        P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(c[w][ring] + rank_in_warp) : 0;
     }
-    if (threadIdx.x < P.R) {
-        int run = 0;
-        for (int ww = 0; ww < LL_TILE / 32; ++ww) { const int c = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += c; }
-        P.tile_hist[((size_t)b * P.R + threadIdx.x) * P.NT + blockIdx.x] = run;  // [lane][ring][tile]: scans run along tiles
+    hi_max = __reduce_max_sync(LL_FULL_MASK, hi_max);
+    fl_min = __reduce_min_sync(LL_FULL_MASK, fl_min);
+    if (lane == 0) {
+        if (hi_max >= 0) atomicMax(&L.last_valid, hi_max);
+        if (fl_min != INT_MAX) atomicMin(&flip_s, fl_min);
     }
     __syncthreads();
-    if (i < P.Nmax) P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(cnt[w][ring] + rank_in_warp) : 0;
-    // about half of all tiles see a flip: one filtered atomic per tile
+    // about half of all CTAs see a flip: one filtered atomic each
     if (threadIdx.x == 0 && flip_s < half_seen) atomicMin(&L.half_idx, flip_s);
 }
 
@@ -235,37 +260,57 @@ __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
     }
 }
 
+// CLS_TPB tiles per CTA as in k_classify: ring offsets in shared memory, all the CTA's loads issued up front
 __global__ void __launch_bounds__(LL_TILE) k_scatter(FeatParams P)
 {
+    __shared__ int ring_begin_s[LL_MAX_RINGS];
     const int b = blockIdx.y;
     const LaneState& L = P.lane[b];
-    const int i = blockIdx.x * LL_TILE + threadIdx.x;
-    if (i >= L.n_raw) return;
-    const int ring = P.ring8[(size_t)b * P.Nmax + i];
-    if (ring < 0) return;
+    const int n = L.n_raw, sw = L.stride_words, half_idx = L.half_idx;
     const float startOri = L.start_ori, endOri = L.end_ori;
-    float ori = P.ori[(size_t)b * P.Nmax + i];
-    if (i <= L.half_idx) {  // SR:178-193 (the flipping point itself still takes this branch)
-        if ((double)ori < (double)startOri - LL_PI / 2)
-            ori = (float)((double)ori + 2 * LL_PI);
-        else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
-            ori = (float)((double)ori - 2 * LL_PI);
-    } else {  // SR:194-205
-        ori = (float)((double)ori + 2 * LL_PI);
-        if ((double)ori < (double)endOri - LL_PI * 3 / 2)
-            ori = (float)((double)ori + 2 * LL_PI);
-        else if ((double)ori > (double)endOri + LL_PI / 2)
-            ori = (float)((double)ori - 2 * LL_PI);
+    if (threadIdx.x < P.R) ring_begin_s[threadIdx.x] = L.ring_begin[threadIdx.x];
+    const int tile0 = blockIdx.x * CLS_TPB;
+    int ring[CLS_TPB], rank[CLS_TPB];
+    float orv[CLS_TPB];
+    float4 pt[CLS_TPB];
+#pragma unroll
+    for (int t = 0; t < CLS_TPB; ++t) {
+        const int i = (tile0 + t) * LL_TILE + threadIdx.x;
+        ring[t] = -1;
+        if (i < n) {
+            ring[t] = P.ring8[(size_t)b * P.Nmax + i];
+            orv[t] = P.ori[(size_t)b * P.Nmax + i];
+            rank[t] = P.rank8[(size_t)b * P.Nmax + i];
+            const uint32_t* p = L.raw + (size_t)i * sw;
+            if (sw == 4) pt[t] = __ldg(reinterpret_cast<const float4*>(p));
+            else pt[t] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), 0.f);
+        }
     }
-    const float relTime = (ori - startOri) / (endOri - startOri);          // SR:207
-    const float intensity = (float)((double)ring + 0.1 * (double)relTime);  // SR:208
-    const int pos = L.ring_begin[ring] + P.tile_hist[((size_t)b * P.R + ring) * P.NT + blockIdx.x] + P.rank8[(size_t)b * P.Nmax + i];
-    const uint32_t* p = L.raw + (size_t)i * L.stride_words;
-    float4 o;
-    if (L.stride_words == 4) o = __ldg(reinterpret_cast<const float4*>(p));
-    else o = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), 0.f);
-    o.w = intensity;
-    P.full[(size_t)b * P.Nmax + pos] = o;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < CLS_TPB; ++t) {
+        if (ring[t] < 0) continue;
+        const int tile = tile0 + t, i = tile * LL_TILE + threadIdx.x;
+        float ori = orv[t];
+        if (i <= half_idx) {  // SR:178-193 (the flipping point itself still takes this branch)
+            if ((double)ori < (double)startOri - LL_PI / 2)
+                ori = (float)((double)ori + 2 * LL_PI);
+            else if ((double)ori > (double)startOri + LL_PI * 3 / 2)
+                ori = (float)((double)ori - 2 * LL_PI);
+        } else {  // SR:194-205
+            ori = (float)((double)ori + 2 * LL_PI);
+            if ((double)ori < (double)endOri - LL_PI * 3 / 2)
+                ori = (float)((double)ori + 2 * LL_PI);
+            else if ((double)ori > (double)endOri + LL_PI / 2)
+                ori = (float)((double)ori - 2 * LL_PI);
+        }
+        const float relTime = (ori - startOri) / (endOri - startOri);             // SR:207
+        const float intensity = (float)((double)ring[t] + 0.1 * (double)relTime);  // SR:208
+        const int pos = ring_begin_s[ring[t]] + P.tile_hist[((size_t)b * P.R + ring[t]) * P.NT + tile] + rank[t];
+        float4 o = pt[t];
+        o.w = intensity;
+        P.full[(size_t)b * P.Nmax + pos] = o;
+    }
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------------------------
@@ -843,9 +888,9 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     cudaStream_t s = c->stream;
     const dim3 tiles(c->NT, n_lanes);
     { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<n_lanes, 32, 0, s>>>(c->d_lane, n_lanes, P.thres); }
-    { LLProf pr(c, "k_classify"); k_classify<<<tiles, LL_TILE, 0, s>>>(P); }
+    { LLProf pr(c, "k_classify"); k_classify<<<dim3((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes), LL_TILE, 0, s>>>(P); }
     { LLProf pr(c, "k_ring_scan"); k_ring_scan<<<n_lanes, 1024, 0, s>>>(P); }
-    { LLProf pr(c, "k_scatter"); k_scatter<<<tiles, LL_TILE, 0, s>>>(P); }
+    { LLProf pr(c, "k_scatter"); k_scatter<<<dim3((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes), LL_TILE, 0, s>>>(P); }
     const size_t smem_sort = ll_feature_smem_bytes(c->SCAP);
     const size_t smem_lf = ll_lessflat_smem_bytes(c->SCAP);
     const size_t smem_pick = (size_t)PICK_WARPS * (2 * ((c->RCAP + 31) / 32 + 2) + c->RCAP / 2) * 4;

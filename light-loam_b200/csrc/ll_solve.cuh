@@ -44,7 +44,13 @@ struct LmComm {
     unsigned long long timeout_ns;              // a peer that never shows up must not hang the GPU
 };
 
+struct LmCtl {   // trust-region controller state (thread 0 only); kept out of the registers of the evaluation loops
+    double H[21], g[6], scale[6], diagonal[6];
+    double x_cost, x_norm, radius, decrease_factor, se_cost, model_cost_change, gmax, initial_cost;
+    int reuse_diagonal, last_successful, atleast_one, iteration, invalid, term, jac_evals, cost_evals;
+};
 struct LmShared {
+    LmCtl ctl;
     double x[7], cand[7];
     double red[LM_THREADS / 32][LM_NRED];
     double out[LM_NRED];
@@ -102,94 +108,133 @@ __device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b
 //   type 0 EDGE        p0 = a, p1 = b
 //   type 1 PLANE_MODIFY p0 = j, p1 = ljm_norm, w = weight
 //   type 2 PLANE_NORM   p0 = unit normal, w = negative_OA_dot_norm
+// HuberLoss(0.1): returns rho(s); sq = sqrt(rho'(s)) - the Corrector with rho'' <= 0 scales r and J by it
+__device__ __forceinline__ double lm_huber(double s, double& sq)
+{
+    double rho0 = s, rho1 = 1.0;
+    if (s > 0.01) {
+        const double rr = sqrt(s);
+        rho0 = 2.0 * 0.1 * rr - 0.01;
+        rho1 = fmax(DBL_MIN, 0.1 / rr);
+    }
+    sq = sqrt(rho1);
+    return rho0;
+}
+// one residual row: J = d * [ -2 [R cp]x | I ] scaled by sq; JtJ (upper triangle), Jtr
+__device__ __forceinline__ void lm_row(double acc[LM_NRED], double d0, double d1, double d2, double rk, double Rx, double Ry, double Rz, double sq)
+{
+    double J[6];
+    J[0] = (d1 * (-2.0 * Rz) + d2 * (2.0 * Ry)) * sq;
+    J[1] = (d0 * (2.0 * Rz) + d2 * (-2.0 * Rx)) * sq;
+    J[2] = (d0 * (-2.0 * Ry) + d1 * (2.0 * Rx)) * sq;
+    J[3] = d0 * sq; J[4] = d1 * sq; J[5] = d2 * sq;
+    rk = rk * sq;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = a; c < 6; ++c) acc[q++] += J[a] * J[c];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * rk;
+}
+struct LmRecord { double v[11]; };
+__device__ __forceinline__ void lm_load_record(LmRecord& r, const double* __restrict__ blk, int cap, int i)
+{
+#pragma unroll
+    for (int k = 0; k < 11; ++k) r.v[k] = __ldg(blk + (size_t)k * cap + i);
+}
 template <bool FULL>
-__device__ __forceinline__ void lm_accumulate(const double* blk, int cap, int nb, const double* x, double acc[LM_NRED], int part = 0, int nparts = 1)
+__device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, int cap, int nb, const double* x, double acc[LM_NRED], int part = 0, int nparts = 1)
 {
 #pragma unroll
     for (int k = 0; k < LM_NRED; ++k) acc[k] = 0.0;
-    for (int i = part * LM_THREADS + threadIdx.x; i < nb; i += LM_THREADS * nparts) {
-        const int type = (int)blk[i];
-        if (type < 0) continue;  // dense mapping records: slot without a correspondence
-        const double cpx = blk[1 * cap + i], cpy = blk[2 * cap + i], cpz = blk[3 * cap + i];
-        const double ax = blk[4 * cap + i], ay = blk[5 * cap + i], az = blk[6 * cap + i];
-        const double bx = blk[7 * cap + i], by = blk[8 * cap + i], bz = blk[9 * cap + i];
-        const double w = blk[10 * cap + i];
+    // the record of the thread's next block is in flight while the current one is evaluated (all eleven fields are
+    // loaded before the type is looked at: a slot without a correspondence still holds readable numbers)
+    const int stride = LM_THREADS * nparts;
+    int i = part * LM_THREADS + threadIdx.x;
+    LmRecord cur, nxt;
+    if (i < nb) lm_load_record(cur, blk, cap, i);
+    for (; i < nb; i += stride) {
+        if (i + stride < nb) lm_load_record(nxt, blk, cap, i + stride);
+        const int type = (int)cur.v[0];
+        if (type >= 0) {  // dense mapping records: type -1 = slot without a correspondence
+        const double cpx = cur.v[1], cpy = cur.v[2], cpz = cur.v[3];
+        const double ax = cur.v[4], ay = cur.v[5], az = cur.v[6];
+        const double bx = cur.v[7], by = cur.v[8], bz = cur.v[9];
+        const double w = cur.v[10];
         double Rx, Ry, Rz;
         quat_rotate(x, cpx, cpy, cpz, Rx, Ry, Rz);
         const double lx = Rx + x[4], ly = Ry + x[5], lz = Rz + x[6];
-        double r[3], D[3][3];
-        int nr;
         if (type == 0) {
-            // r = ((lp - a) x (lp - b)) / |a - b| ; d r / d lp = [b - a]x / |a - b|
+            // LidarEdgeFactor: r = ((lp - a) x (lp - b)) / |a - b| ; d r / d lp = [b - a]x / |a - b|
             const double ux = lx - ax, uy = ly - ay, uz = lz - az, vx = lx - bx, vy = ly - by, vz = lz - bz;
             const double dex = ax - bx, dey = ay - by, dez = az - bz;
             const double dn = sqrt(dex * dex + dey * dey + dez * dez);
-            r[0] = (uy * vz - uz * vy) / dn;
-            r[1] = (uz * vx - ux * vz) / dn;
-            r[2] = (ux * vy - uy * vx) / dn;
+            const double r0 = (uy * vz - uz * vy) / dn, r1 = (uz * vx - ux * vz) / dn, r2 = (ux * vy - uy * vx) / dn;
             const double ex = -dex / dn, ey = -dey / dn, ez = -dez / dn;
-            D[0][0] = 0; D[0][1] = -ez; D[0][2] = ey;
-            D[1][0] = ez; D[1][1] = 0; D[1][2] = -ex;
-            D[2][0] = -ey; D[2][1] = ex; D[2][2] = 0;
-            nr = 3;
-        } else if (type == 1) {
-            r[0] = ((lx - ax) * bx + (ly - ay) * by + (lz - az) * bz) * w;
-            D[0][0] = w * bx; D[0][1] = w * by; D[0][2] = w * bz;
-            nr = 1;
-        } else {
-            r[0] = (ax * lx + ay * ly + az * lz) + w;
-            D[0][0] = ax; D[0][1] = ay; D[0][2] = az;
-            nr = 1;
-        }
-        double s = 0.0;
-        for (int k = 0; k < nr; ++k) s += r[k] * r[k];
-        // HuberLoss(0.1): rho(s), rho'(s); Corrector with rho'' <= 0: scale r and J by sqrt(rho')
-        double rho0 = s, rho1 = 1.0;
-        if (s > 0.01) {
-            const double rr = sqrt(s);
-            rho0 = 2.0 * 0.1 * rr - 0.01;
-            rho1 = fmax(DBL_MIN, 0.1 / rr);
-        }
-        acc[27] += 0.5 * rho0;
-        if (FULL) {
-            const double sq = sqrt(rho1);
-            for (int k = 0; k < nr; ++k) {
-                // J row = D_k * [ -2 [R cp]x | I ]
-                const double d0 = D[k][0], d1 = D[k][1], d2 = D[k][2];
-                double J[6];
-                J[0] = (d1 * (-2.0 * Rz) + d2 * (2.0 * Ry)) * sq;
-                J[1] = (d0 * (2.0 * Rz) + d2 * (-2.0 * Rx)) * sq;
-                J[2] = (d0 * (-2.0 * Ry) + d1 * (2.0 * Rx)) * sq;
-                J[3] = d0 * sq; J[4] = d1 * sq; J[5] = d2 * sq;
-                const double rk = r[k] * sq;
-                int q = 0;
-#pragma unroll
-                for (int a = 0; a < 6; ++a) {
-#pragma unroll
-                    for (int c = a; c < 6; ++c) acc[q++] += J[a] * J[c];
-                }
-#pragma unroll
-                for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * rk;
+            const double s = (r0 * r0 + r1 * r1) + r2 * r2;
+            double sq;
+            acc[27] += 0.5 * lm_huber(s, sq);
+            if (FULL) {
+                lm_row(acc, 0.0, -ez, ey, r0, Rx, Ry, Rz, sq);
+                lm_row(acc, ez, 0.0, -ex, r1, Rx, Ry, Rz, sq);
+                lm_row(acc, -ey, ex, 0.0, r2, Rx, Ry, Rz, sq);
             }
+        } else {
+            // type 1 LidarPlaneFactor_modify: r = w (lp - j) . n ; type 2 LidarPlaneNormFactor: r = n . lp + d
+            const double r0 = type == 1 ? ((lx - ax) * bx + (ly - ay) * by + (lz - az) * bz) * w : (ax * lx + ay * ly + az * lz) + w;
+            const double d0 = type == 1 ? w * bx : ax, d1 = type == 1 ? w * by : ay, d2 = type == 1 ? w * bz : az;
+            double sq;
+            acc[27] += 0.5 * lm_huber(0.0 + r0 * r0, sq);
+            if (FULL) lm_row(acc, d0, d1, d2, r0, Rx, Ry, Rz, sq);
         }
+        }
+        cur = nxt;
     }
 }
 
-// fixed-order block reduction of acc[first..LM_NRED) into S.out
+// fixed-order block reduction of acc[first..LM_NRED) into S.out.
+// Warp level: a transposed reduction - every round the lanes swap half of the values they still hold with the lane
+// `m` away and add, so after rounds m = 16, 8, 4, 2, 1 each lane owns the warp total of ONE value (31 exchanges of
+// a double instead of 5 per value).  The tree is fixed, so the sums are run-to-run deterministic.
+template <int CNT, int M>
+__device__ __forceinline__ void lm_fold(double (&v)[32], int lane)
+{
+    const bool upper = (lane & M) != 0;
+#pragma unroll
+    for (int k = 0; k < CNT / 2; ++k) {
+        const double send = upper ? v[k] : v[k + CNT / 2];
+        const double keep = upper ? v[k + CNT / 2] : v[k];
+        v[k] = keep + shfl_xor_f64(send, M);
+    }
+}
 template <bool FULL>
 __device__ __forceinline__ void lm_reduce(LmShared& S, double acc[LM_NRED])
 {
     const int lane = lane_id(), w = warp_id();
+    if (FULL) {
+        double v[32];
 #pragma unroll
-    for (int k = FULL ? 0 : 27; k < LM_NRED; ++k) {
-        double v = acc[k];
+        for (int k = 0; k < 32; ++k) v[k] = k < LM_NRED ? acc[k] : 0.0;
+        lm_fold<32, 16>(v, lane);
+        lm_fold<16, 8>(v, lane);
+        lm_fold<8, 4>(v, lane);
+        lm_fold<4, 2>(v, lane);
+        lm_fold<2, 1>(v, lane);
+        // the lane's value index: bit 4 of the lane picked the upper half of 32, bit 3 of 16, ... bit 0 of 2
+        const int idx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+        if (idx < LM_NRED) S.red[w][idx] = v[0];
+    } else {
+        double v = acc[27];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += shfl_down_f64(v, d);
-        if (lane == 0) S.red[w][k] = v;
+        if (lane == 0) S.red[w][27] = v;
     }
     __syncthreads();
     if (threadIdx.x < LM_NRED && (FULL || threadIdx.x == 27)) {
         double v = 0.0;
+#pragma unroll
         for (int ww = 0; ww < LM_THREADS / 32; ++ww) v += S.red[ww][threadIdx.x];
         S.out[threadIdx.x] = v;
     }
@@ -271,13 +316,11 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         return;
     }
     double acc[LM_NRED];
-    // controller state (meaningful on thread 0 only)
-    double H[21], g[6], scale[6], diagonal[6], x_cost = 0, x_norm = 0, radius = 1e4, decrease_factor = 2.0, se_cost = 0;
-    double model_cost_change = 0, gmax = 0;
-    bool reuse_diagonal = false, last_successful = true, atleast_one = false;
-    int iteration = 0, invalid = 0, term = 0, jac_evals = 0, cost_evals = 0;
-    double initial_cost = 0;
-
+    LmCtl& C = S.ctl;
+    if (tid == 0) {
+        C.x_cost = 0; C.x_norm = 0; C.radius = 1e4; C.decrease_factor = 2.0; C.se_cost = 0; C.model_cost_change = 0; C.gmax = 0; C.initial_cost = 0;
+        C.reuse_diagonal = 0; C.last_successful = 1; C.atleast_one = 0; C.iteration = 0; C.invalid = 0; C.term = 0; C.jac_evals = 0; C.cost_evals = 0;
+    }
     auto norm7 = [](const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); };
 
     // IterationZero: cost, gradient, Jacobian (as JtJ) at x
@@ -285,66 +328,66 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     lm_reduce<true>(S, acc);
     if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
     if (tid == 0) {
-        for (int k = 0; k < 21; ++k) H[k] = S.out[k];
-        for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
-        x_cost = S.out[27];
-        initial_cost = x_cost;
-        se_cost = x_cost;
-        jac_evals = 1;
-        x_norm = norm7(S.x);
-        const int dq[6] = {0, 6, 11, 15, 18, 20};  // packed index of the diagonal
-        for (int c = 0; c < 6; ++c) scale[c] = 1.0 / (1.0 + sqrt(H[dq[c]]));  // jacobi_scaling, first Jacobian only
+        for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
+        for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
+        C.x_cost = S.out[27];
+        C.initial_cost = C.x_cost;
+        C.se_cost = C.x_cost;
+        C.jac_evals = 1;
+        C.x_norm = norm7(S.x);
+        const int dq[6] = {0, 6, 11, 15, 18, 20};  // packed index of the C.diagonal
+        for (int c = 0; c < 6; ++c) C.scale[c] = 1.0 / (1.0 + sqrt(C.H[dq[c]]));  // jacobi_scaling, first Jacobian only
         double ng[6], xp[7];
-        for (int c = 0; c < 6; ++c) ng[c] = -g[c];
+        for (int c = 0; c < 6; ++c) ng[c] = -C.g[c];
         lm_plus(S.x, ng, xp);
-        gmax = 0;
-        for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(S.x[i] - xp[i]));
+        C.gmax = 0;
+        for (int i = 0; i < 7; ++i) C.gmax = fmax(C.gmax, fabs(S.x[i] - xp[i]));
     }
     for (;;) {
-        // ---- thread 0: finalize previous iteration, compute the trust-region step ----------------------
+        // ---- thread 0: finalize previous C.iteration, compute the trust-region step ----------------------
         if (tid == 0) {
             int go = 1;  // 1: evaluate candidate cost, 0: stop
             for (;;) {
-                if (iteration >= 4) { term = 0; go = 0; break; }                         // max_num_iterations (LO:822)
-                if (last_successful && gmax <= 1e-10) { term = 1; go = 0; break; }       // gradient_tolerance
-                if (radius <= 1e-32) { term = 4; go = 0; break; }                        // min_trust_region_radius
-                ++iteration;
+                if (C.iteration >= 4) { C.term = 0; go = 0; break; }                         // max_num_iterations (LO:822)
+                if (C.last_successful && C.gmax <= 1e-10) { C.term = 1; go = 0; break; }       // gradient_tolerance
+                if (C.radius <= 1e-32) { C.term = 4; go = 0; break; }                        // min_trust_region_radius
+                ++C.iteration;
                 const int dq[6] = {0, 6, 11, 15, 18, 20};
-                if (!reuse_diagonal)
-                    for (int c = 0; c < 6; ++c) diagonal[c] = fmin(fmax(H[dq[c]] * scale[c] * scale[c], 1e-6), 1e32);
-                // (S H S + D^2) y = S g ; step = -y
+                if (!C.reuse_diagonal)
+                    for (int c = 0; c < 6; ++c) C.diagonal[c] = fmin(fmax(C.H[dq[c]] * C.scale[c] * C.scale[c], 1e-6), 1e32);
+                // (S C.H S + D^2) y = S C.g ; step = -y
                 double A[21], rhs[6], y[6], step[6];
                 int q = 0;
                 for (int a = 0; a < 6; ++a)
-                    for (int c = a; c < 6; ++c) { A[q] = H[q] * scale[a] * scale[c]; ++q; }
-                for (int c = 0; c < 6; ++c) { A[dq[c]] += diagonal[c] / radius; rhs[c] = g[c] * scale[c]; }
+                    for (int c = a; c < 6; ++c) { A[q] = C.H[q] * C.scale[a] * C.scale[c]; ++q; }
+                for (int c = 0; c < 6; ++c) { A[dq[c]] += C.diagonal[c] / C.radius; rhs[c] = C.g[c] * C.scale[c]; }
                 const bool ok = chol6_solve(A, rhs, y);
-                reuse_diagonal = true;
+                C.reuse_diagonal = true;
                 bool valid = false;
                 if (ok) {
                     for (int c = 0; c < 6; ++c) step[c] = -y[c];
-                    // model_cost_change = -(J step).(r + J step / 2) = -step.(S g) - step^T (S H S) step / 2
+                    // C.model_cost_change = -(J step).(r + J step / 2) = -step.(S C.g) - step^T (S C.H S) step / 2
                     double lin = 0, quad = 0;
                     for (int c = 0; c < 6; ++c) lin += step[c] * rhs[c];
                     q = 0;
                     for (int a = 0; a < 6; ++a)
                         for (int c = a; c < 6; ++c) {
-                            const double hv = H[q] * scale[a] * scale[c];
+                            const double hv = C.H[q] * C.scale[a] * C.scale[c];
                             quad += (a == c ? 1.0 : 2.0) * hv * step[a] * step[c];
                             ++q;
                         }
-                    model_cost_change = -lin - 0.5 * quad;
-                    valid = model_cost_change > 0.0;
+                    C.model_cost_change = -lin - 0.5 * quad;
+                    valid = C.model_cost_change > 0.0;
                 }
                 if (!valid) {  // HandleInvalidStep
-                    last_successful = false;
-                    if (++invalid >= 5) { term = 5; go = 0; break; }
-                    radius *= 0.5;
+                    C.last_successful = false;
+                    if (++C.invalid >= 5) { C.term = 5; go = 0; break; }
+                    C.radius *= 0.5;
                     continue;
                 }
-                invalid = 0;
+                C.invalid = 0;
                 double delta[6];
-                for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
+                for (int c = 0; c < 6; ++c) delta[c] = step[c] * C.scale[c];
                 lm_plus(S.x, delta, S.cand);
                 break;
             }
@@ -358,30 +401,30 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 27, L);
         if (tid == 0) {
             const double cand_cost = S.out[27];
-            ++cost_evals;
+            ++C.cost_evals;
             int go = 2;  // 2: accepted -> re-linearise, 1: rejected -> next step, 0: stop
             double sn = 0;
             for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
-            if (atleast_one && sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { term = 2; go = 0; }           // parameter_tolerance
-            else if (atleast_one && fabs(x_cost - cand_cost) <= 1e-6 * x_cost) { term = 3; go = 0; }  // function_tolerance
+            if (C.atleast_one && sqrt(sn) <= 1e-8 * (C.x_norm + 1e-8)) { C.term = 2; go = 0; }           // parameter_tolerance
+            else if (C.atleast_one && fabs(C.x_cost - cand_cost) <= 1e-6 * C.x_cost) { C.term = 3; go = 0; }  // function_tolerance
             else {
-                const double rel = (se_cost - cand_cost) / model_cost_change;
+                const double rel = (C.se_cost - cand_cost) / C.model_cost_change;
                 if (rel > 1e-3) {  // min_relative_decrease: HandleSuccessfulStep
                     for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
-                    x_norm = norm7(S.x);
-                    radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
-                    radius = fmin(1e16, radius);
-                    decrease_factor = 2.0;
-                    reuse_diagonal = false;
-                    se_cost = cand_cost;
-                    atleast_one = true;
-                    last_successful = true;
+                    C.x_norm = norm7(S.x);
+                    C.radius = C.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+                    C.radius = fmin(1e16, C.radius);
+                    C.decrease_factor = 2.0;
+                    C.reuse_diagonal = false;
+                    C.se_cost = cand_cost;
+                    C.atleast_one = true;
+                    C.last_successful = true;
                     go = 2;
                 } else {  // StepRejected
-                    radius = radius / decrease_factor;
-                    decrease_factor *= 2.0;
-                    reuse_diagonal = true;
-                    last_successful = false;
+                    C.radius = C.radius / C.decrease_factor;
+                    C.decrease_factor *= 2.0;
+                    C.reuse_diagonal = true;
+                    C.last_successful = false;
                     go = 1;
                 }
             }
@@ -395,15 +438,15 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
             lm_reduce<true>(S, acc);
             if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
             if (tid == 0) {
-                for (int k = 0; k < 21; ++k) H[k] = S.out[k];
-                for (int k = 0; k < 6; ++k) g[k] = S.out[21 + k];
-                x_cost = S.out[27];
-                ++jac_evals;
+                for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
+                for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
+                C.x_cost = S.out[27];
+                ++C.jac_evals;
                 double ng[6], xp[7];
-                for (int c = 0; c < 6; ++c) ng[c] = -g[c];
+                for (int c = 0; c < 6; ++c) ng[c] = -C.g[c];
                 lm_plus(S.x, ng, xp);
-                gmax = 0;
-                for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(S.x[i] - xp[i]));
+                C.gmax = 0;
+                for (int i = 0; i < 7; ++i) C.gmax = fmax(C.gmax, fabs(S.x[i] - xp[i]));
             }
         }
         __syncthreads();
@@ -413,11 +456,11 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         for (int i = 0; i < 3; ++i) t_io[i] = S.x[4 + i];
         if (dist) comm->seq_out[comm_b] = seq;
         if (L) {
-            L->initial_cost[slot] = initial_cost;
-            L->final_cost[slot] = x_cost;
-            L->jac_evals[slot] = jac_evals;
-            L->cost_evals[slot] = cost_evals;
-            L->termination[slot] = term;
+            L->initial_cost[slot] = C.initial_cost;
+            L->final_cost[slot] = C.x_cost;
+            L->jac_evals[slot] = C.jac_evals;
+            L->cost_evals[slot] = C.cost_evals;
+            L->termination[slot] = C.term;
         }
     }
 }
