@@ -89,9 +89,10 @@ def algorithmic_bytes(counts):
         "k_ring_pick": 2 * P + feats,                          # read sorted order (+ a few points), write picks
         "k_ring_lessflat": 2 * 16 * P + 1 * P + 16 * nlf,      # two passes over the ring (bbox, keys), labels, DS output
         "k_compact": 2 * (16 * nlf) + 2 * feats,
-        "k_odom_assoc": 3 * 0 + 16 * (ns + nf) + 16 * (nls + nlf) + 8 * ns + 16 * nf,  # upper bound 16 (Q + M) per launch
+        "k_odom_assoc": 16 * (ns + nf) + 16 * (nls + nlf) + 8 * ns + 16 * nf,  # NN + ring window: queries + every indexed target once (upper bound 16 (Q + M)) + results
         "k_index_count": 16 * (nls + nlf),
-        "k_index_scatter": 16 * (nls + nlf) + 2 * 16 * (nls + nlf),   # read once, write the spatial and the ring-azimuth copy
+        "k_index_scatter": 16 * (nls + nlf) + 16 * (nls + nlf),       # read the *Last clouds, write the bucket-ordered copy
+        "k_lm_solve_odom": 88 * (ns + nf),                            # residual-block records, read once per solve (upper bound: every feature matched)
     }
 
 
@@ -311,10 +312,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "128")), help="scan streams (lanes) per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "256")), help="scan streams (lanes) per GPU")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
