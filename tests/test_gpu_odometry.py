@@ -164,3 +164,63 @@ def test_async_submit_collect_equals_sync_call(ll):
         b.collect()                      # nothing outstanding
     a.close()
     b.close()
+
+
+def _scene_cloud(rng, n, ring_map):
+    """Points sampled in CARTESIAN space (ground, walls, a cluster hugging the sensor axis, a wedge across the +-pi
+    azimuth seam): nothing like the even (azimuth, ring) spread of a spinning sensor.  Ring ids come from the
+    elevation (64-line formula, clipped: rings 0 and 63 get wide bands), optionally scrambled by ring_map."""
+    parts = []
+    g = np.c_[rng.uniform(-40, 40, n // 2), rng.uniform(-40, 40, n // 2), rng.normal(-1.7, 0.02, n // 2)]
+    parts.append(g)
+    w = np.c_[np.full(n // 6, 18.0) + rng.normal(0, 0.02, n // 6), rng.uniform(-30, 30, n // 6), rng.uniform(-1.7, 6, n // 6)]
+    parts.append(w)
+    axis = np.c_[rng.normal(0, 0.3, n // 8), rng.normal(0, 0.3, n // 8), rng.uniform(2, 8, n // 8)]
+    parts.append(axis)
+    seam = np.c_[rng.uniform(-25, -6, n // 6), rng.normal(0, 0.4, n // 6), rng.uniform(-1.7, 2, n // 6)]
+    parts.append(seam)
+    p = np.concatenate(parts).astype(np.float32)
+    el = np.degrees(np.arctan2(p[:, 2], np.hypot(p[:, 0], p[:, 1])))
+    ring = np.clip(np.floor((el + 24.9) * (63.0 / 26.9) + 0.5), 0, 63).astype(np.int64)
+    ring = ring_map[ring]
+    order = np.argsort(ring, kind="stable")
+    p, ring = p[order], ring[order]
+    return np.c_[p, ring + rng.uniform(0, 0.09, len(p))].astype(np.float32)
+
+
+@pytest.mark.parametrize("case", ["ordered_bands", "scrambled_rings"])
+def test_polar_search_exact_on_non_sensor_like_clouds(ll, orc, case):
+    """The exact 1-NN / ring-window search prunes with the rings' elevation bands and azimuth offsets.  Clouds whose
+    geometry has nothing to do with a spinning sensor (Cartesian sampling, points on the sensor axis, a cluster
+    across the azimuth seam, ring ids that do not follow the elevation, queries with nothing within 5 m) must still
+    give the oracle's kd-tree + literal-loop correspondences index for index."""
+    line = 64
+    rng = np.random.default_rng(11 if case == "ordered_bands" else 12)
+    ring_map = np.arange(64) if case == "ordered_bands" else (np.arange(64) * 27) % 64   # a permutation of the rings
+    ctx = ll.Context(scan_line=line)
+    ocfg = orc.config(line, voxel_stable=1)
+    odo = orc.Odometry(ocfg)
+    ls = _scene_cloud(rng, 6000, ring_map)
+    lf = _scene_cloud(rng, 40000, ring_map)
+
+    def queries(tgt, m):
+        near = tgt[rng.choice(len(tgt), m - m // 8, replace=False)].copy()
+        near[:, :3] += rng.normal(0, 0.08, (len(near), 3)).astype(np.float32)
+        far = np.c_[rng.uniform(-60, 60, m // 8), rng.uniform(-60, 60, m // 8), rng.uniform(8, 30, m // 8), np.zeros(m // 8)].astype(np.float32)
+        return np.concatenate([near, far]).astype(np.float32)
+
+    for k in range(3):
+        sharp, flat = queries(ls, 700), queries(lf, 1500)
+        po = odo.step(sharp, ls, flat, lf)
+        pg = ctx.odometry_step(sharp, ls, flat, lf)
+        if k == 0:
+            continue
+        oc, op = odo.assoc(len(sharp), len(flat))
+        gc, gp = ctx.debug_assoc(0)
+        got_c = np.array([[i, a, b] for i, (a, b) in enumerate(gc[:len(sharp)]) if b >= 0], np.int32).reshape(-1, 3)
+        got_p = np.array([[i, a, b, c] for i, (a, b, c, _) in enumerate(gp[:len(flat)]) if a >= 0], np.int32).reshape(-1, 4)
+        assert len(oc) > 50 and len(op) > 100, (len(oc), len(op))
+        assert np.array_equal(got_c, oc), k
+        assert np.array_equal(got_p, op), k
+        assert np.abs(pg["t_w"] - po["t_w"]).max() < 1e-7 and np.abs(pg["q_w"] - po["q_w"]).max() < 1e-7, k
+    ctx.close()
