@@ -674,19 +674,33 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
     const float4* pts = P.full + (size_t)b * P.Nmax + base;
     const int8_t* label = P.label + (size_t)b * P.Nmax + base;
 
-    const int c0 = tid * CH, c1 = min(c0 + CH, n);
-    int mycnt = 0;
+    // pass 1 (coalesced: round k, thread t owns point k * 512 + t): less-flat flag, floor(coordinate / leaf) as three
+    // int16 parked in the (still unused) sort-key area, bounding box, per-(round, warp) counts for the compaction
+    short4* cell = reinterpret_cast<short4*>(keys);   // [RCAP] x, y, z cell, w = 1: less-flat
+    int* rcnt = reinterpret_cast<int*>(red + 112);    // [CH * 16 + 1] -> exclusive offsets
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = c0; i < c1; ++i) {
-        if (i >= 5 && i < n - 6 && label[i] <= 0) {
-            ++mycnt;
-            const float4 q = pts[i];
-            mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
-            mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+    const float inv = P.inv_leaf;
+    bool wide = false;   // a cell index that does not fit int16 (|coordinate| > 6.5 km at leaf 0.2)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int i = k * NTH + tid;
+        bool lf = false;
+        if (i < n) {
+            lf = i >= 5 && i < n - 6 && label[i] <= 0;
+            short4 c4 = make_short4(0, 0, 0, 0);
+            if (lf) {
+                const float4 q = pts[i];
+                mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
+                mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+                const float f0 = floorf(q.x * inv), f1 = floorf(q.y * inv), f2 = floorf(q.z * inv);
+                wide |= !(fabsf(f0) < 32000.f && fabsf(f1) < 32000.f && fabsf(f2) < 32000.f);
+                c4 = make_short4((short)f0, (short)f1, (short)f2, 1);
+            }
+            cell[i] = c4;
         }
+        const unsigned bl = __ballot_sync(LL_FULL_MASK, lf);
+        if (lane == 0) rcnt[k * 16 + wid] = __popc(bl);
     }
-    int m = 0;
-    const int off = block_exclusive_scan(mycnt, ws, &m);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -696,42 +710,63 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
         }
         if (lane == 0) { red[a * 16 + wid] = mn[a]; red[(3 + a) * 16 + wid] = mx[a]; }
     }
-    __syncthreads();
+    const int any_wide = __syncthreads_or(wide);
     if (tid < 6) {
         float v = red[tid * 16];
         for (int k = 1; k < NTH / 32; ++k) v = tid < 3 ? fminf(v, red[tid * 16 + k]) : fmaxf(v, red[tid * 16 + k]);
         red[96 + tid] = v;
     }
+    if (wid == 1) {  // exclusive scan of the CH * 16 counts (round-major = input order)
+        constexpr int NC = CH * 16, PER = (NC + 31) / 32;
+        int v[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int e = lane * PER + q; v[q] = e < NC ? rcnt[e] : 0; sum += v[q]; }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (lane >= d) incl += o; }
+        int run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int e = lane * PER + q; if (e < NC) rcnt[e] = run; run += v[q]; }
+        if (lane == 31) rcnt[NC] = incl;
+    }
     __syncthreads();
+    const int m = rcnt[CH * 16];
     if (m == 0) { if (tid == 0) my_counts[3] = 0; return; }
-    const float inv = P.inv_leaf;
     const float bmn[3] = {red[96], red[97], red[98]}, bmx[3] = {red[99], red[100], red[101]};
     const long long ddx = (long long)((bmx[0] - bmn[0]) * inv) + 1, ddy = (long long)((bmx[1] - bmn[1]) * inv) + 1,
                     ddz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
     float4* gout = P.lf_tmp + (size_t)b * P.Nmax + base;
-    if (ddx * ddy * ddz > (long long)INT_MAX) {  // PCL "leaf size too small": output = input
-        int o = off;
-        for (int i = c0; i < c1; ++i)
-            if (i >= 5 && i < n - 6 && label[i] <= 0) gout[o++] = pts[i];
-        if (tid == 0) my_counts[3] = m;
-        return;
-    }
+    const bool too_small = ddx * ddy * ddz > (long long)INT_MAX;   // PCL "leaf size too small": output = input
     const int min_b0 = (int)floorf(bmn[0] * inv), min_b1 = (int)floorf(bmn[1] * inv), min_b2 = (int)floorf(bmn[2] * inv);
     const int div0 = (int)floorf(bmx[0] * inv) - min_b0 + 1, div1 = (int)floorf(bmx[1] * inv) - min_b1 + 1;
     const int mul1 = div0, mul2 = div0 * div1;
-    {
-        int o = off;
-        for (int i = c0; i < c1; ++i)
-            if (i >= 5 && i < n - 6 && label[i] <= 0) {
-                const float4 q = pts[i];
-                const int i0 = (int)(floorf(q.x * inv) - (float)min_b0);
-                const int i1 = (int)(floorf(q.y * inv) - (float)min_b1);
-                const int i2 = (int)(floorf(q.z * inv) - (float)min_b2);
+    // pass 2: order-preserving compaction, voxel ids (from shared memory unless a cell index overflowed int16)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int i = k * NTH + tid;
+        const short4 c4 = i < n ? cell[i] : make_short4(0, 0, 0, 0);
+        const bool lf = c4.w != 0;
+        const unsigned bl = __ballot_sync(LL_FULL_MASK, lf);
+        if (lf) {
+            const int o = rcnt[k * 16 + wid] + __popc(bl & ((1u << lane) - 1u));
+            if (too_small) {
+                gout[o] = pts[i];
+            } else {
+                int i0, i1, i2;
+                if (!any_wide) {
+                    i0 = (int)c4.x - min_b0; i1 = (int)c4.y - min_b1; i2 = (int)c4.z - min_b2;   // = (int)(floorf(x * inv) - (float)min_b), both exact integers
+                } else {
+                    const float4 q = pts[i];
+                    i0 = (int)(floorf(q.x * inv) - (float)min_b0);
+                    i1 = (int)(floorf(q.y * inv) - (float)min_b1);
+                    i2 = (int)(floorf(q.z * inv) - (float)min_b2);
+                }
                 vid[o] = i0 + i1 * mul1 + i2 * mul2;
                 pidx[o] = (uint16_t)i;
-                ++o;
             }
+        }
     }
+    if (too_small) { if (tid == 0) my_counts[3] = m; return; }
     __syncthreads();
     // runs of consecutive equal voxel ids (threads own consecutive chunks of the compacted positions)
     const int MCH = (m + NTH - 1) / NTH;
@@ -767,6 +802,7 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
             for (int g = q; g < R && (unsigned)(keys[g] >> 32) == v; ++g) {  // runs in ascending run number = input order
                 const int run = (int)(unsigned)keys[g];
                 const int e0 = run_start[run], e1 = run_start[run + 1];
+#pragma unroll 4
                 for (int p = e0; p < e1; ++p) {
                     const float4 a = pts[pidx[p]];
                     sx += a.x; sy += a.y; sz += a.z; si += a.w;
@@ -871,7 +907,8 @@ size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + curvature + six
 size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxel ids, point indices, run starts, scratch
 {
     const int RCAP = 6 * SCAP + 16, KCAP = RCAP <= 4096 ? 4096 : 8192;
-    return (size_t)KCAP * 8 + (size_t)RCAP * 4 + (size_t)RCAP * 2 + (size_t)(RCAP + 2) * 2 + 40 * 4 + 112 * 4;
+    const int CH = (RCAP + 511) / 512;
+    return (size_t)KCAP * 8 + (size_t)RCAP * 4 + (size_t)RCAP * 2 + (size_t)(RCAP + 2) * 2 + 40 * 4 + 112 * 4 + (size_t)(CH * 16 + 4) * 4;
 }
 
 int ll_launch_features(ll_ctx* c, int n_lanes)
