@@ -128,7 +128,7 @@ struct IndexSet {
     int* start[2];
     int* partial[2];
     float4* sorted[2];
-    unsigned* ebound[2];       // [B][R][2] order-preserving encodings: max of ~enc(elevation), max of enc(elevation); 0 = empty
+    unsigned* ebound[2];       // [B][R][2] order-preserving encodings: max of ~enc(tan elevation), max of enc(tan elevation); 0 = empty
     float* bands[2];           // [B][BAND_STRIDE] decoded: elo[R], ehi[R] (empty rings filled in), then the "bands are ordered" flag
     int T[2], cap[2];
     int chunk_begin[3];        // prefix of T / GRID_CHUNK over the tables
@@ -138,7 +138,14 @@ struct IndexSet {
 #define BAND_STRIDE (2 * LL_MAX_RINGS + 4)
 __device__ __forceinline__ unsigned enc_f32(float f) { const unsigned b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float dec_f32(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
-__device__ __forceinline__ float elevation_of(float x, float y, float z) { return atan2f(z, sqrtf(x * x + y * y)); }
+// tangent of the elevation angle: monotone in the elevation, so a ring's band can be tracked as min / max of this
+// (one rsqrt per point) and converted to angles once per ring (k_index_partial)
+__device__ __forceinline__ float elevation_tan(float x, float y, float z)
+{
+    const float r2 = x * x + y * y;
+    if (!(r2 > 0.f)) return z > 0.f ? INFINITY : (z < 0.f ? -INFINITY : 0.f);
+    return z * rsqrtf(r2);
+}
 __device__ __forceinline__ int index_ring(const IndexSet& S, const float4 p)
 {
     int r = (int)p.w;
@@ -148,6 +155,7 @@ __device__ __forceinline__ int index_bucket(const IndexSet& S, int cloud, const 
 {
     return azimuth_bin(p.x, p.y, S.az_bins[cloud]) * S.rings + index_ring(S, p);
 }
+#define IDX_UNROLL 4
 __global__ void k_index_count(IndexSet S, LaneState* lane)
 {
     const int b = blockIdx.y, cloud = blockIdx.z;
@@ -155,29 +163,45 @@ __global__ void k_index_count(IndexSet S, LaneState* lane)
     const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     unsigned* eb = S.ebound[cloud] + (size_t)b * S.rings * 2;
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + (threadIdx.x & 31);
-        int ring = -1;
-        unsigned elo = 0u, ehi = 0u;
-        if (i < n) {
-            const float4 p = pts[i];
-            atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, p)], 1);
-            // is the cloud ring-monotone? (LO:504-553 assumes it; the ring-window search needs it)
-            const int r0 = (int)p.w, r1 = i + 1 < n ? (int)pts[i + 1].w : r0;
-            if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (cloud == 0) L.mono_corner = 0; else L.mono_surf = 0; }
-            ring = index_ring(S, p);
-            const unsigned e = enc_f32(elevation_of(p.x, p.y, p.z));
-            elo = ~e; ehi = e;
+    // a warp takes IDX_UNROLL chunks of 32 consecutive points per round; their loads are all issued before the first is used
+    const int ln = threadIdx.x & 31;
+    for (int base0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gridDim.x * blockDim.x * IDX_UNROLL) {
+        float4 pv[IDX_UNROLL];
+        float wn[IDX_UNROLL];
+#pragma unroll
+        for (int u = 0; u < IDX_UNROLL; ++u) {
+            const int i = base0 + u * 32 + ln;
+            if (i < n) { pv[u] = pts[i]; wn[u] = i + 1 < n ? pts[i + 1].w : pv[u].w; }
         }
-        // a warp's 32 consecutive points nearly always share the ring: one pair of atomics per warp
-        const unsigned have = __ballot_sync(LL_FULL_MASK, ring >= 0);
-        if (!have) continue;
-        const int ring0 = __shfl_sync(LL_FULL_MASK, ring, __ffs(have) - 1);
-        if (__all_sync(LL_FULL_MASK, ring < 0 || ring == ring0)) {
-            const unsigned mlo = __reduce_max_sync(LL_FULL_MASK, elo), mhi = __reduce_max_sync(LL_FULL_MASK, ehi);
-            if ((threadIdx.x & 31) == 0) { atomicMax(&eb[ring0 * 2], mlo); atomicMax(&eb[ring0 * 2 + 1], mhi); }
-        } else if (ring >= 0) {
-            atomicMax(&eb[ring * 2], elo); atomicMax(&eb[ring * 2 + 1], ehi);
+#pragma unroll
+        for (int u = 0; u < IDX_UNROLL; ++u) {
+            const int i = base0 + u * 32 + ln;
+            if (base0 + u * 32 >= n) break;   // warp-uniform
+            int ring = -1, bk = -1 - ln;      // distinct invalid ids: match_any never groups idle lanes
+            unsigned elo = 0u, ehi = 0u;
+            if (i < n) {
+                const float4 p = pv[u];
+                bk = index_bucket(S, cloud, p);
+                // is the cloud ring-monotone? (LO:504-553 assumes it; the ring-window search needs it)
+                const int r0 = (int)p.w, r1 = (int)wn[u];
+                if (r0 < 0 || r0 >= S.rings || r1 < r0) { if (cloud == 0) L.mono_corner = 0; else L.mono_surf = 0; }
+                ring = index_ring(S, p);
+                const unsigned e = enc_f32(elevation_tan(p.x, p.y, p.z));
+                elo = ~e; ehi = e;
+            }
+            // neighbouring points of the cloud mostly share their bucket: one atomic per distinct bucket of the warp
+            const unsigned grp = __match_any_sync(LL_FULL_MASK, bk);
+            if (bk >= 0 && ln == __ffs(grp) - 1) atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + bk], __popc(grp));
+            // a warp's 32 consecutive points nearly always share the ring: one pair of atomics per warp
+            const unsigned have = __ballot_sync(LL_FULL_MASK, ring >= 0);
+            if (!have) continue;
+            const int ring0 = __shfl_sync(LL_FULL_MASK, ring, __ffs(have) - 1);
+            if (__all_sync(LL_FULL_MASK, ring < 0 || ring == ring0)) {
+                const unsigned mlo = __reduce_max_sync(LL_FULL_MASK, elo), mhi = __reduce_max_sync(LL_FULL_MASK, ehi);
+                if (ln == 0) { atomicMax(&eb[ring0 * 2], mlo); atomicMax(&eb[ring0 * 2 + 1], mhi); }
+            } else if (ring >= 0) {
+                atomicMax(&eb[ring * 2], elo); atomicMax(&eb[ring * 2 + 1], ehi);
+            }
         }
     }
 }
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
             const unsigned lo = eb[r * 2], hi = eb[r * 2 + 1];
             float elo = phi, ehi = phi;
             if (hi != 0u) {
-                elo = dec_f32(~lo); ehi = dec_f32(hi);
+                elo = atanf(dec_f32(~lo)) - 1e-5f; ehi = atanf(dec_f32(hi)) + 1e-5f;   // tangents -> angles, widened by the rsqrt / atanf error
                 if (elo < plo || ehi < phi) ordered = 0;
                 plo = elo; phi = ehi;
             }
@@ -245,11 +269,30 @@ __global__ void k_index_scatter(IndexSet S, const LaneState* lane)
     const LaneState& L = lane[b];
     const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = pts[i];
-        const int ring = index_ring(S, p);
-        const int pos = atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + index_bucket(S, cloud, p)], 1);
-        S.sorted[cloud][(size_t)b * S.cap[cloud] + pos] = make_float4(p.x, p.y, p.z, __int_as_float((i & 0xFFFFFF) | (ring << 24)));
+    const int ln = threadIdx.x & 31;
+    for (int base0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gridDim.x * blockDim.x * IDX_UNROLL) {
+        float4 pv[IDX_UNROLL];
+#pragma unroll
+        for (int u = 0; u < IDX_UNROLL; ++u) {
+            const int i = base0 + u * 32 + ln;
+            pv[u] = i < n ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < IDX_UNROLL; ++u) {
+            const int i = base0 + u * 32 + ln;
+            if (base0 + u * 32 >= n) break;   // warp-uniform
+            const float4 p = pv[u];
+            int bk = -1 - ln, ring = 0;
+            if (i < n) { ring = index_ring(S, p); bk = index_bucket(S, cloud, p); }
+            // one cursor atomic per distinct bucket of the warp; the order inside a bucket is free (every consumer takes
+            // a minimum over a total order)
+            const unsigned grp = __match_any_sync(LL_FULL_MASK, bk);
+            const int leader = __ffs(grp) - 1;
+            int pos = 0;
+            if (bk >= 0 && ln == leader) pos = atomicAdd(&S.cursor[cloud][(size_t)b * S.T[cloud] + bk], __popc(grp));
+            pos = __shfl_sync(LL_FULL_MASK, pos, leader) + __popc(grp & ((1u << ln) - 1u));
+            if (bk >= 0) S.sorted[cloud][(size_t)b * S.cap[cloud] + pos] = make_float4(p.x, p.y, p.z, __int_as_float((i & 0xFFFFFF) | (ring << 24)));
+        }
     }
 }
 
@@ -392,7 +435,7 @@ __device__ __forceinline__ void polar_query_init(PolarQuery& pq, float qx, float
 {
     pq.rho = sqrtf(qx * qx + qy * qy);
     pq.qn = sqrtf(pq.rho * pq.rho + qz * qz);
-    pq.eq = atan2f(qz, pq.rho);   // = elevation_of()
+    pq.eq = atan2f(qz, pq.rho);   // elevation angle (the bands hold atanf of the tangents, widened by 1e-5)
     pq.b0 = azimuth_bin_frac(qx, qy, NB, pq.frac);
     pq.inv_w = (float)NB * 0.15915494f;
 }
@@ -1064,7 +1107,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
             LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_ebound[t], 0, sizeof(unsigned) * (size_t)c->R * 2 * n_lanes, s));
         }
         S.az_bins[0] = c->az_bins_corner; S.az_bins[1] = c->az_bins_surf; S.rings = c->R;
-        const int gx = (c->Nmax / 2 + 255) / 256 < 148 ? (c->Nmax / 2 + 255) / 256 : 148;
+        const int gx = (c->Nmax / 2 + 256 * IDX_UNROLL - 1) / (256 * IDX_UNROLL) < 148 ? (c->Nmax / 2 + 256 * IDX_UNROLL - 1) / (256 * IDX_UNROLL) : 148;
         { LLProf pr(c, "k_index_count"); k_index_count<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
         { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
         { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }

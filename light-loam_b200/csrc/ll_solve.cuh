@@ -248,42 +248,55 @@ __device__ __forceinline__ void lm_plus(const double* x, const double* delta, do
     if (nd == 0.0) {
         for (int i = 0; i < 4; ++i) out[i] = x[i];
     } else {
-        const double sbd = sin(nd) / nd;
-        const double dq[4] = {sbd * delta[0], sbd * delta[1], sbd * delta[2], cos(nd)};
+        double sn, cs;
+        sincos(nd, &sn, &cs);
+        const double sbd = sn / nd;
+        const double dq[4] = {sbd * delta[0], sbd * delta[1], sbd * delta[2], cs};
         quat_mul(dq, x, out);
     }
     for (int i = 0; i < 3; ++i) out[4 + i] = x[4 + i] + delta[3 + i];
 }
 
 // 6x6 SPD solve A y = b by Cholesky (A given as packed upper triangle row-major, 21 entries). false if not SPD.
+// One thread runs it between two evaluations while the CTA waits, so the dependent chain is what counts: the
+// pivots are kept as reciprocal square roots (one rsqrt per column, multiplications everywhere else).
 __device__ __forceinline__ bool chol6_solve(const double* Ap, const double* b, double* y)
 {
-    double Lm[6][6];
+    double Lm[6][6], inv[6];
     int q = 0;
+#pragma unroll
     for (int a = 0; a < 6; ++a)
+#pragma unroll
         for (int c = a; c < 6; ++c) { Lm[a][c] = Ap[q]; Lm[c][a] = Ap[q]; ++q; }
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double d = Lm[j][j];
+#pragma unroll
         for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k];
         if (!(d > 0.0)) return false;
-        d = sqrt(d);
-        Lm[j][j] = d;
+        inv[j] = rsqrt(d);
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = Lm[i][j];
+#pragma unroll
             for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
-            Lm[i][j] = s / d;
+            Lm[i][j] = s * inv[j];
         }
     }
     double z[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         double s = b[i];
+#pragma unroll
         for (int k = 0; k < i; ++k) s -= Lm[i][k] * z[k];
-        z[i] = s / Lm[i][i];
+        z[i] = s * inv[i];
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = z[i];
+#pragma unroll
         for (int k = i + 1; k < 6; ++k) s -= Lm[k][i] * y[k];
-        y[i] = s / Lm[i][i];
+        y[i] = s * inv[i];
         if (!isfinite(y[i])) return false;
     }
     return true;
@@ -412,7 +425,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
                 if (rel > 1e-3) {  // min_relative_decrease: HandleSuccessfulStep
                     for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
                     C.x_norm = norm7(S.x);
-                    C.radius = C.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+                    { const double u = 2.0 * rel - 1.0; C.radius = C.radius / fmax(1.0 / 3.0, 1.0 - u * u * u); }
                     C.radius = fmin(1e16, C.radius);
                     C.decrease_factor = 2.0;
                     C.reuse_diagonal = false;
