@@ -348,32 +348,49 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // The sorted order is written back as one u16 per point: local index | over(c > 0.1) << 14 | under(c < 0.1) << 15 —
 // everything the greedy pick needs to know about the curvature.
 // ---------------------------------------------------------------------------------------------------------
+// Warp-wide ascending sort of NREG * 32 keys in registers, BLOCKED layout: element e = lane * NREG + q lives in register q
+// of lane `lane`.  Compare-exchange distances below NREG stay inside a lane (plain min / max on registers); only the
+// log2(32) largest distances of a merge cross lanes — 15 shuffle stages out of 45 for 512 keys (a striped layout needs
+// 35), and shuffles issue at a quarter of the ALU rate.  The network is the all-ascending form of the bitonic sort:
+// the first stage of every merge pairs e with its mirror image e ^ (kk - 1), the following ones e with e ^ j, and the
+// lower index always keeps the minimum, so no stage needs a direction.
 template <int NREG>
-__device__ __forceinline__ void warp_bitonic_sort_regs(unsigned (&k)[NREG], int lane)
+__device__ __forceinline__ void warp_sort_regs_blocked(unsigned (&k)[NREG], int lane)
 {
     constexpr int N = NREG * 32;
 #pragma unroll
     for (int kk = 2; kk <= N; kk <<= 1) {
+        // mirror stage: partner = e ^ (kk - 1)
+        if (kk <= NREG) {
 #pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {  // partner lives in the same lane: registers r and r ^ (j / 32)
+            for (int q = 0; q < NREG; ++q) {
+                const int pq = q ^ (kk - 1);
+                if (q < pq) { const unsigned a = k[q], c = k[pq]; k[q] = min(a, c); k[pq] = max(a, c); }
+            }
+        } else {
+            const int m = kk / NREG - 1;                       // lane distance mask: lane ^ m
+            const bool lower = (lane & (kk / (2 * NREG))) == 0; // bit kk/2 of e
+            unsigned o[NREG];
 #pragma unroll
-                for (int r = 0; r < NREG; ++r) {
-                    if ((r & (j >> 5)) == 0) {
-                        const bool asc = (((r * 32) & kk) == 0) || kk == N;  // kk >= 64 here: the direction depends on r only
-                        const unsigned a = k[r], c = k[r | (j >> 5)];
-                        const unsigned lo = min(a, c), hi = max(a, c);
-                        k[r] = asc ? lo : hi;
-                        k[r | (j >> 5)] = asc ? hi : lo;
-                    }
+            for (int q = 0; q < NREG; ++q) o[q] = __shfl_xor_sync(LL_FULL_MASK, k[NREG - 1 - q], m);
+#pragma unroll
+            for (int q = 0; q < NREG; ++q) k[q] = lower ? min(k[q], o[q]) : max(k[q], o[q]);
+        }
+        // remaining stages of the merge: partner = e ^ j
+#pragma unroll
+        for (int j = kk >> 2; j > 0; j >>= 1) {
+            if (j < NREG) {
+#pragma unroll
+                for (int q = 0; q < NREG; ++q) {
+                    if ((q & j) == 0) { const unsigned a = k[q], c = k[q | j]; k[q] = min(a, c); k[q | j] = max(a, c); }
                 }
             } else {
-                const bool lower = (lane & j) == 0;
+                const int m = j / NREG;
+                const bool lower = (lane & m) == 0;
 #pragma unroll
-                for (int r = 0; r < NREG; ++r) {
-                    const unsigned o = __shfl_xor_sync(LL_FULL_MASK, k[r], j);
-                    const bool asc = kk == N ? true : (((r * 32) | lane) & kk) == 0;  // direction of element e = r * 32 + lane
-                    k[r] = (lower == asc) ? min(k[r], o) : max(k[r], o);
+                for (int q = 0; q < NREG; ++q) {
+                    const unsigned o = __shfl_xor_sync(LL_FULL_MASK, k[q], m);
+                    k[q] = lower ? min(k[q], o) : max(k[q], o);
                 }
             }
         }
@@ -467,13 +484,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
     unsigned k[NREG];
 #pragma unroll
     for (int q = 0; q < NREG; ++q) {
-        const int e = q * 32 + lane;
+        const int e = lane * NREG + q;   // blocked layout
         k[q] = e < slen ? ((__float_as_uint(curv_s[s0 + e]) >> IDXBITS) << IDXBITS) | (unsigned)e : 0xFFFFFFFFu;
     }
-    warp_bitonic_sort_regs<NREG>(k, lane);
+    warp_sort_regs_blocked<NREG>(k, lane);
     unsigned* sk = keys + j * SCAP;
 #pragma unroll
-    for (int q = 0; q < NREG; ++q) sk[q * 32 + lane] = k[q];
+    for (int q = 0; q < NREG; ++q) sk[lane * NREG + q] = k[q];
     __syncwarp();
     // fix-up: groups of equal truncated curvature are re-sorted on (full curvature bits, position)
 #pragma unroll 1
