@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
     float4* pts = reinterpret_cast<float4*>(smem);
     float* curv_s = reinterpret_cast<float*>(smem + (size_t)RCAP * 16);
     unsigned* keys = reinterpret_cast<unsigned*>(curv_s + RCAP);
-    int* sp = reinterpret_cast<int*>(keys + 6 * SCAP);
+    int* sp = reinterpret_cast<int*>(keys + 6 * (SCAP + 32));
     uint64_t* bar = reinterpret_cast<uint64_t*>(sp + 8);
 
     const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
@@ -484,46 +484,50 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
     unsigned k[NREG];
 #pragma unroll
     for (int q = 0; q < NREG; ++q) {
-        const int e = lane * NREG + q;   // blocked layout
+        // any assignment of the keys to the slots will do (the key carries its position): striped reads are conflict-free
+        const int e = q * 32 + lane;
         k[q] = e < slen ? ((__float_as_uint(curv_s[s0 + e]) >> IDXBITS) << IDXBITS) | (unsigned)e : 0xFFFFFFFFu;
     }
     warp_sort_regs_blocked<NREG>(k, lane);
-    unsigned* sk = keys + j * SCAP;
+    // sorted rank rho = lane * NREG + q goes to sk[rho + rho / NREG]: one pad word per lane keeps the stores conflict-free
+    unsigned* sk = keys + j * (SCAP + 32);
+#define SK(e) sk[(e) + (e) / NREG]
 #pragma unroll
-    for (int q = 0; q < NREG; ++q) sk[lane * NREG + q] = k[q];
+    for (int q = 0; q < NREG; ++q) sk[lane * (NREG + 1) + q] = k[q];
     __syncwarp();
     // fix-up: groups of equal truncated curvature are re-sorted on (full curvature bits, position)
 #pragma unroll 1
     for (int q = 0; q < NREG; ++q) {
         const int e = q * 32 + lane;
         if (e + 1 < slen) {
-            const unsigned me = sk[e], nx = sk[e + 1];
-            const bool head = (me >> IDXBITS) == (nx >> IDXBITS) && (e == 0 || (sk[e - 1] >> IDXBITS) != (me >> IDXBITS));
+            const unsigned me = SK(e), nx = SK(e + 1);
+            const bool head = (me >> IDXBITS) == (nx >> IDXBITS) && (e == 0 || (SK(e - 1) >> IDXBITS) != (me >> IDXBITS));
             if (head) {
                 int g = 2;
-                while (e + g < slen && (sk[e + g] >> IDXBITS) == (me >> IDXBITS)) ++g;
+                while (e + g < slen && (SK(e + g) >> IDXBITS) == (me >> IDXBITS)) ++g;
                 for (int a = 1; a < g; ++a) {  // insertion sort of sk[e .. e+g)
-                    const unsigned ka = sk[e + a];
+                    const unsigned ka = SK(e + a);
                     const u64 fa = ((u64)__float_as_uint(curv_s[s0 + (int)(ka & IDXMASK)]) << 32) | (ka & IDXMASK);
                     int c = a - 1;
                     while (c >= 0) {
-                        const unsigned kc = sk[e + c];
+                        const unsigned kc = SK(e + c);
                         const u64 fc = ((u64)__float_as_uint(curv_s[s0 + (int)(kc & IDXMASK)]) << 32) | (kc & IDXMASK);
                         if (fc <= fa) break;
-                        sk[e + c + 1] = kc;
+                        SK(e + c + 1) = kc;
                         --c;
                     }
-                    sk[e + c + 1] = ka;
+                    SK(e + c + 1) = ka;
                 }
             }
         }
     }
     __syncwarp();
     for (int e = lane; e < slen; e += 32) {
-        const int idx = s0 + (int)(sk[e] & IDXMASK);
+        const int idx = s0 + (int)(SK(e) & IDXMASK);
         const float c = curv_s[idx];
         gsorted[base + s0 + e] = (uint16_t)((unsigned)idx | ((double)c > 0.1 ? 0x4000u : 0u) | ((double)c < 0.1 ? 0x8000u : 0u));
     }
+#undef SK
 }
 
 // 64-bit window of a bit array held in 32-bit words
@@ -919,7 +923,7 @@ __global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres)
 size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + curvature + six sector key arrays + sector starts + mbarrier
 {
     const int RCAP = 6 * SCAP + 16;
-    return (size_t)RCAP * 16 + (size_t)RCAP * 4 + (size_t)6 * SCAP * 4 + 8 * 4 + 16;
+    return (size_t)RCAP * 16 + (size_t)RCAP * 4 + (size_t)6 * (SCAP + 32) * 4 + 8 * 4 + 16;
 }
 size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxel ids, point indices, run starts, scratch
 {
