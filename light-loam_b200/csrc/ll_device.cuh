@@ -105,58 +105,106 @@ __device__ __forceinline__ int cell_bucket(int ix, int iy, int iz, int Tmask)
     return (int)((h ^ (h >> 15)) & (unsigned)Tmask);
 }
 
-// ---- block-wide bitonic sort of 64-bit keys in shared memory --------------------------------------------------
-// Sorts every aligned segment of SEG keys (power of two >= 64, N a multiple of SEG) ascending.  Stages whose
-// partner distance is < 64 run in registers: a warp owns 64 consecutive keys (2 per lane) and exchanges them with
-// shuffles, so shared memory is touched once per "register phase" instead of once per stage (10 passes instead of
-// 45 for SEG = 512).  All threads of the block must call it; ends with a barrier.
-__device__ __forceinline__ void bitonic_reg_stages(u64& k0, u64& k1, int ibase, int kk, int jmax, int lane)
+// ---- block-wide ascending sort of NS 64-bit keys (shared memory <-> registers) -----------------------------------
+// All-ascending form of the bitonic network: the first stage of the merge of width kk pairs element e with its mirror
+// image e ^ (kk - 1), the following ones e with e ^ j, and the lower index always keeps the smaller key - no stage
+// needs a direction.  Thread t < NS / KPT holds elements t * KPT .. t * KPT + KPT - 1 in registers (blocked layout):
+// distances below KPT are register-to-register, distances below 32 * KPT are shuffles inside the warp, and only the
+// few largest distances of the last merges go through shared memory (with a block barrier each).  Fully unrolled.
+// Every thread of the block must call it (barriers); on return keys[0 .. NS) is sorted and visible to the block.
+__device__ __forceinline__ void cex_u64(u64& lo, u64& hi)
 {
-    // element indices: i0 = ibase + lane (slot 0), i1 = i0 + 32 (slot 1); stages j = jmax, jmax/2, ..., 1
-    for (int j = jmax; j > 0; j >>= 1) {
-        if (j == 32) {
-            const bool asc = ((ibase + lane) & kk) == 0;
-            if ((k0 > k1) == asc) { const u64 t = k0; k0 = k1; k1 = t; }
-        } else {
-            const bool lower = (lane & j) == 0;
-            const u64 o0 = shfl_xor_u64(k0, j), o1 = shfl_xor_u64(k1, j);
-            const bool asc0 = ((ibase + lane) & kk) == 0, asc1 = ((ibase + 32 + lane) & kk) == 0;
-            k0 = (lower == asc0) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
-            k1 = (lower == asc1) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
-        }
-    }
+    const u64 a = lo, c = hi;
+    const bool sw = c < a;
+    lo = sw ? c : a;
+    hi = sw ? a : c;
 }
-__device__ __forceinline__ void block_bitonic_sort_u64(u64* keys, int N, int SEG)
+template <int NS, int KPT>
+__device__ __forceinline__ void block_sort_u64_asc(u64* keys)
 {
-    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5, nchunk = N >> 6;
-    // phase 0: every 64-chunk fully sorted (k = 2..64) in registers, direction taken from the global network
-    for (int c = w; c < nchunk; c += nw) {
-        const int ibase = (c << 6) & (SEG - 1);
-        u64 k0 = keys[(c << 6) + lane], k1 = keys[(c << 6) + 32 + lane];
-        for (int kk = 2; kk <= 64; kk <<= 1) bitonic_reg_stages(k0, k1, ibase, SEG == 64 && kk == 64 ? 0 : kk, kk >> 1, lane);
-        keys[(c << 6) + lane] = k0;
-        keys[(c << 6) + 32 + lane] = k1;
+    constexpr int NT = NS / KPT;          // threads holding keys
+    constexpr int WSPAN = 32 * KPT;       // elements covered by one warp
+    const int t = threadIdx.x, lane = t & 31;
+    u64 k[KPT];
+    if (t < NT) {
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) k[q] = keys[t * KPT + q];
     }
-    __syncthreads();
-    for (int kk = 128; kk <= SEG; kk <<= 1) {
-        for (int j = kk >> 1; j >= 64; j >>= 1) {
-            for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const u64 a = keys[i], b = keys[i | j];
-                const bool asc = ((i & (SEG - 1)) & kk) == 0;
-                if ((a > b) == asc) { keys[i] = b; keys[i | j] = a; }
+#pragma unroll
+    for (int kk = 2; kk <= NS; kk <<= 1) {
+        if (kk > WSPAN) {
+            // the stages of this merge that reach across warps run on the shared array
+            if (t < NT) {
+#pragma unroll
+                for (int q = 0; q < KPT; ++q) keys[t * KPT + q] = k[q];
             }
             __syncthreads();
+            for (int p = t; p < NS / 2; p += blockDim.x) {   // mirror stage
+                const int blk = p / (kk / 2), off = p % (kk / 2);
+                const int i = blk * kk + off, pr = blk * kk + (kk - 1 - off);
+                u64 a = keys[i], c = keys[pr];
+                cex_u64(a, c);
+                keys[i] = a; keys[pr] = c;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = kk >> 2; j >= WSPAN; j >>= 1) {
+                for (int p = t; p < NS / 2; p += blockDim.x) {
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                    u64 a = keys[i], c = keys[i | j];
+                    cex_u64(a, c);
+                    keys[i] = a; keys[i | j] = c;
+                }
+                __syncthreads();
+            }
+            if (t < NT) {
+#pragma unroll
+                for (int q = 0; q < KPT; ++q) k[q] = keys[t * KPT + q];
+            }
+            __syncthreads();   // the next round's stores must not overtake these loads
         }
-        for (int c = w; c < nchunk; c += nw) {
-            const int ibase = (c << 6) & (SEG - 1);
-            u64 k0 = keys[(c << 6) + lane], k1 = keys[(c << 6) + 32 + lane];
-            bitonic_reg_stages(k0, k1, ibase, kk == SEG ? 0 : kk, 32, lane);
-            keys[(c << 6) + lane] = k0;
-            keys[(c << 6) + 32 + lane] = k1;
+        if (t < NT) {
+            // mirror stage when it stays inside the warp
+            if (kk <= KPT) {
+#pragma unroll
+                for (int q = 0; q < KPT; ++q) {
+                    const int pq = q ^ (kk - 1);
+                    if (q < pq) cex_u64(k[q], k[pq]);
+                }
+            } else if (kk <= WSPAN) {
+                const int m = kk / KPT - 1;
+                const bool lower = (lane & (kk / (2 * KPT))) == 0;
+                u64 o[KPT];
+#pragma unroll
+                for (int q = 0; q < KPT; ++q) o[q] = shfl_xor_u64(k[KPT - 1 - q], m);
+#pragma unroll
+                for (int q = 0; q < KPT; ++q) { const bool take = (o[q] < k[q]) == lower; k[q] = take ? o[q] : k[q]; }
+            }
+            // e ^ j stages inside the warp
+#pragma unroll
+            for (int j = (kk >> 2) < WSPAN ? (kk >> 2) : (WSPAN >> 1); j > 0; j >>= 1) {
+                if (j < KPT) {
+#pragma unroll
+                    for (int q = 0; q < KPT; ++q)
+                        if ((q & j) == 0) cex_u64(k[q], k[q | j]);
+                } else {
+                    const int m = j / KPT;
+                    const bool lower = (lane & m) == 0;
+#pragma unroll
+                    for (int q = 0; q < KPT; ++q) {
+                        const u64 o = shfl_xor_u64(k[q], m);
+                        const bool take = (o < k[q]) == lower;
+                        k[q] = take ? o : k[q];
+                    }
+                }
+            }
         }
-        __syncthreads();
     }
+    if (t < NT) {
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) keys[t * KPT + q] = k[q];
+    }
+    __syncthreads();
 }
 
 // ring x azimuth-bin index: bin of a point / query; NB = bins per ring (power of two)

@@ -672,8 +672,11 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
 // thread that owns a voxel walks its runs in order — the summation order stays the input order.
 // Points and labels are read through L2; voxel ids, run starts and the sort keys live in shared memory.
 // ---------------------------------------------------------------------------------------------------------
+// the many-keys-per-thread variants live in their own functions so that their register needs do not spill the common path
+template <int NS, int KPT>
+__device__ __noinline__ void block_sort_big(u64* keys) { block_sort_u64_asc<NS, KPT>(keys); }
 template <int SCAP>
-__global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
+__global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
 {
     constexpr int RCAP = 6 * SCAP + 16;
     constexpr int KCAP = (RCAP <= 4096) ? 4096 : 8192;
@@ -807,7 +810,16 @@ __global__ void __launch_bounds__(512) k_ring_lessflat(FeatParams P)
     if (tid == 0) run_start[R] = (uint16_t)m;
     for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull;
     __syncthreads();
-    block_bitonic_sort_u64(keys, NS, NS);
+    switch (NS) {   // all 512 threads call; NS / 4 (or NS / 8) of them hold keys
+        case 64: block_sort_u64_asc<64, 2>(keys); break;
+        case 128: block_sort_u64_asc<128, 4>(keys); break;
+        case 256: block_sort_u64_asc<256, 4>(keys); break;
+        case 512: block_sort_u64_asc<512, 4>(keys); break;
+        case 1024: block_sort_u64_asc<1024, 4>(keys); break;
+        case 2048: block_sort_u64_asc<2048, 4>(keys); break;
+        case 4096: block_sort_big<4096, 8>(keys); break;     // rings where nearly every point is its own run: rare
+        default: block_sort_big<8192, 16>(keys); break;
+    }
     // voxels = groups of equal voxel id among the sorted runs; the group's first run's thread accumulates the centroid
     const int RCH = (R + NTH - 1) / NTH;
     const int s0 = min(tid * RCH, R), s1 = min(s0 + RCH, R);
