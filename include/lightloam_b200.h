@@ -91,6 +91,14 @@ int ll_extract_features(ll_ctx* ctx, ll_cloud_view scan, ll_cloud_out* full, ll_
                         ll_cloud_out* flat, ll_cloud_out* less_flat, int* sharp_idx, int* less_sharp_idx, int* flat_idx,
                         float* curvature /* n_full floats or NULL */, int* ring_begin /* scan_line+1 or NULL */);
 
+/* Wire format of the published clouds: packs cloud `which` of lane 0's last extraction (0 = full cloud /velodyne_cloud_2,
+ * 1 = /laser_cloud_sharp, 2 = /laser_cloud_less_sharp, 3 = /laser_cloud_flat, 4 = /laser_cloud_less_flat; SR:382-410) on
+ * the device into pcl::PointXYZI records exactly as pcl::toROSMsg lays them out in sensor_msgs/PointCloud2::data
+ * (point_step 32: x@0, y@4, z@8, intensity@16, little-endian fp32, padding zeroed) and copies them to `data`
+ * (cap_points * 32 bytes).  *n_points = points in the cloud (also when LL_E_CAPACITY is returned).  The input
+ * direction needs no call: ll_cloud_view::stride_bytes = point_step reads PointCloud2 / KITTI .bin records in place. */
+int ll_fetch_pointcloud2(ll_ctx* ctx, int which, void* data, int cap_points, int* n_points);
+
 /* LO:425-896 on lane 0 for one synchronized set of the four feature clouds (float4 xyzi, intensity =
  * ring + 0.1*relTime).  Quaternions are x,y,z,w.  The first call only initialises (LO:427-431). */
 int ll_odometry_step(ll_ctx* ctx, ll_cloud_view sharp, ll_cloud_view less_sharp, ll_cloud_view flat, ll_cloud_view less_flat,

@@ -16,7 +16,7 @@ LL_E_INVAL, LL_E_CAPACITY, LL_E_CUDA, LL_E_NCCL, LL_E_EMPTY = -1, -2, -3, -4, -5
 LL_W_FEW_CORRESPONDENCES = 1
 
 SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
-           "ll_extract_features", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
+           "ll_extract_features", "ll_fetch_pointcloud2", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
            "ll_process_staged", "ll_submit_scans", "ll_collect", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
            "ll_debug_assoc", "ll_cuda_stream", "ll_comm_export", "ll_comm_local_ptr", "ll_comm_attach", "ll_comm_detach", "ll_map_set_slab"]
 
@@ -74,6 +74,7 @@ def lib():
         L.ll_get_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LLStats)]
         L.ll_extract_features.argtypes = [ctypes.c_void_p, LLCloudView] + [ctypes.POINTER(LLCloudOut)] * 5 + [ctypes.c_void_p] * 5
         L.ll_odometry_step.argtypes = [ctypes.c_void_p] + [LLCloudView] * 4 + [ctypes.c_void_p] * 4
+        L.ll_fetch_pointcloud2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.ll_mapping_step.argtypes = [ctypes.c_void_p, LLCloudView, LLCloudView] + [ctypes.c_void_p] * 4
         L.ll_map_insert.argtypes = [ctypes.c_void_p, LLCloudView, LLCloudView]
         L.ll_process_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView), ctypes.c_void_p]
@@ -163,6 +164,16 @@ class Context:
         nf, ns, nls, nfl, nlf = [o.n for o in outs]
         return dict(full=full[:nf], ring_begin=rb, curvature=curv[:nf], sharp=sharp[:ns], less_sharp=lsharp[:nls], flat=flat[:nfl],
                     less_flat=lflat[:nlf], sharp_idx=sidx[:ns], less_sharp_idx=lsidx[:nls], flat_idx=fidx[:nfl])
+
+    def fetch_pointcloud2(self, which, cap_points=None):
+        """Cloud `which` (0 full, 1 sharp, 2 less_sharp, 3 flat, 4 less_flat) of the last extraction as PointCloud2 data:
+        (n, 32) uint8, pcl::PointXYZI records (SR:382-410)."""
+        cap = self.cfg.max_points if cap_points is None else cap_points
+        buf = np.zeros((max(cap, 1), 32), np.uint8)
+        n = ctypes.c_int(0)
+        rc = self.L.ll_fetch_pointcloud2(self.h, which, buf.ctypes.data, cap, ctypes.byref(n))
+        self._check(rc, "ll_fetch_pointcloud2")
+        return buf[: n.value]
 
     def odometry_step(self, sharp, less_sharp, flat, less_flat):
         """laserOdometry.cpp:425-896 for one synchronized set of feature clouds (float32 (n,4))."""

@@ -38,6 +38,18 @@ __global__ void k_set_pool_hdr(LaneState* lane, const int* ids, const int* pool_
     }
 }
 
+// float4 x,y,z,intensity -> pcl::PointXYZI as pcl::toROSMsg lays it out in sensor_msgs/PointCloud2::data (point_step 32:
+// x@0 y@4 z@8 intensity@16, padding zeroed) - SR:382-410, LO:899-913.  Two 16-byte stores per point, coalesced.
+__global__ void k_pack_pointcloud2(const float4* __restrict__ src, float4* __restrict__ dst, const int* n_dev, int n_host)
+{
+    const int n = n_dev ? *n_dev : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = src[i];
+        dst[2 * i] = make_float4(p.x, p.y, p.z, 0.f);
+        dst[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+    }
+}
+
 __global__ void k_init_lanes(LaneState* lane, int n_lanes)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,6 +555,28 @@ int ll_extract_features(ll_ctx* c, ll_cloud_view scan, ll_cloud_out* full, ll_cl
     if (curvature && L.n_full) LL_CUDA_CHECK(c, cudaMemcpyAsync(curvature, c->d_curv, sizeof(float) * L.n_full, cudaMemcpyDeviceToHost, s));
     if (ring_begin) memcpy(ring_begin, L.ring_begin, sizeof(int) * (c->R + 1));
     LL_CUDA_CHECK(c, cudaStreamSynchronize(s));
+    return LL_OK;
+}
+
+int ll_fetch_pointcloud2(ll_ctx* c, int which, void* data, int cap_points, int* n_points)
+{
+    if (!c || which < 0 || which > 4 || (!data && cap_points > 0) || !n_points) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    int rc = fetch_lanes(c, 1);
+    if (rc) return rc;
+    const LaneState& L = c->h_lane[0];
+    const float4* src[5] = {c->d_full, c->d_sharp, c->d_lsharp[L.cur], c->d_flat, c->d_lflat[L.cur]};
+    const int cnt[5] = {L.n_full, L.n_sharp, L.n_less_sharp, L.n_flat, L.n_less_flat};
+    const int n = cnt[which];
+    *n_points = n;
+    if (n > cap_points) return LL_E_CAPACITY;
+    if (n == 0) return LL_OK;
+    // lane 0's raw staging slab (32 bytes per point) is free between two scans: the packed cloud is built there
+    float4* dst = reinterpret_cast<float4*>(c->d_raw);
+    k_pack_pointcloud2<<<(n + 255) / 256 < 592 ? (n + 255) / 256 : 592, 256, 0, c->stream>>>(src[which], dst, nullptr, n);
+    LL_CUDA_CHECK(c, cudaGetLastError());
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(data, dst, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return LL_OK;
 }
 

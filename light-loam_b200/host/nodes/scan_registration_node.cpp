@@ -12,17 +12,18 @@
 
 static ll_ctx* g_ll = nullptr;
 static ros::Publisher pubFull, pubSharp, pubLessSharp, pubFlat, pubLessFlat;
-static std::vector<float> bFull, bSharp, bLessSharp, bFlat, bLessFlat;
+static sensor_msgs::PointCloud2 g_template;   // fields / point_step of pcl::toROSMsg(PointCloud<PointXYZI>), built once
 
-static void publish(ros::Publisher& pub, const ll_cloud_out& c, const std_msgs::Header& h)
+// One of the five clouds of the last extraction, packed on the device into the PointXYZI wire layout
+// (ll_fetch_pointcloud2) straight into msg.data: no per-point work on the host (SR:382-410).
+static void publish(ros::Publisher& pub, int which, int cap, const std_msgs::Header& h)
 {
-    pcl::PointCloud<pcl::PointXYZI> cloud;
-    cloud.resize(c.n);
-    for (int i = 0; i < c.n; ++i) {
-        cloud[i].x = c.xyzi[4 * i]; cloud[i].y = c.xyzi[4 * i + 1]; cloud[i].z = c.xyzi[4 * i + 2]; cloud[i].intensity = c.xyzi[4 * i + 3];
-    }
-    sensor_msgs::PointCloud2 msg;
-    pcl::toROSMsg(cloud, msg);
+    sensor_msgs::PointCloud2 msg = g_template;
+    msg.data.resize((size_t)cap * 32);
+    int n = 0;
+    if (ll_fetch_pointcloud2(g_ll, which, msg.data.data(), cap, &n) < 0) return;
+    msg.data.resize((size_t)n * 32);
+    msg.width = n; msg.height = 1; msg.row_step = n * 32; msg.is_dense = true;
     msg.header.stamp = h.stamp;
     msg.header.frame_id = h.frame_id;
     pub.publish(msg);
@@ -30,19 +31,18 @@ static void publish(ros::Publisher& pub, const ll_cloud_out& c, const std_msgs::
 
 static void laserCloudHandler(const sensor_msgs::PointCloud2ConstPtr& in)
 {
-    pcl::PointCloud<pcl::PointXYZ> cloud;
-    pcl::fromROSMsg(*in, cloud);  // SR:105-106; NaN / range filters run inside the call
-    ll_cloud_view scan{reinterpret_cast<const float*>(cloud.points.data()), (int)cloud.size(), (int)sizeof(pcl::PointXYZ)};
-    ll_cloud_out full{bFull.data(), 0, (int)bFull.size() / 4}, sharp{bSharp.data(), 0, (int)bSharp.size() / 4},
-        lsharp{bLessSharp.data(), 0, (int)bLessSharp.size() / 4}, flat{bFlat.data(), 0, (int)bFlat.size() / 4},
-        lflat{bLessFlat.data(), 0, (int)bLessFlat.size() / 4};
-    const int rc = ll_extract_features(g_ll, scan, &full, &sharp, &lsharp, &flat, &lflat, nullptr, nullptr, nullptr, nullptr, nullptr);
+    // SR:105-106 (fromROSMsg) + SR:109-110: the payload is read in place - x, y, z are the first three fp32 fields of
+    // the sensor drivers' layouts; stride = point_step; the NaN / range filters run inside the call
+    ll_cloud_view scan{reinterpret_cast<const float*>(in->data.data()), (int)(in->width * in->height), (int)in->point_step};
+    const int rc = ll_extract_features(g_ll, scan, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc < 0) { ROS_WARN("lightloam_b200: %s", ll_strerror(rc)); return; }
-    publish(pubFull, full, in->header);
-    publish(pubSharp, sharp, in->header);
-    publish(pubLessSharp, lsharp, in->header);
-    publish(pubFlat, flat, in->header);
-    publish(pubLessFlat, lflat, in->header);
+    ll_stats st;
+    ll_get_last_stats(g_ll, &st);
+    publish(pubFull, 0, st.n_full, in->header);
+    publish(pubSharp, 1, st.n_sharp, in->header);
+    publish(pubLessSharp, 2, st.n_less_sharp, in->header);
+    publish(pubFlat, 3, st.n_flat, in->header);
+    publish(pubLessFlat, 4, st.n_less_flat, in->header);
 }
 
 int main(int argc, char** argv)
@@ -61,7 +61,7 @@ int main(int argc, char** argv)
     ll_default_config(&cfg, n_scans);
     cfg.minimum_range = (float)min_range; cfg.lower_bound = lower; cfg.up_bound = upper; cfg.max_points = 400000;  // SR:34
     if (int rc = ll_create(&cfg, &g_ll)) { ROS_FATAL("lightloam_b200: %s", ll_strerror(rc)); return 1; }
-    bFull.resize(4 * 400000); bLessFlat.resize(4 * 400000); bSharp.resize(4 * n_scans * 12); bLessSharp.resize(4 * n_scans * 120); bFlat.resize(4 * n_scans * 24);
+    { pcl::PointCloud<pcl::PointXYZI> empty; pcl::toROSMsg(empty, g_template); }
     ros::Subscriber sub = nh.subscribe<sensor_msgs::PointCloud2>("/rslidar_points", 100, laserCloudHandler);
     pubFull = nh.advertise<sensor_msgs::PointCloud2>("/velodyne_cloud_2", 100);
     pubSharp = nh.advertise<sensor_msgs::PointCloud2>("/laser_cloud_sharp", 100);

@@ -114,3 +114,27 @@ def test_repeatable_and_idempotent(ll):
     for key in a:
         assert np.array_equal(a[key], b[key]), key
     ctx.close()
+
+
+def test_pointcloud2_wire_format_in_and_out(ll):
+    """Formats at the boundary: a PointCloud2 payload (point_step 32, x@0 y@4 z@8 intensity@16) is read in
+    place through the stride, and the published clouds come back packed on the device in the same pcl::PointXYZI layout."""
+    line = 16
+    scan = ll.synth.scan(line, 3)
+    ctx = ll.Context(scan_line=line)
+    ref = ctx.extract_features(scan)
+    msg = np.zeros((len(scan), 8), np.float32)            # sensor_msgs/PointCloud2::data of a PointXYZI cloud
+    msg[:, 0:3] = scan[:, 0:3]
+    msg[:, 4] = 7.0                                       # input intensity: ignored by scanRegistration (SR:133-209)
+    got = ctx.extract_features(msg)                       # stride 32 bytes
+    for k in ("full", "sharp", "less_sharp", "flat", "less_flat", "sharp_idx", "flat_idx"):
+        assert np.array_equal(got[k], ref[k]), k
+    for which, k in enumerate(("full", "sharp", "less_sharp", "flat", "less_flat")):
+        raw = ctx.fetch_pointcloud2(which)
+        assert raw.shape == (len(ref[k]), 32)
+        f = raw.view(np.float32).reshape(-1, 8)
+        assert np.array_equal(f[:, 0:3], ref[k][:, 0:3]) and np.array_equal(f[:, 4], ref[k][:, 3]), k
+        assert not f[:, 3].any() and not f[:, 5:8].any(), k   # padding zeroed
+    with pytest.raises(Exception):
+        ctx.fetch_pointcloud2(0, cap_points=10)             # LL_E_CAPACITY
+    ctx.close()
