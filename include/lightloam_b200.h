@@ -56,7 +56,10 @@ typedef struct ll_config {
 typedef struct ll_cloud_view {   /* caller-owned HOST memory */
     const float* data;
     int n;
-    int stride_bytes;            /* >= 12, multiple of 4; x,y,z at offsets 0,4,8 (PointCloud2 point_step) */
+    int stride_bytes;            /* >= 12, multiple of 4; x,y,z at offsets 0,4,8 (PointCloud2 point_step).  Where the
+                                  * intensity matters (feature clouds of ll_odometry_step / ll_mapping_step): byte 12 when
+                                  * stride_bytes < 32 (packed float4), byte 16 when stride_bytes >= 32 (pcl::PointXYZI as
+                                  * PointCloud2 carries it) */
 } ll_cloud_view;
 
 typedef struct ll_cloud_out {    /* caller-owned HOST memory, float4 per point */

@@ -848,8 +848,15 @@ static int upload_cloud(ll_ctx* c, const ll_cloud_view& v, float4* dst, int cap)
     if (v.n < 0 || v.n > cap) return LL_E_CAPACITY;
     if (v.n == 0) return LL_OK;
     if (!v.data || v.stride_bytes < 16 || (v.stride_bytes & 3)) return LL_E_INVAL;
-    if (v.stride_bytes == 16) LL_CUDA_CHECK(c, cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
-    else LL_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, 16, v.data, v.stride_bytes, 16, v.n, cudaMemcpyHostToDevice, c->stream));
+    if (v.stride_bytes == 16) {
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
+    } else if (v.stride_bytes >= 32) {  // pcl::PointXYZI in a PointCloud2 payload: x,y,z at 0, intensity at byte 16
+        LL_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, 16, v.data, v.stride_bytes, 12, v.n, cudaMemcpyHostToDevice, c->stream));
+        LL_CUDA_CHECK(c, cudaMemcpy2DAsync(reinterpret_cast<char*>(dst) + 12, 16, reinterpret_cast<const char*>(v.data) + 16, v.stride_bytes, 4, v.n,
+                                           cudaMemcpyHostToDevice, c->stream));
+    } else {
+        LL_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, 16, v.data, v.stride_bytes, 16, v.n, cudaMemcpyHostToDevice, c->stream));
+    }
     return LL_OK;
 }
 

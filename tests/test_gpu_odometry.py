@@ -224,3 +224,24 @@ def test_polar_search_exact_on_non_sensor_like_clouds(ll, orc, case):
         assert np.array_equal(got_p, op), k
         assert np.abs(pg["t_w"] - po["t_w"]).max() < 1e-7 and np.abs(pg["q_w"] - po["q_w"]).max() < 1e-7, k
     ctx.close()
+
+
+def test_odometry_step_reads_pointxyzi_payloads_in_place(ll, orc):
+    """Feature clouds as they travel between the nodes (PointCloud2, pcl::PointXYZI: point_step 32, intensity at byte 16)
+    must give the same poses as packed float4 clouds."""
+    line = 16
+    a, b = ll.Context(scan_line=line), ll.Context(scan_line=line)
+    ocfg = orc.config(line, voxel_stable=1)
+
+    def wire(c):
+        m = np.full((len(c), 8), 9.0, np.float32)      # padding filled with junk: it must not be read
+        m[:, 0:3] = c[:, 0:3]
+        m[:, 4] = c[:, 3]
+        return m
+
+    for k in range(4):
+        f = orc.extract_features(ll.synth.scan(line, k), ocfg)
+        pa = a.odometry_step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        pb = b.odometry_step(wire(f["sharp"]), wire(f["less_sharp"]), wire(f["flat"]), wire(f["less_flat"]))
+        assert np.array_equal(pa["q_w"], pb["q_w"]) and np.array_equal(pa["t_w"], pb["t_w"]), k
+    a.close(); b.close()
