@@ -21,14 +21,6 @@ static std::mutex mBuf;
 #define HANDLER(name, q) static void name(const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(mBuf); q.push(m); }
 HANDLER(hSharp, qSharp) HANDLER(hLessSharp, qLessSharp) HANDLER(hFlat, qFlat) HANDLER(hLessFlat, qLessFlat) HANDLER(hFull, qFull)
 
-static std::vector<float> pack(const sensor_msgs::PointCloud2& msg)
-{   // PointXYZI (intensity at byte 16 of 32) -> float4 x,y,z,i
-    pcl::PointCloud<pcl::PointXYZI> c;
-    pcl::fromROSMsg(msg, c);
-    std::vector<float> v(4 * c.size());
-    for (size_t i = 0; i < c.size(); ++i) { v[4 * i] = c[i].x; v[4 * i + 1] = c[i].y; v[4 * i + 2] = c[i].z; v[4 * i + 3] = c[i].intensity; }
-    return v;
-}
 
 int main(int argc, char** argv)
 {
@@ -66,11 +58,15 @@ int main(int argc, char** argv)
                 ROS_BREAK();  // LO:394-401
             }
             sensor_msgs::PointCloud2ConstPtr mLessSharp = qLessSharp.front(), mLessFlat = qLessFlat.front(), mFull = qFull.front();
-            std::vector<float> a = pack(*qSharp.front()), b = pack(*mLessSharp), c = pack(*qFlat.front()), d = pack(*mLessFlat);
+            sensor_msgs::PointCloud2ConstPtr mSharp = qSharp.front(), mFlat = qFlat.front();
             qSharp.pop(); qLessSharp.pop(); qFlat.pop(); qLessFlat.pop(); qFull.pop();
             mBuf.unlock();
             double q[4], t[3], ql[4], tl[3];
-            ll_cloud_view va{a.data(), (int)a.size() / 4, 16}, vb{b.data(), (int)b.size() / 4, 16}, vc{c.data(), (int)c.size() / 4, 16}, vd{d.data(), (int)d.size() / 4, 16};
+            // the PointXYZI payloads are read in place: point_step 32, x,y,z at 0, intensity at byte 16 (LO:403-423 fromROSMsg)
+            auto view = [](const sensor_msgs::PointCloud2& m) {
+                return ll_cloud_view{reinterpret_cast<const float*>(m.data.data()), (int)(m.width * m.height), (int)m.point_step};
+            };
+            const ll_cloud_view va = view(*mSharp), vb = view(*mLessSharp), vc = view(*mFlat), vd = view(*mLessFlat);
             const int rc = ll_odometry_step(ll, va, vb, vc, vd, q, t, ql, tl);
             if (rc < 0) { ROS_WARN("lightloam_b200: %s", ll_strerror(rc)); continue; }
             nav_msgs::Odometry odom;
