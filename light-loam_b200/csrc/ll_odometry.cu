@@ -1087,6 +1087,11 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
     const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;   // ring-window bins per side a thread walks
     const int minb = getenv("LL_ASSOC_MINB") ? atoi(getenv("LL_ASSOC_MINB")) : 8;   // resident blocks per SM the thread pass is compiled for
+    // The solve needs 128 registers per thread: 512-thread CTAs fill an SM's register file alone.  With more problems than
+    // SMs, 256-thread CTAs run two per SM in ONE wave and fill each other's serial phases (LM controller, barriers).
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->dev);
+    const int lm_threads = getenv("LL_LM_THREADS") ? atoi(getenv("LL_LM_THREADS")) : (n_lanes > n_sm ? 256 : LM_THREADS);
     const int kmax = getenv("LL_ASSOC_KMAX") ? atoi(getenv("LL_ASSOC_KMAX")) : 2;   // 1-NN bins per side a thread walks
     const size_t vote_smem = (size_t)(c->R * LL_FLAT_PER_RING / 10 + 16) * (2 * sizeof(float4) + sizeof(int));
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
@@ -1127,7 +1132,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P); }
-        { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, LM_THREADS, 0, s>>>(P); }
+        { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, lm_threads, 0, s>>>(P); }
         c->launches += 5;
     }
     { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }

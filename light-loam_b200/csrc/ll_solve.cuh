@@ -20,7 +20,7 @@
 #include "ll_ctx.h"
 #include "ll_device.cuh"
 
-#define LM_THREADS 512
+#define LM_THREADS 512   // most threads a solve CTA may have (a launch may use fewer: the loops follow blockDim.x)
 #define LM_NRED 28
 
 #define LM_MAX_GPUS 8
@@ -151,8 +151,8 @@ __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, in
     for (int k = 0; k < LM_NRED; ++k) acc[k] = 0.0;
     // the record of the thread's next block is in flight while the current one is evaluated (all eleven fields are
     // loaded before the type is looked at: a slot without a correspondence still holds readable numbers)
-    const int stride = LM_THREADS * nparts;
-    int i = part * LM_THREADS + threadIdx.x;
+    const int stride = (int)blockDim.x * nparts;   // blockDim.x <= LM_THREADS
+    int i = part * (int)blockDim.x + threadIdx.x;
     LmRecord cur, nxt;
     if (i < nb) lm_load_record(cur, blk, cap, i);
     for (; i < nb; i += stride) {
@@ -234,8 +234,9 @@ __device__ __forceinline__ void lm_reduce(LmShared& S, double acc[LM_NRED])
     __syncthreads();
     if (threadIdx.x < LM_NRED && (FULL || threadIdx.x == 27)) {
         double v = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < LM_THREADS / 32; ++ww) v += S.red[ww][threadIdx.x];
+        const int nw = (int)blockDim.x >> 5;
+#pragma unroll 4
+        for (int ww = 0; ww < nw; ++ww) v += S.red[ww][threadIdx.x];
         S.out[threadIdx.x] = v;
     }
     __syncthreads();

@@ -15,8 +15,10 @@ def _ang(qa, qb):
     return 2 * np.arccos(min(1.0, d))
 
 
-@pytest.mark.parametrize("line,n,az", [(16, 10, None), (64, 9, None), (32, 8, 1200)])
-def test_fused_pipeline_trajectory_matches_oracle(ll, orc, line, n, az):
+@pytest.mark.parametrize("line,n,az,lm_threads", [(16, 10, None, None), (64, 9, None, None), (32, 8, 1200, None), (64, 8, None, "256")])
+def test_fused_pipeline_trajectory_matches_oracle(ll, orc, line, n, az, lm_threads, monkeypatch):
+    if lm_threads:   # the CTA shape the solve uses when there are more scan streams than SMs (bench: 256 lanes)
+        monkeypatch.setenv("LL_LM_THREADS", lm_threads)
     ctx = ll.Context(scan_line=line)
     exact = orc.Pipeline(orc.config(line, voxel_stable=1), with_mapping=False)
     faithful = orc.Pipeline(orc.config(line, voxel_stable=0), with_mapping=False)
