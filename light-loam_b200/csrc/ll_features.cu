@@ -14,6 +14,7 @@
 // 16 P (raw) + 16 P (full) read+write in the sort, 16 P read + 4 P + features written by k_ring_features.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "ll_ctx.h"
 #include "ll_device.cuh"
@@ -97,7 +98,8 @@ __device__ __forceinline__ int ring_of(const FeatParams& P, float x, float y, fl
 // One CTA classifies CLS_TPB consecutive 256-point tiles of a lane: the points of all its tiles are requested before
 // the first is used, so the dependent chain (lane state -> raw pointer -> point) is paid once per CTA, not per tile.
 #define CLS_TPB 4
-__global__ void __launch_bounds__(LL_TILE) k_classify(FeatParams P)
+template <int MINB>
+__global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
 {
     __shared__ int cnt[2][LL_TILE / 32][LL_MAX_RINGS];   // per-warp ring counts of a tile, double-buffered over the tiles
     __shared__ int flip_s;
@@ -261,7 +263,8 @@ __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
 }
 
 // CLS_TPB tiles per CTA as in k_classify: ring offsets in shared memory, all the CTA's loads issued up front
-__global__ void __launch_bounds__(LL_TILE) k_scatter(FeatParams P)
+template <int MINB>
+__global__ void __launch_bounds__(LL_TILE, MINB) k_scatter(FeatParams P)
 {
     __shared__ int ring_begin_s[LL_MAX_RINGS];
     const int b = blockIdx.y;
@@ -683,11 +686,10 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     constexpr int NTH = 512;
     constexpr int CH = (RCAP + NTH - 1) / NTH;
     extern __shared__ __align__(128) unsigned char smem[];
-    u64* keys = reinterpret_cast<u64*>(smem);                       // [KCAP] (voxel id << 32) | run number
+    u64* keys = reinterpret_cast<u64*>(smem);                       // [KCAP] (voxel id << 32) | first compacted position of the run << 13 | its length
     int* vid = reinterpret_cast<int*>(keys + KCAP);                 // [RCAP] voxel id per less-flat point (compacted order)
     uint16_t* pidx = reinterpret_cast<uint16_t*>(vid + RCAP);       // [RCAP] ring-local index of that point
-    uint16_t* run_start = pidx + RCAP;                              // [RCAP + 1] first compacted position of every run
-    int* ws = reinterpret_cast<int*>(run_start + RCAP + 2);
+    int* ws = reinterpret_cast<int*>(pidx + RCAP + (RCAP & 1));
     float* red = reinterpret_cast<float*>(ws + 40);
 
     const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
@@ -801,14 +803,21 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     int ro = block_exclusive_scan(heads, ws, &R);
     int NS = 64;
     while (NS < R) NS <<= 1;
+    // key of a run = (voxel id, first compacted position, length): sorting by it groups the runs of a voxel in input
+    // order, and the centroid pass needs nothing else (positions and lengths < 2^13)
+    const int ro0 = ro;
     for (int p = p0; p < p1; ++p)
         if (p == 0 || vid[p] != vid[p - 1]) {
-            keys[ro] = ((u64)(unsigned)vid[p] << 32) | (unsigned)ro;
-            run_start[ro] = (uint16_t)p;
+            keys[ro] = ((u64)(unsigned)vid[p] << 32) | ((unsigned)p << 13);
             ++ro;
         }
-    if (tid == 0) run_start[R] = (uint16_t)m;
     for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull;
+    __syncthreads();
+    for (int q = ro0; q < ro; ++q) {   // length = start of the next run - own start
+        const unsigned ps = (unsigned)keys[q] >> 13;
+        const unsigned pn = q + 1 < R ? (unsigned)keys[q + 1] >> 13 : (unsigned)m;
+        keys[q] |= (u64)(pn - ps);
+    }
     __syncthreads();
     switch (NS) {   // all 512 threads call; NS / 4 (or NS / 8) of them hold keys
         case 64: block_sort_u64_asc<64, 2>(keys); break;
@@ -833,8 +842,8 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
             float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
             int cnt = 0;
             for (int g = q; g < R && (unsigned)(keys[g] >> 32) == v; ++g) {  // runs in ascending run number = input order
-                const int run = (int)(unsigned)keys[g];
-                const int e0 = run_start[run], e1 = run_start[run + 1];
+                const unsigned lo = (unsigned)keys[g];
+                const int e0 = (int)(lo >> 13), e1 = e0 + (int)(lo & 0x1FFFu);
 #pragma unroll 4
                 for (int p = e0; p < e1; ++p) {
                     const float4 a = pts[pidx[p]];
@@ -941,7 +950,7 @@ size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxe
 {
     const int RCAP = 6 * SCAP + 16, KCAP = RCAP <= 4096 ? 4096 : 8192;
     const int CH = (RCAP + 511) / 512;
-    return (size_t)KCAP * 8 + (size_t)RCAP * 4 + (size_t)RCAP * 2 + (size_t)(RCAP + 2) * 2 + 40 * 4 + 112 * 4 + (size_t)(CH * 16 + 4) * 4;
+    return (size_t)KCAP * 8 + (size_t)RCAP * 4 + (size_t)(RCAP + (RCAP & 1)) * 2 + 40 * 4 + 112 * 4 + (size_t)(CH * 16 + 4) * 4;
 }
 
 int ll_launch_features(ll_ctx* c, int n_lanes)
@@ -958,9 +967,24 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     cudaStream_t s = c->stream;
     const dim3 tiles(c->NT, n_lanes);
     { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<n_lanes, 32, 0, s>>>(c->d_lane, n_lanes, P.thres); }
-    { LLProf pr(c, "k_classify"); k_classify<<<dim3((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes), LL_TILE, 0, s>>>(P); }
+    const int cls_minb = getenv("LL_CLS_MINB") ? atoi(getenv("LL_CLS_MINB")) : 8, sct_minb = getenv("LL_SCT_MINB") ? atoi(getenv("LL_SCT_MINB")) : 5;
+    {
+        LLProf pr(c, "k_classify");
+        const dim3 g((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes);
+        if (cls_minb >= 8) k_classify<8><<<g, LL_TILE, 0, s>>>(P);
+        else if (cls_minb >= 6) k_classify<6><<<g, LL_TILE, 0, s>>>(P);
+        else if (cls_minb >= 5) k_classify<5><<<g, LL_TILE, 0, s>>>(P);
+        else k_classify<4><<<g, LL_TILE, 0, s>>>(P);
+    }
     { LLProf pr(c, "k_ring_scan"); k_ring_scan<<<n_lanes, 1024, 0, s>>>(P); }
-    { LLProf pr(c, "k_scatter"); k_scatter<<<dim3((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes), LL_TILE, 0, s>>>(P); }
+    {
+        LLProf pr(c, "k_scatter");
+        const dim3 g((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes);
+        if (sct_minb >= 8) k_scatter<8><<<g, LL_TILE, 0, s>>>(P);
+        else if (sct_minb >= 6) k_scatter<6><<<g, LL_TILE, 0, s>>>(P);
+        else if (sct_minb >= 5) k_scatter<5><<<g, LL_TILE, 0, s>>>(P);
+        else k_scatter<4><<<g, LL_TILE, 0, s>>>(P);
+    }
     const size_t smem_sort = ll_feature_smem_bytes(c->SCAP);
     const size_t smem_lf = ll_lessflat_smem_bytes(c->SCAP);
     const size_t smem_pick = (size_t)PICK_WARPS * (2 * ((c->RCAP + 31) / 32 + 2) + c->RCAP / 2) * 4;
