@@ -401,6 +401,8 @@ __device__ __forceinline__ void warp_sort_regs_blocked(unsigned (&k)[NREG], int 
 }
 
 #define SORT_THREADS 192   // six sectors, one warp each
+#define SORT_CHUNK 1536    // ring points staged per TMA copy (multiple of 32)
+#define SORT_STAGE_BYTES ((SORT_CHUNK + 10) * 16)
 template <int SCAP>
 __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
 {
@@ -410,10 +412,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
     constexpr int IDXBITS = SCAP == 512 ? 9 : 10;
     constexpr unsigned IDXMASK = (1u << IDXBITS) - 1u;
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* pts = reinterpret_cast<float4*>(smem);
-    float* curv_s = reinterpret_cast<float*>(smem + (size_t)RCAP * 16);
-    unsigned* keys = reinterpret_cast<unsigned*>(curv_s + RCAP);
-    int* sp = reinterpret_cast<int*>(keys + 6 * (SCAP + 32));
+    static_assert(6 * (SCAP + 32) * 4 <= SORT_STAGE_BYTES || SCAP > 512, "the sort keys reuse the staging buffer");
+    constexpr size_t STAGE = (size_t)6 * (SCAP + 32) * 4 > SORT_STAGE_BYTES ? (size_t)6 * (SCAP + 32) * 4 : SORT_STAGE_BYTES;
+    float4* pts = reinterpret_cast<float4*>(smem);                    // staging buffer of one chunk (+ halo) ...
+    unsigned* keys = reinterpret_cast<unsigned*>(smem);               // ... reused for the sort keys afterwards
+    float* curv_s = reinterpret_cast<float*>(smem + STAGE);
+    int* sp = reinterpret_cast<int*>(curv_s + RCAP);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sp + 8);
 
     const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
@@ -444,43 +448,50 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
     }
 
     if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) tma_bulk_g2s(pts, gfull + base, (uint32_t)n * 16u, bar);
     const int len = n - 11;
     if (tid <= 6) sp[tid] = 5 + len * tid / 6;  // SR:253-254 with ring-local indices
-    mbar_wait(bar, 0);
     __syncthreads();
-
-    for (int i = tid; i < n; i += NTH) {
-        float c;
-        if (i >= 5 && i < n - 5) {
-            float dx = pts[i - 5].x, dy = pts[i - 5].y, dz = pts[i - 5].z;
+    // The ring is staged through shared memory in chunks of SORT_CHUNK points (+ 5 points of halo on each side) so that
+    // the CTA needs 37 KB instead of 75 KB: six CTAs per SM instead of three.  One TMA bulk copy per chunk; the
+    // mbarrier's phase parity follows the chunk number.
+    for (int c0 = 0, chunk = 0; c0 < n; c0 += SORT_CHUNK, ++chunk) {
+        const int c1 = min(c0 + SORT_CHUNK, n);
+        const int lo = max(c0 - 5, 0), hi = min(c1 + 5, n);
+        if (tid == 0) tma_bulk_g2s(pts, gfull + base + lo, (uint32_t)(hi - lo) * 16u, bar);
+        mbar_wait(bar, (uint32_t)(chunk & 1));
+        const float4* pl = pts - lo;   // pl[i] = ring point i for lo <= i < hi
+        for (int i = c0 + tid; i < c1; i += NTH) {
+            float c;
+            if (i >= 5 && i < n - 5) {
+                float dx = pl[i - 5].x, dy = pl[i - 5].y, dz = pl[i - 5].z;
 #pragma unroll
-            for (int k = -4; k <= -1; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
-            { const float4 q = pts[i]; dx = dx - 10 * q.x; dy = dy - 10 * q.y; dz = dz - 10 * q.z; }
+                for (int k = -4; k <= -1; ++k) { const float4 q = pl[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
+                { const float4 q = pl[i]; dx = dx - 10 * q.x; dy = dy - 10 * q.y; dz = dz - 10 * q.z; }
 #pragma unroll
-            for (int k = 1; k <= 5; ++k) { const float4 q = pts[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
-            c = dx * dx + dy * dy + dz * dz;
-        } else {
-            c = global_curv(base + i);
+                for (int k = 1; k <= 5; ++k) { const float4 q = pl[i + k]; dx = dx + q.x; dy = dy + q.y; dz = dz + q.z; }
+                c = dx * dx + dy * dy + dz * dz;
+            } else {
+                c = global_curv(base + i);
+            }
+            curv_s[i] = c;
+            gcurv[base + i] = c;
+            glabel[base + i] = 0;
         }
-        curv_s[i] = c;
-        gcurv[base + i] = c;
-        glabel[base + i] = 0;
-    }
-    // consecutive-gap break bits for the +-5 suppression (SR:290-293): bit i = |p[i] - p[i-1]|^2 > 0.05;
-    // each warp covers 32 consecutive points, the ballot is the bitmask word
-    for (int i0 = (tid & ~31); i0 < P.brk_words * 32; i0 += NTH) {
-        const int i = i0 + lane;
-        bool brk = false;
-        if (i >= 1 && i < n) {
-            const float4 a = pts[i], c = pts[i - 1];
-            brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
+        // consecutive-gap break bits for the +-5 suppression (SR:290-293): bit i = |p[i] - p[i-1]|^2 > 0.05;
+        // each warp covers 32 consecutive points (SORT_CHUNK is a multiple of 32), the ballot is the bitmask word
+        const int w1 = c1 == n ? P.brk_words * 32 : c1;
+        for (int i0 = c0 + (tid & ~31); i0 < w1; i0 += NTH) {
+            const int i = i0 + lane;
+            bool brk = false;
+            if (i >= 1 && i < n) {
+                const float4 a = pl[i], c = pl[i - 1];
+                brk = (double)sqdist3(a.x, a.y, a.z, c.x, c.y, c.z) > 0.05;
+            }
+            const unsigned bits = __ballot_sync(LL_FULL_MASK, brk);
+            if (lane == 0) gbrk[i0 >> 5] = bits;
         }
-        const unsigned bits = __ballot_sync(LL_FULL_MASK, brk);
-        if (lane == 0) gbrk[i0 >> 5] = bits;
+        __syncthreads();   // everybody is done with this chunk before the next copy (or the sort keys) overwrite it
     }
-    __syncthreads();
 
     // ---- one warp per sector (sectors tile [5, n-6)) ---------------------------------------------------------------
     const int j = wid, s0 = sp[j], slen = sp[j + 1] - s0;
@@ -944,7 +955,8 @@ __global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres)
 size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + curvature + six sector key arrays + sector starts + mbarrier
 {
     const int RCAP = 6 * SCAP + 16;
-    return (size_t)RCAP * 16 + (size_t)RCAP * 4 + (size_t)6 * (SCAP + 32) * 4 + 8 * 4 + 16;
+    const size_t keys = (size_t)6 * (SCAP + 32) * 4, stage = keys > (size_t)SORT_STAGE_BYTES ? keys : (size_t)SORT_STAGE_BYTES;
+    return stage + (size_t)RCAP * 4 + 8 * 4 + 16;
 }
 size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxel ids, point indices, run starts, scratch
 {
