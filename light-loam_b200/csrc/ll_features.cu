@@ -572,6 +572,25 @@ __device__ __forceinline__ void suppress_neighbours(const unsigned* brk, unsigne
     }
 }
 
+// the same as a range: the points a pick at `ind` suppresses are [lo, hi]
+__device__ __forceinline__ void suppress_range(const unsigned* brk, int ind, int& lo, int& hi)
+{
+    const unsigned f = (unsigned)bits_at(brk, ind + 1) & 0x1Fu;
+    const int nf = f ? __ffs(f) - 1 : 5;
+    const unsigned back = (unsigned)bits_at(brk, ind - 4) & 0x1Fu;   // bits: brk[ind-4 .. ind]
+    const unsigned rev = __brev(back) >> 27;                          // bit k = brk[ind - k]
+    const int nr = rev ? __ffs(rev) - 1 : 5;
+    lo = ind - nr; hi = ind + nf;
+}
+// sets bits [lo, hi] (at most 11 bits, two words) of a bitmask several lanes may update at once
+__device__ __forceinline__ void mark_range(unsigned* picked, int lo, int hi)
+{
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    const unsigned m_lo = 0xFFFFFFFFu << (lo & 31), m_hi = 0xFFFFFFFFu >> (31 - (hi & 31));
+    if (w0 == w1) atomicOr(&picked[w0], m_lo & m_hi);
+    else { atomicOr(&picked[w0], m_lo); atomicOr(&picked[w1], m_hi); }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // k_ring_pick: the greedy, order-dependent part of SR:251-359, one WARP per (ring, lane) so that thousands of
 // rings run concurrently.  Per warp, shared memory holds the sorted candidates (u16), the gap-break bits and the
@@ -610,69 +629,74 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
     for (int j = 0; j < 6; ++j) {
         const int s0 = 5 + len * j / 6, size = 5 + len * (j + 1) / 6 - s0;
         const uint16_t* seg = sorted + s0;
+        // Both walks examine 32 sorted candidates per round and resolve the whole round in registers: every eligible
+        // lane works out the range its pick would suppress, then the lanes are taken in sorted order - the first
+        // eligible one is picked and every candidate inside its range drops out - which is exactly what the serial
+        // loop does one candidate at a time.  Shared memory (the picked bits) is touched once per round.
         // corners: from the largest curvature down (SR:261-313)
-        int pos = size - 1, npick = 0;
-        while (pos >= 0) {
+        int npick = 0;
+        for (int pos = size - 1; pos >= 0; pos -= 32) {
             const int p = pos - lane;
             const unsigned key = p >= 0 ? seg[p] : 0u;
             const int idx = (int)(key & 0x3FFFu);
             const bool over = p >= 0 && (key & 0x4000u);
-            const bool elig = over && !((picked[idx >> 5] >> (idx & 31)) & 1u);
-            const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+            bool elig = over && !((picked[idx >> 5] >> (idx & 31)) & 1u);
             const unsigned nm = __ballot_sync(LL_FULL_MASK, p >= 0 && !over);
-            if (em == 0) {
-                if (nm) break;  // reached curvature <= 0.1: nothing below can be picked
-                pos -= 32;
-                continue;
+            int lo = 0, hi = -1;
+            if (elig) suppress_range(brk, idx, lo, hi);
+            int my_pick = 0;   // 1-based pick number of this lane's candidate
+            bool full = false;
+            unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+            while (em) {
+                const int f = __ffs(em) - 1;
+                if (npick + 1 > 20) { full = true; break; }  // SR:281-284: the 21st candidate ends the walk
+                ++npick;
+                if (lane == f) my_pick = npick;
+                const int flo = __shfl_sync(LL_FULL_MASK, lo, f), fhi = __shfl_sync(LL_FULL_MASK, hi, f);
+                if (idx >= flo && idx <= fhi) elig = false;   // includes the picked candidate itself
+                em = __ballot_sync(LL_FULL_MASK, elig);
             }
-            const int f = __ffs(em) - 1;
-            const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
-            ++npick;
-            if (npick > 20) break;  // SR:281-284
-            if (lane == 0) {
-                label[ind] = npick <= 2 ? 2 : 1;
-                if (npick <= 2) my_lists[n_sharp] = base + ind;
-                my_lists[LL_SHARP_PER_RING + n_lsharp] = base + ind;
-                picked[ind >> 5] |= 1u << (ind & 31);
-                suppress_neighbours(brk, picked, ind);
+            if (my_pick) {
+                label[idx] = my_pick <= 2 ? 2 : 1;
+                if (my_pick <= 2) my_lists[n_sharp + my_pick - 1] = base + idx;   // n_sharp / n_lsharp: counts before this sector
+                my_lists[LL_SHARP_PER_RING + n_lsharp + my_pick - 1] = base + idx;
+                mark_range(picked, lo, hi);
             }
-            if (npick <= 2) ++n_sharp;
-            ++n_lsharp;
             __syncwarp();
-            pos -= f + 1;
+            if (full || nm) break;  // 20 picked, or reached curvature <= 0.1: nothing below can be picked
         }
+        n_sharp += min(npick, 2);
+        n_lsharp += npick;
         // flats: from the smallest curvature up (SR:316-359)
-        pos = 0;
         int nsm = 0;
-        while (pos < size) {
+        for (int pos = 0; pos < size; pos += 32) {
             const int p = pos + lane;
             const unsigned key = p < size ? seg[p] : 0u;
             const int idx = (int)(key & 0x3FFFu);
             const bool under = p < size && (key & 0x8000u);
-            const bool elig = under && !((picked[idx >> 5] >> (idx & 31)) & 1u);
-            const unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+            bool elig = under && !((picked[idx >> 5] >> (idx & 31)) & 1u);
             const unsigned nm = __ballot_sync(LL_FULL_MASK, p < size && !under);
-            if (em == 0) {
-                if (nm) break;
-                pos += 32;
-                continue;
+            int lo = 0, hi = -1;
+            if (elig) suppress_range(brk, idx, lo, hi);
+            int my_pick = 0;
+            unsigned em = __ballot_sync(LL_FULL_MASK, elig);
+            while (em && nsm < 4) {
+                const int f = __ffs(em) - 1;
+                ++nsm;
+                if (lane == f) my_pick = nsm;
+                const int flo = __shfl_sync(LL_FULL_MASK, lo, f), fhi = __shfl_sync(LL_FULL_MASK, hi, f);
+                if (idx >= flo && idx <= fhi) elig = false;
+                em = __ballot_sync(LL_FULL_MASK, elig);
             }
-            const int f = __ffs(em) - 1;
-            const int ind = __shfl_sync(LL_FULL_MASK, idx, f);
-            if (lane == 0) {
-                label[ind] = -1;
-                my_lists[LL_SHARP_PER_RING + LL_LSHARP_PER_RING + n_flat] = base + ind;
-            }
-            ++n_flat;
-            ++nsm;
-            if (nsm >= 4) break;  // SR:328-331: before picked / suppression
-            if (lane == 0) {
-                picked[ind >> 5] |= 1u << (ind & 31);
-                suppress_neighbours(brk, picked, ind);
+            if (my_pick) {
+                label[idx] = -1;
+                my_lists[LL_SHARP_PER_RING + LL_LSHARP_PER_RING + n_flat + my_pick - 1] = base + idx;
+                if (my_pick < 4) mark_range(picked, lo, hi);   // SR:328-331: the 4th pick leaves before picked / suppression
             }
             __syncwarp();
-            pos += f + 1;
+            if (nsm >= 4 || nm) break;
         }
+        n_flat += nsm;
         __syncwarp();
     }
     if (lane == 0) { my_counts[0] = n_sharp; my_counts[1] = n_lsharp; my_counts[2] = n_flat; }
