@@ -136,7 +136,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "NONE")  # keep stdout to the one JSON line (WARN and above print a version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
     ctx = ll.Context(scan_line=64, batch=B, device=local_rank)
