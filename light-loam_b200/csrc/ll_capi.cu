@@ -274,8 +274,8 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_vote_tgt, B * R * LL_FLAT_PER_RING));
     c->assoc_queue_cap = (int)(B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING));
     CK(dalloc(c->d_assoc_queue, (size_t)c->assoc_queue_cap));
-    CK(dalloc(c->d_assoc_queue_n, 8));
-    CK(cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, c->stream));
+    CK(dalloc(c->d_assoc_queue_n, 16));
+    CK(cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 16, c->stream));
     c->nblk_cap = (int)R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     CK(dalloc(c->d_blocks, B * (size_t)LL_BLOCK_DOUBLES * c->nblk_cap));
     CK(cudaMemsetAsync(c->d_raw, 0, sizeof(uint32_t) * B * N * 8, c->stream));

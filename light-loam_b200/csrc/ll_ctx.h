@@ -126,7 +126,7 @@ struct ll_ctx {
     float4* d_vote_src = nullptr;  // [B][R*24] compacted plane matches for the graph vote (current point, w = feature index)
     float4* d_vote_tgt = nullptr;  // [B][R*24] ... and their closest points
     int4* d_assoc_queue = nullptr; // [B * R * 36] queries handed to the warp pass of the association
-    int* d_assoc_queue_n = nullptr;// [8] queue lengths [0..2] and pop cursors [4..6] per outer iteration
+    int* d_assoc_queue_n = nullptr;// [16] per outer iteration: long entries queued [0..2], pop cursors [4..6], short entries queued [8..10]
     int assoc_queue_cap = 0;
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;

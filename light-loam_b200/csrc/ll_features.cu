@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
     const int b = blockIdx.y;
     LaneState& L = P.lane[b];
     const int n = L.n_raw, sw = L.stride_words;
-    const float startOri = L.start_ori;                  // found by k_reset_scan_state
+    const float startOri = L.start_ori, endOri = L.end_ori;   // found by k_reset_scan_state
     const int half_seen = *(volatile int*)&L.half_idx;   // filter for the atomic below; a stale (larger) value only costs an atomic
     const int w = warp_id(), lane = lane_id();
     const int tile0 = blockIdx.x * CLS_TPB;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
         }
     }
     __syncthreads();
-    int hi_max = -1, fl_min = INT_MAX;
+    int fl_min = INT_MAX;
 #pragma unroll
     for (int t = 0; t < CLS_TPB; ++t) {
         const int tile = tile0 + t;
@@ -138,7 +138,17 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
         bool flip = false;
         if (valid) {
             ring = ring_of(P, x, y, z);
-            ori = -(float)atan2((double)y, (double)x);  // SR:177
+            // SR:177.  The reference's -atan2f is reproduced as the fp64 atan2 rounded once; only DECISIONS need that
+            // value to the last bit: the branch thresholds startOri - pi/2, startOri + 3pi/2, (ori - startOri) > pi
+            // (SR:180-192), endOri - 3pi/2 and endOri + pi/2 on ori + 2pi (SR:196-205), and the sign of relTime at
+            // ori = startOri (SR:207-208: int(intensity) is the ring id the odometry reads).  Modulo 2pi these are
+            // startOri + k pi/2 and endOri + pi/2, so a point farther than 1e-5 rad from all of them takes the fp32
+            // atan2f (<= 2 ulp: its intensity moves by at most one ulp of the fraction, which nothing consumes).
+            ori = -atan2f(y, x);
+            {
+                const float qa = (ori - startOri) * 0.63661977f, qb = (ori - endOri) * 0.63661977f;   // in units of pi/2
+                if (fabsf(qa - rintf(qa)) < 1e-5f || fabsf(qb - rintf(qb)) < 1e-5f) ori = -(float)atan2((double)y, (double)x);
+            }
             if (ring >= 0) {
                 // SR:180-192 in the !halfPassed state: the first point for which this holds flips halfPassed
                 float o = ori;
@@ -151,7 +161,6 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
         }
         P.ring8[(size_t)b * P.Nmax + i] = (int8_t)ring;
         P.ori[(size_t)b * P.Nmax + i] = ori;
-        hi_max = max(hi_max, valid ? i : -1);
         if (flip) fl_min = min(fl_min, i);
         // stable rank inside the tile (SR:209 push_back order): warp match on the ring id, then prefix over the tile's warps
         const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
@@ -169,12 +178,8 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
         __syncthreads();
         P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(c[w][ring] + rank_in_warp) : 0;
     }
-    hi_max = __reduce_max_sync(LL_FULL_MASK, hi_max);
     fl_min = __reduce_min_sync(LL_FULL_MASK, fl_min);
-    if (lane == 0) {
-        if (hi_max >= 0) atomicMax(&L.last_valid, hi_max);
-        if (fl_min != INT_MAX) atomicMin(&flip_s, fl_min);
-    }
+    if (lane == 0 && fl_min != INT_MAX) atomicMin(&flip_s, fl_min);
     __syncthreads();
     // about half of all CTAs see a flip: one filtered atomic each
     if (threadIdx.x == 0 && flip_s < half_seen) atomicMin(&L.half_idx, flip_s);
@@ -253,11 +258,7 @@ __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
             L.ring_begin[P.R] = run;
             L.n_full = run;
             L.cur = L.last_slot ^ 1;  // this frame's less-sharp / less-flat go to the slot not holding the *Last clouds
-            if (L.first_valid != INT_MAX) {
-                L.end_ori = end_ori_of(P.ori[(size_t)b * P.Nmax + L.last_valid], L.start_ori);
-            } else {
-                L.err = LL_E_EMPTY;
-            }
+            if (L.first_valid == INT_MAX) L.err = LL_E_EMPTY;
         }
     }
 }
@@ -944,8 +945,8 @@ __global__ void __launch_bounds__(256) k_compact(FeatParams P)
     }
 }
 
-// one warp per lane: per-scan state, and startOri (SR:114) = azimuth of the first point that survives the filters
-// (nearly always point 0) so that k_classify can decide where halfPassed flips (SR:178-193) in its single pass
+// one warp per lane: per-scan state; startOri (SR:114) = azimuth of the first point that survives the filters (nearly
+// always point 0) so that k_classify can decide where halfPassed flips (SR:178-193) in its single pass ...
 __global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres)
 {
     const int b = blockIdx.x, ln = lane_id();
@@ -966,10 +967,27 @@ __global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres)
         const unsigned m = __ballot_sync(LL_FULL_MASK, v);
         if (m) { fv = j0 + __ffs(m) - 1; sx = __shfl_sync(LL_FULL_MASK, x, __ffs(m) - 1); sy = __shfl_sync(LL_FULL_MASK, y, __ffs(m) - 1); }
     }
+    // ... and endOri (SR:116-126) from the last one (nearly always point n - 1)
+    int lv = -1;
+    float ex = 0.f, ey = 0.f;
+    for (int j0 = n - 1; j0 >= 0 && lv < 0 && fv >= 0; j0 -= 32) {
+        const int j = j0 - ln;
+        bool v = false;
+        float x = 0.f, y = 0.f;
+        if (j >= 0) {
+            const uint32_t* p = L.raw + (size_t)j * sw;
+            x = __uint_as_float(p[0]); y = __uint_as_float(p[1]);
+            v = point_valid(x, y, __uint_as_float(p[2]), thres);
+        }
+        const unsigned m = __ballot_sync(LL_FULL_MASK, v);
+        if (m) { lv = j0 - (__ffs(m) - 1); ex = __shfl_sync(LL_FULL_MASK, x, __ffs(m) - 1); ey = __shfl_sync(LL_FULL_MASK, y, __ffs(m) - 1); }
+    }
     if (ln == 0) {
         L.first_valid = fv >= 0 ? fv : INT_MAX;
-        L.start_ori = fv >= 0 ? -(float)atan2((double)sy, (double)sx) : 0.f;   // = the ori k_classify stores for that point
-        L.last_valid = -1;
+        L.last_valid = lv;
+        const float so = fv >= 0 ? -(float)atan2((double)sy, (double)sx) : 0.f;   // = the ori k_classify stores for that point
+        L.start_ori = so;
+        L.end_ori = lv >= 0 ? end_ori_of(-(float)atan2((double)ey, (double)ex), so) : 0.f;
         L.half_idx = INT_MAX;
     }
 }

@@ -320,7 +320,7 @@ struct OdomParams {
     float4* vote_src;      // [B][R*24] compacted plane matches: current point (w = feature index) / closest point
     float4* vote_tgt;
     int4* queue;           // queries handed from the per-thread pass to the warp pass (k_odom_assoc_heavy)
-    int* queue_n;          // [3] entries queued per outer iteration
+    int* queue_n;          // per outer iteration: [0..2] long entries (stored from the front), [4..6] pop cursors, [8..10] short entries (from the back)
     int queue_cap;
 };
 
@@ -601,7 +601,7 @@ __device__ __forceinline__ void nn_consider(u64& best, float qx, float qy, float
 // Per-thread search.  Returns true when `best` is final; false = too wide for one thread (best = what was found so
 // far, the warp pass restarts from it).
 __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R,
-                                                     float qx, float qy, float qz, int kmax, PolarQuery& pq, u64& best)
+                                                     float qx, float qy, float qz, int kmax, PolarQuery& pq, u64& best, int& reach_buckets)
 {
     {
         int lo = 0, hi = R;
@@ -620,6 +620,7 @@ __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const i
     for_spans3(sorted, s0, e0, s1, e1, s2, e2, consider);
     PolarReach W = polar_reach(S, pq, NB, R, best);
     if (W.ra >= sa && W.rb <= sb && W.kl <= 1 && W.kr <= 1) return true;   // nothing closer can lie outside the seed
+    reach_buckets = (W.kl + W.kr + 1) * (W.rb - W.ra + 1);
     if (W.rb - W.ra > 16 || max(W.kl, W.kr) > kmax) return false;
     // outward from the own bin over the rings in reach (buckets of the seed are met again: a minimum does not mind);
     // the reach only shrinks as the best improves
@@ -740,7 +741,7 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
     AssocQuery Q;
     Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0; Q.cut = D2_BITS_25 - 1u;
     int4 entry = make_int4(b, CORNER ? i : (i | ASSOC_PLANE_BIT), -1, -1);
-    bool heavy = false;
+    bool heavy = false, is_long = false;
     if (active) {
         assoc_query_init<CORNER>(P, L, b, i, Q);
         const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
@@ -749,7 +750,9 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
         PolarQuery pq;
         polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
         if (Q.n > 0) {
-            heavy = !polar_nearest_thread(S, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best);
+            int reach_buckets = 0;
+            heavy = !polar_nearest_thread(S, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best, reach_buckets);
+            is_long = heavy && reach_buckets > 200;   // these take tens of microseconds each: they must start first
             if (heavy) { entry.y |= ASSOC_OPEN_BIT; entry.z = (int)(unsigned)(best >> 32); entry.w = (int)(unsigned)best; }
         }
         if (!heavy && best != NN_NONE) {  // d2 < 25: LO:497 / LO:659
@@ -768,14 +771,20 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
         }
         if (!heavy) assoc_store<CORNER>(P, b, i, Q);
     }
-    const unsigned hm = __ballot_sync(LL_FULL_MASK, heavy);
-    if (hm) {
-        const int leader = __ffs(hm) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(P.queue_n + P.outer, __popc(hm));
-        base = __shfl_sync(LL_FULL_MASK, base, leader);
-        const int pos = base + __popc(hm & ((1u << lane) - 1u));
-        if (heavy && pos < P.queue_cap) P.queue[pos] = entry;
+    // the long entries are stored from the front of the queue, the others from its back; the warp pass pops front to back
+    // (longest-first: the kernel cannot end before its longest entry does, so that one must not start last)
+#pragma unroll
+    for (int cls = 0; cls < 2; ++cls) {
+        const bool mine = heavy && (is_long == (cls == 0));
+        const unsigned hm = __ballot_sync(LL_FULL_MASK, mine);
+        if (hm) {
+            const int leader = __ffs(hm) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(P.queue_n + (cls == 0 ? 0 : 8) + P.outer, __popc(hm));
+            base = __shfl_sync(LL_FULL_MASK, base, leader);
+            const int pos = base + __popc(hm & ((1u << lane) - 1u));
+            if (mine) P.queue[cls == 0 ? pos : P.queue_cap - 1 - pos] = entry;   // long + short <= number of queries <= queue_cap
+        }
     }
 }
 // grid: (ceil(R*12 / T) + ceil(R*24 / T), B): corner queries and plane queries never share a block
@@ -833,14 +842,14 @@ __device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int
 }
 __global__ void __launch_bounds__(256, 4) k_odom_assoc_heavy(OdomParams P)
 {
-    const int n = min(P.queue_n[P.outer], P.queue_cap);
+    const int n_long = P.queue_n[P.outer], n = n_long + P.queue_n[8 + P.outer];
     int* head = P.queue_n + 4 + P.outer;  // entries are popped one at a time: their costs differ by orders of magnitude
     for (;;) {
         int e = 0;
         if (lane_id() == 0) e = atomicAdd(head, 1);
         e = __shfl_sync(LL_FULL_MASK, e, 0);
         if (e >= n) break;
-        const int4 en = P.queue[e];
+        const int4 en = P.queue[e < n_long ? e : P.queue_cap - 1 - (e - n_long)];
         const int i = en.y & ~(ASSOC_PLANE_BIT | ASSOC_OPEN_BIT);
         const bool open = (en.y & ASSOC_OPEN_BIT) != 0;
         const long long t0 = (P.dev_skip & 16) ? clock64() : 0;
@@ -1083,7 +1092,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     P.queue = c->d_assoc_queue; P.queue_n = c->d_assoc_queue_n; P.queue_cap = c->assoc_queue_cap;
     cudaStream_t s = c->stream;
     const int cblocks = (c->R * LL_SHARP_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS, pblocks = (c->R * LL_FLAT_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS;
-    LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 8, s));
+    LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 16, s));
     const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
     const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;   // ring-window bins per side a thread walks
     const int minb = getenv("LL_ASSOC_MINB") ? atoi(getenv("LL_ASSOC_MINB")) : 8;   // resident blocks per SM the thread pass is compiled for
