@@ -134,6 +134,7 @@ struct IndexSet {
     int chunk_begin[3];        // prefix of T / GRID_CHUNK over the tables
     int az_bins[2];
     int rings;
+    int gx_corner;             // k_index_count / k_index_scatter: blocks [0, gx_corner) of a lane take the corner cloud, the rest the surf cloud
 };
 #define BAND_STRIDE (2 * LL_MAX_RINGS + 4)
 __device__ __forceinline__ unsigned enc_f32(float f) { const unsigned b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
@@ -158,14 +159,17 @@ __device__ __forceinline__ int index_bucket(const IndexSet& S, int cloud, const 
 #define IDX_UNROLL 4
 __global__ void k_index_count(IndexSet S, LaneState* lane)
 {
-    const int b = blockIdx.y, cloud = blockIdx.z;
+    // one grid for both clouds, sized for what they usually hold (a block that finds nothing to do still pays the
+    // launch and the lane-state load): the first gx_corner blocks of a lane take the corner cloud
+    const int b = blockIdx.y, cloud = (int)blockIdx.x < S.gx_corner ? 0 : 1;
+    const int bx = cloud == 0 ? blockIdx.x : blockIdx.x - S.gx_corner, gxc = cloud == 0 ? S.gx_corner : (int)gridDim.x - S.gx_corner;
     LaneState& L = lane[b];
     const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     unsigned* eb = S.ebound[cloud] + (size_t)b * S.rings * 2;
     // a warp takes IDX_UNROLL chunks of 32 consecutive points per round; their loads are all issued before the first is used
     const int ln = threadIdx.x & 31;
-    for (int base0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gridDim.x * blockDim.x * IDX_UNROLL) {
+    for (int base0 = (bx * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gxc * blockDim.x * IDX_UNROLL) {
         float4 pv[IDX_UNROLL];
         float wn[IDX_UNROLL];
 #pragma unroll
@@ -265,12 +269,13 @@ __global__ void __launch_bounds__(256) k_index_scan(IndexSet S)
 }
 __global__ void k_index_scatter(IndexSet S, const LaneState* lane)
 {
-    const int b = blockIdx.y, cloud = blockIdx.z;
+    const int b = blockIdx.y, cloud = (int)blockIdx.x < S.gx_corner ? 0 : 1;
+    const int bx = cloud == 0 ? blockIdx.x : blockIdx.x - S.gx_corner, gxc = cloud == 0 ? S.gx_corner : (int)gridDim.x - S.gx_corner;
     const LaneState& L = lane[b];
     const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     const int ln = threadIdx.x & 31;
-    for (int base0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gridDim.x * blockDim.x * IDX_UNROLL) {
+    for (int base0 = (bx * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gxc * blockDim.x * IDX_UNROLL) {
         float4 pv[IDX_UNROLL];
 #pragma unroll
         for (int u = 0; u < IDX_UNROLL; ++u) {
@@ -372,7 +377,8 @@ template <typename F>
 __device__ __forceinline__ void for_spans3(const float4* __restrict__ sorted, int s0, int e0, int s1, int e1, int s2, int e2, F&& f)
 {
     const int n0 = e0 - s0, n01 = n0 + (e1 - s1), tot = n01 + (e2 - s2);
-    auto at = [&](int k) { k = min(k, tot - 1); return sorted + (k < n0 ? s0 + k : (k < n01 ? s1 + (k - n0) : s2 + (k - n01))); };
+    const int d1 = s1 - n0, d2 = s2 - n01;   // stream position -> array index: + s0, + d1 or + d2 depending on the span
+    auto at = [&](int k) { k = min(k, tot - 1); return sorted + (k + (k < n0 ? s0 : (k < n01 ? d1 : d2))); };
 #pragma unroll 1
     for (int k = 0; k < tot; k += 4) {
         const float4 t0 = ld_point(at(k)), t1 = ld_point(at(k + 1)), t2 = ld_point(at(k + 2)), t3 = ld_point(at(k + 3));
@@ -1121,11 +1127,16 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
             LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_ebound[t], 0, sizeof(unsigned) * (size_t)c->R * 2 * n_lanes, s));
         }
         S.az_bins[0] = c->az_bins_corner; S.az_bins[1] = c->az_bins_surf; S.rings = c->R;
-        const int gx = (c->Nmax / 2 + 256 * IDX_UNROLL - 1) / (256 * IDX_UNROLL) < 148 ? (c->Nmax / 2 + 256 * IDX_UNROLL - 1) / (256 * IDX_UNROLL) : 148;
-        { LLProf pr(c, "k_index_count"); k_index_count<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
+        // blocks of 256 threads x IDX_UNROLL points: the corner cloud holds at most R * 120 points, the surf cloud usually
+        // about a quarter of the scan (more is covered by the grid-stride loops)
+        const int per_block = 256 * IDX_UNROLL;
+        S.gx_corner = (c->R * LL_LSHARP_PER_RING + per_block - 1) / per_block;
+        const int gx_surf = (c->Nmax * 5 / 16 + per_block - 1) / per_block;
+        const dim3 gidx(S.gx_corner + gx_surf, n_lanes);
+        { LLProf pr(c, "k_index_count"); k_index_count<<<gidx, 256, 0, s>>>(S, c->d_lane); }
         { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
         { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
-        { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<dim3(gx, n_lanes, 2), 256, 0, s>>>(S, c->d_lane); }
+        { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<gidx, 256, 0, s>>>(S, c->d_lane); }
         c->launches += 4;
     }
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
