@@ -10,8 +10,8 @@
 //   ring lists : per ring picked indices (sharp 12, less-sharp 120, flat 24) + per-ring voxel-DS output
 //   compact    : sharp / less_sharp / flat / less_flat clouds in the reference's publish order
 //   last[2]    : ping-pong copies of less_sharp / less_flat = laserCloudCornerLast / SurfLast (LO:882-891)
-//   grid       : hashed uniform grid (bucket_start + bucket-sorted float4 with the original index in .w)
-//                that replaces kdtreeCornerLast / kdtreeSurfLast (LO:895-896) and the map kd-trees
+//   index      : polar index (azimuth bin x ring: bucket_start + bucket-sorted float4 with the original index in .w) that
+//                replaces kdtreeCornerLast / kdtreeSurfLast (LO:895-896); hashed uniform grids replace the map kd-trees
 //   assoc/blocks: correspondence indices and fp64 residual-block records for the LM solve
 #pragma once
 #include <cuda_runtime.h>

@@ -13,12 +13,6 @@ typedef unsigned long long u64;
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
-__device__ __forceinline__ u64 shfl_u64(u64 v, int src)
-{
-    int lo = __shfl_sync(LL_FULL_MASK, (int)(unsigned)v, src);
-    int hi = __shfl_sync(LL_FULL_MASK, (int)(unsigned)(v >> 32), src);
-    return ((u64)(unsigned)hi << 32) | (unsigned)lo;
-}
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
 {
     int lo = __shfl_xor_sync(LL_FULL_MASK, (int)(unsigned)v, m);

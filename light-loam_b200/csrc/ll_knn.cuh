@@ -1,8 +1,8 @@
 // Exact k-nearest-neighbour search over a hashed uniform grid — the replacement for
-// pcl::KdTreeFLANN::nearestKSearch (LO:494, LO:656 with k = 1; LM:1882, LM:1948 with k = 5).
+// pcl::KdTreeFLANN::nearestKSearch in the mapping module (LM:1882, LM:1948 with k = 5); the odometry's 1-NN
+// (LO:494, LO:656) runs over the polar index of ll_odometry.cu and borrows the bucket streaming from here.
 //
-// The reference only ever accepts neighbours under a fixed radius (d2 < 25, LO:497/659; d2[4] < 1.0,
-// LM:1884/1952), so a radius-bounded grid search returns exactly what the kd-tree would, provided the fp32
+// The reference only ever accepts neighbours under a fixed radius (d2[4] < 1.0, LM:1884/1952), so a radius-bounded grid search returns exactly what the kd-tree would, provided the fp32
 // distance arithmetic (FLANN L2_Simple: ((dx*dx)+(dy*dy))+(dz*dz)) and the tie rule (lowest target index)
 // are pinned.  Points are bucketed by hash(cell) without storing cell keys: colliding cells only add
 // candidates that are distance-tested anyway, so the result stays exact.
@@ -131,34 +131,6 @@ __device__ __forceinline__ void grid_visit_shell(const GridView& g, int cx, int 
         if ((__ffs(grp) - 1) != lane) bucket = -1;
         grid_stream_buckets(g, bucket, f);
     }
-}
-
-// Shells 0 + 1 with pruning: the query's own cell first, then only those of the 26 neighbours whose box can still hold
-// a point closer than bound() (a warp-uniform squared distance evaluated after the own cell; INFINITY = keep all).
-// Exact: a skipped cell has every point farther than the bound (1e-3 m slack covers fp32 cell-assignment rounding).
-template <typename F, typename BoundFn>
-__device__ __forceinline__ void grid_visit_near_pruned(const GridView& g, float qx, float qy, float qz, int cx, int cy, int cz, F&& f, BoundFn&& bound)
-{
-    const int lane = lane_id();
-    const int b0 = cell_bucket(cx, cy, cz, g.Tmask);
-    grid_stream_buckets(g, lane == 0 ? b0 : -1, f);
-    const float thr = bound();
-    int bucket = -1 - lane;
-    if (lane < 27 && lane != 13) {
-        const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-        const float lox = (float)(cx + dx) * g.h - 1e-3f, hix = (float)(cx + dx + 1) * g.h + 1e-3f;
-        const float loy = (float)(cy + dy) * g.h - 1e-3f, hiy = (float)(cy + dy + 1) * g.h + 1e-3f;
-        const float loz = (float)(cz + dz) * g.h - 1e-3f, hiz = (float)(cz + dz + 1) * g.h + 1e-3f;
-        const float ex = fmaxf(0.f, fmaxf(lox - qx, qx - hix)), ey = fmaxf(0.f, fmaxf(loy - qy, qy - hiy)),
-                    ez = fmaxf(0.f, fmaxf(loz - qz, qz - hiz));
-        if (ex * ex + ey * ey + ez * ez <= thr) {
-            const int bk = cell_bucket(cx + dx, cy + dy, cz + dz, g.Tmask);
-            if (bk != b0) bucket = bk;
-        }
-    }
-    const unsigned grp = __match_any_sync(LL_FULL_MASK, bucket);
-    if ((__ffs(grp) - 1) != lane) bucket = -1;
-    grid_stream_buckets(g, bucket, f);
 }
 
 // Returns (warp-uniform) the K best keys; the caller applies its own d2 cutoff.

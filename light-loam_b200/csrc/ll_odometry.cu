@@ -1,8 +1,9 @@
 // Scan-to-scan odometry on the device — replaces laserOdometry.cpp:425-896.
 //
-//   k_grid_count / k_grid_scan / k_grid_scatter   kdtree*Last->setInputCloud (LO:895-896) -> hashed grid
-//   k_odom_assoc     LO:491-556 + LO:653-723: TransformToStart, 1-NN (d2 < 25), ring-window 2nd / 3rd point;
-//                    one warp per feature point, literal scan-loop semantics evaluated 32 candidates at a time
+//   k_index_*        kdtree*Last->setInputCloud (LO:895-896) -> polar index (azimuth bin x ring) + ring elevation bands
+//                    (k_grid_* below build the hashed grids of the mapping module, LM:1830-1831)
+//   k_odom_assoc     LO:491-556 + LO:653-723: TransformToStart, exact 1-NN (d2 < 25), ring-window 2nd / 3rd point;
+//                    one thread per feature point, k_odom_assoc_heavy: one warp per query that needs a wide search
 //   k_odom_prep      order-preserving compaction of the matches, residual-block records (LF ctor maths)
 //   k_odom_vote      graph_based_correspondence_vote_simple (LO:165-342) for planes when now_frame > 5, one CTA per region
 //   k_lm_solve       ceres::Solve as configured at LO:819-825 / LM:2079-2087: Levenberg-Marquardt on the
@@ -358,18 +359,6 @@ __device__ __forceinline__ float4 ld_point(const float4* p)
     float4 v;
     asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
-}
-// Per-thread candidate loop with four loads in flight.  Indices past the end are clamped to the last element: a
-// candidate met twice changes nothing because every consumer keeps a minimum over a total order.
-template <typename F>
-__device__ __forceinline__ void for_range4(const float4* __restrict__ sorted, int s, int e, F&& f)
-{
-#pragma unroll 1
-    for (int k = s; k < e; k += 4) {
-        const float4 t0 = ld_point(sorted + k), t1 = ld_point(sorted + min(k + 1, e - 1)), t2 = ld_point(sorted + min(k + 2, e - 1)),
-                     t3 = ld_point(sorted + min(k + 3, e - 1));
-        f(t0); f(t1); f(t2); f(t3);
-    }
 }
 // Up to three spans as ONE candidate stream (four loads in flight across span boundaries): the spans of neighbouring
 // azimuth bins cost one memory round trip together instead of one each.
