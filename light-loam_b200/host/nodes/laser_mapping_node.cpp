@@ -28,13 +28,10 @@ static ll_ctx* g_ll = nullptr;
 static std::string RESULT_PATH;
 static ros::Publisher pubOdomAftMapped, pubPath;
 
-static std::vector<float> pack(const sensor_msgs::PointCloud2& msg)
+// a PointXYZI payload read in place: point_step 32, x,y,z at 0, intensity at byte 16 (LM:1551-1563 fromROSMsg)
+static ll_cloud_view view(const sensor_msgs::PointCloud2& m)
 {
-    pcl::PointCloud<pcl::PointXYZI> c;
-    pcl::fromROSMsg(msg, c);
-    std::vector<float> v(4 * c.size());
-    for (size_t i = 0; i < c.size(); ++i) { v[4 * i] = c[i].x; v[4 * i + 1] = c[i].y; v[4 * i + 2] = c[i].z; v[4 * i + 3] = c[i].intensity; }
-    return v;
+    return ll_cloud_view{reinterpret_cast<const float*>(m.data.data()), (int)(m.width * m.height), (int)m.point_step};
 }
 
 static void process()
@@ -52,7 +49,7 @@ static void process()
             while (!qFull.empty() && qFull.front()->header.stamp.toSec() < tc) qFull.pop();
             if (qOdom.empty() || qSurf.empty() || qFull.empty()) break;
             if (qSurf.front()->header.stamp.toSec() != tc || qFull.front()->header.stamp.toSec() != tc || qOdom.front()->header.stamp.toSec() != tc) break;
-            std::vector<float> corner = pack(*qCorner.front()), surf = pack(*qSurf.front());
+            const sensor_msgs::PointCloud2ConstPtr mCorner = qCorner.front(), mSurf = qSurf.front();
             const nav_msgs::Odometry odom = *qOdom.front();
             qCorner.pop(); qSurf.pop(); qFull.pop(); qOdom.pop();
             while (!qCorner.empty()) qCorner.pop();  // LM:1571-1575 real-time frame dropping
@@ -60,7 +57,7 @@ static void process()
             const double qi[4] = {odom.pose.pose.orientation.x, odom.pose.pose.orientation.y, odom.pose.pose.orientation.z, odom.pose.pose.orientation.w};
             const double ti[3] = {odom.pose.pose.position.x, odom.pose.pose.position.y, odom.pose.pose.position.z};
             double q[4], t[3];
-            ll_cloud_view vc{corner.data(), (int)corner.size() / 4, 16}, vs{surf.data(), (int)surf.size() / 4, 16};
+            const ll_cloud_view vc = view(*mCorner), vs = view(*mSurf);
             const int rc = ll_mapping_step(g_ll, vc, vs, qi, ti, q, t);
             if (rc == LL_W_FEW_CORRESPONDENCES) ROS_WARN("time Map corner and surf num are not enough");  // LM:2097-2100
             if (rc < 0) { ROS_WARN("lightloam_b200: %s", ll_strerror(rc)); continue; }
