@@ -744,24 +744,37 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     const float inv = P.inv_leaf;
     bool wide = false;   // a cell index that does not fit int16 (|coordinate| > 6.5 km at leaf 0.2)
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
-        const int i = k * NTH + tid;
-        bool lf = false;
-        if (i < n) {
-            lf = i >= 5 && i < n - 6 && label[i] <= 0;
-            short4 c4 = make_short4(0, 0, 0, 0);
-            if (lf) {
-                const float4 q = pts[i];
-                mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
-                mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
-                const float f0 = floorf(q.x * inv), f1 = floorf(q.y * inv), f2 = floorf(q.z * inv);
-                wide |= !(fabsf(f0) < 32000.f && fabsf(f1) < 32000.f && fabsf(f2) < 32000.f);
-                c4 = make_short4((short)f0, (short)f1, (short)f2, 1);
-            }
-            cell[i] = c4;
+    for (int k0 = 0; k0 < CH; k0 += 2) {
+        // label and point of two rounds are requested together, whatever the label says: one round trip per pair of rounds
+        int lb[2] = {1, 1};
+        float4 qv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = (k0 + u) * NTH + tid;
+            qv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + u < CH && i < n) { lb[u] = label[i]; qv[u] = pts[i]; }
         }
-        const unsigned bl = __ballot_sync(LL_FULL_MASK, lf);
-        if (lane == 0) rcnt[k * 16 + wid] = __popc(bl);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = k0 + u, i = k * NTH + tid;
+            if (k >= CH) break;
+            bool lf = false;
+            if (i < n) {
+                lf = i >= 5 && i < n - 6 && lb[u] <= 0;
+                short4 c4 = make_short4(0, 0, 0, 0);
+                if (lf) {
+                    const float4 q = qv[u];
+                    mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
+                    mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+                    const float f0 = floorf(q.x * inv), f1 = floorf(q.y * inv), f2 = floorf(q.z * inv);
+                    wide |= !(fabsf(f0) < 32000.f && fabsf(f1) < 32000.f && fabsf(f2) < 32000.f);
+                    c4 = make_short4((short)f0, (short)f1, (short)f2, 1);
+                }
+                cell[i] = c4;
+            }
+            const unsigned bl = __ballot_sync(LL_FULL_MASK, lf);
+            if (lane == 0) rcnt[k * 16 + wid] = __popc(bl);
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {

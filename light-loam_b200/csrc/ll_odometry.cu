@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS, MINB) k_odom_assoc(OdomParams P
     const LaneState& L = P.lane[b];
     if (!L.inited) return;
     const bool corner = (int)blockIdx.x < corner_blocks;
-    const int i = (corner ? blockIdx.x : blockIdx.x - corner_blocks) * ASSOC_THREADS + threadIdx.x;
+    const int i = (corner ? blockIdx.x : blockIdx.x - corner_blocks) * (int)blockDim.x + threadIdx.x;   // blockDim.x <= ASSOC_THREADS
     const int n = corner ? L.n_sharp : L.n_flat;
     if ((int)(i - threadIdx.x) >= n) return;   // whole block idle
     {
@@ -1086,7 +1086,11 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     P.vote_src = c->d_vote_src; P.vote_tgt = c->d_vote_tgt;
     P.queue = c->d_assoc_queue; P.queue_n = c->d_assoc_queue_n; P.queue_cap = c->assoc_queue_cap;
     cudaStream_t s = c->stream;
-    const int cblocks = (c->R * LL_SHARP_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS, pblocks = (c->R * LL_FLAT_PER_RING + ASSOC_THREADS - 1) / ASSOC_THREADS;
+    // threads per CTA of the association's thread pass: smaller CTAs retire sooner (the queries' costs differ a lot)
+    int assoc_threads = getenv("LL_ASSOC_THREADS") ? atoi(getenv("LL_ASSOC_THREADS")) : ASSOC_THREADS;
+    if (assoc_threads != 32 && assoc_threads != 64 && assoc_threads != 128) assoc_threads = ASSOC_THREADS;
+    if (assoc_threads < c->R) assoc_threads = c->R <= 64 ? 64 : 128;   // the CTA's first R threads stage the ring bands
+    const int cblocks = (c->R * LL_SHARP_PER_RING + assoc_threads - 1) / assoc_threads, pblocks = (c->R * LL_FLAT_PER_RING + assoc_threads - 1) / assoc_threads;
     LL_CUDA_CHECK(c, cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 16, s));
     const int heavy_blocks = getenv("LL_HEAVY_BLOCKS") ? atoi(getenv("LL_HEAVY_BLOCKS")) : 148 * 4;
     const int dmax = getenv("LL_ASSOC_DMAX") ? atoi(getenv("LL_ASSOC_DMAX")) : 8;   // ring-window bins per side a thread walks
@@ -1133,10 +1137,10 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         {
             LLProf pr(c, "k_odom_assoc");
             const dim3 g(cblocks + pblocks, n_lanes);
-            if (minb >= 12) k_odom_assoc<12><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
-            else if (minb >= 10) k_odom_assoc<10><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
-            else if (minb >= 8) k_odom_assoc<8><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
-            else k_odom_assoc<6><<<g, ASSOC_THREADS, 0, s>>>(P, cblocks, dmax, kmax);
+            if (minb >= 12) k_odom_assoc<12><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
+            else if (minb >= 10) k_odom_assoc<10><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
+            else if (minb >= 8) k_odom_assoc<8><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
+            else k_odom_assoc<6><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
         }
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
