@@ -99,27 +99,38 @@ __device__ __forceinline__ int cell_bucket(int ix, int iy, int iz, int Tmask)
     return (int)((h ^ (h >> 15)) & (unsigned)Tmask);
 }
 
-// ---- block-wide ascending sort of NS 64-bit keys (shared memory <-> registers) -----------------------------------
+// ---- block-wide ascending sort of NS keys, 64- or 32-bit (shared memory <-> registers) ---------------------------
 // All-ascending form of the bitonic network: the first stage of the merge of width kk pairs element e with its mirror
 // image e ^ (kk - 1), the following ones e with e ^ j, and the lower index always keeps the smaller key - no stage
 // needs a direction.  Thread t < NS / KPT holds elements t * KPT .. t * KPT + KPT - 1 in registers (blocked layout):
 // distances below KPT are register-to-register, distances below 32 * KPT are shuffles inside the warp, and only the
 // few largest distances of the last merges go through shared memory (with a block barrier each).  Fully unrolled.
 // Every thread of the block must call it (barriers); on return keys[0 .. NS) is sorted and visible to the block.
-__device__ __forceinline__ void cex_u64(u64& lo, u64& hi)
+__device__ __forceinline__ void cex_key(u64& lo, u64& hi)
 {
     const u64 a = lo, c = hi;
     const bool sw = c < a;
     lo = sw ? c : a;
     hi = sw ? a : c;
 }
-template <int NS, int KPT>
-__device__ __forceinline__ void block_sort_u64_asc(u64* keys)
+__device__ __forceinline__ void cex_key(unsigned& lo, unsigned& hi)
+{
+    const unsigned a = lo, c = hi;
+    lo = min(a, c);
+    hi = max(a, c);
+}
+__device__ __forceinline__ u64 shfl_xor_key(u64 v, int m) { return shfl_xor_u64(v, m); }
+__device__ __forceinline__ unsigned shfl_xor_key(unsigned v, int m) { return __shfl_xor_sync(LL_FULL_MASK, v, m); }
+// what the element keeps after meeting `o`: the smaller key when it is the lower index of the pair, else the larger
+__device__ __forceinline__ u64 keep_key(bool lower, u64 k, u64 o) { return ((o < k) == lower) ? o : k; }
+__device__ __forceinline__ unsigned keep_key(bool lower, unsigned k, unsigned o) { return lower ? min(k, o) : max(k, o); }
+template <typename K, int NS, int KPT>
+__device__ __forceinline__ void block_sort_asc(K* keys)
 {
     constexpr int NT = NS / KPT;          // threads holding keys
     constexpr int WSPAN = 32 * KPT;       // elements covered by one warp
     const int t = threadIdx.x, lane = t & 31;
-    u64 k[KPT];
+    K k[KPT];
     if (t < NT) {
 #pragma unroll
         for (int q = 0; q < KPT; ++q) k[q] = keys[t * KPT + q];
@@ -136,8 +147,8 @@ __device__ __forceinline__ void block_sort_u64_asc(u64* keys)
             for (int p = t; p < NS / 2; p += blockDim.x) {   // mirror stage
                 const int blk = p / (kk / 2), off = p % (kk / 2);
                 const int i = blk * kk + off, pr = blk * kk + (kk - 1 - off);
-                u64 a = keys[i], c = keys[pr];
-                cex_u64(a, c);
+                K a = keys[i], c = keys[pr];
+                cex_key(a, c);
                 keys[i] = a; keys[pr] = c;
             }
             __syncthreads();
@@ -145,8 +156,8 @@ __device__ __forceinline__ void block_sort_u64_asc(u64* keys)
             for (int j = kk >> 2; j >= WSPAN; j >>= 1) {
                 for (int p = t; p < NS / 2; p += blockDim.x) {
                     const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                    u64 a = keys[i], c = keys[i | j];
-                    cex_u64(a, c);
+                    K a = keys[i], c = keys[i | j];
+                    cex_key(a, c);
                     keys[i] = a; keys[i | j] = c;
                 }
                 __syncthreads();
@@ -163,16 +174,16 @@ __device__ __forceinline__ void block_sort_u64_asc(u64* keys)
 #pragma unroll
                 for (int q = 0; q < KPT; ++q) {
                     const int pq = q ^ (kk - 1);
-                    if (q < pq) cex_u64(k[q], k[pq]);
+                    if (q < pq) cex_key(k[q], k[pq]);
                 }
             } else if (kk <= WSPAN) {
                 const int m = kk / KPT - 1;
                 const bool lower = (lane & (kk / (2 * KPT))) == 0;
-                u64 o[KPT];
+                K o[KPT];
 #pragma unroll
-                for (int q = 0; q < KPT; ++q) o[q] = shfl_xor_u64(k[KPT - 1 - q], m);
+                for (int q = 0; q < KPT; ++q) o[q] = shfl_xor_key(k[KPT - 1 - q], m);
 #pragma unroll
-                for (int q = 0; q < KPT; ++q) { const bool take = (o[q] < k[q]) == lower; k[q] = take ? o[q] : k[q]; }
+                for (int q = 0; q < KPT; ++q) k[q] = keep_key(lower, k[q], o[q]);
             }
             // e ^ j stages inside the warp
 #pragma unroll
@@ -180,16 +191,12 @@ __device__ __forceinline__ void block_sort_u64_asc(u64* keys)
                 if (j < KPT) {
 #pragma unroll
                     for (int q = 0; q < KPT; ++q)
-                        if ((q & j) == 0) cex_u64(k[q], k[q | j]);
+                        if ((q & j) == 0) cex_key(k[q], k[q | j]);
                 } else {
                     const int m = j / KPT;
                     const bool lower = (lane & m) == 0;
 #pragma unroll
-                    for (int q = 0; q < KPT; ++q) {
-                        const u64 o = shfl_xor_u64(k[q], m);
-                        const bool take = (o < k[q]) == lower;
-                        k[q] = take ? o : k[q];
-                    }
+                    for (int q = 0; q < KPT; ++q) k[q] = keep_key(lower, k[q], shfl_xor_key(k[q], m));
                 }
             }
         }
@@ -200,6 +207,8 @@ __device__ __forceinline__ void block_sort_u64_asc(u64* keys)
     }
     __syncthreads();
 }
+template <int NS, int KPT>
+__device__ __forceinline__ void block_sort_u64_asc(u64* keys) { block_sort_asc<u64, NS, KPT>(keys); }
 
 // ring x azimuth-bin index: bin of a point / query; NB = bins per ring (power of two)
 __device__ __forceinline__ int azimuth_bin(float x, float y, int NB)

@@ -714,6 +714,8 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
 // the many-keys-per-thread variants live in their own functions so that their register needs do not spill the common path
 template <int NS, int KPT>
 __device__ __noinline__ void block_sort_big(u64* keys) { block_sort_u64_asc<NS, KPT>(keys); }
+template <int NS, int KPT>
+__device__ __noinline__ void block_sort_big32(unsigned* keys) { block_sort_asc<unsigned, NS, KPT>(keys); }
 template <int SCAP>
 __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
 {
@@ -815,6 +817,7 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     const int min_b0 = (int)floorf(bmn[0] * inv), min_b1 = (int)floorf(bmn[1] * inv), min_b2 = (int)floorf(bmn[2] * inv);
     const int div0 = (int)floorf(bmx[0] * inv) - min_b0 + 1, div1 = (int)floorf(bmx[1] * inv) - min_b1 + 1;
     const int mul1 = div0, mul2 = div0 * div1;
+    const long long vmax = (long long)mul2 * ((int)floorf(bmx[2] * inv) - min_b2 + 1);   // voxel ids are < vmax
     // pass 2: order-preserving compaction, voxel ids (from shared memory unless a cell index overflowed int16)
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
@@ -852,46 +855,73 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     int ro = block_exclusive_scan(heads, ws, &R);
     int NS = 64;
     while (NS < R) NS <<= 1;
-    // key of a run = (voxel id, first compacted position, length): sorting by it groups the runs of a voxel in input
-    // order, and the centroid pass needs nothing else (positions and lengths < 2^13)
+    // Keys of the run sort.  When the voxel id and the run number fit one 32-bit word together (most rings: the bounding
+    // box of a ring on the ground is small) the sort runs on 32-bit keys = voxel id << log2(NS) | run number, and the
+    // run's (start, length) waits in a side array; otherwise 64-bit keys carry (voxel id, start, length) themselves.
+    const int bits_r = 31 - __clz(NS);
+    const int bits_v = vmax <= 1 ? 1 : 64 - __clzll(vmax - 1);
+    const bool fast = bits_v + bits_r <= 31 && NS <= KCAP;   // block-uniform; 31: the padding key 0xFFFFFFFF stays above every real key
+    unsigned* key32 = reinterpret_cast<unsigned*>(keys);       // [NS] in the lower half of the key buffer
+    unsigned* side = key32 + KCAP;                             // [R] in its upper half: run start << 13 | run length
     const int ro0 = ro;
     for (int p = p0; p < p1; ++p)
         if (p == 0 || vid[p] != vid[p - 1]) {
-            keys[ro] = ((u64)(unsigned)vid[p] << 32) | ((unsigned)p << 13);
+            if (fast) { key32[ro] = ((unsigned)vid[p] << bits_r) | (unsigned)ro; side[ro] = (unsigned)p << 13; }
+            else keys[ro] = ((u64)(unsigned)vid[p] << 32) | ((unsigned)p << 13);
             ++ro;
         }
-    for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull;
+    if (fast) { for (int i = R + tid; i < NS; i += NTH) key32[i] = 0xFFFFFFFFu; }
+    else { for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull; }
     __syncthreads();
     for (int q = ro0; q < ro; ++q) {   // length = start of the next run - own start
-        const unsigned ps = (unsigned)keys[q] >> 13;
-        const unsigned pn = q + 1 < R ? (unsigned)keys[q + 1] >> 13 : (unsigned)m;
-        keys[q] |= (u64)(pn - ps);
+        if (fast) {
+            const unsigned ps = side[q] >> 13, pn = q + 1 < R ? side[q + 1] >> 13 : (unsigned)m;
+            side[q] |= pn - ps;
+        } else {
+            const unsigned ps = (unsigned)keys[q] >> 13;
+            const unsigned pn = q + 1 < R ? (unsigned)keys[q + 1] >> 13 : (unsigned)m;
+            keys[q] |= (u64)(pn - ps);
+        }
     }
     __syncthreads();
-    switch (NS) {   // all 512 threads call; NS / 4 (or NS / 8) of them hold keys
-        case 64: block_sort_u64_asc<64, 2>(keys); break;
-        case 128: block_sort_u64_asc<128, 4>(keys); break;
-        case 256: block_sort_u64_asc<256, 4>(keys); break;
-        case 512: block_sort_u64_asc<512, 4>(keys); break;
-        case 1024: block_sort_u64_asc<1024, 4>(keys); break;
-        case 2048: block_sort_u64_asc<2048, 4>(keys); break;
-        case 4096: block_sort_big<4096, 8>(keys); break;     // rings where nearly every point is its own run: rare
-        default: block_sort_big<8192, 16>(keys); break;
+    if (fast) {
+        switch (NS) {   // all 512 threads call; NS / 8 (NS / 4) of them hold keys
+            case 64: block_sort_asc<unsigned, 64, 2>(key32); break;
+            case 128: block_sort_asc<unsigned, 128, 4>(key32); break;
+            case 256: block_sort_asc<unsigned, 256, 8>(key32); break;
+            case 512: block_sort_asc<unsigned, 512, 8>(key32); break;
+            case 1024: block_sort_asc<unsigned, 1024, 8>(key32); break;
+            case 2048: block_sort_asc<unsigned, 2048, 8>(key32); break;
+            case 4096: block_sort_asc<unsigned, 4096, 8>(key32); break;
+            default: block_sort_big32<8192, 16>(key32); break;
+        }
+    } else {
+        switch (NS) {   // all 512 threads call; NS / 4 (or NS / 8) of them hold keys
+            case 64: block_sort_u64_asc<64, 2>(keys); break;
+            case 128: block_sort_u64_asc<128, 4>(keys); break;
+            case 256: block_sort_u64_asc<256, 4>(keys); break;
+            case 512: block_sort_u64_asc<512, 4>(keys); break;
+            case 1024: block_sort_u64_asc<1024, 4>(keys); break;
+            case 2048: block_sort_u64_asc<2048, 4>(keys); break;
+            case 4096: block_sort_big<4096, 8>(keys); break;     // rings where nearly every point is its own run: rare
+            default: block_sort_big<8192, 16>(keys); break;
+        }
     }
     // voxels = groups of equal voxel id among the sorted runs; the group's first run's thread accumulates the centroid
+    auto vox_of = [&](int q) { return fast ? key32[q] >> bits_r : (unsigned)(keys[q] >> 32); };
     const int RCH = (R + NTH - 1) / NTH;
     const int s0 = min(tid * RCH, R), s1 = min(s0 + RCH, R);
     int vheads = 0;
-    for (int q = s0; q < s1; ++q) vheads += (q == 0 || (unsigned)(keys[q] >> 32) != (unsigned)(keys[q - 1] >> 32));
+    for (int q = s0; q < s1; ++q) vheads += (q == 0 || vox_of(q) != vox_of(q - 1));
     int nvox = 0;
     int o = block_exclusive_scan(vheads, ws, &nvox);
     for (int q = s0; q < s1; ++q) {
-        const unsigned v = (unsigned)(keys[q] >> 32);
-        if (q == 0 || v != (unsigned)(keys[q - 1] >> 32)) {
+        const unsigned v = vox_of(q);
+        if (q == 0 || v != vox_of(q - 1)) {
             float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
             int cnt = 0;
-            for (int g = q; g < R && (unsigned)(keys[g] >> 32) == v; ++g) {  // runs in ascending run number = input order
-                const unsigned lo = (unsigned)keys[g];
+            for (int g = q; g < R && vox_of(g) == v; ++g) {  // runs in ascending run number = input order
+                const unsigned lo = fast ? side[key32[g] & (unsigned)(NS - 1)] : (unsigned)keys[g];
                 const int e0 = (int)(lo >> 13), e1 = e0 + (int)(lo & 0x1FFFu);
 #pragma unroll 4
                 for (int p = e0; p < e1; ++p) {
