@@ -26,7 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "scans/sec (HDL-64, 130k pts, 5 GN iters)"
-POOL_SCANS = 157          # one lap of the 25 m loop path at 1 m per scan: a cyclic scan sequence
+LAP = 157                 # one lap of the 25 m loop path at 1 m per scan
+POOL_SCANS = 2 * LAP      # two laps with independent range noise (noise seed = pool index): a cyclic sequence of 314 distinct scans >= lanes
+PARITY_LANES = 4          # lanes checked against the oracle after the timed loops
+PARITY_STEPS = 9          # past now_frame > 5, so the graph vote is on for the last steps
+NN_KERNEL = "k_odom_assoc"
 WORKLOAD = "HDL-64 single scan (~130k pts), 5 GN iters, scan-to-scan odometry on 1xB200 (BASELINE.json configs[1]), batched over independent scan streams"
 
 
@@ -101,13 +105,40 @@ class ClockSampler(threading.Thread):
 
 
 def make_pool(ll, n):
-    return [ll.synth.scan(64, k, mode=1) for k in range(n)]
+    """Pool scan j: pose j mod LAP of the loop path, range noise seeded by j (distinct scans across laps)."""
+    from concurrent.futures import ThreadPoolExecutor   # the generator is a ctypes call: it releases the GIL
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda j: ll.synth.scan(64, j % LAP, mode=1, scan_id=j), range(n)))
+
+
+def lane_base(lanes, rank):
+    return (rank * lanes * 5) % POOL_SCANS
 
 
 def lane_ids(step, lanes, rank):
-    """Lane i of rank r walks the cyclic scan sequence from its own offset: independent streams, same work."""
-    base = (np.arange(lanes) + rank * lanes) * 7
-    return ((base + step) % POOL_SCANS).astype(np.int32)
+    """Lane i walks the cyclic scan sequence one scan ahead of lane i - 1: independent streams doing the same work, and the
+    scans of one step are `lanes` consecutive pool entries (one contiguous block of the host arena for the e2e copy)."""
+    return ((lane_base(lanes, rank) + step + np.arange(lanes)) % POOL_SCANS).astype(np.int32)
+
+
+def pin_to_gpu_numa(index):
+    """CPU affinity of this rank := the cores NVML reports as local to the GPU, BEFORE the pinned arena is allocated
+    (first touch puts it on the GPU's NUMA node).  Returns the number of cores, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 # per-scan algorithmic (compulsory) bytes of each kernel, from the measured point counts (DESIGN.md §kernels)
@@ -128,10 +159,44 @@ def algorithmic_bytes(counts):
     }
 
 
+def parity_check(ll, ctx, pool, B, rank):
+    """Parity gate of THIS configuration in THIS run: the state is reset, PARITY_STEPS steps run through the pool path at
+    the full lane count, and PARITY_LANES lanes (first, two inside, last) are compared with the CPU oracle fed the same
+    scans: per-step pose (<= 1e-9 against the oracle in the device's voxel order, <= 1e-4 m / rad against the
+    reference-faithful order) and, on the last step, the sharp / less-sharp / flat index lists (bit-exact)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc_py
+    lanes = sorted({0, B // 3, (2 * B) // 3, B - 1})[:PARITY_LANES]
+    ctx.reset()
+    gpu = []
+    for k in range(PARITY_STEPS):
+        gpu.append(ctx.process_pool(lane_ids(k, B, rank))[lanes].copy())
+    feats = {i: ctx.debug_features(i) for i in lanes}
+    worst_exact, worst_faithful, idx_ok = 0.0, 0.0, True
+    for li, i in enumerate(lanes):
+        exact = orc_py.Pipeline(orc_py.config(64, voxel_stable=1), with_mapping=False)
+        faithful = orc_py.Pipeline(orc_py.config(64, voxel_stable=0), with_mapping=False)
+        for k in range(PARITY_STEPS):
+            scan = pool[int(lane_ids(k, B, rank)[i])]
+            pe, pf = exact.step(scan), faithful.step(scan)
+            g = gpu[k][li]
+            worst_exact = max(worst_exact, float(np.abs(g[4:7] - pe["t_odom"]).max()), float(np.abs(g[0:4] - pe["q_odom"]).max()))
+            ang = 2 * np.arccos(min(1.0, abs(float(np.dot(g[0:4], pf["q_odom"])))))
+            worst_faithful = max(worst_faithful, float(np.abs(g[4:7] - pf["t_odom"]).max()), float(ang))
+        o = orc_py.extract_features(pool[int(lane_ids(PARITY_STEPS - 1, B, rank)[i])], orc_py.config(64, voxel_stable=1))
+        for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+            idx_ok = idx_ok and np.array_equal(feats[i][key], o[key])
+    ok = idx_ok and worst_exact < 1e-9 and worst_faithful < 1e-4
+    return {"status": "ok" if ok else "FAILED", "lanes": lanes, "steps": PARITY_STEPS, "feature_indices_bit_exact": bool(idx_ok),
+            "max_pose_err_vs_oracle_same_voxel_order": worst_exact, "max_pose_err_vs_reference_faithful_order": worst_faithful,
+            "bars": {"same_order": 1e-9, "faithful": 1e-4}}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     ll = importlib.import_module("light-loam_b200")
     torch.cuda.set_device(local_rank)
+    n_aff = pin_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -139,7 +204,7 @@ def run_ours(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG", "NONE")  # keep stdout to the one JSON line (WARN and above print a version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
-    ctx = ll.Context(scan_line=64, batch=B, device=local_rank)
+    ctx = ll.Context(scan_line=64, batch=B, device=local_rank, max_ring_points=args.max_ring_points)
     pool = make_pool(ll, POOL_SCANS)
     ctx.pool_upload(pool)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=local_rank)
@@ -173,10 +238,10 @@ def run_ours(args, rank, world, local_rank):
     launches = 0
     for _ in range(args.steps):
         ctx.process_pool(lane_ids(step, B, rank), want_poses=False)
+        launches += ctx.L.ll_launch_count(ctx.h)
         step += 1
     e1.record(stream)
     torch.cuda.synchronize()
-    launches = ctx.stats().kernel_launches * args.steps
     sampler.stop_flag = True
     barrier()
     ms_total = maxreduce(e0.elapsed_time(e1))
@@ -186,33 +251,51 @@ def run_ours(args, rank, world, local_rank):
               "n_less_sharp": st.n_less_sharp, "n_sharp": st.n_sharp, "n_flat": st.n_flat}
 
     # ---- e2e: host buffers through the public call, H2D of every scan + D2H of the poses in the timed region ---
-    pinned = [torch.empty((len(p), 4), dtype=torch.float32).pin_memory() for p in pool]
-    for t, p in zip(pinned, pool):
-        t.numpy()[:] = p
-    host = [t.numpy() for t in pinned]
+    # One pinned host arena holds the scan sequence as packed xyz records (12 bytes per point: what scanRegistration
+    # consumes, SR:105-110), with the first `B` scans repeated at the end so that the B scans of any step are one
+    # contiguous block: ll_submit_packed moves a step's input with ONE host-to-device copy.
+    n_pts = [len(p) for p in pool]
+    seq = list(range(POOL_SCANS)) + list(range(B))
+    offs = np.zeros(len(seq) + 1, np.int64)
+    offs[1:] = np.cumsum([n_pts[j] * 12 for j in seq])
+    arena_t = torch.empty(int(offs[-1]), dtype=torch.uint8).pin_memory()
+    arena = arena_t.numpy()
+    for q, j in enumerate(seq):
+        arena[offs[q]:offs[q + 1]] = np.ascontiguousarray(pool[j][:, :3]).view(np.uint8).reshape(-1)
+    cnts = np.array([n_pts[j] for j in seq], np.int32)
+    views12 = [np.frombuffer(arena, dtype=np.float32, count=n_pts[j] * 3, offset=int(offs[q])).reshape(-1, 3) for q, j in enumerate(seq)]
+
+    def first_slot(stp):
+        return (lane_base(B, rank) + stp) % POOL_SCANS   # arena slots first_slot .. first_slot + B - 1 hold the step's scans
+
     for _ in range(3):
-        ids = lane_ids(step, B, rank)
-        ctx.process_scans([host[i] for i in ids])
+        f = first_slot(step)
+        ctx.process_scans(views12[f:f + B])
         step += 1
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ids = lane_ids(step, B, rank)
-        poses = ctx.process_scans([host[i] for i in ids])
+        f = first_slot(step)
+        poses = ctx.process_scans(views12[f:f + B])
         step += 1
     torch.cuda.synchronize()
     e2e_sync_s = maxreduce(time.perf_counter() - t0)
-    # the same through the asynchronous form of the call (ll_submit_scans / ll_collect, two submissions in flight):
-    # the H2D copies of step k+1 overlap the kernels of step k; every byte still crosses PCIe inside the timed region
+    # the same through the asynchronous form of the call (ll_submit_packed / ll_collect, two submissions in flight):
+    # the H2D copy of step k+1 overlaps the kernels of step k; every byte still crosses PCIe inside the timed region
+    for k in range(W):   # warm-up of the asynchronous path (its second staging slab, copy stream and events are created on first use)
+        f = first_slot(step)
+        ctx.submit_packed(arena, offs[f:f + B], cnts[f:f + B], 12)
+        step += 1
+        if k > 0:
+            ctx.collect()
+    ctx.collect()
     barrier()
     h2d = 0
     t0 = time.perf_counter()
-    host_views = ctx.make_views(host)
-    host_bytes = [h.nbytes for h in host]
     for k in range(args.steps):
-        ids = lane_ids(step, B, rank)
-        ctx.submit_views([host_views[i] for i in ids])
-        h2d += sum(host_bytes[i] for i in ids)
+        f = first_slot(step)
+        ctx.submit_packed(arena, offs[f:f + B], cnts[f:f + B], 12)
+        h2d += int(offs[f + B] - offs[f])
         step += 1
         if k > 0:
             poses = ctx.collect()
@@ -230,7 +313,6 @@ def run_ours(args, rank, world, local_rank):
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     total_prof = sum(v[0] for v in prof.values())
-    dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
     peak, peak_src = peaks()
     ab = algorithmic_bytes(counts)
     per_kernel = {}
@@ -239,18 +321,26 @@ def run_ours(args, rank, world, local_rank):
         bytes_launch = ab.get(name, 0.0) * B
         per_kernel[name] = {"ms_per_launch": round(avg_ms, 4), "launches_per_step": n / args.steps, "share": round(ms / total_prof, 4),
                             "alg_gbs": round(bytes_launch / (avg_ms * 1e-3) / 1e9, 1) if bytes_launch else None}
+    # the roofline object is that of the NN kernel (BASELINE.json: "NN + JtJ HBM GB/s vs peak"), which is also the kernel
+    # with the largest share of the odometry stage
+    dom = NN_KERNEL if NN_KERNEL in prof else max(prof.items(), key=lambda kv: kv[1][0])[0]
     dom_ms = prof[dom][0] / prof[dom][1]
     achieved = ab.get(dom, 0.0) * B / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         if tj.get("batch") == B and dom in tj.get("kernels", {}):
             traffic = tj["kernels"][dom]   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at this batch
+            traffic_src = tj.get("source")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": int(ab.get(dom, 0.0) * B),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": int(ab.get(dom, 0.0) * B),
                 "ms_per_launch": round(dom_ms, 4), "share_of_step": round(prof[dom][0] / total_prof, 4), "kernels": per_kernel}
+
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(ll, ctx, pool, B, rank)
 
     # ---- CPU baseline: the oracle port of the same path on one host core, bounded sample (rank 0, N = 1) ---------
     cpu = None
@@ -263,12 +353,14 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (features, NN) + f64 (residuals, LM)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "lanes_per_gpu": B, "scans_per_step": B * world, "points_per_scan": int(counts["n_raw"]),
+                       "distinct_scans_in_pool": POOL_SCANS,
                        "gn_linearisations_per_solve_max": 5, "outer_iterations": 3, "parallelism": "independent scan streams sharded per GPU, no data-path collective",
-                       "l2": "inputs larger than L2: %d lanes x %.2f MB raw scan = %.0f MB read per step (> 126 MB), no flush" % (B, counts["n_raw"] * 16 / 1e6, B * counts["n_raw"] * 16 / 1e6)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": B * 14 * 8,
-                    "api": "ll_submit_scans / ll_collect (pinned host scans, 2 submissions in flight)",
-                    "sync_call_value": round(B * world * args.steps / e2e_sync_s, 1)},
-            "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(),
+                       "l2": "inputs larger than L2: %d lanes x %.2f MB raw scan = %.0f MB read per step (> 126 MB), no flush" % (B, counts["n_raw"] * 16 / 1e6, B * counts["n_raw"] * 16 / 1e6),
+                       "cpu_affinity_cores": n_aff},
+            "e2e": {"value": round(e2e_value, 1), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": B * (14 * 8 + 4),
+                    "api": "ll_submit_packed / ll_collect (one pinned host arena of packed xyz records, one H2D copy per step, 2 submissions in flight)",
+                    "h2d_gbs": round(h2d / e2e_s / 1e9, 2), "sync_call_value": round(B * world * args.steps / e2e_sync_s, 1)},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary(), "parity": parity,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -276,6 +368,8 @@ def run_ours(args, rank, world, local_rank):
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and parity["status"] != "ok":
+        sys.exit(3)
 
 
 def cpu_baseline_sample(pool, n_scans):
@@ -301,7 +395,7 @@ def _ref_worker(arg):
     import orc_py
     pipe = orc_py.Pipeline(orc_py.config(64), with_mapping=False)
     pool = _G["pool"]
-    off = (wid * 7) % POOL_SCANS
+    off = wid % POOL_SCANS
     for k in range(2):  # init frame + one warm frame, untimed
         pipe.step(pool[(off + k) % POOL_SCANS])
     t0 = time.perf_counter()
@@ -350,6 +444,8 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "256")), help="scan streams (lanes) per GPU")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check of the bench configuration")
+    ap.add_argument("--max-ring-points", type=int, default=6155, help="ring capacity (library default 6155; 3083 = 512-key sectors only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -50,13 +50,20 @@ typedef struct ll_config {
     int   max_ring_points;   /* capacity: points in one ring after filtering */
     int   map_capacity;      /* capacity: points per map cloud (corner / surf) in the 5x5x3 local map */
     int   enable_mapping;    /* 0: ll_process_scans stops after odometry */
-    int   reserved[6];
+    int   map_graph_vote;    /* 1: graph_based_correspondence_vote_simple on the scan-to-map plane correspondences (the call the
+                              * reference keeps commented out at LM:2057-2072; BASELINE.json configs[2] "graph matching on") */
+    int   distortion;        /* LO:23 DISTORTION: 1 = motion de-skew (per-point s = relTime, slerp, TransformToEnd); reference build: 0 */
+    int   vote_mode;         /* 0: graph_based_correspondence_vote_simple (LO:165-342, the live code); 1: paper-style
+                              * graph_based_correspondence_vote_partial (LM:261-834, dead in the reference; beyond-reference) */
+    int   reserved[3];
 } ll_config;
 
 typedef struct ll_cloud_view {   /* caller-owned HOST memory */
     const float* data;
     int n;
-    int stride_bytes;            /* >= 12, multiple of 4; x,y,z at offsets 0,4,8 (PointCloud2 point_step).  Where the
+    int stride_bytes;            /* >= 12; x,y,z (fp32) at offsets 0,4,8 (PointCloud2 point_step).  Raw scans: any value (records
+                                  * wider than 32 bytes or not a multiple of 4, e.g. 22-byte XYZIRT or 48-byte Ouster points, are
+                                  * gathered to packed xyz by a strided copy).  Feature clouds: multiple of 4.  Where the
                                   * intensity matters (feature clouds of ll_odometry_step / ll_mapping_step): byte 12 when
                                   * stride_bytes < 32 (packed float4), byte 16 when stride_bytes >= 32 (pcl::PointXYZI as
                                   * PointCloud2 carries it) */
@@ -144,6 +151,16 @@ int ll_process_staged(ll_ctx* ctx, int n_scans, double* poses_out);
  * the copies of step k+1 overlap the kernels of step k.  Scan buffers must stay valid until the matching collect. */
 int ll_submit_scans(ll_ctx* ctx, int n_scans, const ll_cloud_view* scans);
 int ll_collect(ll_ctx* ctx, double* poses_out);
+/* ll_submit_scans for scans that lie in ONE caller-owned (pinned) host buffer: scan i = n_points[i] records of stride_bytes
+ * (12 = packed xyz, what scanRegistration consumes, SR:105-110; 16 = KITTI x,y,z,i; <= 32, multiple of 4) starting
+ * byte_offsets[i] bytes (multiple of 4, ascending, non-overlapping) after host_base.  The whole batch crosses the bus as one
+ * host-to-device copy of [byte_offsets[0], end of the last scan). */
+int ll_submit_packed(ll_ctx* ctx, int n_scans, const void* host_base, const int64_t* byte_offsets, const int* n_points, int stride_bytes);
+/* Per-lane status of the last completed call / collect (n entries): 0, or the LL_E_* code that made the lane skip the scan
+ * (LL_E_EMPTY, LL_E_CAPACITY, LL_E_NCCL).  A lane with a non-zero status did not advance: pose, *Last clouds and map unchanged.
+ * The batch calls (ll_process_*, ll_collect) also return the first non-zero lane status as their (negative) return code
+ * after writing every pose. */
+int ll_get_lane_status(ll_ctx* ctx, int* status, int n);
 
 /* Scan pool: upload many scans once (float4 records in HBM), then feed lane i from pooled scan scan_ids[i].
  * Same per-lane semantics as ll_process_scans without the per-call H2D of the points. */
@@ -161,8 +178,13 @@ int ll_last_timings(ll_ctx* ctx, float ms[4] /* features, odometry, mapping, tot
 /* Parity / debugging: association indices of the last outer iteration of lane `lane`.
  * corner: n_sharp x {closest, minPointInd2} ; plane: n_flat x {closest, minPointInd2, minPointInd3, weight*1000}; -1 = none */
 int ll_debug_assoc(ll_ctx* ctx, int lane, int* corner, int corner_cap, int* plane, int plane_cap);
+/* Parity: feature indices (into the lane's ring-sorted cloud) of the last extraction of lane `lane`.
+ * counts = {n_full, n_sharp, n_less_sharp, n_flat, n_less_flat}; index arrays sized scan_line * 12 / 120 / 24 (or NULL). */
+int ll_debug_features(ll_ctx* ctx, int lane, int counts[5], int* sharp_idx, int* less_sharp_idx, int* flat_idx);
 /* Raw CUDA stream of the context (cudaStream_t as void*), so a host can order its own work after ours. */
 void* ll_cuda_stream(ll_ctx* ctx);
+/* Kernels of this library launched by the last call (no synchronisation; the same number ll_stats::kernel_launches reports). */
+int ll_launch_count(const ll_ctx* ctx);
 
 #ifdef __cplusplus
 }

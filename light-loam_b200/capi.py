@@ -17,8 +17,8 @@ LL_W_FEW_CORRESPONDENCES = 1
 
 SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
            "ll_extract_features", "ll_fetch_pointcloud2", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
-           "ll_process_staged", "ll_submit_scans", "ll_collect", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
-           "ll_debug_assoc", "ll_cuda_stream", "ll_comm_export", "ll_comm_local_ptr", "ll_comm_attach", "ll_comm_detach", "ll_map_set_slab"]
+           "ll_process_staged", "ll_submit_scans", "ll_submit_packed", "ll_collect", "ll_get_lane_status", "ll_debug_features", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
+           "ll_debug_assoc", "ll_cuda_stream", "ll_launch_count", "ll_comm_export", "ll_comm_local_ptr", "ll_comm_attach", "ll_comm_detach", "ll_map_set_slab"]
 
 
 class LLConfig(ctypes.Structure):
@@ -26,7 +26,8 @@ class LLConfig(ctypes.Structure):
                 ("up_bound", ctypes.c_float), ("line_res", ctypes.c_float), ("plane_res", ctypes.c_float),
                 ("skip_frame", ctypes.c_int), ("graph_from_frame", ctypes.c_int), ("device", ctypes.c_int),
                 ("batch", ctypes.c_int), ("max_points", ctypes.c_int), ("max_ring_points", ctypes.c_int),
-                ("map_capacity", ctypes.c_int), ("enable_mapping", ctypes.c_int), ("reserved", ctypes.c_int * 6)]
+                ("map_capacity", ctypes.c_int), ("enable_mapping", ctypes.c_int), ("map_graph_vote", ctypes.c_int),
+                ("distortion", ctypes.c_int), ("vote_mode", ctypes.c_int), ("reserved", ctypes.c_int * 3)]
 
 
 class LLCloudView(ctypes.Structure):
@@ -68,6 +69,7 @@ def lib():
         L.ll_last_error.argtypes = [ctypes.c_void_p]
         L.ll_cuda_stream.restype = ctypes.c_void_p
         L.ll_cuda_stream.argtypes = [ctypes.c_void_p]
+        L.ll_launch_count.argtypes = [ctypes.c_void_p]
         L.ll_create.argtypes = [ctypes.POINTER(LLConfig), ctypes.POINTER(ctypes.c_void_p)]
         L.ll_destroy.argtypes = [ctypes.c_void_p]
         L.ll_reset.argtypes = [ctypes.c_void_p]
@@ -82,6 +84,9 @@ def lib():
         L.ll_process_staged.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.ll_submit_scans.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
         L.ll_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ll_submit_packed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.ll_get_lane_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.ll_debug_features.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ll_pool_upload.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
         L.ll_process_pool.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.ll_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -109,8 +114,8 @@ def default_config(scan_line=64, **overrides):
 def _view(a):
     if a is None or len(a) == 0:
         return LLCloudView(None, 0, 16)
-    assert a.dtype == np.float32 and a.ndim == 2 and a.flags["C_CONTIGUOUS"]
-    return LLCloudView(a.ctypes.data, a.shape[0], a.shape[1] * 4)
+    assert a.ndim == 2 and a.flags["C_CONTIGUOUS"] and a.dtype in (np.float32, np.uint8)
+    return LLCloudView(a.ctypes.data, a.shape[0], a.shape[1] * a.dtype.itemsize)   # uint8 rows = raw records of any point_step
 
 
 class Context:
@@ -140,12 +145,26 @@ class Context:
             raise LightLoamError("%s: %s (%s)" % (what, self.L.ll_strerror(rc).decode(), self.L.ll_last_error(self.h).decode()))
         return rc
 
+    def _check_batch(self, rc, what):
+        """Batch calls return the first failing lane's code AFTER writing every pose: keep it in last_rc, raise only for
+        call-level failures (the lane codes are in lane_status())."""
+        self.last_rc = rc
+        if rc < 0 and rc in (LL_E_EMPTY, LL_E_CAPACITY, LL_E_NCCL) and any(self.lane_status()):
+            return rc
+        return self._check(rc, what)
+
+    def lane_status(self, n=None):
+        n = self.B if n is None else n
+        st = np.zeros(n, np.int32)
+        self._check(self.L.ll_get_lane_status(self.h, st.ctypes.data, n), "ll_get_lane_status")
+        return st
+
     def reset(self):
         self._check(self.L.ll_reset(self.h), "ll_reset")
 
     def extract_features(self, points):
         """scanRegistration.cpp:100-377. points: (n, 3..8) float32. Returns a dict like oracle/orc_py.extract_features."""
-        pts = np.ascontiguousarray(points, dtype=np.float32)
+        pts = np.ascontiguousarray(points) if getattr(points, "dtype", None) == np.uint8 else np.ascontiguousarray(points, dtype=np.float32)
         n, R = pts.shape[0], self.R
         full = np.zeros((n, 4), np.float32)
         sharp = np.zeros((R * 12, 4), np.float32)
@@ -200,7 +219,7 @@ class Context:
         self._check(self.L.ll_map_insert(self.h, _view(c), _view(s)), "ll_map_insert")
 
     def _views(self, scans):
-        self._keep = [np.ascontiguousarray(s, dtype=np.float32) for s in scans]
+        self._keep = [np.ascontiguousarray(s) if getattr(s, "dtype", None) == np.uint8 else np.ascontiguousarray(s, dtype=np.float32) for s in scans]
         arr = (LLCloudView * len(scans))()
         for i, a in enumerate(self._keep):
             arr[i] = _view(a)
@@ -210,7 +229,7 @@ class Context:
         """Fused pipeline: scan i feeds lane i. Returns (n, 14) float64 poses."""
         views = self._views(scans)
         poses = np.zeros((len(scans), 14))
-        self._check(self.L.ll_process_scans(self.h, len(scans), views, poses.ctypes.data), "ll_process_scans")
+        self._check_batch(self.L.ll_process_scans(self.h, len(scans), views, poses.ctypes.data), "ll_process_scans")
         return poses
 
     def stage_scans(self, scans):
@@ -219,7 +238,7 @@ class Context:
 
     def process_staged(self, n, want_poses=True):
         poses = np.zeros((n, 14)) if want_poses else None
-        self._check(self.L.ll_process_staged(self.h, n, poses.ctypes.data if want_poses else None), "ll_process_staged")
+        self._check_batch(self.L.ll_process_staged(self.h, n, poses.ctypes.data if want_poses else None), "ll_process_staged")
         return poses
 
     def submit_scans(self, scans):
@@ -245,10 +264,24 @@ class Context:
         self._check(self.L.ll_submit_scans(self.h, len(views), arr), "ll_submit_scans")
         self._inflight.append(arr)
 
+    def submit_packed(self, arena, offsets, counts, stride_bytes):
+        """ll_submit_packed: `arena` = one (pinned) uint8 / float32 host array holding every scan, offsets in bytes."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        cnt = np.ascontiguousarray(counts, dtype=np.int32)
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._check(self.L.ll_submit_packed(self.h, len(cnt), arena.ctypes.data, off.ctypes.data, cnt.ctypes.data, stride_bytes), "ll_submit_packed")
+        self._inflight.append((arena, len(cnt)))
+
     def collect(self):
         poses = np.zeros((self.B, 14))
-        n = self._check(self.L.ll_collect(self.h, poses.ctypes.data), "ll_collect")
-        self._inflight.pop(0)
+        n = self.L.ll_collect(self.h, poses.ctypes.data)
+        if not getattr(self, "_inflight", None):
+            self._check(n, "ll_collect")           # nothing outstanding: LL_E_INVAL
+        held = self._inflight.pop(0)
+        if n < 0:
+            self._check_batch(n, "ll_collect")
+            n = held[1] if isinstance(held, tuple) else len(held)
         return poses[:n]
 
     def pool_upload(self, scans):
@@ -260,7 +293,7 @@ class Context:
     def process_pool(self, scan_ids, want_poses=True):
         ids = np.ascontiguousarray(scan_ids, dtype=np.int32)
         poses = np.zeros((len(ids), 14)) if want_poses else None
-        self._check(self.L.ll_process_pool(self.h, len(ids), ids.ctypes.data, poses.ctypes.data if want_poses else None), "ll_process_pool")
+        self._check_batch(self.L.ll_process_pool(self.h, len(ids), ids.ctypes.data, poses.ctypes.data if want_poses else None), "ll_process_pool")
         return poses
 
     def profile_enable(self, on=True):
@@ -284,6 +317,15 @@ class Context:
         s = LLStats()
         self._check(self.L.ll_get_last_stats(self.h, ctypes.byref(s)), "ll_get_last_stats")
         return s
+
+    def debug_features(self, lane=0):
+        """Feature indices of lane `lane`'s last extraction: dict(counts, sharp_idx, less_sharp_idx, flat_idx)."""
+        cnt = np.zeros(5, np.int32)
+        s_ = np.zeros(self.R * 12, np.int32)
+        ls = np.zeros(self.R * 120, np.int32)
+        f = np.zeros(self.R * 24, np.int32)
+        self._check(self.L.ll_debug_features(self.h, lane, cnt.ctypes.data, s_.ctypes.data, ls.ctypes.data, f.ctypes.data), "ll_debug_features")
+        return dict(counts=cnt, sharp_idx=s_[:cnt[1]], less_sharp_idx=ls[:cnt[2]], flat_idx=f[:cnt[3]])
 
     def debug_assoc(self, lane=0):
         c = np.zeros((self.R * 12, 2), np.int32)

@@ -14,13 +14,13 @@ size_t ll_feature_smem_bytes(int SCAP);
 
 namespace {
 
-struct ScanHdr { int n_raw, stride_words; };
+struct ScanHdr { int n_raw, stride_words; unsigned off_lo, off_hi; };   // off = word offset of the scan inside the staging slab
 
-__global__ void k_set_scan_hdr(LaneState* lane, const ScanHdr* hdr, const uint32_t* raw, size_t lane_words, int n_lanes)
+__global__ void k_set_scan_hdr(LaneState* lane, const ScanHdr* hdr, const uint32_t* raw, int n_lanes)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n_lanes) {
-        lane[b].raw = raw + (size_t)b * lane_words;
+        lane[b].raw = raw + (((size_t)hdr[b].off_hi << 32) | hdr[b].off_lo);
         lane[b].n_raw = hdr[b].n_raw;
         lane[b].stride_words = hdr[b].stride_words;
         lane[b].err = 0;
@@ -39,13 +39,13 @@ __global__ void k_set_pool_hdr(LaneState* lane, const int* ids, const int* pool_
 }
 
 // float4 x,y,z,intensity -> pcl::PointXYZI as pcl::toROSMsg lays it out in sensor_msgs/PointCloud2::data (point_step 32:
-// x@0 y@4 z@8 intensity@16, padding zeroed) - SR:382-410, LO:899-913.  Two 16-byte stores per point, coalesced.
+// x@0 y@4 z@8 data[3]@12 = 1.0f intensity@16, padding zeroed) - SR:382-410, LO:899-913.  Two 16-byte stores per point, coalesced.
 __global__ void k_pack_pointcloud2(const float4* __restrict__ src, float4* __restrict__ dst, const int* n_dev, int n_host)
 {
     const int n = n_dev ? *n_dev : n_host;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = src[i];
-        dst[2 * i] = make_float4(p.x, p.y, p.z, 0.f);
+        dst[2 * i] = make_float4(p.x, p.y, p.z, 1.0f);      // PCL_ADD_POINT4D: data[3] = 1.0f (set by the PointXYZI constructor)
         dst[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
     }
 }
@@ -141,7 +141,10 @@ void ll_default_config(ll_config* cfg, int scan_line)
     cfg->device = 0;
     cfg->batch = 1;
     cfg->max_points = scan_line == 64 ? 131072 : (scan_line == 32 ? 73728 : 32768);
-    cfg->max_ring_points = 3083;
+    // Ring capacity: the 64-line formula (SR:162) bins real HDL-64 elevations uniformly although the beams are not, so a
+    // scanID can collect two lasers (3.5-4k points); a VLP-16 at 5 Hz also has ~3.6k points per ring.  6155 = 6 x 1024 + 11
+    // enables the wide-sector kernels next to the 512-key ones (rings of up to 3083 points keep the fast path).
+    cfg->max_ring_points = 6155;
     cfg->map_capacity = 1 << 20;
     cfg->enable_mapping = 0;
 }
@@ -180,7 +183,9 @@ void ll_destroy(ll_ctx* c)
     if (c->h_hdr2) cudaFreeHost(c->h_hdr2);
     if (c->h_pose2) cudaFreeHost(c->h_pose2);
     if (c->h_ids) cudaFreeHost(c->h_ids);
-    void* ptrs[] = {c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
+    if (c->h_status) cudaFreeHost(c->h_status);
+    free(c->last_status);
+    void* ptrs[] = {c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->d_ebound[0], c->d_ebound[1], c->d_bands[0], c->d_bands[1], c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
                     c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n, c->d_vote_src, c->d_vote_tgt};
@@ -228,8 +233,13 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(cudaHostAlloc((void**)&c->h_lane, sizeof(LaneState) * B, cudaHostAllocDefault));
     CK(cudaHostAlloc((void**)&c->h_pose, sizeof(double) * 14 * B, cudaHostAllocDefault));
     CK(dalloc(c->d_pose, B * 14));
-    CK(cudaHostAlloc((void**)&c->h_hdr, sizeof(int) * 2 * B, cudaHostAllocDefault));
-    CK(dalloc(c->d_hdr, B * 2));
+    CK(cudaHostAlloc((void**)&c->h_hdr, sizeof(int) * 4 * B, cudaHostAllocDefault));
+    CK(dalloc(c->d_hdr, B * 4));
+    CK(dalloc(c->d_status, B));
+    CK(cudaMemsetAsync(c->d_status, 0, sizeof(int) * B, c->stream));
+    CK(cudaHostAlloc((void**)&c->h_status, sizeof(int) * 3 * B, cudaHostAllocDefault));
+    memset(c->h_status, 0, sizeof(int) * 3 * B);
+    c->last_status = (int*)calloc(B, sizeof(int));
     CK(dalloc(c->d_raw, B * N * 8));
     CK(dalloc(c->d_ring8, B * N));
     CK(dalloc(c->d_rank8, B * N));
@@ -276,6 +286,9 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_assoc_queue, (size_t)c->assoc_queue_cap));
     CK(dalloc(c->d_assoc_queue_n, 16));
     CK(cudaMemsetAsync(c->d_assoc_queue_n, 0, sizeof(int) * 16, c->stream));
+    CK(dalloc(c->d_qa, B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING)));
+    CK(dalloc(c->d_qb, B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING)));
+    CK(dalloc(c->d_qstart, B * (size_t)c->qstart_stride));
     c->nblk_cap = (int)R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     CK(dalloc(c->d_blocks, B * (size_t)LL_BLOCK_DOUBLES * c->nblk_cap));
     CK(cudaMemsetAsync(c->d_raw, 0, sizeof(uint32_t) * B * N * 8, c->stream));
@@ -302,6 +315,7 @@ int ll_reset(ll_ctx* c)
 }
 
 void* ll_cuda_stream(ll_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int ll_launch_count(const ll_ctx* c) { return c ? c->launches : 0; }
 
 static int fetch_lanes(ll_ctx* c, int n)
 {
@@ -310,25 +324,55 @@ static int fetch_lanes(ll_ctx* c, int n)
     return LL_OK;
 }
 
+// Raw-scan records a kernel can read in place: x,y,z at words 0..2 of a record of 3..8 words.  Anything else (point_step
+// above 32 or not a multiple of 4: velodyne XYZIRT 22 B, Ouster 48 B ...) is gathered to packed xyz by a strided copy,
+// which is what pcl::fromROSMsg does on the host in the reference (SR:105-106).
+static bool stride_in_place(int stride_bytes) { return stride_bytes >= 12 && stride_bytes <= 32 && (stride_bytes & 3) == 0; }
+static int check_scan_view(const ll_ctx* c, const ll_cloud_view& v)
+{
+    if (!v.data || v.n < 1 || v.stride_bytes < 12) return LL_E_INVAL;
+    if (v.n > c->Nmax) return LL_E_CAPACITY;
+    return LL_OK;
+}
+// enqueues the copy of one scan into lane slot i of a staging slab and fills its header
+static int stage_one(ll_ctx* c, const ll_cloud_view& v, uint32_t* slab, int i, ScanHdr* hdr, cudaStream_t st)
+{
+    const size_t off = (size_t)i * c->Nmax * 8;
+    hdr[i].n_raw = v.n;
+    hdr[i].off_lo = (unsigned)off; hdr[i].off_hi = (unsigned)(off >> 32);
+    if (stride_in_place(v.stride_bytes)) {
+        hdr[i].stride_words = v.stride_bytes / 4;
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(slab + off, v.data, (size_t)v.n * v.stride_bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        hdr[i].stride_words = 3;
+        LL_CUDA_CHECK(c, cudaMemcpy2DAsync(slab + off, 12, v.data, v.stride_bytes, 12, v.n, cudaMemcpyHostToDevice, st));
+    }
+    return LL_OK;
+}
+
 int ll_stage_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
 {
     if (!c || !scans || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
     LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    if (c->sub_count > 0) return LL_E_INVAL;           // the staging slab belongs to an outstanding submission
     LL_CUDA_CHECK(c, cudaEventSynchronize(c->ev[4]));  // the previous staging must have consumed h_hdr
     ScanHdr* hdr = reinterpret_cast<ScanHdr*>(c->h_hdr);
-    for (int i = 0; i < n_scans; ++i) {
-        const ll_cloud_view& v = scans[i];
-        if (!v.data || v.n < 1 || v.stride_bytes < 12 || v.stride_bytes > 32 || (v.stride_bytes & 3)) return LL_E_INVAL;
-        if (v.n > c->Nmax) return LL_E_CAPACITY;
-        hdr[i].n_raw = v.n;
-        hdr[i].stride_words = v.stride_bytes / 4;
-        LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_raw + (size_t)i * c->Nmax * 8, v.data, (size_t)v.n * v.stride_bytes, cudaMemcpyHostToDevice, c->stream));
-    }
+    for (int i = 0; i < n_scans; ++i) { const int rc = check_scan_view(c, scans[i]); if (rc) return rc; }
+    for (int i = 0; i < n_scans; ++i) { const int rc = stage_one(c, scans[i], c->d_raw, i, hdr, c->stream); if (rc) return rc; }
     LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_hdr, hdr, sizeof(ScanHdr) * n_scans, cudaMemcpyHostToDevice, c->stream));
     LL_CUDA_CHECK(c, cudaEventRecord(c->ev[4], c->stream));
-    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, reinterpret_cast<const ScanHdr*>(c->d_hdr), c->d_raw, (size_t)c->Nmax * 8, n_scans);
+    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, reinterpret_cast<const ScanHdr*>(c->d_hdr), c->d_raw, n_scans);
+    c->pre_launches = 1;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
+}
+
+// first non-zero lane status of a finished batch (kept for ll_get_lane_status)
+static int publish_status(ll_ctx* c, const int* st, int n)
+{
+    int first = LL_OK;
+    for (int i = 0; i < n; ++i) { c->last_status[i] = st[i]; if (first == LL_OK && st[i] < 0) first = st[i]; }
+    return first;
 }
 
 int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
@@ -336,7 +380,8 @@ int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
     if (!c || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
     LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
     if (c->prof) ll_prof_harvest(c);
-    c->launches = 0;
+    c->launches = c->pre_launches;   // the header kernel of ll_stage_scans / ll_process_pool belongs to this step
+    c->pre_launches = 0;
     LL_CUDA_CHECK(c, cudaEventRecord(c->ev[0], c->stream));
     int rc = ll_launch_features(c, n_scans);
     if (rc) return rc;
@@ -351,8 +396,10 @@ int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
     LL_CUDA_CHECK(c, cudaEventRecord(c->ev[3], c->stream));
     if (poses_out) {
         LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 14 * n_scans, cudaMemcpyDeviceToHost, c->stream));
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int) * n_scans, cudaMemcpyDeviceToHost, c->stream));
         LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
         memcpy(poses_out, c->h_pose, sizeof(double) * 14 * n_scans);
+        return publish_status(c, c->h_status, n_scans);
     }
     return LL_OK;
 }
@@ -363,7 +410,11 @@ int ll_process_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans, double*
     if (rc) return rc;
     rc = ll_process_staged(c, n_scans, poses_out);
     if (rc) return rc;
-    if (!poses_out) LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (!poses_out) {
+        LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int) * n_scans, cudaMemcpyDeviceToHost, c->stream));
+        LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        return publish_status(c, c->h_status, n_scans);
+    }
     return LL_OK;
 }
 
@@ -388,7 +439,7 @@ int ll_pool_upload(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
     std::vector<int> ns(n_scans);
     for (int i = 0; i < n_scans; ++i) {
         const ll_cloud_view& v = scans[i];
-        if (!v.data || v.n < 1 || v.stride_bytes < 12 || (v.stride_bytes & 3)) return LL_E_INVAL;
+        if (!v.data || v.n < 1 || v.stride_bytes < 12) return LL_E_INVAL;
         if (v.n > c->Nmax) return LL_E_CAPACITY;
         ns[i] = v.n;
         uint32_t* dst = c->d_pool + (size_t)i * c->Nmax * 4;
@@ -415,6 +466,7 @@ int ll_process_pool(ll_ctx* c, int n_lanes, const int* scan_ids, double* poses_o
     LL_CUDA_CHECK(c, cudaMemcpyAsync(c->d_ids, c->h_ids, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, c->stream));
     LL_CUDA_CHECK(c, cudaEventRecord(c->ev[4], c->stream));
     k_set_pool_hdr<<<(n_lanes + 63) / 64, 64, 0, c->stream>>>(c->d_lane, c->d_ids, c->d_pool_n, c->d_pool, (size_t)c->Nmax * 4, n_lanes);
+    c->pre_launches = 1;
     return ll_process_staged(c, n_lanes, poses_out);
 }
 
@@ -458,14 +510,36 @@ static int submit_alloc(ll_ctx* c)
     const size_t B = c->B;
     LL_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_raw2, sizeof(uint32_t) * B * c->Nmax * 8));
-    LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_hdr2, sizeof(int) * 2 * B * 2));
-    LL_CUDA_CHECK(c, cudaHostAlloc((void**)&c->h_hdr2, sizeof(int) * 2 * B * 2, cudaHostAllocDefault));
+    LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_hdr2, sizeof(ScanHdr) * B * 2));
+    LL_CUDA_CHECK(c, cudaHostAlloc((void**)&c->h_hdr2, sizeof(ScanHdr) * B * 2, cudaHostAllocDefault));
     LL_CUDA_CHECK(c, cudaHostAlloc((void**)&c->h_pose2, sizeof(double) * 2 * B * 14, cudaHostAllocDefault));
     for (int k = 0; k < 2; ++k) {
         LL_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_staged[k], cudaEventDisableTiming));
         LL_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_raw_free[k], cudaEventDisableTiming));
         LL_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
     }
+    return LL_OK;
+}
+
+// the part of a submission after its host-to-device copies have been enqueued on the copy stream
+static int submit_launch(ll_ctx* c, int slot, int n_scans, uint32_t* raw, ScanHdr* hdr, ScanHdr* dhdr)
+{
+    int rc;
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(dhdr, hdr, sizeof(ScanHdr) * n_scans, cudaMemcpyHostToDevice, c->copy_stream));
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_staged[slot], c->copy_stream));
+    LL_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_staged[slot], 0));
+    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, dhdr, raw, n_scans);
+    if (c->prof) ll_prof_harvest(c);
+    c->launches = 1;
+    if ((rc = ll_launch_features(c, n_scans))) return rc;
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_raw_free[slot], c->stream));
+    if ((rc = ll_launch_odometry(c, n_scans))) return rc;
+    if (c->cfg.enable_mapping && (rc = ll_launch_mapping(c, n_scans))) return rc;
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_pose2 + (size_t)slot * c->B * 14, c->d_pose, sizeof(double) * 14 * n_scans, cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_status + (size_t)(1 + slot) * c->B, c->d_status, sizeof(int) * n_scans, cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_done[slot], c->stream));
+    c->sub_n[slot] = n_scans;
+    c->sub_count++;
     return LL_OK;
 }
 
@@ -480,34 +554,38 @@ int ll_submit_scans(ll_ctx* c, int n_scans, const ll_cloud_view* scans)
     uint32_t* raw = slot == 0 ? c->d_raw : c->d_raw2;
     ScanHdr* hdr = reinterpret_cast<ScanHdr*>(c->h_hdr2) + (size_t)slot * c->B;
     ScanHdr* dhdr = reinterpret_cast<ScanHdr*>(c->d_hdr2) + (size_t)slot * c->B;
-    for (int i = 0; i < n_scans; ++i) {
-        const ll_cloud_view& v = scans[i];
-        if (!v.data || v.n < 1 || v.stride_bytes < 12 || v.stride_bytes > 32 || (v.stride_bytes & 3)) return LL_E_INVAL;
-        if (v.n > c->Nmax) return LL_E_CAPACITY;
-    }
+    for (int i = 0; i < n_scans; ++i) { if ((rc = check_scan_view(c, scans[i]))) return rc; }
     // the slab may still be read by the feature kernels of the submission before last (already collected => done)
     LL_CUDA_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_raw_free[slot], 0));
+    for (int i = 0; i < n_scans; ++i) { if ((rc = stage_one(c, scans[i], raw, i, hdr, c->copy_stream))) return rc; }
+    return submit_launch(c, slot, n_scans, raw, hdr, dhdr);
+}
+
+int ll_submit_packed(ll_ctx* c, int n_scans, const void* host_base, const int64_t* byte_offsets, const int* n_points, int stride_bytes)
+{
+    if (!c || !host_base || !byte_offsets || !n_points || n_scans < 1 || n_scans > c->B || !stride_in_place(stride_bytes)) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    int rc = submit_alloc(c);
+    if (rc) return rc;
+    if (c->sub_count >= 2) return LL_E_CAPACITY;  // collect first
+    const int slot = (c->sub_head + c->sub_count) & 1;
+    uint32_t* raw = slot == 0 ? c->d_raw : c->d_raw2;
+    ScanHdr* hdr = reinterpret_cast<ScanHdr*>(c->h_hdr2) + (size_t)slot * c->B;
+    ScanHdr* dhdr = reinterpret_cast<ScanHdr*>(c->d_hdr2) + (size_t)slot * c->B;
+    const int64_t lo = byte_offsets[0];
+    int64_t end = lo;
     for (int i = 0; i < n_scans; ++i) {
-        const ll_cloud_view& v = scans[i];
-        hdr[i].n_raw = v.n;
-        hdr[i].stride_words = v.stride_bytes / 4;
-        LL_CUDA_CHECK(c, cudaMemcpyAsync(raw + (size_t)i * c->Nmax * 8, v.data, (size_t)v.n * v.stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        if (n_points[i] < 1 || byte_offsets[i] < end || (byte_offsets[i] & 3)) return LL_E_INVAL;
+        if (n_points[i] > c->Nmax) return LL_E_CAPACITY;
+        end = byte_offsets[i] + (int64_t)n_points[i] * stride_bytes;
+        const uint64_t off = (uint64_t)(byte_offsets[i] - lo) / 4;
+        hdr[i].n_raw = n_points[i]; hdr[i].stride_words = stride_bytes / 4;
+        hdr[i].off_lo = (unsigned)off; hdr[i].off_hi = (unsigned)(off >> 32);
     }
-    LL_CUDA_CHECK(c, cudaMemcpyAsync(dhdr, hdr, sizeof(ScanHdr) * n_scans, cudaMemcpyHostToDevice, c->copy_stream));
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_staged[slot], c->copy_stream));
-    LL_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_staged[slot], 0));
-    k_set_scan_hdr<<<(n_scans + 63) / 64, 64, 0, c->stream>>>(c->d_lane, dhdr, raw, (size_t)c->Nmax * 8, n_scans);
-    if (c->prof) ll_prof_harvest(c);
-    c->launches = 0;
-    if ((rc = ll_launch_features(c, n_scans))) return rc;
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_raw_free[slot], c->stream));
-    if ((rc = ll_launch_odometry(c, n_scans))) return rc;
-    if (c->cfg.enable_mapping && (rc = ll_launch_mapping(c, n_scans))) return rc;
-    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_pose2 + (size_t)slot * c->B * 14, c->d_pose, sizeof(double) * 14 * n_scans, cudaMemcpyDeviceToHost, c->stream));
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev_done[slot], c->stream));
-    c->sub_n[slot] = n_scans;
-    c->sub_count++;
-    return LL_OK;
+    if ((uint64_t)(end - lo) > (uint64_t)c->B * c->Nmax * 32) return LL_E_CAPACITY;   // the staging slab holds B x Nmax x 32 bytes
+    LL_CUDA_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_raw_free[slot], 0));
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(raw, static_cast<const char*>(host_base) + lo, (size_t)(end - lo), cudaMemcpyHostToDevice, c->copy_stream));
+    return submit_launch(c, slot, n_scans, raw, hdr, dhdr);
 }
 
 int ll_collect(ll_ctx* c, double* poses_out)
@@ -520,7 +598,32 @@ int ll_collect(ll_ctx* c, double* poses_out)
     if (poses_out) memcpy(poses_out, c->h_pose2 + (size_t)slot * c->B * 14, sizeof(double) * 14 * c->sub_n[slot]);
     c->sub_head ^= 1;
     c->sub_count--;
-    return c->sub_n[slot];
+    const int st = publish_status(c, c->h_status + (size_t)(1 + slot) * c->B, c->sub_n[slot]);
+    return st < 0 ? st : c->sub_n[slot];
+}
+
+int ll_get_lane_status(ll_ctx* c, int* status, int n)
+{
+    if (!c || !status || n < 0 || n > c->B) return LL_E_INVAL;
+    memcpy(status, c->last_status, sizeof(int) * n);
+    return LL_OK;
+}
+
+int ll_debug_features(ll_ctx* c, int lane, int counts[5], int* sharp_idx, int* less_sharp_idx, int* flat_idx)
+{
+    if (!c || lane < 0 || lane >= c->B || !counts) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_lane, c->d_lane + lane, sizeof(LaneState), cudaMemcpyDeviceToHost, c->stream));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    const LaneState L = c->h_lane[0];
+    counts[0] = L.n_full; counts[1] = L.n_sharp; counts[2] = L.n_less_sharp; counts[3] = L.n_flat; counts[4] = L.n_less_flat;
+    cudaStream_t s = c->stream;
+    const size_t R = c->R;
+    if (sharp_idx && L.n_sharp) LL_CUDA_CHECK(c, cudaMemcpyAsync(sharp_idx, c->d_sharp_idx + lane * R * LL_SHARP_PER_RING, sizeof(int) * L.n_sharp, cudaMemcpyDeviceToHost, s));
+    if (less_sharp_idx && L.n_less_sharp) LL_CUDA_CHECK(c, cudaMemcpyAsync(less_sharp_idx, c->d_lsharp_idx + lane * R * LL_LSHARP_PER_RING, sizeof(int) * L.n_less_sharp, cudaMemcpyDeviceToHost, s));
+    if (flat_idx && L.n_flat) LL_CUDA_CHECK(c, cudaMemcpyAsync(flat_idx, c->d_flat_idx + lane * R * LL_FLAT_PER_RING, sizeof(int) * L.n_flat, cudaMemcpyDeviceToHost, s));
+    LL_CUDA_CHECK(c, cudaStreamSynchronize(s));
+    return LL_OK;
 }
 
 int ll_last_timings(ll_ctx* c, float ms[4])
@@ -576,8 +679,9 @@ int ll_fetch_pointcloud2(ll_ctx* c, int which, void* data, int cap_points, int* 
     *n_points = n;
     if (n > cap_points) return LL_E_CAPACITY;
     if (n == 0) return LL_OK;
-    // lane 0's raw staging slab (32 bytes per point) is free between two scans: the packed cloud is built there
-    float4* dst = reinterpret_cast<float4*>(c->d_raw);
+    if (c->sub_count > 0) return LL_E_INVAL;   // outstanding submissions own the stream order; collect first
+    if (!c->d_pc2) LL_CUDA_CHECK(c, cudaMalloc((void**)&c->d_pc2, (size_t)c->Nmax * 32));   // own scratch: staged inputs stay intact
+    float4* dst = c->d_pc2;
     k_pack_pointcloud2<<<(n + 255) / 256 < 592 ? (n + 255) / 256 : 592, 256, 0, c->stream>>>(src[which], dst, nullptr, n);
     LL_CUDA_CHECK(c, cudaGetLastError());
     LL_CUDA_CHECK(c, cudaMemcpyAsync(data, dst, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));

@@ -87,14 +87,20 @@ struct ll_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     int launches = 0;
+    int pre_launches = 0;     // launches issued by the staging half of a call, folded into `launches` by the processing half
     float vote_t_min = 0.f;   // smallest fp32 t with expf(-t) < 0.96f on this host's libm (LO:239-242)
 
     LaneState* d_lane = nullptr;
     LaneState* h_lane = nullptr;   // pinned mirror
     double* h_pose = nullptr;      // pinned [B][14]
     double* d_pose = nullptr;      // [B][14]
-    int* h_hdr = nullptr;          // pinned [B][2] {n_raw, stride_words}
-    int* d_hdr = nullptr;          // [B][2]
+    int* h_hdr = nullptr;          // pinned [B][4] {n_raw, stride_words, word offset lo, hi}
+    int* d_hdr = nullptr;          // [B][4]
+    int* d_status = nullptr;       // [B] per-lane status of the last step (LaneState::err at k_odom_finalize / k_map_end)
+    int* h_status = nullptr;       // pinned [3][B]: slot 0 = synchronous calls, 1..2 = submit slots
+    int* last_status = nullptr;    // host [B]: what ll_get_lane_status reports
+    bool feat_attr_set = false;    // dynamic shared-memory limits of the per-ring kernels set on this context's device
+    float4* d_pc2 = nullptr;       // scratch of ll_fetch_pointcloud2 (allocated on first use)
 
     uint32_t* d_raw = nullptr;     // [B][Nmax * 8] words (stride <= 32 B)
     int8_t* d_ring8 = nullptr;     // [B][Nmax]
@@ -128,6 +134,11 @@ struct ll_ctx {
     int4* d_assoc_queue = nullptr; // [B * R * 36] queries handed to the warp pass of the association
     int* d_assoc_queue_n = nullptr;// [16] per outer iteration: long entries queued [0..2], pop cursors [4..6], short entries queued [8..10]
     int assoc_queue_cap = 0;
+    float4* d_qa = nullptr;        // [B][R*36] transformed queries of the outer iteration, grouped by azimuth slab (k_odom_queries)
+    float4* d_qb = nullptr;        // [B][R*36] their polar coordinates
+    int* d_qstart = nullptr;       // [B][qstart_stride] slab offsets
+    int qstart_stride = 260;
+    bool slab_attr_set = false;
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;
 
@@ -135,8 +146,8 @@ struct ll_ctx {
     // kernels of step k (ll_submit_scans / ll_collect)
     cudaStream_t copy_stream = nullptr;
     uint32_t* d_raw2 = nullptr;        // second staging slab [B][Nmax * 8]
-    int* h_hdr2 = nullptr;             // pinned headers per slot [2][B][2]
-    int* d_hdr2 = nullptr;             // [2][B][2]
+    int* h_hdr2 = nullptr;             // pinned headers per slot [2][B][4]
+    int* d_hdr2 = nullptr;             // [2][B][4]
     double* h_pose2 = nullptr;         // pinned poses per slot [2][B][14]
     cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_raw_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     int sub_n[2] = {0, 0};             // scans of the submission occupying each slot

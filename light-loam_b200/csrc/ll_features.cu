@@ -47,6 +47,10 @@ struct FeatParams {
     int scan_line;
     float thres, lower_bound, up_bound, factor;
     float inv_leaf;   // 1.0f / 0.2f
+    // ring sizes handled by this launch of the per-ring kernels: ring_lo < n <= 6 * SCAP + 11.  With the wide-sector
+    // variant enabled the kernels run twice: <512> takes the rings of up to 3083 points, <1024> the longer ones (a CTA
+    // whose ring belongs to the other variant leaves after two loads).  Rings longer than ring_cap are an error.
+    int ring_lo, ring_cap;
 };
 
 // SR:114-126: endOri from the last valid point and startOri
@@ -317,29 +321,6 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_scatter(FeatParams P)
     }
 }
 
-// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
-            smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // k_ring_sort: one CTA per (ring, lane), one WARP per sector.  TMA bulk load of the ring slab into shared memory,
 // 11-tap curvature (SR:225-235), then each warp sorts its sector (SR:257) entirely in registers: SCAP / 32 keys per
@@ -442,11 +423,14 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
         return c;
     };
 
-    if (n - 11 < 6 || n > 6 * SCAP + 11) {  // SR:248 skip; or capacity overflow
-        if (tid == 0 && n > 6 * SCAP + 11) L.err = LL_E_CAPACITY;
-        for (int i = tid; i < n; i += NTH) { gcurv[base + i] = global_curv(base + i); glabel[base + i] = 0; }
+    if (n - 11 < 6 || n > P.ring_cap) {  // SR:248 skip; or capacity overflow
+        if (P.ring_lo == 0) {
+            if (tid == 0 && n > P.ring_cap) L.err = LL_E_CAPACITY;
+            for (int i = tid; i < n; i += NTH) { gcurv[base + i] = global_curv(base + i); glabel[base + i] = 0; }
+        }
         return;
     }
+    if (n <= P.ring_lo || n > 6 * SCAP + 11) return;   // the other variant's ring
 
     if (tid == 0) mbar_init(bar, 1);
     const int len = n - 11;
@@ -615,10 +599,11 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
     const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base;
     int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
     int* my_lists = P.ring_lists + ((size_t)b * P.R + r) * (LL_SHARP_PER_RING + LL_LSHARP_PER_RING + LL_FLAT_PER_RING);
-    if (n - 11 < 6 || n > 6 * SCAP + 11) {
-        if (lane == 0) { my_counts[0] = my_counts[1] = my_counts[2] = 0; }
+    if (n - 11 < 6 || n > P.ring_cap) {
+        if (lane == 0 && P.ring_lo == 0) { my_counts[0] = my_counts[1] = my_counts[2] = 0; }
         return;
     }
+    if (n <= P.ring_lo || n > 6 * SCAP + 11) return;   // the other variant's ring
     const unsigned* gbrk = P.brk + ((size_t)b * P.R + r) * P.brk_words;
     const uint16_t* gsorted = P.sorted16 + (size_t)b * P.Nmax + base;
     for (int i = lane; i < WORDS; i += 32) { picked[i] = 0; brk[i] = i < P.brk_words ? gbrk[i] : 0u; }
@@ -734,7 +719,8 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     LaneState& L = P.lane[b];
     const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base;
     int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
-    if (n - 11 < 6 || n > 6 * SCAP + 11) { if (tid == 0) my_counts[3] = 0; return; }
+    if (n - 11 < 6 || n > P.ring_cap) { if (tid == 0 && P.ring_lo == 0) my_counts[3] = 0; return; }
+    if (n <= P.ring_lo || n > 6 * SCAP + 11) return;   // the other variant's ring
     const float4* pts = P.full + (size_t)b * P.Nmax + base;
     const int8_t* label = P.label + (size_t)b * P.Nmax + base;
 
@@ -1043,6 +1029,7 @@ size_t ll_feature_smem_bytes(int SCAP)  // k_ring_sort: points + curvature + six
     const size_t keys = (size_t)6 * (SCAP + 32) * 4, stage = keys > (size_t)SORT_STAGE_BYTES ? keys : (size_t)SORT_STAGE_BYTES;
     return stage + (size_t)RCAP * 4 + 8 * 4 + 16;
 }
+size_t ll_lessflat_smem_bytes(int SCAP);
 size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxel ids, point indices, run starts, scratch
 {
     const int RCAP = 6 * SCAP + 16, KCAP = RCAP <= 4096 ? 4096 : 8192;
@@ -1082,28 +1069,33 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
         else if (sct_minb >= 5) k_scatter<5><<<g, LL_TILE, 0, s>>>(P);
         else k_scatter<4><<<g, LL_TILE, 0, s>>>(P);
     }
-    const size_t smem_sort = ll_feature_smem_bytes(c->SCAP);
-    const size_t smem_lf = ll_lessflat_smem_bytes(c->SCAP);
-    const size_t smem_pick = (size_t)PICK_WARPS * (2 * ((c->RCAP + 31) / 32 + 2) + c->RCAP / 2) * 4;
     const dim3 rings(c->R, n_lanes);
     const int pick_blocks = (c->R * n_lanes + PICK_WARPS - 1) / PICK_WARPS;
-    if (c->SCAP == 512) {
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
-        { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, SORT_THREADS, smem_sort, s>>>(P); }
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick));
-        { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, smem_pick, s>>>(P, n_lanes); }
-        { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512><<<rings, 512, smem_lf, s>>>(P); }
-    } else {
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lf));
-        { LLProf pr(c, "k_ring_sort"); k_ring_sort<1024><<<rings, SORT_THREADS, smem_sort, s>>>(P); }
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick));
-        { LLProf pr(c, "k_ring_pick"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, smem_pick, s>>>(P, n_lanes); }
-        { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<1024><<<rings, 512, smem_lf, s>>>(P); }
+    auto smem_pick_of = [](int SCAP) { const int RCAP = 6 * SCAP + 16; return (size_t)PICK_WARPS * (2 * ((RCAP + 31) / 32 + 2) + RCAP / 2) * 4; };
+    if (!c->feat_attr_set) {
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_feature_smem_bytes(512)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_lessflat_smem_bytes(512)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick_of(512)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_feature_smem_bytes(1024)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_lessflat_smem_bytes(1024)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick_of(1024)));
+        c->feat_attr_set = true;
+    }
+    // rings of up to 3083 points: one warp sorts a sector of <= 512 keys in registers
+    P.ring_lo = 0; P.ring_cap = 6 * c->SCAP + 11;
+    { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, SORT_THREADS, ll_feature_smem_bytes(512), s>>>(P); }
+    { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, smem_pick_of(512), s>>>(P, n_lanes); }
+    { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512><<<rings, 512, ll_lessflat_smem_bytes(512), s>>>(P); }
+    c->launches += 3;
+    if (c->SCAP == 1024) {   // longer rings (up to 6155 points): the 1024-key variants; every other CTA leaves at once
+        P.ring_lo = 6 * 512 + 11;
+        { LLProf pr(c, "k_ring_sort_wide"); k_ring_sort<1024><<<rings, SORT_THREADS, ll_feature_smem_bytes(1024), s>>>(P); }
+        { LLProf pr(c, "k_ring_pick_wide"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, smem_pick_of(1024), s>>>(P, n_lanes); }
+        { LLProf pr(c, "k_ring_lessflat_wide"); k_ring_lessflat<1024><<<rings, 512, ll_lessflat_smem_bytes(1024), s>>>(P); }
+        c->launches += 3;
     }
     { LLProf pr(c, "k_compact"); k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P); }
-    c->launches += 8;
+    c->launches += 5;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }

@@ -402,11 +402,16 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_map(LaneState* lane, co
 }
 
 // LM:119-123 transformUpdate + pose output
-__global__ void k_map_end(LaneState* lane, double* pose_out, int n_lanes)
+__global__ void k_map_end(LaneState* lane, double* pose_out, int* status, int n_lanes)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_lanes) return;
     LaneState& L = lane[b];
+    status[b] = L.err;
+    if (L.err) {   // rejected scan or dead collective: the map-to-odometry correction stays as it was
+        if (pose_out) for (int k = 0; k < 7; ++k) pose_out[(size_t)b * 14 + 7 + k] = L.map_par[k];
+        return;
+    }
     const double* qo = L.map_odom;
     const double n2 = qo[0] * qo[0] + qo[1] * qo[1] + qo[2] * qo[2] + qo[3] * qo[3];  // Eigen inverse = conjugate / squaredNorm
     double qi[4] = {0, 0, 0, 0};
@@ -597,7 +602,7 @@ __global__ void k_vg_fill_rebuild(LaneState* lane, const float4* map_old, const 
     LaneState& L = lane[b];
     const int* off = off_old + (size_t)b * (MAP_NUM + 1);
     const int n_old = off[MAP_NUM];
-    const int n_new = t == 0 ? L.n_stack_corner : L.n_stack_surf;
+    const int n_new = L.err ? 0 : (t == 0 ? L.n_stack_corner : L.n_stack_surf);   // a lane in error inserts nothing (the shift still applies)
     const int n = min(n_old + n_new, E);
     if (blockIdx.x == 0 && threadIdx.x == 0) { vg_n[b] = n; if (n_old + n_new > E) L.err = LL_E_CAPACITY; }
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -796,10 +801,17 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     A.lane = c->d_lane; A.stack[0] = m->stack[0]; A.stack[1] = m->stack[1]; A.frommap[0] = m->frommap[0]; A.frommap[1] = m->frommap[1];
     A.stack_cap[0] = m->stack_cap[0]; A.stack_cap[1] = m->stack_cap[1]; A.map_cap = m->map_cap; A.g[0] = m->grid[0]; A.g[1] = m->grid[1];
     A.blocks = m->blocks; A.nblk_cap = m->nblk_cap; A.slab_lo = (float)m->slab_lo; A.slab_hi = (float)m->slab_hi;
-    // solve split: `parts` CTAs per lane on this GPU (all co-resident: lanes x parts <= SM count) x the attached GPUs
-    int parts = 148 / n_lanes;
+    // solve split: `parts` CTAs per lane on this GPU x the attached GPUs.  The CTAs of one lane spin on each other's
+    // mailbox flags, so they must all be resident at once: the split launch is a cooperative launch (the driver refuses
+    // it when the grid does not fit) and its size comes from the device's SM count and the kernel's occupancy.
+    int n_sm = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lm_solve_map, LM_THREADS, 0);
+    const int resident = n_sm * (per_sm > 0 ? per_sm : 1);
+    int parts = n_sm / n_lanes;
     parts = parts < 1 ? 1 : (parts > LM_MAX_PARTS ? LM_MAX_PARTS : parts);
-    if (const char* e = getenv("LL_LM_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= LM_MAX_PARTS && v * n_lanes <= 148) parts = v; }
+    if (const char* e = getenv("LL_LM_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= LM_MAX_PARTS && v * n_lanes <= resident) parts = v; }
+    if (m->gworld > 1 && n_lanes * parts > resident) { c->last_error = "multi-GPU solve: lanes x parts exceed the co-resident CTAs"; return LL_E_CAPACITY; }
     LmComm comm;
     for (int g = 0; g < LM_MAX_GPUS; ++g) {
         char* base = reinterpret_cast<char*>(g == m->grank ? m->comm_buf : m->peer_buf[g]);
@@ -812,11 +824,20 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
         { LLProf pr(c, "k_map_reset_corr"); k_map_reset_corr<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
         { LLProf pr(c, "k_map_assoc"); k_map_assoc<<<dim3((m->nblk_cap + 7) / 8, n_lanes), 256, 0, s>>>(A); }
         comm.seq_in = m->comm_seq[m->comm_flip]; comm.seq_out = m->comm_seq[m->comm_flip ^ (dist ? 1 : 0)];
-        { LLProf pr(c, "k_lm_solve_map"); k_lm_solve_map<<<dim3(n_lanes, parts), LM_THREADS, 0, s>>>(c->d_lane, m->blocks, m->nblk_cap, iter, comm, c->B); }
+        {
+            LLProf pr(c, "k_lm_solve_map");
+            if (dist) {
+                LaneState* a_lane = c->d_lane; const double* a_blk = m->blocks; int a_cap = m->nblk_cap, a_iter = iter, a_B = c->B;
+                void* args[] = {&a_lane, &a_blk, &a_cap, &a_iter, &comm, &a_B};
+                LL_CUDA_CHECK(c, cudaLaunchCooperativeKernel((const void*)k_lm_solve_map, dim3(n_lanes, parts), dim3(LM_THREADS), args, 0, s));
+            } else {
+                k_lm_solve_map<<<dim3(n_lanes, parts), LM_THREADS, 0, s>>>(c->d_lane, m->blocks, m->nblk_cap, iter, comm, c->B);
+            }
+        }
         if (dist) m->comm_flip ^= 1;
         c->launches += 3;
     }
-    { LLProf pr(c, "k_map_end"); k_map_end<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
+    { LLProf pr(c, "k_map_end"); k_map_end<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, c->d_pose, c->d_status, n_lanes); }
     c->launches += 1;
     // LM:2104-2168: insert + per-cube filter + shift, one CSR rebuild per cloud type
     for (int t = 0; t < 2; ++t) {

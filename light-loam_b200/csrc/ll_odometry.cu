@@ -165,7 +165,7 @@ __global__ void k_index_count(IndexSet S, LaneState* lane)
     const int b = blockIdx.y, cloud = (int)blockIdx.x < S.gx_corner ? 0 : 1;
     const int bx = cloud == 0 ? blockIdx.x : blockIdx.x - S.gx_corner, gxc = cloud == 0 ? S.gx_corner : (int)gridDim.x - S.gx_corner;
     LaneState& L = lane[b];
-    const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
+    const int n = (!L.inited || L.err) ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);   // laserCloudCornerLast / SurfLast
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     unsigned* eb = S.ebound[cloud] + (size_t)b * S.rings * 2;
     // a warp takes IDX_UNROLL chunks of 32 consecutive points per round; their loads are all issued before the first is used
@@ -273,7 +273,7 @@ __global__ void k_index_scatter(IndexSet S, const LaneState* lane)
     const int b = blockIdx.y, cloud = (int)blockIdx.x < S.gx_corner ? 0 : 1;
     const int bx = cloud == 0 ? blockIdx.x : blockIdx.x - S.gx_corner, gxc = cloud == 0 ? S.gx_corner : (int)gridDim.x - S.gx_corner;
     const LaneState& L = lane[b];
-    const int n = !L.inited ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);
+    const int n = (!L.inited || L.err) ? 0 : (cloud == 0 ? L.n_last_corner : L.n_last_surf);
     const float4* pts = S.pts[cloud][L.last_slot] + (size_t)b * S.lane_stride[cloud];
     const int ln = threadIdx.x & 31;
     for (int base0 = (bx * blockDim.x + (threadIdx.x & ~31)) * IDX_UNROLL; base0 < n; base0 += gxc * blockDim.x * IDX_UNROLL) {
@@ -360,17 +360,43 @@ __device__ __forceinline__ float4 ld_point(const float4* p)
     asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// Where a search reads the polar index from.  StageGlobal: the lane's tables in global memory (bin = absolute azimuth
+// bin).  StageShared: the part of the tables a CTA staged in shared memory (k_odom_assoc_slab): `nbins` consecutive
+// bins starting at absolute bin `bin0`, headers rewritten to positions inside the staged point array.
+struct StageGlobal {
+    const int* __restrict__ start;
+    const float4* __restrict__ sorted;
+    int NB, R;
+    __device__ __forceinline__ float4 point(int k) const { return ld_point(sorted + k); }
+    __device__ __forceinline__ int header(int bin, int ring) const { return __ldg(start + (bin & (NB - 1)) * R + ring); }   // NB is a power of two
+};
+struct StageShared {
+    unsigned hdr, pts;   // shared-window addresses
+    int bin0, NB, R;
+    __device__ __forceinline__ float4 point(int k) const
+    {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(pts + (unsigned)k * 16u));
+        return v;
+    }
+    __device__ __forceinline__ int header(int bin, int ring) const
+    {
+        int v;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(hdr + (unsigned)((((bin - bin0) & (NB - 1)) * R + ring) * 4)));
+        return v;
+    }
+};
 // Up to three spans as ONE candidate stream (four loads in flight across span boundaries): the spans of neighbouring
 // azimuth bins cost one memory round trip together instead of one each.
-template <typename F>
-__device__ __forceinline__ void for_spans3(const float4* __restrict__ sorted, int s0, int e0, int s1, int e1, int s2, int e2, F&& f)
+template <typename ST, typename F>
+__device__ __forceinline__ void for_spans3(const ST& st, int s0, int e0, int s1, int e1, int s2, int e2, F&& f)
 {
     const int n0 = e0 - s0, n01 = n0 + (e1 - s1), tot = n01 + (e2 - s2);
     const int d1 = s1 - n0, d2 = s2 - n01;   // stream position -> array index: + s0, + d1 or + d2 depending on the span
-    auto at = [&](int k) { k = min(k, tot - 1); return sorted + (k + (k < n0 ? s0 : (k < n01 ? d1 : d2))); };
+    auto at = [&](int k) { k = min(k, tot - 1); return k + (k < n0 ? s0 : (k < n01 ? d1 : d2)); };
 #pragma unroll 1
     for (int k = 0; k < tot; k += 4) {
-        const float4 t0 = ld_point(at(k)), t1 = ld_point(at(k + 1)), t2 = ld_point(at(k + 2)), t3 = ld_point(at(k + 3));
+        const float4 t0 = st.point(at(k)), t1 = st.point(at(k + 1)), t2 = st.point(at(k + 2)), t3 = st.point(at(k + 3));
         f(t0); f(t1); f(t2); f(t3);
     }
 }
@@ -460,19 +486,16 @@ __device__ __forceinline__ float assoc_window_dist(const AssocQuery& Q)
 }
 // Per-thread part: up to dmax bins per side.  Returns false when the window needs more than that (the warp pass
 // restarts it).
-template <bool CORNER>
-__device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuery& pq, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int dmax)
+template <bool CORNER, typename ST>
+__device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuery& pq, const ST& st, int NB, int R, int dmax)
 {
     const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
-    auto header = [&](int off, int& s, int& e) {
-        const int* h = start + ((pq.b0 + off) & (NB - 1)) * R + r_lo;  // NB is a power of two
-        s = __ldg(h); e = __ldg(h + r_n);
-    };
+    auto header = [&](int off, int& s, int& e) { s = st.header(pq.b0 + off, r_lo); e = st.header(pq.b0 + off, r_lo + r_n); };
     auto consider = [&](const float4 t) { assoc_consider<CORNER>(Q, t); };
     const int near = pq.frac < 0.5f ? -1 : 1;
     int s0, e0, s1, e1;
     header(0, s0, e0); header(near, s1, e1);
-    for_spans3(sorted, s0, e0, s1, e1, 0, 0, consider);
+    for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
     int kl, kr;
 #pragma unroll 1
     for (int k = 1;; ++k) {
@@ -482,7 +505,7 @@ __device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuer
         s0 = e0 = s1 = e1 = 0;
         if (k <= kl && !(k == 1 && near < 0)) header(-k, s0, e0);
         if (k <= kr && !(k == 1 && near > 0)) header(k, s1, e1);
-        for_spans3(sorted, s0, e0, s1, e1, 0, 0, consider);
+        for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
     }
 }
 // Warp part: one query's whole ring window, the bins in reach shared out over the lanes (at most 16 per side and
@@ -593,26 +616,32 @@ __device__ __forceinline__ void nn_consider(u64& best, float qx, float qy, float
     const u64 key = ((u64)__float_as_uint(d2) << 32) | ((unsigned)__float_as_int(t.w) & 0xFFFFFFu);
     if (key < best) best = key;   // NaN distances have bits above 25.0f's and never win
 }
+// the same, remembering the winner's ring (bits 24..31 of .w)
+__device__ __forceinline__ void nn_consider_ring(u64& best, int& best_ring, float qx, float qy, float qz, const float4 t)
+{
+    const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
+    const unsigned bits = (unsigned)__float_as_int(t.w);
+    const u64 key = ((u64)__float_as_uint(d2) << 32) | (bits & 0xFFFFFFu);
+    if (key < best) { best = key; best_ring = (int)(bits >> 24); }
+}
 // Per-thread search.  Returns true when `best` is final; false = too wide for one thread (best = what was found so
 // far, the warp pass restarts from it).
-__device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R,
-                                                     float qx, float qy, float qz, int kmax, PolarQuery& pq, u64& best, int& reach_buckets)
+template <typename ST>
+__device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const ST& st, int NB, int R, float qx, float qy, float qz, int kmax, PolarQuery& pq, u64& best,
+                                                     int& best_ring, int& reach_buckets)
 {
     {
         int lo = 0, hi = R;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.ehi[mid] < pq.eq) lo = mid + 1; else hi = mid; }
         pq.r0 = min(lo, R - 1);
     }
-    auto consider = [&](const float4 t) { nn_consider(best, qx, qy, qz, t); };
-    auto span = [&](int off, int ra, int rb, int& s, int& e) {
-        const int* h = start + ((pq.b0 + off) & (NB - 1)) * R;   // NB is a power of two
-        s = __ldg(h + ra); e = __ldg(h + rb + 1);
-    };
+    auto consider = [&](const float4 t) { nn_consider_ring(best, best_ring, qx, qy, qz, t); };
+    auto span = [&](int off, int ra, int rb, int& s, int& e) { s = st.header(pq.b0 + off, ra); e = st.header(pq.b0 + off, rb + 1); };
     // seed: rings r0-1 .. r0+1 of the own bin and its two neighbours, one stream
     const int sa = max(pq.r0 - 1, 0), sb = min(pq.r0 + 1, R - 1);
     int s0, e0, s1, e1, s2, e2;
     span(0, sa, sb, s0, e0); span(-1, sa, sb, s1, e1); span(1, sa, sb, s2, e2);
-    for_spans3(sorted, s0, e0, s1, e1, s2, e2, consider);
+    for_spans3(st, s0, e0, s1, e1, s2, e2, consider);
     PolarReach W = polar_reach(S, pq, NB, R, best);
     if (W.ra >= sa && W.rb <= sb && W.kl <= 1 && W.kr <= 1) return true;   // nothing closer can lie outside the seed
     reach_buckets = (W.kl + W.kr + 1) * (W.rb - W.ra + 1);
@@ -627,7 +656,7 @@ __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const i
         s0 = e0 = s1 = e1 = 0;
         if (k >= 1 && k <= W.kl) span(-k, W.ra, W.rb, s0, e0);
         if (k <= W.kr) span(k, W.ra, W.rb, s1, e1);
-        for_spans3(sorted, s0, e0, s1, e1, 0, 0, consider);
+        for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
     }
 }
 // Warp version (one query per warp; bands read from global memory): every step streams the rings in reach of up to
@@ -729,34 +758,30 @@ __device__ __forceinline__ void assoc_query_init(const OdomParams& P, const Lane
 #define ASSOC_OPEN_BIT (1 << 29)
 
 // Per-thread pass.  Writes the correspondences of the queries it resolves, queues the others for k_odom_assoc_heavy.
-template <bool CORNER>
-__device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const RingBands& S, const LaneState& L, int b, int i, bool active, int dmax, int kmax)
+// Q / pq arrive initialised (query point, own azimuth bin); st = where the polar index is read from.
+template <bool CORNER, typename ST>
+__device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const RingBands& S, const ST& st, const LaneState& L, int b, int i, bool active, int dmax, int kmax,
+                                                  AssocQuery& Q, PolarQuery& pq)
 {
     const int lane = lane_id();
-    AssocQuery Q;
-    Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0; Q.cut = D2_BITS_25 - 1u;
     int4 entry = make_int4(b, CORNER ? i : (i | ASSOC_PLANE_BIT), -1, -1);
     bool heavy = false, is_long = false;
     if (active) {
-        assoc_query_init<CORNER>(P, L, b, i, Q);
-        const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
         const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
         u64 best = NN_NONE;
-        PolarQuery pq;
-        polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
+        int best_ring = 0;
         if (Q.n > 0) {
             int reach_buckets = 0;
-            heavy = !polar_nearest_thread(S, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best, reach_buckets);
+            heavy = !polar_nearest_thread(S, st, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best, best_ring, reach_buckets);
             is_long = heavy && reach_buckets > 200;   // these take tens of microseconds each: they must start first
             if (heavy) { entry.y |= ASSOC_OPEN_BIT; entry.z = (int)(unsigned)(best >> 32); entry.w = (int)(unsigned)best; }
         }
         if (!heavy && best != NN_NONE) {  // d2 < 25: LO:497 / LO:659
-            const float4* last = CORNER ? P.lsharp[last_slot(L)] + (size_t)b * P.R * LL_LSHARP_PER_RING : P.lflat[last_slot(L)] + (size_t)b * P.Nmax;
             Q.closest = (int)(unsigned)best;
-            Q.cring = (int)last[Q.closest].w;  // int(intensity), LO:500 / LO:664
+            Q.cring = best_ring;               // int(intensity) of the closest point (LO:500 / LO:664): the index carries it for ring-monotone clouds
             int pending = -2;                  // clouds that are not ring-sorted: literal walk
             if (CORNER ? L.mono_corner : L.mono_surf) {
-                pending = assoc_ring_window<CORNER>(Q, pq, av.start, av.sorted, NB, P.R, dmax) ? -3 : -1;
+                pending = assoc_ring_window<CORNER>(Q, pq, st, NB, P.R, dmax) ? -3 : -1;
                 heavy = pending == -1;
             } else {
                 heavy = true;
@@ -782,6 +807,23 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
         }
     }
 }
+template <bool CORNER>
+__device__ __forceinline__ void assoc_thread_query_global(const OdomParams& P, const RingBands& S, const LaneState& L, int b, int i, bool active, int dmax, int kmax)
+{
+    AssocQuery Q;
+    Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0; Q.cut = D2_BITS_25 - 1u;
+    PolarQuery pq;
+    pq.rho = pq.qn = pq.eq = pq.frac = pq.inv_w = 0.f; pq.b0 = pq.r0 = 0;
+    const KnnGrid& G = CORNER ? P.ac : P.as_;
+    const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
+    StageGlobal st;
+    st.start = G.start + (size_t)b * (G.T + 1); st.sorted = G.sorted + (size_t)b * G.cap; st.NB = NB; st.R = P.R;
+    if (active) {
+        assoc_query_init<CORNER>(P, L, b, i, Q);
+        polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
+    }
+    assoc_thread_pass<CORNER>(P, S, st, L, b, i, active, dmax, kmax, Q, pq);
+}
 // grid: (ceil(R*12 / T) + ceil(R*24 / T), B): corner queries and plane queries never share a block
 template <int MINB>
 __global__ void __launch_bounds__(ASSOC_THREADS, MINB) k_odom_assoc(OdomParams P, int corner_blocks, int dmax, int kmax)
@@ -789,7 +831,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS, MINB) k_odom_assoc(OdomParams P
     __shared__ RingBands S;
     const int b = blockIdx.y;
     const LaneState& L = P.lane[b];
-    if (!L.inited) return;
+    if (!L.inited || L.err) return;
     const bool corner = (int)blockIdx.x < corner_blocks;
     const int i = (corner ? blockIdx.x : blockIdx.x - corner_blocks) * (int)blockDim.x + threadIdx.x;   // blockDim.x <= ASSOC_THREADS
     const int n = corner ? L.n_sharp : L.n_flat;
@@ -801,8 +843,187 @@ __global__ void __launch_bounds__(ASSOC_THREADS, MINB) k_odom_assoc(OdomParams P
         __syncthreads();
     }
     if ((i & ~31) >= n) return;   // whole warp idle
-    if (corner) assoc_thread_pass<true>(P, S, L, b, i, i < n, dmax, kmax);
-    else assoc_thread_pass<false>(P, S, L, b, i, i < n, dmax, kmax);
+    if (corner) assoc_thread_query_global<true>(P, S, L, b, i, i < n, dmax, kmax);
+    else assoc_thread_query_global<false>(P, S, L, b, i, i < n, dmax, kmax);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Slab form of the thread pass (the default): the polar index is bin-major, so the buckets of a range of azimuth bins
+// - all rings - are ONE contiguous span of the bucket-sorted array.  k_odom_queries transforms the lane's feature
+// points once per outer iteration (TransformToStart) and groups them by azimuth slab; one CTA of k_odom_assoc_slab
+// then takes one (slab, lane): it pulls the slab's span plus `halo` bins on each side into shared memory with TMA bulk
+// copies (cp.async.bulk + mbarrier; two pieces when the range wraps past bin NB - 1), rewrites the bucket headers of
+// those bins to positions inside the staged array, and runs the same per-thread searches as above out of shared
+// memory: every target point crosses the memory system once per slab as part of a bulk copy instead of once per
+// visiting query as a dependent 16-byte load.  A thread walks at most `halo` bins to either side (kmax = dmax = halo),
+// so it never leaves the stage; what needs more goes to the warp pass as before.  A span that does not fit the
+// CTA's shared memory (a direction crowded with points) is searched in global memory by the same code.
+// ------------------------------------------------------------------------------------------------------
+struct SlabParams {
+    float4* qa;        // [B][R*36] x, y, z of the transformed query, w = feature index bits
+    float4* qb;        // [B][R*36] elevation angle, position inside the azimuth bin, own bin (int bits), unused
+    int* qstart;       // [B][ns_corner + ns_surf + 2] slab offsets into qa / qb (corner slabs, then surf slabs from R*12)
+    int ns_corner, ns_surf;       // slabs per table
+    int slab_corner, slab_surf;   // bins per slab
+    int halo_corner, halo_surf;
+    int pcap;                     // points the stage of one CTA holds
+};
+#define QPREP_THREADS 1024
+__global__ void __launch_bounds__(QPREP_THREADS) k_odom_queries(OdomParams P, SlabParams Sp)
+{
+    __shared__ int cnt[2][130];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const LaneState& L = P.lane[b];
+    const int nsl[2] = {Sp.ns_corner, Sp.ns_surf};
+    int* qs = Sp.qstart + (size_t)b * (Sp.ns_corner + Sp.ns_surf + 2);
+    for (int k = tid; k < 2 * 130; k += QPREP_THREADS) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    const bool live = L.inited && !L.err;
+    const int ns = live ? L.n_sharp : 0, nf = live ? L.n_flat : 0;
+    const int maxc = P.R * LL_SHARP_PER_RING;
+    // work items: corner i = tid (R*12 <= 768), planes i = tid, tid + 1024 (R*24 <= 1536)
+    float4 a[3], c[3];
+    int slab[3], slot[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const bool corner = u == 0;
+        const int i = corner ? tid : tid + (u - 1) * QPREP_THREADS;
+        slab[u] = -1;
+        if (i < (corner ? ns : nf)) {
+            AssocQuery Q;
+            if (corner) assoc_query_init<true>(P, L, b, i, Q); else assoc_query_init<false>(P, L, b, i, Q);
+            PolarQuery pq;
+            const int NB = corner ? P.az_bins_corner : P.az_bins_surf;
+            polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
+            a[u] = make_float4(Q.qx, Q.qy, Q.qz, __int_as_float(i));
+            c[u] = make_float4(pq.eq, pq.frac, __int_as_float(pq.b0), 0.f);
+            slab[u] = pq.b0 / (corner ? Sp.slab_corner : Sp.slab_surf);
+            slot[u] = atomicAdd(&cnt[corner ? 0 : 1][slab[u]], 1);
+        }
+    }
+    __syncthreads();
+    if (tid < 64) {   // exclusive scans of the two count arrays (<= 128 slabs each), one warp each
+        const int t = tid >> 5, ln = tid & 31;
+        int run = 0;
+        for (int k0 = 0; k0 < nsl[t]; k0 += 32) {
+            const int k = k0 + ln;
+            const int v = k < nsl[t] ? cnt[t][k] : 0;
+            int incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(LL_FULL_MASK, incl, d); if (ln >= d) incl += o; }
+            if (k < nsl[t]) cnt[t][k] = run + incl - v;
+            run += __shfl_sync(LL_FULL_MASK, incl, 31);
+        }
+        if (ln == 0) cnt[t][nsl[t]] = run;
+    }
+    __syncthreads();
+    for (int k = tid; k <= Sp.ns_corner; k += QPREP_THREADS) qs[k] = cnt[0][k];
+    for (int k = tid; k <= Sp.ns_surf; k += QPREP_THREADS) qs[Sp.ns_corner + 1 + k] = maxc + cnt[1][k];
+    float4* qa = Sp.qa + (size_t)b * P.R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
+    float4* qb = Sp.qb + (size_t)b * P.R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        if (slab[u] < 0) continue;
+        const int pos = (u == 0 ? 0 : maxc) + cnt[u == 0 ? 0 : 1][slab[u]] + slot[u];
+        qa[pos] = a[u];
+        qb[pos] = c[u];
+    }
+}
+
+template <bool CORNER, typename ST>
+__device__ __forceinline__ void slab_queries(const OdomParams& P, const SlabParams& Sp, const RingBands& S, const ST& st, const LaneState& L, int b, int q0, int q1, int halo)
+{
+    const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
+    const float4* qa = Sp.qa + (size_t)b * P.R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
+    const float4* qb = Sp.qb + (size_t)b * P.R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
+    const int n_last = CORNER ? L.n_last_corner : L.n_last_surf;
+    for (int base = q0 + (int)(threadIdx.x & ~31u); base < q1; base += (int)blockDim.x) {   // warps stay whole: the queue push uses ballots
+        const int q = base + lane_id();
+        const bool active = q < q1;
+        AssocQuery Q;
+        Q.qx = Q.qy = Q.qz = 0.f; Q.k2 = Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.n = 0; Q.cut = D2_BITS_25 - 1u;
+        PolarQuery pq;
+        pq.rho = pq.qn = pq.eq = pq.frac = pq.inv_w = 0.f; pq.b0 = pq.r0 = 0;
+        int i = 0;
+        if (active) {
+            const float4 a = __ldg(qa + q), c = __ldg(qb + q);
+            Q.qx = a.x; Q.qy = a.y; Q.qz = a.z; Q.n = n_last;
+            i = __float_as_int(a.w);
+            pq.rho = sqrtf(a.x * a.x + a.y * a.y);
+            pq.qn = sqrtf(pq.rho * pq.rho + a.z * a.z);
+            pq.eq = c.x; pq.frac = c.y; pq.b0 = __float_as_int(c.z);
+            pq.inv_w = (float)NB * 0.15915494f;
+        }
+        assoc_thread_pass<CORNER>(P, S, st, L, b, i, active, halo, halo, Q, pq);
+    }
+}
+
+#define SLAB_THREADS 128
+template <bool CORNER>
+__device__ __forceinline__ void slab_cta(const OdomParams& P, const SlabParams& Sp, RingBands& S, unsigned char* smem, uint64_t* bar, const LaneState& L, int b, int slab)
+{
+    const int tid = threadIdx.x;
+    const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf, R = P.R;
+    const int sl = CORNER ? Sp.slab_corner : Sp.slab_surf, halo = CORNER ? Sp.halo_corner : Sp.halo_surf;
+    const int* qs = Sp.qstart + (size_t)b * (Sp.ns_corner + Sp.ns_surf + 2) + (CORNER ? 0 : Sp.ns_corner + 1);
+    const int q0 = __ldg(qs + slab), q1 = __ldg(qs + slab + 1);
+    if (q1 <= q0) return;
+    const KnnGrid& G = CORNER ? P.ac : P.as_;
+    const int* start = G.start + (size_t)b * (G.T + 1);
+    const float4* sorted = G.sorted + (size_t)b * G.cap;
+    // staged bins: [slab * sl - halo, slab * sl + sl + halo) modulo NB, or the whole table when that is all of it
+    int nb = sl + 2 * halo, lo = (slab * sl - halo) & (NB - 1);
+    if (nb >= NB) { nb = NB; lo = 0; }
+    const int hiA = min(lo + nb, NB), nbB = lo + nb - hiA;          // piece A: bins [lo, hiA), piece B (wrap): bins [0, nbB)
+    const int n_total = __ldg(start + NB * R);
+    const int pA0 = __ldg(start + lo * R), pA1 = __ldg(start + hiA * R), pB1 = nbB > 0 ? __ldg(start + nbB * R) : 0;
+    const int lenA = pA1 - pA0, lenB = pB1;
+    int* hdr = reinterpret_cast<int*>(smem);
+    float4* pts = reinterpret_cast<float4*>(smem + (((size_t)(sl + 2 * halo) * R + 1) * 4 + 15) / 16 * 16);
+    {
+        const float* bd = P.bands[CORNER ? 0 : 1] + (size_t)b * BAND_STRIDE;
+        if (tid < R) { S.elo[tid] = __ldg(bd + tid); S.ehi[tid] = __ldg(bd + LL_MAX_RINGS + tid); }
+        if (tid == 0) S.ordered = __ldg(reinterpret_cast<const int*>(bd) + 2 * LL_MAX_RINGS);
+    }
+    if (lenA + lenB > Sp.pcap) {   // does not fit: the same searches out of global memory
+        __syncthreads();
+        StageGlobal st;
+        st.start = start; st.sorted = sorted; st.NB = NB; st.R = R;
+        slab_queries<CORNER>(P, Sp, S, st, L, b, q0, q1, halo);
+        return;
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)(lenA + lenB) * 16u;
+        if (bytes) {
+            mbar_expect_tx(bar, bytes);
+            if (lenA) tma_bulk_copy(pts, sorted + pA0, (uint32_t)lenA * 16u, bar);
+            if (lenB) tma_bulk_copy(pts + lenA, sorted, (uint32_t)lenB * 16u, bar);
+        }
+    }
+    // headers of the staged bins, rewritten to positions inside `pts` (piece B sits behind piece A)
+    for (int h = tid; h <= nb * R; h += SLAB_THREADS) {
+        const int g = lo * R + h;   // header index on the unwrapped bin axis
+        hdr[h] = g <= NB * R ? __ldg(start + g) - pA0 : __ldg(start + (g - NB * R)) + (n_total - pA0);
+    }
+    __syncthreads();   // headers and bands visible, mbarrier initialised
+    if (lenA + lenB > 0) mbar_wait(bar, 0);
+    StageShared st;
+    st.hdr = smem_u32(hdr); st.pts = smem_u32(pts); st.bin0 = lo; st.NB = NB; st.R = R;
+    slab_queries<CORNER>(P, Sp, S, st, L, b, q0, q1, halo);
+}
+template <int MINB>
+__global__ void __launch_bounds__(SLAB_THREADS, MINB) k_odom_assoc_slab(OdomParams P, SlabParams Sp)
+{
+    extern __shared__ __align__(128) unsigned char slab_smem[];
+    __shared__ RingBands S;
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.y;
+    const LaneState& L = P.lane[b];
+    if (!L.inited || L.err) return;
+    // surf slabs first: they carry the larger stages
+    if ((int)blockIdx.x < Sp.ns_surf) slab_cta<false>(P, Sp, S, slab_smem, &bar, L, b, blockIdx.x);
+    else slab_cta<true>(P, Sp, S, slab_smem, &bar, L, b, blockIdx.x - Sp.ns_surf);
 }
 
 // One WARP per queued query, the queue spread over a fixed grid: the long searches (no target nearby, wide ring
@@ -874,7 +1095,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
     const int maxp = P.R * LL_FLAT_PER_RING;
     const int b = blockIdx.x, tid = threadIdx.x;
     LaneState& L = P.lane[b];
-    if (!L.inited) { if (tid == 0) L.n_blocks = 0; return; }
+    if (!L.inited || L.err) { if (tid == 0) L.n_blocks = 0; return; }
     const int ns = L.n_sharp, nf = L.n_flat, slot = last_slot(L);
     const float4* sharp = P.sharp + (size_t)b * P.R * LL_SHARP_PER_RING;
     const float4* flat = P.flat + (size_t)b * P.R * LL_FLAT_PER_RING;
@@ -954,7 +1175,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_odom_vote(OdomParams P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.y, reg = blockIdx.x, tid = threadIdx.x;
     LaneState& L = P.lane[b];
-    if (!L.inited || !(L.now_frame > P.graph_from_frame)) return;  // LO:781 / LO:794
+    if (!L.inited || L.err || !(L.now_frame > P.graph_from_frame)) return;  // LO:781 / LO:794
     const int nplane = L.n_plane_corr, ncorner = L.n_corner_corr;
     const int region_len = nplane / 10;                              // LO:202-215
     const int r0 = region_len * reg, r1 = reg == 9 ? nplane : region_len * (reg + 1);
@@ -1023,16 +1244,27 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P)
 {
     const int b = blockIdx.x;
     LaneState& L = P.lane[b];
-    if (!L.inited) return;
+    if (!L.inited || L.err) return;
     lm_solve(P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap, P.nblk_cap, L.n_blocks, L.para_q, L.para_t, &L, P.outer);
 }
 
 // LO:830-831 pose accumulation; LO:882-896 swap (the grids are rebuilt right after); counters LO:925-926
-__global__ void k_odom_finalize(LaneState* lane, double* pose_out, int n_lanes)
+__global__ void k_odom_finalize(LaneState* lane, double* pose_out, int* status, int n_lanes)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_lanes) return;
     LaneState& L = lane[b];
+    status[b] = L.err;
+    if (L.err) {
+        // a scan the feature stage rejected (no valid point, ring over capacity) does not advance the stream: pose, *Last
+        // clouds, warm start and frame counter stay as they were; the caller sees the code in the lane's status
+        if (pose_out) {
+            double* o = pose_out + (size_t)b * 14;
+            for (int k = 0; k < 4; ++k) { o[k] = L.q_w[k]; o[7 + k] = L.q_w[k]; }
+            for (int k = 0; k < 3; ++k) { o[4 + k] = L.t_w[k]; o[11 + k] = L.t_w[k]; }
+        }
+        return;
+    }
     if (!L.inited) {
         L.inited = 1;  // LO:427-431
     } else {
@@ -1132,9 +1364,41 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<gidx, 256, 0, s>>>(S, c->d_lane); }
         c->launches += 4;
     }
+    // slab form of the thread pass (LL_ASSOC_SLAB=1) or the global-memory form
+    const bool slab_mode = getenv("LL_ASSOC_SLAB") && atoi(getenv("LL_ASSOC_SLAB")) == 1;
+    SlabParams Sp;
+    auto env_pow2 = [](const char* name, int dflt, int lo, int hi) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; if (v < lo || v > hi || (v & (v - 1))) v = dflt; return v; };
+    auto env_int = [](const char* name, int dflt, int lo, int hi) { const char* e = getenv(name); const int v = e ? atoi(e) : dflt; return v < lo || v > hi ? dflt : v; };
+    Sp.qa = c->d_qa; Sp.qb = c->d_qb; Sp.qstart = c->d_qstart;
+    Sp.slab_surf = env_pow2("LL_SLAB_SURF", 16, 1, c->az_bins_surf); Sp.slab_corner = env_pow2("LL_SLAB_CORNER", 8, 1, c->az_bins_corner);
+    while (c->az_bins_surf / Sp.slab_surf > 128) Sp.slab_surf <<= 1;
+    while (c->az_bins_corner / Sp.slab_corner > 128) Sp.slab_corner <<= 1;
+    Sp.ns_surf = c->az_bins_surf / Sp.slab_surf; Sp.ns_corner = c->az_bins_corner / Sp.slab_corner;
+    Sp.halo_surf = env_int("LL_HALO_SURF", 4, 1, 64); Sp.halo_corner = env_int("LL_HALO_CORNER", 2, 1, 64);
+    const int slab_minb = env_int("LL_SLAB_MINB", 3, 1, 3);
+    const size_t hdr_bins = (size_t)((Sp.slab_surf + 2 * Sp.halo_surf) > (Sp.slab_corner + 2 * Sp.halo_corner) ? (Sp.slab_surf + 2 * Sp.halo_surf) : (Sp.slab_corner + 2 * Sp.halo_corner));
+    const size_t hdr_bytes = ((hdr_bins * c->R + 1) * 4 + 15) / 16 * 16;
+    Sp.pcap = env_int("LL_SLAB_PCAP", 4032, 64, 13000);
+    const size_t slab_smem = hdr_bytes + (size_t)Sp.pcap * 16;
+    if (slab_mode && !c->slab_attr_set) {
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_assoc_slab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_assoc_slab<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_assoc_slab<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        c->slab_attr_set = true;
+    }
+    if (slab_mode && slab_smem > (size_t)(slab_minb >= 3 ? 72 : (slab_minb == 2 ? 110 : 220)) * 1024) { c->last_error = "slab stage larger than the shared memory of the chosen occupancy"; return LL_E_INVAL; }
+    if (Sp.ns_surf + Sp.ns_corner + 2 > c->qstart_stride) { c->last_error = "too many slabs"; return LL_E_INVAL; }
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
-        {
+        if (slab_mode) {
+            { LLProf pr(c, "k_odom_queries"); k_odom_queries<<<n_lanes, QPREP_THREADS, 0, s>>>(P, Sp); }
+            LLProf pr(c, "k_odom_assoc");
+            const dim3 g(Sp.ns_surf + Sp.ns_corner, n_lanes);
+            if (slab_minb >= 3) k_odom_assoc_slab<3><<<g, SLAB_THREADS, slab_smem, s>>>(P, Sp);
+            else if (slab_minb == 2) k_odom_assoc_slab<2><<<g, SLAB_THREADS, slab_smem, s>>>(P, Sp);
+            else k_odom_assoc_slab<1><<<g, SLAB_THREADS, slab_smem, s>>>(P, Sp);
+            c->launches += 1;
+        } else {
             LLProf pr(c, "k_odom_assoc");
             const dim3 g(cblocks + pblocks, n_lanes);
             if (minb >= 12) k_odom_assoc<12><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
@@ -1148,7 +1412,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, lm_threads, 0, s>>>(P); }
         c->launches += 5;
     }
-    { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, n_lanes); }
+    { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, c->d_status, n_lanes); }
     c->launches += 1;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;

@@ -466,8 +466,10 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         __syncthreads();
     }
     if (tid == 0 && part == 0) {  // every part holds the same result; one writes it
-        for (int i = 0; i < 4; ++i) q_io[i] = S.x[i];
-        for (int i = 0; i < 3; ++i) t_io[i] = S.x[4 + i];
+        if (!S.comm_dead) {       // a collective that timed out leaves partial sums behind: the parameters stay untouched (L->err = LL_E_NCCL)
+            for (int i = 0; i < 4; ++i) q_io[i] = S.x[i];
+            for (int i = 0; i < 3; ++i) t_io[i] = S.x[4 + i];
+        }
         if (dist) comm->seq_out[comm_b] = seq;
         if (L) {
             L->initial_cost[slot] = C.initial_cost;

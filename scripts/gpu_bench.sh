@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -${TAILN:-6}
+if [ -n "$TESTS" ]; then timeout 1500 python -m pytest tests -m gpu -x -q $TESTS 2>&1 | tail -${TAILN:-8}; fi
 timeout 900 python bench.py --steps ${STEPS:-20} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench_latest.json 2> gpurun_out/bench_latest.err
 tail -3 gpurun_out/bench_latest.err
 python -c "

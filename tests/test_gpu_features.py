@@ -95,12 +95,12 @@ def test_degenerate_inputs(ll, orc):
 
 
 def test_ring_capacity_switch_and_overflow(ll, orc):
-    # 3200 points per ring needs the 1024-key sector sort; with the default capacity it must report LL_E_CAPACITY
+    # 3200 points per ring needs the 1024-key sector sort; a context created with the 512-key capacity must report LL_E_CAPACITY
     scan = ll.synth.scan(16, 2, az_steps=3200)
     big = ll.Context(scan_line=16, max_points=65536, max_ring_points=3300)
     _compare(big.extract_features(scan), orc.extract_features(scan, orc.config(16, voxel_stable=1)))
     big.close()
-    small = ll.Context(scan_line=16, max_points=65536)
+    small = ll.Context(scan_line=16, max_points=65536, max_ring_points=3083)
     with pytest.raises(ll.LightLoamError):
         small.extract_features(scan)
     small.close()
@@ -134,7 +134,51 @@ def test_pointcloud2_wire_format_in_and_out(ll):
         assert raw.shape == (len(ref[k]), 32)
         f = raw.view(np.float32).reshape(-1, 8)
         assert np.array_equal(f[:, 0:3], ref[k][:, 0:3]) and np.array_equal(f[:, 4], ref[k][:, 3]), k
-        assert not f[:, 3].any() and not f[:, 5:8].any(), k   # padding zeroed
+        assert (f[:, 3] == 1.0).all() and not f[:, 5:8].any(), k   # data[3] = 1.0f (PCL_ADD_POINT4D), the rest of the padding zeroed
     with pytest.raises(Exception):
         ctx.fetch_pointcloud2(0, cap_points=10)             # LL_E_CAPACITY
     ctx.close()
+
+
+def test_arbitrary_point_step_records(ll, orc):
+    """PointCloud2 layouts pcl::fromROSMsg accepts (SR:105-106) beyond the 12..32-byte in-place range: 22-byte XYZIRT
+    (not a multiple of 4) and 48-byte records are gathered to xyz by the strided copy; results equal the float4 path."""
+    scan = ll.synth.scan(16, 1)
+    ctx = ll.Context(scan_line=16)
+    want = ctx.extract_features(scan)
+    for step in (22, 48, 12, 20):
+        raw = np.zeros((len(scan), step), np.uint8)
+        raw[:, :12] = np.ascontiguousarray(scan[:, :3]).view(np.uint8).reshape(-1, 12)
+        raw[:, 12:] = 0xAB                                      # whatever else the driver packs behind x,y,z
+        got = ctx.extract_features(raw)
+        for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+            assert np.array_equal(got[key], want[key]), (step, key)
+        assert np.array_equal(got["full"][:, :3], want["full"][:, :3])
+    ctx.close()
+
+
+def test_rings_longer_than_3083_points_take_the_wide_sector_kernels(ll, orc):
+    """Default ring capacity is 6155 points (real HDL-64 scanIDs that collect two lasers, VLP-16 at 5 Hz): rings above
+    3083 points run the 1024-key sector variants next to the 512-key ones; feature indices stay bit-exact.  A context
+    created with the small capacity rejects the same scan with LL_E_CAPACITY and leaves the lane where it was."""
+    line, az = 16, 4000
+    scan = ll.synth.scan(line, 0, az_steps=az)
+    ocfg = orc.config(line, voxel_stable=1)
+    o = orc.extract_features(scan, ocfg)
+    assert np.diff(o["ring_begin"]).max() > 3083
+    ctx = ll.Context(scan_line=line, max_points=65536)
+    g = ctx.extract_features(scan)
+    for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+        assert np.array_equal(g[key], o[key]), key
+    assert np.array_equal(g["curvature"], o["curvature"])
+    assert np.array_equal(g["less_flat"], o["less_flat"])
+    # mixed: a normal scan through the same context still takes the fast path with identical results
+    s2 = ll.synth.scan(line, 1)
+    g2, o2 = ctx.extract_features(s2), orc.extract_features(s2, ocfg)
+    for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+        assert np.array_equal(g2[key], o2[key]), key
+    ctx.close()
+    small = ll.Context(scan_line=line, max_points=65536, max_ring_points=3083)
+    with pytest.raises(ll.capi.LightLoamError):
+        small.extract_features(scan)
+    small.close()

@@ -247,3 +247,92 @@ def test_odometry_step_reads_pointxyzi_payloads_in_place(ll, orc):
         pb = b.odometry_step(wire(f["sharp"]), wire(f["less_sharp"]), wire(f["flat"]), wire(f["less_flat"]))
         assert np.array_equal(pa["q_w"], pb["q_w"]) and np.array_equal(pa["t_w"], pb["t_w"]), k
     a.close(); b.close()
+
+
+def test_bench_configuration_parity_256_lanes(ll, orc):
+    """The configuration bench.py times (HDL-64, 256 lanes, scan pool path, 256-thread solve CTAs, two per SM) against the
+    oracle: 9 steps (past now_frame > 5), 8 sampled lanes incl. lanes >= 149 and lane 255.  Feature indices and association
+    index triples bit-exact, per-step pose <= 1e-9 (same voxel order) and <= 1e-4 m / rad (reference-faithful order)."""
+    import bench
+    B, steps = 256, 9
+    lanes = [0, 37, 100, 148, 149, 200, 254, 255]
+    pool = bench.make_pool(ll, bench.POOL_SCANS)
+    ctx = ll.Context(scan_line=64, batch=B)
+    ctx.pool_upload(pool)
+    ocfg = orc.config(64, voxel_stable=1)
+    odos = {i: orc.Odometry(ocfg) for i in lanes}
+    faithful = {i: orc.Pipeline(orc.config(64, voxel_stable=0), with_mapping=False) for i in lanes}
+    for k in range(steps):
+        ids = bench.lane_ids(k, B, 0)
+        assert len(set(ids.tolist())) == B                      # every lane reads its own scan
+        pg = ctx.process_pool(ids)
+        assert not ctx.lane_status().any()
+        for i in lanes:
+            scan = pool[int(ids[i])]
+            f = orc.extract_features(scan, ocfg)
+            gf = ctx.debug_features(i)
+            for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+                assert np.array_equal(gf[key], f[key]), (k, i, key)
+            po = odos[i].step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+            assert np.abs(pg[i][4:7] - po["t_w"]).max() < 1e-9 and np.abs(pg[i][0:4] - po["q_w"]).max() < 1e-9, (k, i)
+            pf = faithful[i].step(scan)
+            assert np.abs(pg[i][4:7] - pf["t_odom"]).max() < 1e-4 and _ang(pg[i][0:4], pf["q_odom"]) < 1e-4, (k, i)
+            if k == 0:
+                continue
+            oc, op = odos[i].assoc(len(f["sharp"]), len(f["flat"]))
+            gc, gp = ctx.debug_assoc(i)
+            gc, gp = gc[:len(f["sharp"])], gp[:len(f["flat"])]
+            got_c = np.array([[q, a, b] for q, (a, b) in enumerate(gc) if b >= 0], np.int32).reshape(-1, 3)
+            got_p = np.array([[q, a, b, c] for q, (a, b, c, _) in enumerate(gp) if a >= 0], np.int32).reshape(-1, 4)
+            assert np.array_equal(got_c, oc), (k, i)
+            assert np.array_equal(got_p, op), (k, i)
+    ctx.close()
+
+
+def test_packed_submit_equals_per_scan_calls(ll):
+    """ll_submit_packed (one host arena of packed 12-byte xyz records, one copy per batch) == ll_process_scans on float4 scans."""
+    line, B, n = 16, 3, 5
+    a = ll.Context(scan_line=line, batch=B)
+    b = ll.Context(scan_line=line, batch=B)
+    for k in range(n):
+        scans = [ll.synth.scan(line, k + 2 * i) for i in range(B)]
+        pa = a.process_scans(scans)
+        xyz = [np.ascontiguousarray(s[:, :3]) for s in scans]
+        offs = np.concatenate([[0], np.cumsum([x.nbytes for x in xyz])]).astype(np.int64)
+        arena = np.concatenate([x.reshape(-1) for x in xyz]).view(np.uint8)
+        b.submit_packed(arena, offs[:-1], [len(x) for x in xyz], 12)
+        pb = b.collect()
+        assert np.array_equal(pa, pb), k
+    a.close()
+    b.close()
+
+
+def test_lane_status_bad_scan_does_not_advance_the_stream(ll):
+    """A scan without a valid point (the reference would index points[0] of an empty cloud, SR:114): the lane reports
+    LL_E_EMPTY in its status, the call returns that code after writing every pose, and the lane's state is untouched -
+    the next good scan continues as if the bad one had never arrived.  Other lanes are not affected."""
+    line = 16
+    ctx = ll.Context(scan_line=line, batch=2)
+    ref = ll.Context(scan_line=line, batch=2)
+    bad = np.full((500, 4), np.nan, np.float32)
+    seq = [ll.synth.scan(line, k) for k in range(5)]
+    for k in range(5):
+        p = ctx.process_scans([seq[k], seq[k]])
+        r = ref.process_scans([seq[k], seq[k]])
+        assert np.array_equal(p, r)
+        if k == 2:
+            before = p.copy()
+            p = ctx.process_scans([seq[3], bad])
+            assert ctx.last_rc == ll.capi.LL_E_EMPTY
+            assert list(ctx.lane_status()) == [0, ll.capi.LL_E_EMPTY]
+            assert np.array_equal(p[1], before[1])                       # pose unchanged
+            r2 = ref.process_scans([seq[3], seq[3]])
+            assert np.array_equal(p[0], r2[0])                           # the good lane ran normally
+            # lane 1 now catches up with the scan it missed: same result as the reference context's lane 1
+            p = ctx.process_scans([seq[4], seq[3]])
+            r3 = ref.process_scans([seq[4], seq[4]])
+            assert list(ctx.lane_status()) == [0, 0]
+            assert np.array_equal(p[1], r2[1]) and np.array_equal(p[0], r3[0])
+            break
+    ctx.close()
+    ref.close()
