@@ -443,6 +443,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("LL_BENCH_BATCH", "256")), help="scan streams (lanes) per GPU")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans in the cpu_baseline sample")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (1-based): 2 = the headline (default); 1, 3, 4, 5 in bench_configs.py")
+    ap.add_argument("--stream-scans", type=int, default=10000, help="--config 4: scans in the stream")
+    ap.add_argument("--lanes", type=int, default=128, help="--config 4: sub-segments (lanes) per GPU")
+    ap.add_argument("--small", action="store_true", help="--config 5: 3e5-point map")
+    ap.add_argument("--check", action="store_true", help="--config 5: compare with a single-GPU context")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check of the bench configuration")
     ap.add_argument("--max-ring-points", type=int, default=6155, help="ring capacity (library default 6155; 3083 = 512-key sectors only)")
@@ -450,7 +455,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.config != 2:
+        import bench_configs
+        {1: bench_configs.run_config1, 3: bench_configs.run_config3, 4: bench_configs.run_config4, 5: bench_configs.run_config5}[args.config](args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

@@ -85,6 +85,7 @@ typedef struct ll_stats {
     double map_initial_cost[2], map_final_cost[2];
     int frame;                                                   /* now_frame of lane 0 */
     int kernel_launches;                                         /* launches issued by the last call */
+    int map_vote_corr, map_vote_selected;                        /* scan-to-map graph vote (map_graph_vote): planes seen / selected, last iteration */
 } ll_stats;
 
 void ll_default_config(ll_config* cfg, int scan_line);   /* launch-file values for 16 / 32 / 64 lines */

@@ -46,7 +46,7 @@ class LLStats(ctypes.Structure):
                 ("map_corner", ctypes.c_int), ("map_surf", ctypes.c_int), ("stack_corner", ctypes.c_int), ("stack_surf", ctypes.c_int),
                 ("map_corner_corr", ctypes.c_int), ("map_surf_corr", ctypes.c_int), ("map_jacobian_evals", ctypes.c_int * 2),
                 ("map_termination", ctypes.c_int * 2), ("map_initial_cost", ctypes.c_double * 2), ("map_final_cost", ctypes.c_double * 2),
-                ("frame", ctypes.c_int), ("kernel_launches", ctypes.c_int)]
+                ("frame", ctypes.c_int), ("kernel_launches", ctypes.c_int), ("map_vote_corr", ctypes.c_int), ("map_vote_selected", ctypes.c_int)]
 
 
 class LightLoamError(RuntimeError):

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <new>
@@ -89,6 +90,20 @@ float calibrate_vote_threshold()
     while (hi - lo > 1) {
         const uint32_t mid = lo + (hi - lo) / 2;
         if (expf(-flt(mid)) < 0.96f) hi = mid; else lo = mid;
+    }
+    return flt(hi);
+}
+
+// the same for laserMapping.cpp's copy (LM:918-924): float score compared with the double literal 0.95
+float calibrate_vote_threshold95()
+{
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto flt = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    uint32_t lo = bits(0.04f);  // expf(-0.04) = 0.961 >= 0.95
+    uint32_t hi = bits(0.06f);  // expf(-0.06) = 0.942 <  0.95
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if ((double)expf(-flt(mid)) < 0.95) hi = mid; else lo = mid;
     }
     return flt(hi);
 }
@@ -185,7 +200,7 @@ void ll_destroy(ll_ctx* c)
     if (c->h_ids) cudaFreeHost(c->h_ids);
     if (c->h_status) cudaFreeHost(c->h_status);
     free(c->last_status);
-    void* ptrs[] = {c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
+    void* ptrs[] = {c->d_wide_list, c->d_wide_n, c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->d_ebound[0], c->d_ebound[1], c->d_bands[0], c->d_bands[1], c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
                     c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n, c->d_vote_src, c->d_vote_tgt};
@@ -216,6 +231,7 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     c->RCAP = 6 * c->SCAP + 16;
     c->dev = cfg->device;
     c->vote_t_min = calibrate_vote_threshold();
+    c->vote_t95 = calibrate_vote_threshold95();
 #define CK(expr)                                                                     \
     do {                                                                             \
         cudaError_t e__ = (expr);                                                    \
@@ -235,6 +251,9 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_pose, B * 14));
     CK(cudaHostAlloc((void**)&c->h_hdr, sizeof(int) * 4 * B, cudaHostAllocDefault));
     CK(dalloc(c->d_hdr, B * 4));
+    CK(dalloc(c->d_wide_list, B * R));
+    CK(dalloc(c->d_wide_n, 1));
+    CK(cudaMemsetAsync(c->d_wide_n, 0, sizeof(int), c->stream));
     CK(dalloc(c->d_status, B));
     CK(cudaMemsetAsync(c->d_status, 0, sizeof(int) * B, c->stream));
     CK(cudaHostAlloc((void**)&c->h_status, sizeof(int) * 3 * B, cudaHostAllocDefault));
@@ -736,6 +755,7 @@ int ll_get_last_stats(ll_ctx* c, ll_stats* o)
         o->map_initial_cost[k] = L.initial_cost[3 + k]; o->map_final_cost[k] = L.final_cost[3 + k];
     }
     o->frame = L.now_frame;
+    o->map_vote_corr = L.n_map_vote; o->map_vote_selected = L.n_map_vote_sel;
     if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg (all lanes, cumulative): queued with the 1-NN open %d (kcycles %d, longest %d cycles), queued for the ring window %d (kcycles %d, longest %d cycles)\n", L.dbg[1], L.dbg[3], L.dbg[5] * 16, L.dbg[2], L.dbg[4], L.dbg[6] * 16);
     o->kernel_launches = c->launches;
     return LL_OK;

@@ -65,6 +65,7 @@ struct LaneState {
     int n_valid;                     // laserCloudValidNum (<= 125)
     int map_ok;                      // LM:1826 guard: map corner > 10 && map surf > 50
     int n_map_corner, n_map_surf, n_stack_corner, n_stack_surf, n_map_corner_corr, n_map_surf_corr;
+    int n_map_vote, n_map_vote_sel;  // plane correspondences the LM:2057-2072 vote saw / selected (last iteration)
     int err;                         // sticky device-side error (LL_E_*)
     int dbg[8];                      // association statistics (plane queries resolved per shell / by the walk)
 };
@@ -89,6 +90,7 @@ struct ll_ctx {
     int launches = 0;
     int pre_launches = 0;     // launches issued by the staging half of a call, folded into `launches` by the processing half
     float vote_t_min = 0.f;   // smallest fp32 t with expf(-t) < 0.96f on this host's libm (LO:239-242)
+    float vote_t95 = 0.f;     // smallest fp32 t with (double)expf(-t) < 0.95 (LM:918-924: float score against a double literal)
 
     LaneState* d_lane = nullptr;
     LaneState* h_lane = nullptr;   // pinned mirror
@@ -100,6 +102,8 @@ struct ll_ctx {
     int* h_status = nullptr;       // pinned [3][B]: slot 0 = synchronous calls, 1..2 = submit slots
     int* last_status = nullptr;    // host [B]: what ll_get_lane_status reports
     bool feat_attr_set = false;    // dynamic shared-memory limits of the per-ring kernels set on this context's device
+    int* d_wide_list = nullptr;    // [B * R] rings longer than 3083 points of the current step (lane * R + ring)
+    int* d_wide_n = nullptr;       // [1]
     float4* d_pc2 = nullptr;       // scratch of ll_fetch_pointcloud2 (allocated on first use)
 
     uint32_t* d_raw = nullptr;     // [B][Nmax * 8] words (stride <= 32 B)

@@ -51,6 +51,8 @@ struct FeatParams {
     // variant enabled the kernels run twice: <512> takes the rings of up to 3083 points, <1024> the longer ones (a CTA
     // whose ring belongs to the other variant leaves after two loads).  Rings longer than ring_cap are an error.
     int ring_lo, ring_cap;
+    int* wide_list;   // rings longer than 3083 points as lane * R + ring, appended by k_ring_scan; [0] of wide_n = how many
+    int* wide_n;
 };
 
 // SR:114-126: endOri from the last valid point and startOri
@@ -257,6 +259,10 @@ __global__ void __launch_bounds__(1024) k_ring_scan(FeatParams P)
         const int t0 = __shfl_sync(LL_FULL_MASK, i0, 31), t1 = __shfl_sync(LL_FULL_MASK, i1, 31);
         if (lane < P.R) L.ring_begin[lane] = i0 - a0;
         if (lane + 32 < P.R) L.ring_begin[lane + 32] = t0 + i1 - a1;
+        if (P.ring_cap > 6 * 512 + 11) {   // wide-sector variant enabled: hand it the rings the 512-key kernels leave alone
+            if (lane < P.R && a0 > 6 * 512 + 11 && a0 <= P.ring_cap) P.wide_list[atomicAdd(P.wide_n, 1)] = b * P.R + lane;
+            if (lane + 32 < P.R && a1 > 6 * 512 + 11 && a1 <= P.ring_cap) P.wide_list[atomicAdd(P.wide_n, 1)] = b * P.R + lane + 32;
+        }
         if (lane == 0) {
             const int run = t0 + t1;
             L.ring_begin[P.R] = run;
@@ -386,7 +392,7 @@ __device__ __forceinline__ void warp_sort_regs_blocked(unsigned (&k)[NREG], int 
 #define SORT_CHUNK 1536    // ring points staged per TMA copy (multiple of 32)
 #define SORT_STAGE_BYTES ((SORT_CHUNK + 10) * 16)
 template <int SCAP>
-__global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
+__device__ __forceinline__ void ring_sort_body(const FeatParams& P, const int r, const int b)
 {
     constexpr int RCAP = 6 * SCAP + 16;
     constexpr int NTH = SORT_THREADS;
@@ -402,7 +408,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
     int* sp = reinterpret_cast<int*>(curv_s + RCAP);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sp + 8);
 
-    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     LaneState& L = P.lane[b];
     const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base, ntot = L.n_full;
     const float4* gfull = P.full + (size_t)b * P.Nmax;
@@ -527,6 +533,21 @@ __global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
         gsorted[base + s0 + e] = (uint16_t)((unsigned)idx | ((double)c > 0.1 ? 0x4000u : 0u) | ((double)c < 0.1 ? 0x8000u : 0u));
     }
 #undef SK
+    __syncthreads();
+    if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");   // the list form initialises it again for its next ring
+}
+// LIST = false: one CTA per (ring, lane).  LIST = true: a small fixed grid walks the list of long rings k_ring_scan made
+// (normally empty: the launch then costs a few hundred CTAs that read one word and leave).
+template <int SCAP, bool LIST>
+__global__ void __launch_bounds__(SORT_THREADS) k_ring_sort(FeatParams P)
+{
+    if (!LIST) { ring_sort_body<SCAP>(P, blockIdx.x, blockIdx.y); return; }
+    const int n = *P.wide_n;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int v = P.wide_list[e];
+        ring_sort_body<SCAP>(P, v % P.R, v / P.R);
+        __syncthreads();
+    }
 }
 
 // 64-bit window of a bit array held in 32-bit words
@@ -583,7 +604,7 @@ __device__ __forceinline__ void mark_range(unsigned* picked, int lo, int hi)
 // ---------------------------------------------------------------------------------------------------------
 #define PICK_WARPS 4
 template <int SCAP>
-__global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int n_lanes)
+__device__ __forceinline__ void ring_pick_body(const FeatParams& P, const int r, const int b)
 {
     constexpr int RCAP = 6 * SCAP + 16;
     constexpr int WORDS = (RCAP + 31) / 32 + 2;
@@ -592,9 +613,6 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
     unsigned* picked = reinterpret_cast<unsigned*>(smem_pick) + (size_t)wid * (2 * WORDS + RCAP / 2);
     unsigned* brk = picked + WORDS;
     uint16_t* sorted = reinterpret_cast<uint16_t*>(brk + WORDS);
-    const int ring_lane = blockIdx.x * PICK_WARPS + wid;
-    if (ring_lane >= P.R * n_lanes) return;
-    const int b = ring_lane / P.R, r = ring_lane % P.R;
     LaneState& L = P.lane[b];
     const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base;
     int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
@@ -687,6 +705,21 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int
     }
     if (lane == 0) { my_counts[0] = n_sharp; my_counts[1] = n_lsharp; my_counts[2] = n_flat; }
 }
+template <int SCAP, bool LIST>
+__global__ void __launch_bounds__(PICK_WARPS * 32) k_ring_pick(FeatParams P, int n_lanes)
+{
+    if (!LIST) {
+        const int ring_lane = blockIdx.x * PICK_WARPS + warp_id();
+        if (ring_lane < P.R * n_lanes) ring_pick_body<SCAP>(P, ring_lane % P.R, ring_lane / P.R);
+        return;
+    }
+    const int n = *P.wide_n;
+    for (int e = blockIdx.x * PICK_WARPS + warp_id(); e < n; e += gridDim.x * PICK_WARPS) {
+        const int v = P.wide_list[e];
+        ring_pick_body<SCAP>(P, v % P.R, v / P.R);
+        __syncwarp();
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // k_ring_lessflat: less-flat = every sector point with label <= 0 (SR:361-367), then pcl::VoxelGrid(0.2) on
@@ -702,7 +735,7 @@ __device__ __noinline__ void block_sort_big(u64* keys) { block_sort_u64_asc<NS, 
 template <int NS, int KPT>
 __device__ __noinline__ void block_sort_big32(unsigned* keys) { block_sort_asc<unsigned, NS, KPT>(keys); }
 template <int SCAP>
-__global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
+__device__ __forceinline__ void ring_lessflat_body(const FeatParams& P, const int r, const int b)
 {
     constexpr int RCAP = 6 * SCAP + 16;
     constexpr int KCAP = (RCAP <= 4096) ? 4096 : 8192;
@@ -715,7 +748,7 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     int* ws = reinterpret_cast<int*>(pidx + RCAP + (RCAP & 1));
     float* red = reinterpret_cast<float*>(ws + 40);
 
-    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     LaneState& L = P.lane[b];
     const int base = L.ring_begin[r], n = L.ring_begin[r + 1] - base;
     int* my_counts = P.ring_counts + ((size_t)b * P.R + r) * 4;
@@ -922,6 +955,17 @@ __global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
     }
     if (tid == 0) my_counts[3] = nvox;
 }
+template <int SCAP, bool LIST>
+__global__ void __launch_bounds__(512, 4) k_ring_lessflat(FeatParams P)
+{
+    if (!LIST) { ring_lessflat_body<SCAP>(P, blockIdx.x, blockIdx.y); return; }
+    const int n = *P.wide_n;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int v = P.wide_list[e];
+        ring_lessflat_body<SCAP>(P, v % P.R, v / P.R);
+        __syncthreads();
+    }
+}
 
 // one CTA per (ring, lane): offsets = sums over the earlier rings; copy lists / clouds to their compact places
 __global__ void __launch_bounds__(256) k_compact(FeatParams P)
@@ -976,10 +1020,11 @@ __global__ void __launch_bounds__(256) k_compact(FeatParams P)
 
 // one warp per lane: per-scan state; startOri (SR:114) = azimuth of the first point that survives the filters (nearly
 // always point 0) so that k_classify can decide where halfPassed flips (SR:178-193) in its single pass ...
-__global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres)
+__global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres, int* wide_n)
 {
     const int b = blockIdx.x, ln = lane_id();
     if (b >= n_lanes) return;
+    if (b == 0 && ln == 0) *wide_n = 0;
     LaneState& L = lane[b];
     const int n = L.n_raw, sw = L.stride_words;
     int fv = -1;
@@ -1048,9 +1093,11 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     P.thres = c->cfg.minimum_range; P.lower_bound = c->cfg.lower_bound; P.up_bound = c->cfg.up_bound;
     P.factor = (c->cfg.scan_line - 1) / (c->cfg.up_bound - c->cfg.lower_bound);  // SR:441, fp32
     P.inv_leaf = 1.0f / 0.2f;
+    P.wide_list = c->d_wide_list; P.wide_n = c->d_wide_n;
+    P.ring_lo = 0; P.ring_cap = 6 * c->SCAP + 11;
     cudaStream_t s = c->stream;
     const dim3 tiles(c->NT, n_lanes);
-    { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<n_lanes, 32, 0, s>>>(c->d_lane, n_lanes, P.thres); }
+    { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<n_lanes, 32, 0, s>>>(c->d_lane, n_lanes, P.thres, c->d_wide_n); }
     const int cls_minb = getenv("LL_CLS_MINB") ? atoi(getenv("LL_CLS_MINB")) : 8, sct_minb = getenv("LL_SCT_MINB") ? atoi(getenv("LL_SCT_MINB")) : 5;
     {
         LLProf pr(c, "k_classify");
@@ -1073,25 +1120,26 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     const int pick_blocks = (c->R * n_lanes + PICK_WARPS - 1) / PICK_WARPS;
     auto smem_pick_of = [](int SCAP) { const int RCAP = 6 * SCAP + 16; return (size_t)PICK_WARPS * (2 * ((RCAP + 31) / 32 + 2) + RCAP / 2) * 4; };
     if (!c->feat_attr_set) {
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_feature_smem_bytes(512)));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_lessflat_smem_bytes(512)));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick_of(512)));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_feature_smem_bytes(1024)));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_lessflat_smem_bytes(1024)));
-        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick_of(1024)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_feature_smem_bytes(512)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_lessflat_smem_bytes(512)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick_of(512)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_sort<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_feature_smem_bytes(1024)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_lessflat<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_lessflat_smem_bytes(1024)));
+        LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_ring_pick<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pick_of(1024)));
         c->feat_attr_set = true;
     }
     // rings of up to 3083 points: one warp sorts a sector of <= 512 keys in registers
     P.ring_lo = 0; P.ring_cap = 6 * c->SCAP + 11;
-    { LLProf pr(c, "k_ring_sort"); k_ring_sort<512><<<rings, SORT_THREADS, ll_feature_smem_bytes(512), s>>>(P); }
-    { LLProf pr(c, "k_ring_pick"); k_ring_pick<512><<<pick_blocks, PICK_WARPS * 32, smem_pick_of(512), s>>>(P, n_lanes); }
-    { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512><<<rings, 512, ll_lessflat_smem_bytes(512), s>>>(P); }
+    { LLProf pr(c, "k_ring_sort"); k_ring_sort<512, false><<<rings, SORT_THREADS, ll_feature_smem_bytes(512), s>>>(P); }
+    { LLProf pr(c, "k_ring_pick"); k_ring_pick<512, false><<<pick_blocks, PICK_WARPS * 32, smem_pick_of(512), s>>>(P, n_lanes); }
+    { LLProf pr(c, "k_ring_lessflat"); k_ring_lessflat<512, false><<<rings, 512, ll_lessflat_smem_bytes(512), s>>>(P); }
     c->launches += 3;
     if (c->SCAP == 1024) {   // longer rings (up to 6155 points): the 1024-key variants; every other CTA leaves at once
         P.ring_lo = 6 * 512 + 11;
-        { LLProf pr(c, "k_ring_sort_wide"); k_ring_sort<1024><<<rings, SORT_THREADS, ll_feature_smem_bytes(1024), s>>>(P); }
-        { LLProf pr(c, "k_ring_pick_wide"); k_ring_pick<1024><<<pick_blocks, PICK_WARPS * 32, smem_pick_of(1024), s>>>(P, n_lanes); }
-        { LLProf pr(c, "k_ring_lessflat_wide"); k_ring_lessflat<1024><<<rings, 512, ll_lessflat_smem_bytes(1024), s>>>(P); }
+        const int wide_grid = 296;   // a fixed small grid over the (normally empty) list of long rings
+        { LLProf pr(c, "k_ring_sort_wide"); k_ring_sort<1024, true><<<wide_grid, SORT_THREADS, ll_feature_smem_bytes(1024), s>>>(P); }
+        { LLProf pr(c, "k_ring_pick_wide"); k_ring_pick<1024, true><<<wide_grid, PICK_WARPS * 32, smem_pick_of(1024), s>>>(P, n_lanes); }
+        { LLProf pr(c, "k_ring_lessflat_wide"); k_ring_lessflat<1024, true><<<wide_grid, 512, ll_lessflat_smem_bytes(1024), s>>>(P); }
         c->launches += 3;
     }
     { LLProf pr(c, "k_compact"); k_compact<<<dim3(c->R, n_lanes), 256, 0, s>>>(P); }

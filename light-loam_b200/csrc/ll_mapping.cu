@@ -69,6 +69,11 @@ struct MapState {
     size_t cub_bytes = 0;
     double* blocks = nullptr;  // dense records [B][LL_BLOCK_DOUBLES][nblk_cap]
     int nblk_cap = 0;
+    // graph vote on the plane correspondences (LM:2057-2072, cfg.map_graph_vote)
+    float4* vote_tgt_raw = nullptr;   // [B][stack_cap[1]] centroid of the 5 map neighbours per surf stack point (LM:1960-1972)
+    float4* vote_src = nullptr;       // [B][stack_cap[1]] compacted Corre_Match::src (w = stack index bits) ...
+    float4* vote_tgt = nullptr;       // ... and ::tgt, in correspondence order
+    int* vote_cnt = nullptr;          // [B][stack_cap[1]] votes per correspondence (regions too large for shared memory)
     // split / multi-GPU solve (LmComm, ll_solve.cuh)
     void* comm_buf = nullptr;          // this context's mailbox: mbox doubles followed by the flags
     size_t comm_mbox_bytes = 0, comm_bytes = 0;
@@ -300,6 +305,7 @@ struct MapAssocParams {
     double* blocks;
     int nblk_cap;
     float slab_lo, slab_hi;   // multi-GPU: only the stack points whose map-frame x lies in [slab_lo, slab_hi) are this rank's
+    float4* vote_tgt_raw;     // [B][stack_cap[1]] or nullptr: Corre_Match::tgt of every accepted plane (LM:1997-2007)
 };
 
 // one warp per stack point; the fit runs on lane 0 (fp64, a few hundred flops)
@@ -372,6 +378,11 @@ __global__ void __launch_bounds__(256) k_map_assoc(MapAssocParams P)
                     if (fabs(nrm[0] * m.x + nrm[1] * m.y + nrm[2] * m.z + d) > 0.2) { ok = false; break; }
                 }
                 if (ok) {
+                    if (P.vote_tgt_raw) {   // LM:1949, 1960-1972: fp32 centroid of the five neighbours, in the search's result order
+                        float cx = 0.f, cy = 0.f, cz = 0.f;
+                        for (int j = 0; j < 5; ++j) { const float4 m = mp[(int)(unsigned)best[j]]; cx += m.x; cy += m.y; cz += m.z; }
+                        P.vote_tgt_raw[(size_t)b * P.stack_cap[1] + i] = make_float4(cx / 5, cy / 5, cz / 5, 0.f);
+                    }
                     type = 2.0;
                     blk[1 * cap + q] = pointOri.x; blk[2 * cap + q] = pointOri.y; blk[3 * cap + q] = pointOri.z;
                     for (int a = 0; a < 3; ++a) { blk[(4 + a) * cap + q] = nrm[a]; blk[(7 + a) * cap + q] = 0.0; }
@@ -399,6 +410,108 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_map(LaneState* lane, co
     if (comm.gworld * comm.nparts > 1 && b == 0 && part == 0)   // lanes outside this launch keep their collective counters
         for (int i = gridDim.x + threadIdx.x; i < n_all_lanes; i += LM_THREADS) comm.seq_out[i] = comm.seq_in[i];
     lm_solve(blocks + (size_t)b * LL_BLOCK_DOUBLES * nblk_cap, nblk_cap, nb, L.map_par, L.map_par + 4, &L, 3 + iter, &comm, b, part);
+}
+
+// ---- graph vote on the scan-to-map plane correspondences (LM:2057-2072 + LM:836-1027) -------------------------------------
+// The reference keeps the call commented out; cfg.map_graph_vote = N > 0 enables it from mapping frame N - 1 on
+// (BASELINE.json configs[2] "graph matching on").  k_map_vote_prep compacts the accepted planes in stack order
+// (= correspondences[], LM:1997-2007); k_map_vote runs one CTA per (region, lane) over LM's 20 contiguous regions: a pair
+// votes when  (double)expf(-(gap * gap)) < 0.95  (gap * gap >= t95, calibrated on the host's expf), and a correspondence
+// with fewer votes than 0.75 * region size is selected (LM:979-1027) - the reference then adds its LidarPlaneNormFactor
+// block a SECOND time (LM:2064-2067), which the solve kernel applies as a multiplicity of 2 on the record.
+struct MapVoteParams {
+    LaneState* lane;
+    const float4* stack_surf;   // [B][stack_cap]
+    const float4* tgt_raw;
+    float4* src;
+    float4* tgt;
+    int* cnt;
+    double* blocks;
+    int stack_cap, nblk_cap;
+    int from_frame;             // vote when map_frame >= from_frame
+    float t95;
+};
+__global__ void __launch_bounds__(1024) k_map_vote_prep(MapVoteParams P)
+{
+    __shared__ int ws[40];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    LaneState& L = P.lane[b];
+    const bool on = L.map_ok && !L.err && L.map_frame >= P.from_frame;
+    const int nc = L.n_stack_corner, ns = on ? L.n_stack_surf : 0;
+    const double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    const int per = (ns + 1023) / 1024;
+    const int i0 = min(tid * per, ns), i1 = min(i0 + per, ns);
+    int mine = 0;
+    for (int i = i0; i < i1; ++i) mine += blk[nc + i] == 2.0;
+    int total = 0;
+    int pos = block_exclusive_scan(mine, ws, &total);
+    for (int i = i0; i < i1; ++i)
+        if (blk[nc + i] == 2.0) {
+            const float4 p = P.stack_surf[(size_t)b * P.stack_cap + i];
+            P.src[(size_t)b * P.stack_cap + pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+            P.tgt[(size_t)b * P.stack_cap + pos] = P.tgt_raw[(size_t)b * P.stack_cap + i];
+            P.cnt[(size_t)b * P.stack_cap + pos] = 0;
+            ++pos;
+        }
+    if (tid == 0) { L.n_map_vote = total; L.n_map_vote_sel = 0; }
+}
+#define MAP_VOTE_REGIONS 20
+#define MAP_VOTE_SMEM 4096   // correspondences of one region whose counters fit shared memory
+__global__ void __launch_bounds__(256) k_map_vote(MapVoteParams P)
+{
+    __shared__ int votes_s[MAP_VOTE_SMEM];
+    __shared__ int nsel_s;
+    const int b = blockIdx.y, reg = blockIdx.x, tid = threadIdx.x;
+    LaneState& L = P.lane[b];
+    const int n = L.n_map_vote;
+    const int region_len = n / MAP_VOTE_REGIONS;
+    const int r0 = region_len * reg, r1 = reg == MAP_VOTE_REGIONS - 1 ? n : region_len * (reg + 1);
+    const int m = r1 - r0;
+    if (m <= 0) return;
+    const float4* src = P.src + (size_t)b * P.stack_cap + r0;
+    const float4* tgt = P.tgt + (size_t)b * P.stack_cap + r0;
+    int* votes = m <= MAP_VOTE_SMEM ? votes_s : P.cnt + (size_t)b * P.stack_cap + r0;
+    if (m <= MAP_VOTE_SMEM) for (int k = tid; k < m; k += 256) votes_s[k] = 0;
+    if (tid == 0) nsel_s = 0;
+    __syncthreads();
+    const float t95 = P.t95, g_mid = sqrtf(t95);
+    // rows k and m-1-k together hold m-1 pairs; four threads share a row pair
+    for (int k = tid >> 2; k < (m + 1) / 2; k += 256 / 4) {
+        const int q = tid & 3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int row = half == 0 ? k : m - 1 - k;
+            if (half == 1 && row == k) break;
+            const float4 a = __ldg(src + row), c = __ldg(tgt + row);
+            int mine = 0;
+            for (int j = row + 1 + q; j < m; j += 4) {
+                const float4 sj = __ldg(src + j), tj = __ldg(tgt + j);
+                const float d1 = sqdist3(a.x, a.y, a.z, sj.x, sj.y, sj.z), d2 = sqdist3(c.x, c.y, c.z, tj.x, tj.y, tj.z);
+                const float ge = fabsf(d1 * rsqrtf(fmaxf(d1, 1e-30f)) - d2 * rsqrtf(fmaxf(d2, 1e-30f)));
+                bool v = ge > g_mid;
+                if (fabsf(ge - g_mid) < 1e-3f) {   // too close to call with the approximation: LM:250-259 + LM:918-924 to the letter
+                    const float gap = fabsf(sqrtf(d1) - sqrtf(d2));
+                    v = gap * gap >= t95;
+                }
+                if (v) { ++mine; atomicAdd(&votes[j], 1); }
+            }
+            if (mine) atomicAdd(&votes[row], mine);
+        }
+    }
+    __syncthreads();
+    double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    const int nc = L.n_stack_corner;
+    const float num_selected = 0.75f * (float)m;   // LM:979-980
+    int sel = 0;
+    for (int k = tid; k < m; k += 256) {
+        if ((float)votes[k] < num_selected) {      // LM:1003: selected -> its block is added once more (LM:2064-2067)
+            blk[(size_t)7 * P.nblk_cap + nc + __float_as_int(__ldg(src + k).w)] = 2.0;
+            ++sel;
+        }
+    }
+    if (sel) atomicAdd(&nsel_s, sel);
+    __syncthreads();
+    if (tid == 0 && nsel_s) atomicAdd(&L.n_map_vote_sel, nsel_s);
 }
 
 // LM:119-123 transformUpdate + pose output
@@ -655,6 +768,7 @@ void ll_map_free(ll_ctx* c)
     cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->vg_in); cudaFree(m->vg_seg);
     cudaFree(m->vg_n); cudaFree(m->vg_head); cudaFree(m->vg_scan); cudaFree(m->vg_bbox); cudaFree(m->seg_count); cudaFree(m->lane_base);
     cudaFree(m->cub_tmp); cudaFree(m->blocks);
+    cudaFree(m->vote_tgt_raw); cudaFree(m->vote_src); cudaFree(m->vote_tgt); cudaFree(m->vote_cnt);
     for (int g = 0; g < LM_MAX_GPUS; ++g) if (m->peer_ipc[g] && m->peer_buf[g]) cudaIpcCloseMemHandle(m->peer_buf[g]);
     cudaFree(m->comm_buf); cudaFree(m->comm_seq[0]); cudaFree(m->comm_seq[1]);
     delete m;
@@ -729,6 +843,12 @@ int ll_map_alloc(ll_ctx* c)
     MK(cudaMalloc(&m->cub_tmp, m->cub_bytes));
     m->nblk_cap = m->stack_cap[0] + m->stack_cap[1];
     MK(cudaMalloc((void**)&m->blocks, sizeof(double) * B * LL_BLOCK_DOUBLES * (size_t)m->nblk_cap));
+    if (c->cfg.map_graph_vote > 0) {
+        MK(cudaMalloc((void**)&m->vote_tgt_raw, sizeof(float4) * B * m->stack_cap[1]));
+        MK(cudaMalloc((void**)&m->vote_src, sizeof(float4) * B * m->stack_cap[1]));
+        MK(cudaMalloc((void**)&m->vote_tgt, sizeof(float4) * B * m->stack_cap[1]));
+        MK(cudaMalloc((void**)&m->vote_cnt, sizeof(int) * B * m->stack_cap[1]));
+    }
     m->comm_mbox_bytes = sizeof(double) * B * 2 * LM_MAX_WORLD * LM_MBOX_DOUBLES;
     m->comm_bytes = m->comm_mbox_bytes + sizeof(unsigned long long) * B * LM_MAX_WORLD;
     MK(cudaMalloc(&m->comm_buf, m->comm_bytes));
@@ -801,6 +921,7 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     A.lane = c->d_lane; A.stack[0] = m->stack[0]; A.stack[1] = m->stack[1]; A.frommap[0] = m->frommap[0]; A.frommap[1] = m->frommap[1];
     A.stack_cap[0] = m->stack_cap[0]; A.stack_cap[1] = m->stack_cap[1]; A.map_cap = m->map_cap; A.g[0] = m->grid[0]; A.g[1] = m->grid[1];
     A.blocks = m->blocks; A.nblk_cap = m->nblk_cap; A.slab_lo = (float)m->slab_lo; A.slab_hi = (float)m->slab_hi;
+    A.vote_tgt_raw = m->vote_tgt_raw;
     // solve split: `parts` CTAs per lane on this GPU x the attached GPUs.  The CTAs of one lane spin on each other's
     // mailbox flags, so they must all be resident at once: the split launch is a cooperative launch (the driver refuses
     // it when the grid does not fit) and its size comes from the device's SM count and the kernel's occupancy.
@@ -823,6 +944,14 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     for (int iter = 0; iter < 2; ++iter) {  // LM:1834
         { LLProf pr(c, "k_map_reset_corr"); k_map_reset_corr<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
         { LLProf pr(c, "k_map_assoc"); k_map_assoc<<<dim3((m->nblk_cap + 7) / 8, n_lanes), 256, 0, s>>>(A); }
+        if (m->vote_src && m->gworld == 1) {   // (slab-sharded ranks each see only their own correspondences: the vote needs them all)
+            MapVoteParams V;
+            V.lane = c->d_lane; V.stack_surf = m->stack[1]; V.tgt_raw = m->vote_tgt_raw; V.src = m->vote_src; V.tgt = m->vote_tgt; V.cnt = m->vote_cnt;
+            V.blocks = m->blocks; V.stack_cap = m->stack_cap[1]; V.nblk_cap = m->nblk_cap; V.from_frame = c->cfg.map_graph_vote - 1; V.t95 = c->vote_t95;
+            { LLProf pr(c, "k_map_vote_prep"); k_map_vote_prep<<<n_lanes, 1024, 0, s>>>(V); }
+            { LLProf pr(c, "k_map_vote"); k_map_vote<<<dim3(MAP_VOTE_REGIONS, n_lanes), 256, 0, s>>>(V); }
+            c->launches += 2;
+        }
         comm.seq_in = m->comm_seq[m->comm_flip]; comm.seq_out = m->comm_seq[m->comm_flip ^ (dist ? 1 : 0)];
         {
             LLProf pr(c, "k_lm_solve_map");

@@ -321,6 +321,7 @@ struct OdomParams {
     int nblk_cap;
     int graph_from_frame;
     float vote_t_min;
+    int distortion;        // LO:23 DISTORTION: 0 reference build; 1 per-point interpolation ratio; 2 additionally TransformToEnd (LO:861-880)
     int outer;             // opti_counter
     int dev_skip;          // development only: bit mask of association stages to skip (timing experiments)
     float4* vote_src;      // [B][R*24] compacted plane matches: current point (w = feature index) / closest point
@@ -620,6 +621,7 @@ __device__ __forceinline__ void nn_consider(u64& best, float qx, float qy, float
 __device__ __forceinline__ void nn_consider_ring(u64& best, int& best_ring, float qx, float qy, float qz, const float4 t)
 {
     const float d2 = sqdist3(qx, qy, qz, t.x, t.y, t.z);
+    if (__float_as_uint(d2) > (unsigned)(best >> 32)) return;   // most candidates: one 32-bit compare (equal bits go on to the index tie-break)
     const unsigned bits = (unsigned)__float_as_int(t.w);
     const u64 key = ((u64)__float_as_uint(d2) << 32) | (bits & 0xFFFFFFu);
     if (key < best) { best = key; best_ring = (int)(bits >> 24); }
@@ -740,14 +742,25 @@ __device__ __forceinline__ void assoc_store(const OdomParams& P, int b, int i, c
         *reinterpret_cast<int4*>(o) = ok ? make_int4(Q.closest, ind2, ind3, 0) : make_int4(-1, -1, -1, 0);
     }
 }
+// LO:81-84 / LO:569-573 / LO:739-743 with DISTORTION 1: (intensity - int(intensity)) / SCAN_PERIOD - a float difference divided in double
+__device__ __forceinline__ double point_ratio(const float4 p) { return (double)(p.w - (float)(int)p.w) / 0.1; }
 template <bool CORNER>
 __device__ __forceinline__ void assoc_query_init(const OdomParams& P, const LaneState& L, int b, int i, AssocQuery& Q)
 {
     const float4 p = CORNER ? P.sharp[(size_t)b * P.R * LL_SHARP_PER_RING + i] : P.flat[(size_t)b * P.R * LL_FLAT_PER_RING + i];
-    // TransformToStart, LO:77-95 with DISTORTION 0: slerp(1, q) = +-q, same rotation bit for bit
     double sx, sy, sz;
-    quat_rotate(L.para_q, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
-    Q.qx = (float)(sx + L.para_t[0]); Q.qy = (float)(sy + L.para_t[1]); Q.qz = (float)(sz + L.para_t[2]);
+    if (P.distortion) {
+        // TransformToStart, LO:77-95 with DISTORTION 1: s = fraction of the intensity / SCAN_PERIOD, q_s = Identity.slerp(s, q), t_s = s t
+        const double s = point_ratio(p);
+        double qs[4];
+        lm_identity_slerp<double>(s, L.para_q, qs);
+        quat_rotate(qs, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
+        Q.qx = (float)(sx + s * L.para_t[0]); Q.qy = (float)(sy + s * L.para_t[1]); Q.qz = (float)(sz + s * L.para_t[2]);
+    } else {
+        // TransformToStart, LO:77-95 with DISTORTION 0: slerp(1, q) = +-q, same rotation bit for bit
+        quat_rotate(L.para_q, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
+        Q.qx = (float)(sx + L.para_t[0]); Q.qy = (float)(sy + L.para_t[1]); Q.qz = (float)(sz + L.para_t[2]);
+    }
     Q.k2 = ~0ull; Q.k3 = ~0ull; Q.closest = -1; Q.cring = 0; Q.cut = D2_BITS_25 - 1u;
     Q.n = CORNER ? L.n_last_corner : L.n_last_surf;
 }
@@ -1121,6 +1134,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
             blk[4 * cap + pos] = a.x; blk[5 * cap + pos] = a.y; blk[6 * cap + pos] = a.z;
             blk[7 * cap + pos] = c.x; blk[8 * cap + pos] = c.y; blk[9 * cap + pos] = c.z;
             blk[10 * cap + pos] = 1.0;
+            if (P.distortion) blk[11 * cap + pos] = point_ratio(cp);   // feature_s, LO:569-573
         }
     }
     // ---- planes: compaction (R*24 <= 1536: up to 2 per thread, contiguous chunks keep the order) --------
@@ -1148,6 +1162,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
             blk[4 * cap + o] = pj.x; blk[5 * cap + o] = pj.y; blk[6 * cap + o] = pj.z;
             blk[7 * cap + o] = nx; blk[8 * cap + o] = ny; blk[9 * cap + o] = nz;
             blk[10 * cap + o] = 1.0;             // LO:783: weight 1 while now_frame <= 5
+            if (P.distortion) blk[11 * cap + o] = point_ratio(cp);   // feature_s, LO:739-743
             pa[i * 4 + 3] = 1000;
             ++pos;
         }
@@ -1240,12 +1255,40 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_odom_vote(OdomParams P)
     if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
 }
 
+template <bool DIST>
 __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P)
 {
     const int b = blockIdx.x;
     LaneState& L = P.lane[b];
     if (!L.inited || L.err) return;
-    lm_solve(P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap, P.nblk_cap, L.n_blocks, L.para_q, L.para_t, &L, P.outer);
+    lm_solve<DIST>(P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap, P.nblk_cap, L.n_blocks, L.para_q, L.para_t, &L, P.outer);
+}
+
+// LO:861-880 TransformToEnd of this frame's less-sharp / less-flat clouds (they become *Last at the swap), distortion == 2:
+// the reference keeps the block behind a literal `if (0)`; with it enabled the clouds are expressed at the scan's end and
+// lose their time fraction (intensity = int(intensity)).  Frames that only initialise are left alone.
+__global__ void k_odom_to_end(OdomParams P, float4* ls0, float4* ls1, float4* lf0, float4* lf1)
+{
+    const int b = blockIdx.y;
+    const LaneState& L = P.lane[b];
+    if (!L.inited || L.err) return;
+    float4* ls = (L.cur == 0 ? ls0 : ls1) + (size_t)b * P.R * LL_LSHARP_PER_RING;
+    float4* lf = (L.cur == 0 ? lf0 : lf1) + (size_t)b * P.Nmax;
+    const int nc = L.n_less_sharp, ns = L.n_less_flat;
+    const double n2 = L.para_q[0] * L.para_q[0] + L.para_q[1] * L.para_q[1] + L.para_q[2] * L.para_q[2] + L.para_q[3] * L.para_q[3];
+    double qi[4] = {0, 0, 0, 0};   // Eigen inverse(): conjugate / squaredNorm
+    if (n2 > 0.0) { qi[0] = -L.para_q[0] / n2; qi[1] = -L.para_q[1] / n2; qi[2] = -L.para_q[2] / n2; qi[3] = L.para_q[3] / n2; }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nc + ns; e += gridDim.x * blockDim.x) {
+        float4* pp = e < nc ? ls + e : lf + (e - nc);
+        const float4 p = *pp;
+        const double s = point_ratio(p);
+        double qs[4], sx, sy, sz, ex, ey, ez;
+        lm_identity_slerp<double>(s, L.para_q, qs);
+        quat_rotate(qs, (double)p.x, (double)p.y, (double)p.z, sx, sy, sz);
+        const float ux = (float)(sx + s * L.para_t[0]), uy = (float)(sy + s * L.para_t[1]), uz = (float)(sz + s * L.para_t[2]);   // un_point_tmp is a PointXYZI: fp32
+        quat_rotate(qi, (double)ux - L.para_t[0], (double)uy - L.para_t[1], (double)uz - L.para_t[2], ex, ey, ez);
+        *pp = make_float4((float)ex, (float)ey, (float)ez, (float)(int)p.w);
+    }
 }
 
 // LO:830-831 pose accumulation; LO:882-896 swap (the grids are rebuilt right after); counters LO:925-926
@@ -1314,7 +1357,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
     P.Nmax = c->Nmax; P.R = c->R; P.ac = c->a_corner; P.as_ = c->a_surf; P.bands[0] = c->d_bands[0]; P.bands[1] = c->d_bands[1]; P.az_bins_corner = c->az_bins_corner; P.az_bins_surf = c->az_bins_surf;
     P.corner_assoc = c->d_corner_assoc; P.plane_assoc = c->d_plane_assoc; P.blocks = c->d_blocks; P.nblk_cap = c->nblk_cap;
-    P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
+    P.distortion = c->cfg.distortion; P.graph_from_frame = c->cfg.graph_from_frame; P.vote_t_min = c->vote_t_min; P.dev_skip = getenv("LL_DEV_SKIP") ? atoi(getenv("LL_DEV_SKIP")) : 0;
     P.vote_src = c->d_vote_src; P.vote_tgt = c->d_vote_tgt;
     P.queue = c->d_assoc_queue; P.queue_n = c->d_assoc_queue_n; P.queue_cap = c->assoc_queue_cap;
     cudaStream_t s = c->stream;
@@ -1409,8 +1452,17 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P); }
-        { LLProf pr(c, "k_lm_solve_odom"); k_lm_solve_odom<<<n_lanes, lm_threads, 0, s>>>(P); }
+        {
+            LLProf pr(c, "k_lm_solve_odom");
+            if (P.distortion) k_lm_solve_odom<true><<<n_lanes, lm_threads, 0, s>>>(P);
+            else k_lm_solve_odom<false><<<n_lanes, lm_threads, 0, s>>>(P);
+        }
         c->launches += 5;
+    }
+    if (P.distortion == 2) {
+        LLProf pr(c, "k_odom_to_end");
+        k_odom_to_end<<<dim3(32, n_lanes), 256, 0, s>>>(P, c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1]);
+        c->launches += 1;
     }
     { LLProf pr(c, "k_odom_finalize"); k_odom_finalize<<<(n_lanes + 63) / 64, 64, 0, s>>>(c->d_lane, c->d_pose, c->d_status, n_lanes); }
     c->launches += 1;

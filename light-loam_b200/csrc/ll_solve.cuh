@@ -107,7 +107,7 @@ __device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b
 // residual-block record (SoA, stride = cap): [0] type, [1..3] cp, [4..6] p0, [7..9] p1, [10] w
 //   type 0 EDGE        p0 = a, p1 = b
 //   type 1 PLANE_MODIFY p0 = j, p1 = ljm_norm, w = weight
-//   type 2 PLANE_NORM   p0 = unit normal, w = negative_OA_dot_norm
+//   type 2 PLANE_NORM   p0 = unit normal, w = negative_OA_dot_norm, p1.x = 2 when the block counts twice (map vote)
 // HuberLoss(0.1): returns rho(s); sq = sqrt(rho'(s)) - the Corrector with rho'' <= 0 scales r and J by it
 __device__ __forceinline__ double lm_huber(double s, double& sq)
 {
@@ -138,13 +138,131 @@ __device__ __forceinline__ void lm_row(double acc[LM_NRED], double d0, double d1
 #pragma unroll
     for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * rk;
 }
-struct LmRecord { double v[11]; };
+// ---- DISTORTION 1 (LO:23): the factors interpolate the pose per point, q_s = Identity.slerp(s, q), t_s = s t (LF:23-31,
+// LF:227-235), and the closed form above (s = 1) no longer applies.  The slow path evaluates the functors the way
+// ceres::AutoDiffCostFunction<.., 4, 3> does: forward-mode duals (ceres/jet.h) through Eigen's slerp and q * v, then the
+// ambient quaternion columns times EigenQuaternionManifold's plus-Jacobian.  Only the de-skew mode compiles into the
+// kernel that runs it (lm_solve<true>); the reference build's path is untouched.
+struct LmJet {
+    double a, v[7];
+    __device__ LmJet() {}
+    __device__ LmJet(double s) : a(s) { for (int i = 0; i < 7; ++i) v[i] = 0.0; }
+    __device__ LmJet(double s, int k) : a(s) { for (int i = 0; i < 7; ++i) v[i] = 0.0; v[k] = 1.0; }
+};
+__device__ __forceinline__ LmJet operator+(const LmJet& f, const LmJet& g) { LmJet h; h.a = f.a + g.a; for (int i = 0; i < 7; ++i) h.v[i] = f.v[i] + g.v[i]; return h; }
+__device__ __forceinline__ LmJet operator-(const LmJet& f, const LmJet& g) { LmJet h; h.a = f.a - g.a; for (int i = 0; i < 7; ++i) h.v[i] = f.v[i] - g.v[i]; return h; }
+__device__ __forceinline__ LmJet operator-(const LmJet& f) { LmJet h; h.a = -f.a; for (int i = 0; i < 7; ++i) h.v[i] = -f.v[i]; return h; }
+__device__ __forceinline__ LmJet operator*(const LmJet& f, const LmJet& g) { LmJet h; h.a = f.a * g.a; for (int i = 0; i < 7; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+__device__ __forceinline__ LmJet operator/(const LmJet& f, const LmJet& g)
+{
+    LmJet h;
+    const double gi = 1.0 / g.a, fg = f.a * gi;
+    h.a = fg;
+    for (int i = 0; i < 7; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi;
+    return h;
+}
+__device__ __forceinline__ bool operator<(const LmJet& f, const LmJet& g) { return f.a < g.a; }
+__device__ __forceinline__ bool operator>=(const LmJet& f, const LmJet& g) { return f.a >= g.a; }
+__device__ __forceinline__ LmJet lm_sqrt(const LmJet& f) { LmJet h; const double t = sqrt(f.a); h.a = t; const double k = 1.0 / (2.0 * t); for (int i = 0; i < 7; ++i) h.v[i] = f.v[i] * k; return h; }
+__device__ __forceinline__ LmJet lm_sin(const LmJet& f) { LmJet h; double sn, cs; sincos(f.a, &sn, &cs); h.a = sn; for (int i = 0; i < 7; ++i) h.v[i] = cs * f.v[i]; return h; }
+__device__ __forceinline__ LmJet lm_acos(const LmJet& f) { LmJet h; h.a = acos(f.a); const double t = -1.0 / sqrt(1.0 - f.a * f.a); for (int i = 0; i < 7; ++i) h.v[i] = t * f.v[i]; return h; }
+__device__ __forceinline__ LmJet lm_abs(const LmJet& f) { return f.a < 0.0 ? -f : f; }
+__device__ __forceinline__ double lm_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double lm_sin(double x) { return sin(x); }
+__device__ __forceinline__ double lm_acos(double x) { return acos(x); }
+__device__ __forceinline__ double lm_abs(double x) { return fabs(x); }
+// Eigen QuaternionBase::slerp(t, other) with *this = Identity (LF:25-26, LO:86): d = this.dot(other)
+template <typename T>
+__device__ __forceinline__ void lm_identity_slerp(const T& t, const T q[4], T out[4])
+{
+    const T one = T(1.0 - 2.220446049250313e-16);
+    const T d = T(0.0) * q[0] + T(0.0) * q[1] + T(0.0) * q[2] + T(1.0) * q[3];
+    const T absD = lm_abs(d);
+    T scale0, scale1;
+    if (absD >= one) {
+        scale0 = T(1.0) - t;
+        scale1 = t;
+    } else {
+        const T theta = lm_acos(absD);
+        const T sinTheta = lm_sin(theta);
+        scale0 = lm_sin((T(1.0) - t) * theta) / sinTheta;
+        scale1 = lm_sin(t * theta) / sinTheta;
+    }
+    if (d < T(0.0)) scale1 = -scale1;
+    out[0] = scale0 * T(0.0) + scale1 * q[0];
+    out[1] = scale0 * T(0.0) + scale1 * q[1];
+    out[2] = scale0 * T(0.0) + scale1 * q[2];
+    out[3] = scale0 * T(1.0) + scale1 * q[3];
+}
+// LidarEdgeFactor (LF:23-38) / LidarPlaneFactor_modify (LF:227-237) for T = double or LmJet; returns the residual count
+template <typename T>
+__device__ __forceinline__ int lm_functor_s(int type, const double* rec /* cp, p0, p1, w */, double s, const T q[4], const T t[3], T res[3])
+{
+    T qs[4];
+    lm_identity_slerp(T(s), q, qs);
+    const T ts[3] = {T(s) * t[0], T(s) * t[1], T(s) * t[2]};
+    const T cp[3] = {T(rec[0]), T(rec[1]), T(rec[2])};
+    // Eigen _transformVector: uv = 2 (u x v); v + w uv + u x uv
+    T uv[3] = {qs[1] * cp[2] - qs[2] * cp[1], qs[2] * cp[0] - qs[0] * cp[2], qs[0] * cp[1] - qs[1] * cp[0]};
+    uv[0] = uv[0] + uv[0]; uv[1] = uv[1] + uv[1]; uv[2] = uv[2] + uv[2];
+    const T lp[3] = {(cp[0] + qs[3] * uv[0]) + (qs[1] * uv[2] - qs[2] * uv[1]) + ts[0], (cp[1] + qs[3] * uv[1]) + (qs[2] * uv[0] - qs[0] * uv[2]) + ts[1],
+                     (cp[2] + qs[3] * uv[2]) + (qs[0] * uv[1] - qs[1] * uv[0]) + ts[2]};
+    if (type == 0) {
+        const T a[3] = {T(rec[3]), T(rec[4]), T(rec[5])}, b[3] = {T(rec[6]), T(rec[7]), T(rec[8])};
+        const T u[3] = {lp[0] - a[0], lp[1] - a[1], lp[2] - a[2]}, v[3] = {lp[0] - b[0], lp[1] - b[1], lp[2] - b[2]};
+        const T de[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+        const T dn = lm_sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+        res[0] = (u[1] * v[2] - u[2] * v[1]) / dn;
+        res[1] = (u[2] * v[0] - u[0] * v[2]) / dn;
+        res[2] = (u[0] * v[1] - u[1] * v[0]) / dn;
+        return 3;
+    }
+    const T j[3] = {T(rec[3]), T(rec[4]), T(rec[5])}, n[3] = {T(rec[6]), T(rec[7]), T(rec[8])};
+    res[0] = ((lp[0] - j[0]) * n[0] + (lp[1] - j[1]) * n[1] + (lp[2] - j[2]) * n[2]) * T(rec[9]);
+    return 1;
+}
+// one block of the de-skew mode: cost (+ JtJ / Jtr when FULL) into acc
+template <bool FULL>
+__device__ __noinline__ void lm_block_distort(int type, const double* rec, double s, const double* x, double acc[LM_NRED])
+{
+    if (!FULL) {
+        double r[3];
+        const int nr = lm_functor_s<double>(type, rec, s, x, x + 4, r);
+        double ss = 0.0;
+        for (int k = 0; k < nr; ++k) ss += r[k] * r[k];
+        double sq;
+        acc[27] += 0.5 * lm_huber(ss, sq);
+        return;
+    }
+    LmJet q[4], t[3], r[3];
+    for (int k = 0; k < 4; ++k) q[k] = LmJet(x[k], k);
+    for (int k = 0; k < 3; ++k) t[k] = LmJet(x[4 + k], 4 + k);
+    const int nr = lm_functor_s<LmJet>(type, rec, s, q, t, r);
+    double ss = 0.0;
+    for (int k = 0; k < nr; ++k) ss += r[k].a * r[k].a;
+    double sq;
+    acc[27] += 0.5 * lm_huber(ss, sq);
+    // EigenQuaternionManifold::PlusJacobian, rows x, y, z, w
+    const double PJ[4][3] = {{x[3], x[2], -x[1]}, {-x[2], x[3], x[0]}, {x[1], -x[0], x[3]}, {-x[0], -x[1], -x[2]}};
+    for (int k = 0; k < nr; ++k) {
+        double J[6];
+        for (int c = 0; c < 3; ++c) J[c] = (r[k].v[0] * PJ[0][c] + r[k].v[1] * PJ[1][c] + r[k].v[2] * PJ[2][c] + r[k].v[3] * PJ[3][c]) * sq;
+        for (int c = 0; c < 3; ++c) J[3 + c] = r[k].v[4 + c] * sq;
+        const double rk = r[k].a * sq;
+        int qi = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int c = a; c < 6; ++c) acc[qi++] += J[a] * J[c];
+        for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * rk;
+    }
+}
+
+struct LmRecord { double v[12]; };
 __device__ __forceinline__ void lm_load_record(LmRecord& r, const double* __restrict__ blk, int cap, int i)
 {
 #pragma unroll
     for (int k = 0; k < 11; ++k) r.v[k] = __ldg(blk + (size_t)k * cap + i);
 }
-template <bool FULL>
+template <bool FULL, bool DIST = false>
 __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, int cap, int nb, const double* x, double acc[LM_NRED], int part = 0, int nparts = 1)
 {
 #pragma unroll
@@ -158,6 +276,9 @@ __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, in
     for (; i < nb; i += stride) {
         if (i + stride < nb) lm_load_record(nxt, blk, cap, i + stride);
         const int type = (int)cur.v[0];
+        if (DIST && (type == 0 || type == 1)) {   // de-skew mode: per-point interpolation ratio s in record slot 11
+            lm_block_distort<FULL>(type, &cur.v[1], __ldg(blk + (size_t)11 * cap + i), x, acc);
+        } else
         if (type >= 0) {  // dense mapping records: type -1 = slot without a correspondence
         const double cpx = cur.v[1], cpy = cur.v[2], cpz = cur.v[3];
         const double ax = cur.v[4], ay = cur.v[5], az = cur.v[6];
@@ -185,9 +306,12 @@ __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, in
             // type 1 LidarPlaneFactor_modify: r = w (lp - j) . n ; type 2 LidarPlaneNormFactor: r = n . lp + d
             const double r0 = type == 1 ? ((lx - ax) * bx + (ly - ay) * by + (lz - az) * bz) * w : (ax * lx + ay * ly + az * lz) + w;
             const double d0 = type == 1 ? w * bx : ax, d1 = type == 1 ? w * by : ay, d2 = type == 1 ? w * bz : az;
+            // a PLANE_NORM record the scan-to-map vote selected stands for two identical blocks (LM:2064-2067): p1.x = 2
+            const bool twice = type == 2 && bx == 2.0;
             double sq;
-            acc[27] += 0.5 * lm_huber(0.0 + r0 * r0, sq);
-            if (FULL) lm_row(acc, d0, d1, d2, r0, Rx, Ry, Rz, sq);
+            const double rho = lm_huber(0.0 + r0 * r0, sq);
+            acc[27] += twice ? rho : 0.5 * rho;
+            if (FULL) lm_row(acc, d0, d1, d2, r0, Rx, Ry, Rz, twice ? sq * 1.4142135623730951 : sq);
         }
         }
         cur = nxt;
@@ -304,6 +428,7 @@ __device__ __forceinline__ bool chol6_solve(const double* Ap, const double* b, d
 }
 
 // The whole Solve. q_io / t_io point at the parameter blocks (global memory); all threads of the CTA call it.
+template <bool DIST = false>
 static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb, double* q_io, double* t_io, LaneState* L, int slot,
                                              const LmComm* comm = nullptr, int comm_b = 0, int part = 0)
 {
@@ -338,7 +463,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     auto norm7 = [](const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); };
 
     // IterationZero: cost, gradient, Jacobian (as JtJ) at x
-    lm_accumulate<true>(blk, cap, nb, S.x, acc, part, nparts);
+    lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
     lm_reduce<true>(S, acc);
     if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
     if (tid == 0) {
@@ -410,7 +535,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         __syncthreads();
         if (!S.go) break;
         // ---- all threads: cost at the candidate --------------------------------------------------------
-        lm_accumulate<false>(blk, cap, nb, S.cand, acc, part, nparts);
+        lm_accumulate<false, DIST>(blk, cap, nb, S.cand, acc, part, nparts);
         lm_reduce<false>(S, acc);
         if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 27, L);
         if (tid == 0) {
@@ -448,7 +573,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         const int go = S.go;
         if (go == 0) break;
         if (go == 2) {
-            lm_accumulate<true>(blk, cap, nb, S.x, acc, part, nparts);
+            lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
             lm_reduce<true>(S, acc);
             if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
             if (tid == 0) {

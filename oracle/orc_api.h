@@ -66,6 +66,9 @@ struct CorreMatch { int index; P4 src, tgt; float score, s; };  // common.h:20-3
 void graph_vote_simple(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected,
                        std::vector<float>* votes_out /* per correspondence, optional */);
 
+// the copy laserMapping.cpp carries (LM:836-1027): 20 regions, threshold 0.95, corner_case branch selects votes < 0.75 m
+void graph_vote_simple_mapping(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected_idx);
+
 struct OdomIterStats { int corner_corr, plane_corr, plane_selected; SolveSummary solve; };
 struct Odometry {
     Config cfg;
@@ -97,6 +100,7 @@ struct Mapping {
     int frameCount = 0;
     int last_corner_num = 0, last_surf_num = 0, last_map_corner = 0, last_map_surf = 0;
     int last_stack_corner = 0, last_stack_surf = 0;
+    int last_vote_selected = 0;                                  // plane correspondences the LM:2057-2072 vote selected (last iteration)
     std::vector<SolveSummary> last_solves;
     Mapping() : cornerArray(NUM), surfArray(NUM) {}
     // LM:1581-2168 for one (corner_last, surf_last, odom pose) triple; returns 0 or 1 (map too small, LM:2097-2100)

@@ -13,6 +13,7 @@ struct orc_config {
     int scan_line;
     float minimum_range, lower_bound, up_bound, line_res, plane_res;
     int skip_frame, voxel_stable, graph_from_frame;
+    int map_graph_vote, distortion, vote_mode;
 };
 
 static Config to_cfg(const orc_config* c)
@@ -22,6 +23,7 @@ static Config to_cfg(const orc_config* c)
     k.scan_line = c->scan_line; k.minimum_range = c->minimum_range; k.lower_bound = c->lower_bound; k.up_bound = c->up_bound;
     k.line_res = c->line_res; k.plane_res = c->plane_res; k.skip_frame = c->skip_frame; k.voxel_stable = c->voxel_stable;
     k.graph_from_frame = c->graph_from_frame;
+    k.map_graph_vote = c->map_graph_vote; k.distortion = c->distortion; k.vote_mode = c->vote_mode;
     return k;
 }
 
@@ -190,12 +192,12 @@ void orc_map_destroy(void* h) { delete (Mapping*)h; }
 void orc_map_insert(void* h, const float* corner, int nc, const float* surf, int ns) { ((Mapping*)h)->insert_map_points(to_cloud(corner, nc), to_cloud(surf, ns)); }
 // pose_out: q_w_curr[4], t_w_curr[3]; info: {rc, map_corner, map_surf, stack_corner, stack_surf, corner_num, surf_num}
 int orc_map_step(void* h, const float* corner_last, int nc, const float* surf_last, int ns, const double q_wodom[4], const double t_wodom[3],
-                 double pose_out[7], int info[7])
+                 double pose_out[7], int info[8])
 {
     Mapping* m = (Mapping*)h;
     const int rc = m->step(to_cloud(corner_last, nc), to_cloud(surf_last, ns), q_wodom, t_wodom);
     std::memcpy(pose_out, m->parameters, sizeof(double) * 7);
-    if (info) { info[0] = rc; info[1] = m->last_map_corner; info[2] = m->last_map_surf; info[3] = m->last_stack_corner; info[4] = m->last_stack_surf; info[5] = m->last_corner_num; info[6] = m->last_surf_num; }
+    if (info) { info[0] = rc; info[1] = m->last_map_corner; info[2] = m->last_map_surf; info[3] = m->last_stack_corner; info[4] = m->last_stack_surf; info[5] = m->last_corner_num; info[6] = m->last_surf_num; info[7] = m->last_vote_selected; }
     return rc;
 }
 long long orc_map_total_points(void* h, int which)
@@ -231,7 +233,8 @@ int orc_pipeline_step(void* h, const float* pts, int n, int stride_floats, doubl
     std::memcpy(poses + 4, p->odom.t_w_curr, sizeof(double) * 3);
     if (p->with_mapping) {
         // laserOdometry publishes laserCloudCornerLast = this frame's less-sharp cloud, SurfLast = less-flat (LO:882-912)
-        p->map.step(f.less_sharp, f.less_flat, p->odom.q_w_curr, p->odom.t_w_curr);
+        // (= f.less_sharp / f.less_flat unless the de-skew's TransformToEnd rewrote them, cfg.distortion == 2)
+        p->map.step(p->odom.cornerLast, p->odom.surfLast, p->odom.q_w_curr, p->odom.t_w_curr);
         std::memcpy(poses + 7, p->map.parameters, sizeof(double) * 7);
     } else {
         std::memcpy(poses + 7, poses, sizeof(double) * 7);

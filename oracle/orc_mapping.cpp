@@ -149,6 +149,55 @@ void Mapping::insert_map_points(const std::vector<P4>& corner, const std::vector
     }
 }
 
+// graph_based_correspondence_vote_simple as laserMapping.cpp carries it (LM:836-1027; Distance LM:250-259): 20 contiguous
+// regions, a vote when  std::exp(-(gap * gap) / (1 * 1)) < 0.95  (float score against a double literal), and in the
+// corner_case branch - the only one this copy has, and the one the commented call passes - every correspondence with
+// fewer votes than 0.75 * region size is selected with score 1.0, walking the descending sort from its end.
+void graph_vote_simple_mapping(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected_idx)
+{
+    struct by_score { bool operator()(VertexVote const& a, VertexVote const& b) { return a.score > b.score; } };  // common.h:50-52
+    auto Distance = [](const P4& a, const P4& b) { float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z; return std::sqrt(dx * dx + dy * dy + dz * dz); };
+    const int cor_size_all = (int)correspondences.size();
+    const int number_of_region = 20;
+    for (int num_region = 0; num_region < number_of_region; num_region++) {
+        const int initial_pos = cor_size_all / number_of_region * (num_region);
+        const int end_pos = (num_region == number_of_region - 1) ? cor_size_all : cor_size_all / number_of_region * (num_region + 1);
+        const int cor_size = end_pos - initial_pos;
+        const CorreMatch* sel = correspondences.data() + initial_pos;
+        const float resolution = 1;
+        std::vector<VertexVote> vote_record(cor_size, VertexVote{0, 0.0f});
+        for (int i = 0; i < cor_size; i++) {
+            vote_record[i].index = i;
+            for (int j = i + 1; j < cor_size; j++) {
+                const float s1 = Distance(sel[i].src, sel[j].src);
+                const float s2 = Distance(sel[i].tgt, sel[j].tgt);
+                const float dis_gap = std::abs(s1 - s2);
+                const float score = std::exp(-(dis_gap * dis_gap) / (resolution * resolution));
+                if (score < 0.95) {
+                    vote_record[j].score += 1;
+                    vote_record[i].score += 1;
+                }
+            }
+        }
+        std::sort(vote_record.begin(), vote_record.end(), by_score());
+        if (corner_case) {
+            const float selected_ratio = 0.75;
+            const float num_selected = selected_ratio * cor_size;
+            for (int i = cor_size - 1; i >= 0; i--) {
+                if (vote_record[i].score < num_selected) {
+                    VertexVote obj;
+                    if (sel[vote_record[i].index].index > (int)correspondences.size()) continue;
+                    obj.index = sel[vote_record[i].index].index;
+                    obj.score = 1.0;
+                    selected_idx.push_back(obj);
+                } else {
+                    break;
+                }
+            }
+        }
+    }
+}
+
 int Mapping::step(const std::vector<P4>& laserCloudCornerLast, const std::vector<P4>& laserCloudSurfLast,
                   const double q_wodom_curr[4], const double t_wodom_curr[3])
 {
@@ -269,6 +318,11 @@ int Mapping::step(const std::vector<P4>& laserCloudCornerLast, const std::vector
                     }
                 }
             }
+            // LM:2057-2072 (commented out in the reference; cfg.map_graph_vote turns it on): the plane correspondences are
+            // collected as Corre_Match records (LM:1997-2007) and the voted ones get a SECOND LidarPlaneNormFactor block
+            const bool map_vote = cfg.map_graph_vote > 0 && frameCount >= cfg.map_graph_vote - 1;
+            std::vector<CorreMatch> correspondences;
+            std::vector<ResidualBlock> vote_blocks;
             for (size_t i = 0; i < surfStack.size(); i++) {  // LM:1943-2055
                 const P4 pointOri = surfStack[i];
                 const P4 pointSel = associate_to_map(pointOri, parameters);
@@ -276,10 +330,13 @@ int Mapping::step(const std::vector<P4>& laserCloudCornerLast, const std::vector
                 kdSurf.knn(qf, 5, pointSearchInd, pointSearchSqDis);
                 if (pointSearchSqDis[4] < 1.0) {
                     double matA0[15];
+                    float cx = 0, cy = 0, cz = 0;   // LM:1949, 1960-1962: fp32 accumulation
                     for (int j = 0; j < 5; j++) {
                         const P4& m = surfFromMap[pointSearchInd[j]];
                         matA0[j * 3 + 0] = m.x; matA0[j * 3 + 1] = m.y; matA0[j * 3 + 2] = m.z;
+                        cx += m.x; cy += m.y; cz += m.z;
                     }
+                    cx /= 5; cy /= 5; cz /= 5;      // LM:1970-1972
                     double nrm[3];
                     plane_fit5(matA0, nrm);
                     const double nn = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
@@ -293,10 +350,26 @@ int Mapping::step(const std::vector<P4>& laserCloudCornerLast, const std::vector
                     }
                     if (planeValid) {
                         const double cp[3] = {pointOri.x, pointOri.y, pointOri.z};
+                        if (map_vote) {
+                            CorreMatch cor;
+                            cor.index = (int)correspondences.size();
+                            cor.src = surfStack[i];
+                            cor.tgt = P4{cx, cy, cz, 0.f};
+                            cor.score = 0; cor.s = 0;
+                            correspondences.push_back(cor);
+                            vote_blocks.push_back(make_plane_norm(cp, nrm, negative_OA_dot_norm));
+                        }
                         problem.push_back(make_plane_norm(cp, nrm, negative_OA_dot_norm));
                         surf_num++;
                     }
                 }
+            }
+            last_vote_selected = 0;
+            if (map_vote) {   // LM:2057-2072
+                std::vector<VertexVote> selected_idx;
+                graph_vote_simple_mapping(correspondences, true, selected_idx);
+                for (const VertexVote& v : selected_idx) problem.push_back(vote_blocks[v.index]);
+                last_vote_selected = (int)selected_idx.size();
             }
             SolveSummary ss;
             solve(problem, parameters, parameters + 4, &ss, 4, true);  // LM:2079-2087

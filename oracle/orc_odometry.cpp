@@ -17,10 +17,19 @@ namespace {
 const double DISTANCE_SQ_THRESHOLD = 25;  // LO:29
 const double NEARBY_SCAN = 2.5;           // LO:30
 
-// LO:77-95 with DISTORTION 0 (s = 1.0)
-inline P4 transform_to_start(const P4& pi, const double para_q[4], const double para_t[3])
+const double SCAN_PERIOD = 0.1;           // LO:28
+
+// interpolation ratio of a point (LO:81-84, 569-573, 739-743): DISTORTION 0 (the reference build) -> 1.0;
+// DISTORTION 1 -> fraction of the intensity (= 0.1 * relTime, SR:208) / SCAN_PERIOD
+inline double point_s(const P4& p, int distortion)
 {
-    const double s = 1.0;
+    if (distortion) return (p.i - int(p.i)) / SCAN_PERIOD;   // float - int -> float, then / double
+    return 1.0;
+}
+
+// LO:77-95
+inline P4 transform_to_start(const P4& pi, const double para_q[4], const double para_t[3], double s)
+{
     const Quat<double> q_last_curr{para_q[0], para_q[1], para_q[2], para_q[3]};
     const Quat<double> q_point_last = identity_slerp(s, q_last_curr);
     const V3<double> t_point_last{s * para_t[0], s * para_t[1], s * para_t[2]};
@@ -103,6 +112,7 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
                     const std::vector<P4>& surfPointsFlat, const std::vector<P4>& surfPointsLessFlat)
 {
     last_stats.clear();
+    const bool was_inited = systemInited;
     if (!systemInited) {  // LO:427-431
         systemInited = true;
     } else {
@@ -120,7 +130,7 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
 
             // LO:491-620 corner correspondences
             for (int i = 0; i < cornerPointsSharpNum; ++i) {
-                const P4 pointSel = transform_to_start(cornerPointsSharp[i], para_q, para_t);
+                const P4 pointSel = transform_to_start(cornerPointsSharp[i], para_q, para_t, point_s(cornerPointsSharp[i], cfg.distortion));
                 const float qf[3] = {pointSel.x, pointSel.y, pointSel.z};
                 if (kdCorner.knn(qf, 1, idx1, d1) < 1) continue;  // empty tree: PCL returns 0 neighbours
                 int closestPointInd = -1, minPointInd2 = -1;
@@ -145,7 +155,7 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
                     const double cp[3] = {cornerPointsSharp[i].x, cornerPointsSharp[i].y, cornerPointsSharp[i].z};
                     const double a[3] = {laserCloudCornerLast[closestPointInd].x, laserCloudCornerLast[closestPointInd].y, laserCloudCornerLast[closestPointInd].z};
                     const double b[3] = {laserCloudCornerLast[minPointInd2].x, laserCloudCornerLast[minPointInd2].y, laserCloudCornerLast[minPointInd2].z};
-                    problem.push_back(make_edge(cp, a, b, 1.0));
+                    problem.push_back(make_edge(cp, a, b, point_s(cornerPointsSharp[i], cfg.distortion)));   // LO:569-573
                     last_corner_assoc.push_back({i, closestPointInd, minPointInd2});
                     st.corner_corr++;
                 }
@@ -155,9 +165,10 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
             std::vector<CorreMatch> correspondences;
             std::vector<ResidualBlock> plane_blocks;  // weight 1; re-weighted after the vote
             std::vector<std::array<double, 12>> plane_pts;
+            std::vector<double> plane_s;   // LO:739-743
             int index = 0;
             for (int i = 0; i < surfPointsFlatNum; ++i) {
-                const P4 pointSel = transform_to_start(surfPointsFlat[i], para_q, para_t);
+                const P4 pointSel = transform_to_start(surfPointsFlat[i], para_q, para_t, point_s(surfPointsFlat[i], cfg.distortion));
                 const float qf[3] = {pointSel.x, pointSel.y, pointSel.z};
                 if (kdSurf.knn(qf, 1, idx1, d1) < 1) continue;
                 int closestPointInd = -1, minPointInd2 = -1, minPointInd3 = -1;
@@ -190,6 +201,7 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
                         plane_pts.push_back({(double)surfPointsFlat[i].x, (double)surfPointsFlat[i].y, (double)surfPointsFlat[i].z,
                                              (double)pa.x, (double)pa.y, (double)pa.z, (double)pb.x, (double)pb.y, (double)pb.z,
                                              (double)pc.x, (double)pc.y, (double)pc.z});
+                        plane_s.push_back(point_s(surfPointsFlat[i], cfg.distortion));
                         CorreMatch cor;
                         cor.index = index;
                         cor.src = surfPointsFlat[i];
@@ -201,7 +213,7 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
                         last_plane_assoc.push_back({i, closestPointInd, minPointInd2, minPointInd3});
                         if (now_frame <= cfg.graph_from_frame) {  // LO:781-787
                             const auto& pp = plane_pts.back();
-                            problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], 1.0, 1));
+                            problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], plane_s.back(), 1));
                             st.plane_selected++;
                         }
                         st.plane_corr++;
@@ -213,7 +225,7 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
                 graph_vote_simple(correspondences, false, selected_idx, nullptr);
                 for (size_t i = 0; i < selected_idx.size(); i++) {
                     const auto& pp = plane_pts[selected_idx[i].index];
-                    problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], 1.0, selected_idx[i].score));
+                    problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], plane_s[selected_idx[i].index], selected_idx[i].score));
                 }
                 st.plane_selected = (int)selected_idx.size();
             }
@@ -233,6 +245,21 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
     // LO:882-896: swap in the less-sharp / less-flat clouds and rebuild both kd-trees
     cornerLast = cornerPointsLessSharp;
     surfLast = surfPointsLessFlat;
+    // LO:861-880 TransformToEnd of the clouds about to become *Last.  The reference guards the block with a literal
+    // `if (0)` even when DISTORTION is 1; cfg.distortion == 2 is DISTORTION 1 with that block enabled (the LOAM-family
+    // de-skew in full).  Runs only for frames that went through the solve (the block sits inside the else branch).
+    if (cfg.distortion == 2 && was_inited) {
+        const Quat<double> ql{para_q[0], para_q[1], para_q[2], para_q[3]};
+        const Quat<double> qi = qinverse(ql);
+        auto to_end = [&](P4& p) {  // LO:98-114
+            const P4 un = transform_to_start(p, para_q, para_t, point_s(p, 1));   // stored as fp32 (pcl::PointXYZI un_point_tmp)
+            const V3<double> d{(double)un.x - para_t[0], (double)un.y - para_t[1], (double)un.z - para_t[2]};
+            const V3<double> e = rotate(qi, d);
+            p = P4{(float)e.x, (float)e.y, (float)e.z, (float)int(p.i)};
+        };
+        for (P4& p : cornerLast) to_end(p);
+        for (P4& p : surfLast) to_end(p);
+    }
     kdCorner.build(cornerLast);
     kdSurf.build(surfLast);
     now_frame++;  // LO:926

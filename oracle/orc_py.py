@@ -16,11 +16,12 @@ _LIB = None
 class OrcConfig(ctypes.Structure):
     _fields_ = [("scan_line", ctypes.c_int), ("minimum_range", ctypes.c_float), ("lower_bound", ctypes.c_float),
                 ("up_bound", ctypes.c_float), ("line_res", ctypes.c_float), ("plane_res", ctypes.c_float),
-                ("skip_frame", ctypes.c_int), ("voxel_stable", ctypes.c_int), ("graph_from_frame", ctypes.c_int)]
+                ("skip_frame", ctypes.c_int), ("voxel_stable", ctypes.c_int), ("graph_from_frame", ctypes.c_int),
+                ("map_graph_vote", ctypes.c_int), ("distortion", ctypes.c_int), ("vote_mode", ctypes.c_int)]
 
 
 def config(scan_line=64, minimum_range=None, lower_bound=-24.9, up_bound=2.0, line_res=None, plane_res=None,
-           voxel_stable=0, graph_from_frame=5):
+           voxel_stable=0, graph_from_frame=5, map_graph_vote=0, distortion=0, vote_mode=0):
     """Launch-file values: HDL-64 -> 5 m / 0.4 / 0.8 (launch/aloam_velodyne_HDL_64.launch:2-12),
     VLP-16 and HDL-32 -> 0.3 m / 0.2 / 0.4 (launch/aloam_velodyne_VLP_16.launch:3-13)."""
     if minimum_range is None:
@@ -29,7 +30,8 @@ def config(scan_line=64, minimum_range=None, lower_bound=-24.9, up_bound=2.0, li
         line_res = 0.4 if scan_line == 64 else 0.2
     if plane_res is None:
         plane_res = 0.8 if scan_line == 64 else 0.4
-    return OrcConfig(scan_line, minimum_range, lower_bound, up_bound, line_res, plane_res, 1, voxel_stable, graph_from_frame)
+    return OrcConfig(scan_line, minimum_range, lower_bound, up_bound, line_res, plane_res, 1, voxel_stable, graph_from_frame,
+                     map_graph_vote, distortion, vote_mode)
 
 
 def build():
@@ -212,7 +214,7 @@ class Mapping:
         q = np.ascontiguousarray(q_wodom, np.float64)
         t = np.ascontiguousarray(t_wodom, np.float64)
         pose = np.zeros(7)
-        info = np.zeros(7, np.int32)
+        info = np.zeros(8, np.int32)
         self.L.orc_map_step(self.h, _p(c), c.shape[0], _p(s), s.shape[0], _p(q), _p(t), _p(pose), _p(info))
         return dict(q=pose[:4].copy(), t=pose[4:].copy(), info=info)
 

@@ -33,6 +33,10 @@ struct Config {
     int   voxel_stable  = 0;       // 0: std::sort like PCL (reference-faithful, within-voxel order
                                    //    implementation-defined); 1: stable input order (what the GPU does)
     int   graph_from_frame = 5;    // laserOdometry.cpp:781,794: vote when now_frame > 5
+    int   map_graph_vote = 0;      // laserMapping.cpp:2057-2072 (commented out in the reference): 0 = off as shipped; N > 0 = the
+                                   // block enabled from mapping frame N - 1 on (the reference text reads "now_frame > 20" = 22)
+    int   distortion = 0;          // laserOdometry.cpp:23 DISTORTION (reference build: 0)
+    int   vote_mode = 0;           // 0: vote_simple (live); 1: vote_partial (laserMapping.cpp:261-834, dead in the reference)
 };
 
 struct Features {

@@ -168,10 +168,7 @@ def test_rings_longer_than_3083_points_take_the_wide_sector_kernels(ll, orc):
     assert np.diff(o["ring_begin"]).max() > 3083
     ctx = ll.Context(scan_line=line, max_points=65536)
     g = ctx.extract_features(scan)
-    for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
-        assert np.array_equal(g[key], o[key]), key
-    assert np.array_equal(g["curvature"], o["curvature"])
-    assert np.array_equal(g["less_flat"], o["less_flat"])
+    _compare(g, o)      # indices, curvature and x, y, z bit-exact; intensity fraction within the documented 4e-6
     # mixed: a normal scan through the same context still takes the fast path with identical results
     s2 = ll.synth.scan(line, 1)
     g2, o2 = ctx.extract_features(s2), orc.extract_features(s2, ocfg)

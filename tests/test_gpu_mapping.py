@@ -232,3 +232,32 @@ def test_multi_process_config5_when_two_gpus(ll, tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
     assert "config5 ok" in out.stdout
+
+
+def test_scan_to_map_graph_vote_matches_oracle(ll, orc):
+    """BASELINE.json configs[2] "graph matching on": the vote the reference keeps commented out at LM:2057-2072 (LM's own
+    copy of vote_simple, LM:836-1027: 20 regions, threshold 0.95, votes < 0.75 m selected, selected blocks added twice),
+    switched on from the first mapping frame (map_graph_vote = 1).  Selected counts equal the oracle's, poses agree."""
+    line = 16
+    ocfg = orc.config(line, voxel_stable=1, map_graph_vote=1)
+    ctx = ll.Context(scan_line=line, map_capacity=1 << 17, map_graph_vote=1)
+    plain = ll.Context(scan_line=line, map_capacity=1 << 17)
+    omap = orc.Mapping(ocfg)
+    odo = orc.Odometry(ocfg)
+    differs = False
+    for k in range(8):
+        f = orc.extract_features(ll.synth.scan(line, k), ocfg)
+        po = odo.step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        mo = omap.step(f["less_sharp"], f["less_flat"], po["q_w"], po["t_w"])
+        mg = ctx.mapping_step(f["less_sharp"], f["less_flat"], po["q_w"], po["t_w"])
+        mp = plain.mapping_step(f["less_sharp"], f["less_flat"], po["q_w"], po["t_w"])
+        assert np.abs(mg["t"] - mo["t"]).max() < 1e-7 and np.abs(mg["q"] - mo["q"]).max() < 1e-7, k
+        st, info = ctx.stats(), mo["info"]
+        if not info[0]:
+            assert st.map_surf_corr == int(info[6]) and st.map_vote_corr == int(info[6]), k
+            assert st.map_vote_selected == int(info[7]), (k, st.map_vote_selected, int(info[7]))
+            assert 0 < st.map_vote_selected <= st.map_vote_corr
+            differs |= bool(np.abs(mg["t"] - mp["t"]).max() > 1e-12)
+    assert differs          # the doubled blocks do change the solve
+    ctx.close()
+    plain.close()
