@@ -34,6 +34,13 @@ NN_KERNEL = "k_odom_assoc"
 WORKLOAD = "HDL-64 single scan (~130k pts), 5 GN iters, scan-to-scan odometry on 1xB200 (BASELINE.json configs[1]), batched over independent scan streams"
 
 
+def quiet_nccl():
+    """stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION / WARN, which some boxes export) must not
+    join it.  An explicit INFO / TRACE request is left alone."""
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "NONE"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -201,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        os.environ.setdefault("NCCL_DEBUG", "NONE")  # keep stdout to the one JSON line (WARN and above print a version banner)
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
     ctx = ll.Context(scan_line=64, batch=B, device=local_rank, max_ring_points=args.max_ring_points)
@@ -446,6 +453,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (1-based): 2 = the headline (default); 1, 3, 4, 5 in bench_configs.py")
     ap.add_argument("--stream-scans", type=int, default=10000, help="--config 4: scans in the stream")
     ap.add_argument("--lanes", type=int, default=128, help="--config 4: sub-segments (lanes) per GPU")
+    ap.add_argument("--overlap", type=int, default=6, help="--config 4: scans a sub-segment starts before its own first scan (1 = the anchor only)")
     ap.add_argument("--small", action="store_true", help="--config 5: 3e5-point map")
     ap.add_argument("--check", action="store_true", help="--config 5: compare with a single-GPU context")
     ap.add_argument("--no-cpu", action="store_true")

@@ -33,11 +33,13 @@ def _orc():
 
 def _dist_init(world, local_rank):
     import torch
+    sys.path.insert(0, ROOT)
+    from bench import quiet_nccl
     torch.cuda.set_device(local_rank)
     if world <= 1:
         return None
     import torch.distributed as dist
-    os.environ.setdefault("NCCL_DEBUG", "NONE")
+    quiet_nccl()
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     return dist
 
@@ -223,6 +225,12 @@ def chain_prefix(ends):
     return out
 
 
+def _qinv_apply(P0, P):
+    """inverse(P0) o P for (..., 7) pose arrays (unit quaternions up to rounding: the conjugate is the inverse)."""
+    qi = P0[..., :4] * np.array([-1.0, -1.0, -1.0, 1.0])
+    return np.concatenate([_qmul(qi, P[..., :4]), _qrot(qi, P[..., 4:7] - P0[..., 4:7])], -1)
+
+
 def run_config4(args, rank, world, local_rank):
     import torch
     ll = _ll()
@@ -230,10 +238,13 @@ def run_config4(args, rank, world, local_rank):
     from bench import pin_to_gpu_numa
     pin_to_gpu_numa(local_rank)
     dist = _dist_init(world, local_rank)
-    S, L = args.stream_scans, args.lanes
+    S, L, K = args.stream_scans, args.lanes, max(1, args.overlap)
     seg = ll.multigpu.segment_ranges(S, world)[rank]
     subs = [(seg[0] + a, seg[0] + b) for a, b in ll.multigpu.segment_ranges(seg[1] - seg[0], L)]      # this rank's sub-segments, stream order
-    first = [b - 1 if b > 0 else b for b, _ in subs]                                                  # + 1 overlap scan (none at the stream's start)
+    # Sub-segment l owns the poses of scans [b, e).  It starts K scans early (scan b - 1 is the anchor that ties it to its
+    # predecessor; the K - 1 before that only re-converge the warm start and the graph-vote gate) and throws those poses away.
+    first = [max(0, b - K) for b, _ in subs]
+    anchor = [(b - 1 - f) if b > 0 else 0 for f, (b, _) in zip(first, subs)]                         # local index of the anchor scan
     nsteps = [e - f for f, (_, e) in zip(first, subs)]
     order = sorted(range(L), key=lambda l: -nsteps[l])                                               # slot -> sub-segment: the longest first (a prefix stays active)
     T = max(nsteps)
@@ -243,7 +254,6 @@ def run_config4(args, rank, world, local_rank):
         scans = list(ex.map(lambda g: ll.synth.scan(64, g, mode=1, scan_id=g), range(g0, seg[1])))
     ctx = ll.Context(scan_line=64, batch=L, device=local_rank)
     ctx.pool_upload(scans)
-    stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,43 +268,43 @@ def run_config4(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    n_act = [sum(1 for l in order if nsteps[l] > t) for t in range(T)]
+    slot_of = np.argsort(np.array(order))                                                             # sub-segment -> slot
+    last_idx = np.array([nsteps[l] - 1 for l in range(L)])
+    anchor_idx = np.array(anchor)
+
     def run_stream(feed):
-        """All sub-segments in lockstep; returns poses[sub][k] (local frame) and the seconds spent in the exchange."""
+        """All sub-segments in lockstep; returns the poses in the stream's frame and the seconds spent in the exchange."""
         ctx.reset()     # every lane starts like a fresh stream: identity warm start, frame counter 0 (no graph vote on its first 5 pairs, LO:794)
-        local = [np.zeros((nsteps[l], 7)) for l in range(L)]
+        local = np.zeros((L, T, 7))
+        local[:, :, 3] = 1.0
         launches = 0
         for t in range(T):
-            n_act = sum(1 for l in order if nsteps[l] > t)
-            poses = feed(t, n_act)
+            poses = feed(t, n_act[t])
             launches += ctx.L.ll_launch_count(ctx.h)
-            for slot in range(n_act):
-                local[order[slot]][t] = poses[slot][:7]
+            local[np.array(order[:n_act[t]]), t] = poses[:, :7]
         t_x = time.perf_counter()
-        ends = torch.tensor(np.stack([local[l][-1] for l in range(L)]), dtype=torch.float64, device="cuda")     # (L, 7) on the device
+        rel = _qinv_apply(local[np.arange(L), anchor_idx][:, None, :], local)                            # poses relative to each lane's anchor scan
+        ends = torch.from_numpy(rel[np.arange(L), last_idx]).to("cuda")                                  # (L, 7): anchor -> last scan
         if dist is not None:
             allends = torch.empty((world * L, 7), dtype=torch.float64, device="cuda")
-            dist.all_gather_into_tensor(allends, ends)                                                            # the one exchange: N x L x 56 bytes over NVLink
+            dist.all_gather_into_tensor(allends, ends)                                                    # the one exchange: N x L x 56 bytes over NVLink
         else:
             allends = ends
-        starts = chain_prefix(allends.cpu().numpy())[rank * L:(rank + 1) * L]
-        glob = []
-        for l in range(L):                                                                                       # place every scan's pose in the stream's frame
-            q0, t0 = starts[l, :4], starts[l, 4:]
-            glob.append(np.concatenate([_qmul(q0[None, :], local[l][:, :4]), t0[None, :] + _qrot(q0[None, :], local[l][:, 4:7])], 1))
-        torch.cuda.synchronize()
-        return local, glob, time.perf_counter() - t_x, launches
+        starts = chain_prefix(allends.cpu().numpy())[rank * L:(rank + 1) * L]                             # stream-frame pose of every anchor
+        q0, t0 = starts[:, None, :4], starts[:, None, 4:]
+        glob = np.concatenate([_qmul(q0, rel[..., :4]), t0 + _qrot(q0, rel[..., 4:7])], -1)               # (L, T, 7), valid from the anchor on
+        return glob, time.perf_counter() - t_x, launches
 
     ids = np.array([[first[l] - g0 + min(t, nsteps[l] - 1) for l in order] for t in range(T)], np.int32)       # pool index per (step, slot)
 
-    def feed_pool(t, n_act):
-        return ctx.process_pool(ids[t, :n_act])
+    def feed_pool(t, n):
+        return ctx.process_pool(ids[t, :n])
 
-    W = max(args.warmup, 3)
-    for _ in range(1):
-        run_stream(feed_pool)                                  # warm-up pass over the whole segment (allocations, clocks)
+    run_stream(feed_pool)                                      # warm-up pass over the whole segment (allocations, NCCL communicator, clocks)
     barrier()
     t0 = time.perf_counter()
-    local, glob, t_exchange, launches = run_stream(feed_pool)
+    glob, t_exchange, launches = run_stream(feed_pool)
     barrier()
     dt = maxreduce(time.perf_counter() - t0)
     value = S / dt
@@ -318,16 +328,13 @@ def run_config4(args, rank, world, local_rank):
                 j = ids[t, slot]
                 cnts[t, slot] = n_pts[j]
                 arena[offs[t, slot]:offs[t, slot] + n_pts[j] * 12] = np.ascontiguousarray(scans[j][:, :3]).view(np.uint8).reshape(-1)
-    def n_active(t):
-        return sum(1 for l in order if nsteps[l] > t)
 
-    def feed_packed(t, n_act):
+    def feed_packed(t, n):
         """Step t's poses; step t + 1 is already on its way (two submissions in flight: its copy overlaps step t's kernels)."""
         if t == 0:
-            ctx.submit_packed(arena, offs[0, :n_act], cnts[0, :n_act], 12)
+            ctx.submit_packed(arena, offs[0, :n], cnts[0, :n], 12)
         if t + 1 < T:
-            na = n_active(t + 1)
-            ctx.submit_packed(arena, offs[t + 1, :na], cnts[t + 1, :na], 12)
+            ctx.submit_packed(arena, offs[t + 1, :n_act[t + 1]], cnts[t + 1, :n_act[t + 1]], 12)
         return ctx.collect()
 
     run_stream(feed_packed)            # warm-up of the asynchronous path
@@ -337,7 +344,7 @@ def run_config4(args, rank, world, local_rank):
     barrier()
     e2e_dt = maxreduce(time.perf_counter() - t0)
 
-    # ---- deviation from the unsegmented chain (rank 0, its own segment): what restarting the warm start costs -----------
+    # ---- deviation from the unsegmented chain (rank 0, its own segment): what cutting the stream costs -----------------
     dev = None
     if rank == 0:
         one = ll.Context(scan_line=64, batch=1, device=local_rank)
@@ -347,26 +354,29 @@ def run_config4(args, rank, world, local_rank):
         one.close()
         mine = np.zeros((len(scans), 7))
         for l in range(L):
-            mine[first[l] - g0:first[l] - g0 + nsteps[l]] = glob[l]      # rank 0: the stream's frame = its segment's frame
+            b, e = subs[l]
+            mine[b - g0:e - g0] = glob[l, b - first[l]:e - first[l]]      # rank 0: the stream's frame = its segment's frame
         dtm = np.abs(mine[:, 4:] - chain[:, 4:]).max(1)
         ang = 2 * np.arccos(np.minimum(1.0, np.abs((mine[:, :4] * chain[:, :4]).sum(1))))
         # per-scan increments in the sensor frame (inverse(pose k-1) * pose k): what a scan pair's solve changes when the lane
-        # restarted shortly before (identity warm start on its first pair, no graph vote on its first five)
+        # restarted K scans before
+
         def increments(P):
-            qi = P[:-1, :4] * np.array([-1.0, -1.0, -1.0, 1.0])
-            return _qrot(qi, P[1:, 4:] - P[:-1, 4:]), _qmul(qi, P[1:, :4])
+            r = _qinv_apply(P[:-1], P[1:])
+            return r[:, 4:], r[:, :4]
         (ti_m, qi_m), (ti_c, qi_c) = increments(mine), increments(chain)
         inc_t = np.linalg.norm(ti_m - ti_c, axis=1)
         inc_r = 2 * np.arccos(np.minimum(1.0, np.abs((qi_m * qi_c).sum(1))))
-        dev = {"scans": len(scans), "sub_segments": L, "max_abs_translation_m": float(dtm.max()), "max_rotation_rad": float(ang.max()),
+        dev = {"scans": len(scans), "sub_segments": L, "overlap_scans": K, "max_abs_translation_m": float(dtm.max()), "max_rotation_rad": float(ang.max()),
                "end_of_segment_translation_m": float(dtm[-1]), "max_per_scan_increment_m": float(inc_t.max()), "median_per_scan_increment_m": float(np.median(inc_t)),
                "max_per_scan_increment_rad": float(inc_r.max()), "increments_within_1e-4": float(np.mean((inc_t < 1e-4) & (inc_r < 1e-4))), "path_length_m": float(len(scans) - 1)}
     if rank == 0:
         line = {"metric": "scans/sec (HDL-64, 130k pts, 5 GN iters)", "value": round(value, 1), "unit": "scans/s", "n_gpus": world, "steps": T, "warmup": T,
                 "ms_per_step": round(dt / T * 1e3, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (features, NN) + f64 (residuals, LM)", "data": "synthetic",
-                "config": {"workload": CONFIGS[3], "stream_scans": S, "segments": world, "sub_segments_per_gpu": L, "overlap_scans": 1,
-                           "steps_per_gpu": T, "parallelism": "contiguous segments per GPU (+1 overlap scan), %d lanes per GPU; one ncclAllGather of the %d x 7-double segment transforms + prefix product" % (L, world * L),
+                "config": {"workload": CONFIGS[3], "stream_scans": S, "segments": world, "sub_segments_per_gpu": L, "overlap_scans": K,
+                           "steps_per_gpu": T, "scans_processed_incl_overlap": int(sum(nsteps)) * world,
+                           "parallelism": "contiguous segments per GPU, %d lanes per GPU, each starting %d scans early; one ncclAllGather of the %d x 7-double segment transforms + log-step prefix product" % (L, K, world * L),
                            "l2": "inputs larger than L2: %d lanes x 2.08 MB per step" % L},
                 "exchange": {"collective": "all_gather_into_tensor (NCCL, device tensors) of %d x 56 B + prefix product + pose placement" % (world * L), "ms": round(t_exchange * 1e3, 3),
                              "share_of_run": round(t_exchange / dt, 5)},

@@ -142,7 +142,7 @@ struct ll_ctx {
     float4* d_qb = nullptr;        // [B][R*36] their polar coordinates
     int* d_qstart = nullptr;       // [B][qstart_stride] slab offsets
     int qstart_stride = 260;
-    bool slab_attr_set = false;
+    bool slab_attr_set = false, vp_attr_set = false;
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;
 

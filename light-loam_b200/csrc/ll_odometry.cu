@@ -1255,6 +1255,152 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_odom_vote(OdomParams P)
     if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
 }
 
+// graph_based_correspondence_vote_partial (laserMapping.cpp:321-834, graph_construction_partial LM:261-318): the paper-style
+// scoring, DEAD in the reference (its only call is commented out, LO:622).  Optional mode cfg.vote_mode = 1, beyond-reference:
+// it replaces vote_simple on the odometry's plane correspondences.  One CTA per (region, lane); the region's m x m
+// compatibility matrix G(i,j) = expf(-gap^2) lives in shared memory (expf and cbrt evaluated in fp64 and rounded once,
+// which is what glibc's float routines return in all but double-rounding cases).  Steps as in the source: neighbours
+// G > 0.95; first score = mean over neighbour pairs of cbrt(G_ia G_ib G_ab); threshold = min(ratio of the sums, mean
+// score); pruning; final score = 0.1 * mean G(a,i) + 0.9 * (pairs with G_ab != 0) / (d (d - 2) / 2) - the source's
+// pow(x, 1 / 3) has the integer exponent 0 - for d > 2; selected = score != 0 with weight = score.
+#define VP_THREADS 256
+#define VP_WORDS 8   // neighbour bitmask words per vertex: regions of up to 256 correspondences
+__global__ void __launch_bounds__(VP_THREADS) k_odom_vote_partial(OdomParams P, int mcap)
+{
+    extern __shared__ __align__(16) unsigned char vp_smem[];
+    const int b = blockIdx.y, reg = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    LaneState& L = P.lane[b];
+    if (!L.inited || L.err || !(L.now_frame > P.graph_from_frame)) return;
+    const int nplane = L.n_plane_corr, ncorner = L.n_corner_corr;
+    const int region_len = nplane / 10;
+    const int r0 = region_len * reg, r1 = reg == 9 ? nplane : region_len * (reg + 1);
+    const int m = r1 - r0;
+    if (m <= 0) return;
+    const int maxp = P.R * LL_FLAT_PER_RING;
+    float* G = reinterpret_cast<float*>(vp_smem);                       // [m][m]
+    unsigned* conn = reinterpret_cast<unsigned*>(G + (size_t)mcap * mcap);   // [m][VP_WORDS]
+    float* score = reinterpret_cast<float*>(conn + (size_t)mcap * VP_WORDS);  // [m] first-pass score
+    float* numer = score + mcap;                                        // [m]
+    float* fin = numer + mcap;                                          // [m] final score
+    __shared__ float thr_s;
+    __shared__ int any_s, nsel_s;
+    const float4* src = P.vote_src + (size_t)b * maxp + r0;
+    const float4* tgt = P.vote_tgt + (size_t)b * maxp + r0;
+    double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    int* pa = P.plane_assoc + (size_t)b * P.R * LL_FLAT_PER_RING * 4;
+    if (tid == 0) { any_s = 0; nsel_s = 0; }
+    if (m > mcap || m > 32 * VP_WORDS) {   // cannot happen with the configured capacities; never leave the blocks half-decided
+        for (int k = tid; k < m; k += VP_THREADS) blk[ncorner + r0 + k] = -1.0;
+        return;
+    }
+    for (int k = tid; k < m * VP_WORDS; k += VP_THREADS) conn[k] = 0u;
+    __syncthreads();
+    // graph_construction_partial
+    int any = 0;
+    for (int p = tid; p < m * m; p += VP_THREADS) {
+        const int i = p / m, j = p % m;
+        float g = 0.f;
+        if (i != j) {
+            const float4 a = __ldg(src + i), c = __ldg(src + j), ta = __ldg(tgt + i), tc = __ldg(tgt + j);
+            const float s1 = sqrtf(sqdist3(a.x, a.y, a.z, c.x, c.y, c.z)), s2 = sqrtf(sqdist3(ta.x, ta.y, ta.z, tc.x, tc.y, tc.z));
+            const float gap = fabsf(s1 - s2);
+            g = (float)exp(-(double)(gap * gap));
+            if ((double)g > 0.95) atomicOr(&conn[i * VP_WORDS + (j >> 5)], 1u << (j & 31));
+            any |= g != 0.f;
+        }
+        G[i * m + j] = g;
+    }
+    if (any) any_s = 1;
+    __syncthreads();
+    if (!any_s) {   // LM:399-403: "Graph is not connected!" -> nothing selected from this region
+        for (int k = tid; k < m; k += VP_THREADS) { blk[ncorner + r0 + k] = -1.0; pa[__float_as_int(__ldg(src + k).w) * 4 + 3] = 0; }
+        return;
+    }
+    auto nth_words = [&](const unsigned* w, int words) { int d = 0; for (int q = 0; q < words; ++q) d += __popc(w[q]); return d; };
+    const int words = (m + 31) >> 5;
+    // first pass (LM:445-500): one warp per vertex, lanes share the first neighbour of the pair
+    for (int i = wid; i < m; i += VP_THREADS / 32) {
+        const unsigned* ci = conn + i * VP_WORDS;
+        const int deg = nth_words(ci, words);
+        double acc = 0.0;
+        for (int a = lane; a < m; a += 32) {
+            if (!((ci[a >> 5] >> (a & 31)) & 1u)) continue;
+            const float gia = G[i * m + a];
+            for (int bq = a + 1; bq < m; ++bq) {
+                if (!((ci[bq >> 5] >> (bq & 31)) & 1u)) continue;
+                const float gab = G[a * m + bq];
+                if (gab != 0.f) acc += (double)(float)pow((double)(gia * G[i * m + bq] * gab), 1.0 / 3);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += shfl_xor_f64(acc, d);
+        if (lane == 0) {
+            float sc = 0.f, nu = 0.f;
+            if (deg > 1) { nu = (float)acc; sc = nu / (float)(deg * (deg - 1) * 0.5); }
+            score[i] = sc; numer[i] = deg > 1 ? nu : -1.f;   // -1: does not enter the filter sums
+            fin[i] = (float)deg;                              // parked for thread 0
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {   // LM:493-503, vertex order, fp32
+        float fa_n = 0.f, fa_d = 0.f, fb = 0.f;
+        for (int i = 0; i < m; ++i) {
+            if (numer[i] >= 0.f) { const int deg = (int)fin[i]; fa_n += numer[i]; fa_d += (float)(deg * (deg - 1) * 0.5); }
+            fb += score[i];
+        }
+        const float fa = fa_n / fa_d;
+        fb = fb / (float)m;
+        thr_s = fminf(fa, fb);   // std::min: a NaN ratio (no vertex with two neighbours) never wins over fb... std::min(a, b) = b < a ? b : a
+        if (!(fb < fa)) thr_s = fa;
+    }
+    __syncthreads();
+    const float thr = thr_s;
+    // prune (LM:560-580): a neighbour stays when its first-pass score reaches the threshold
+    for (int k = tid; k < m * words; k += VP_THREADS) {
+        const int i = k / words, q = k % words;
+        unsigned w = conn[i * VP_WORDS + q], keep = 0u;
+        while (w) { const int bit = __ffs(w) - 1; w &= w - 1; if (score[q * 32 + bit] >= thr) keep |= 1u << bit; }
+        conn[i * VP_WORDS + q] = keep;
+    }
+    __syncthreads();
+    // final score (LM:600-690)
+    for (int i = wid; i < m; i += VP_THREADS / 32) {
+        const unsigned* ci = conn + i * VP_WORDS;
+        const int d = nth_words(ci, words);
+        double loose = 0.0;
+        int tight = 0;
+        if (d > 2) {
+            for (int a = lane; a < m; a += 32) {
+                if (!((ci[a >> 5] >> (a & 31)) & 1u)) continue;
+                loose += (double)G[a * m + i];
+                for (int bq = a + 1; bq < m; ++bq)
+                    if (((ci[bq >> 5] >> (bq & 31)) & 1u) && G[a * m + bq] != 0.f) ++tight;
+            }
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) { loose += shfl_xor_f64(loose, dd); tight += __shfl_xor_sync(LL_FULL_MASK, tight, dd); }
+        if (lane == 0) {
+            float tight_sum = 0.f, looser_sum = 0.f;
+            if (d > 2) { tight_sum = (float)(double)tight; tight_sum /= (float)(d * (d - 2) / 2); }
+            if (d != 0) { looser_sum = (float)loose; looser_sum = looser_sum / (float)d; }
+            const float wb = 0.9f;
+            fin[i] = (1 - wb) * looser_sum + wb * tight_sum;
+        }
+    }
+    __syncthreads();
+    int sel = 0;
+    for (int k = tid; k < m; k += VP_THREADS) {
+        const float w = fin[k];
+        const int o = ncorner + r0 + k;
+        if (w != 0.f) { blk[10 * P.nblk_cap + o] = (double)w; ++sel; }
+        else blk[o] = -1.0;
+        pa[__float_as_int(__ldg(src + k).w) * 4 + 3] = (int)(w * 1000.f);
+    }
+    if (sel) atomicAdd(&nsel_s, sel);
+    __syncthreads();
+    if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
+}
+
 template <bool DIST>
 __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P)
 {
@@ -1451,7 +1597,15 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         }
         { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
-        { LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P); }
+        if (c->cfg.vote_mode == 1) {
+            const int mcap = c->R * LL_FLAT_PER_RING / 10 + 16;
+            const size_t vp_smem = ((size_t)mcap * mcap + (size_t)mcap * (VP_WORDS + 3)) * 4;
+            if (!c->vp_attr_set) { LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_vote_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vp_smem)); c->vp_attr_set = true; }
+            LLProf pr(c, "k_odom_vote_partial");
+            k_odom_vote_partial<<<dim3(10, n_lanes), VP_THREADS, vp_smem, s>>>(P, mcap);
+        } else {
+            LLProf pr(c, "k_odom_vote"); k_odom_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem, s>>>(P);
+        }
         {
             LLProf pr(c, "k_lm_solve_odom");
             if (P.distortion) k_lm_solve_odom<true><<<n_lanes, lm_threads, 0, s>>>(P);

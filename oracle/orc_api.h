@@ -66,6 +66,8 @@ struct CorreMatch { int index; P4 src, tgt; float score, s; };  // common.h:20-3
 void graph_vote_simple(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected,
                        std::vector<float>* votes_out /* per correspondence, optional */);
 
+// graph_based_correspondence_vote_partial (LM:321-834, dead in the reference): optional scoring mode, cfg.vote_mode = 1
+void graph_vote_partial(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected_idx);
 // the copy laserMapping.cpp carries (LM:836-1027): 20 regions, threshold 0.95, corner_case branch selects votes < 0.75 m
 void graph_vote_simple_mapping(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected_idx);
 

@@ -108,6 +108,141 @@ void graph_vote_simple(const std::vector<CorreMatch>& correspondences, bool corn
     }
 }
 
+// graph_based_correspondence_vote_partial (laserMapping.cpp:321-834; graph_construction_partial LM:261-318) - the
+// paper-style scoring.  DEAD in the reference: the only call is commented out (LO:622), and the function lives in the
+// mapping node.  Restated for the optional mode cfg.vote_mode = 1, where it scores the odometry's plane correspondences
+// in place of vote_simple (beyond-reference behaviour).  Per region of m correspondences:
+//   G(i,j) = expf(-gap^2); neighbours N(i) = {j : G(i,j) > 0.95}; first pass: s_i = mean over neighbour pairs (a,b) with
+//   G(a,b) != 0 of cbrt(G(i,a) G(i,b) G(a,b)) (pairs with G(a,b) = 0 count as 0); threshold = min(sum_i num_i / sum_i den_i,
+//   mean_i s_i); neighbours with s < threshold are pruned; final score = 0.1 * mean G(a,i) + 0.9 * tight, where - as
+//   written, std::pow(x, 1/3) with the INTEGER quotient 1/3 = 0 - every surviving neighbour pair with G(a,b) != 0
+//   contributes 1, divided by the integer d (d - 2) / 2; both parts are 0 unless d > 2.  Selected = score != 0, in
+//   descending score order, weight = score.
+void graph_vote_partial(const std::vector<CorreMatch>& correspondences, bool corner_case, std::vector<VertexVote>& selected_idx)
+{
+    (void)corner_case;   // LM:716-787: the two branches are textually identical (selected_ratio = 1)
+    const int cor_size_all = (int)correspondences.size();
+    const int number_of_region = 10;   // LM:327
+    for (int num_region = 0; num_region < number_of_region; num_region++) {
+        const int initial_pos = cor_size_all / number_of_region * (num_region);
+        const int end_pos = (num_region == number_of_region - 1) ? cor_size_all : cor_size_all / number_of_region * (num_region + 1);
+        const int cor_size = end_pos - initial_pos;
+        const CorreMatch* sel = correspondences.data() + initial_pos;
+        // graph_construction_partial, LM:261-318
+        std::vector<float> G((size_t)cor_size * cor_size, 0.f);
+        double gnorm = 0.0;
+        for (int i = 0; i < cor_size; i++)
+            for (int j = i + 1; j < cor_size; j++) {
+                const float s1 = Distance(sel[i].src, sel[j].src);
+                const float s2 = Distance(sel[i].tgt, sel[j].tgt);
+                const float dis_gap = std::abs(s1 - s2);
+                const float resolution = 1;
+                const float score = std::exp(-(dis_gap * dis_gap) / (resolution * resolution));
+                G[(size_t)i * cor_size + j] = score;
+                G[(size_t)j * cor_size + i] = score;
+                gnorm += (double)score * score;
+            }
+        if (gnorm == 0) continue;   // LM:399-403 "Graph is not connected!"
+        auto g = [&](int i, int j) { return G[(size_t)i * cor_size + j]; };
+        std::vector<std::vector<int>> conn(cor_size);
+        std::vector<int> degree(cor_size, 0);
+        for (int i = 0; i < cor_size; i++)   // LM:407-430
+            for (int j = 0; j < cor_size; j++)
+                if (i != j && g(i, j) > 0.95) { degree[i]++; conn[i].push_back(j); }
+        std::vector<VertexVote> neighbor_voter;
+        float filter_param_numerator_a = 0, filter_param_denominator_a = 0, filter_param_b = 0;
+        for (int i = 0; i < cor_size; i++) {   // LM:445-500
+            VertexVote ob;
+            std::vector<float> weight_s((size_t)(degree[i] * (degree[i] - 1) * 0.5), 0);
+            for (int j = 0; j < degree[i]; j++) {
+                const int a = conn[i][j];
+                int count_b = 0;
+                for (int k = j + 1; k < degree[i]; k++) {
+                    const int b = conn[i][k];
+                    if (g(a, b)) weight_s[int(j * (2 * degree[i] - 1 - j) / 2 + count_b)] = std::pow(g(i, a) * g(i, b) * g(a, b), 1.0 / 3);
+                    count_b++;
+                }
+            }
+            if (degree[i] > 1) {
+                double acc = 0.0;
+                for (float w : weight_s) acc += w;   // std::accumulate(..., 0.0)
+                const float numerator = acc;
+                const float denominator = degree[i] * (degree[i] - 1) * 0.5;
+                filter_param_numerator_a += numerator;
+                filter_param_denominator_a += denominator;
+                ob.index = i;
+                ob.score = numerator / denominator;
+            } else {
+                ob.index = i;
+                ob.score = 0;
+            }
+            neighbor_voter.push_back(ob);
+            filter_param_b += ob.score;
+        }
+        const float filter_param_a = filter_param_numerator_a / filter_param_denominator_a;
+        filter_param_b = filter_param_b / neighbor_voter.size();
+        const float threshold_param = std::min(filter_param_a, filter_param_b);
+        for (int i = 0; i < cor_size; i++) {   // LM:560-580 prune
+            std::vector<int> index_pruned;
+            for (int idx : conn[i])
+                if (neighbor_voter[idx].score >= threshold_param) index_pruned.push_back(idx);
+            conn[i] = index_pruned;
+            degree[i] = (int)index_pruned.size();
+        }
+        const float weight_balance = 0.9;
+        std::vector<VertexVote> voter;
+        for (int i = 0; i < cor_size; i++) {   // LM:600-690
+            float score_all = 0;
+            const size_t d = conn[i].size();
+            std::vector<float> looser_score(d, 0);
+            std::vector<float> tight_score((size_t)(d * (d - 1) * 0.5), 0);
+            float tight_score_sum = 0, looser_score_sum = 0;
+            if (d > 2) {
+                for (size_t j = 0; j < d; j++) {
+                    const int idx_a = conn[i][j];
+                    looser_score[j] = g(idx_a, i);
+                    int count_b = 0;
+                    for (size_t k = j + 1; k < d; k++) {
+                        const int idx_b = conn[i][k];
+                        if (g(idx_a, idx_b)) tight_score[int(j * (2 * d - 1 - j) / 2 + count_b)] = std::pow(g(idx_a, idx_b) * g(idx_a, i) * g(idx_b, i), 1 / 3);
+                        count_b++;
+                    }
+                }
+                double acc = 0.0;
+                for (float w : tight_score) acc += w;
+                tight_score_sum = acc;
+                tight_score_sum /= (degree[i] * (degree[i] - 2) / 2);
+            }
+            if (degree[i] != 0) {
+                double acc = 0.0;
+                for (float w : looser_score) acc += w;
+                looser_score_sum = acc;
+                looser_score_sum = looser_score_sum / degree[i];
+            }
+            score_all = (1 - weight_balance) * looser_score_sum + weight_balance * tight_score_sum;
+            VertexVote obj;
+            obj.index = i;
+            obj.score = score_all;
+            voter.push_back(obj);
+        }
+        std::vector<VertexVote> voter_ordered(voter.begin(), voter.end());
+        std::sort(voter_ordered.begin(), voter_ordered.end(), compare_score());   // LM:700
+        const float selected_ratio = 1;
+        const int num_selected = selected_ratio * cor_size;
+        for (int i = 0; i < cor_size; i++) {   // LM:716-787
+            if (i < num_selected) {
+                VertexVote obj;
+                if (sel[voter_ordered[i].index].index > (int)correspondences.size()) continue;
+                obj.index = sel[voter_ordered[i].index].index;
+                obj.score = voter_ordered[i].score;
+                if (obj.score != 0) selected_idx.push_back(obj);
+            } else {
+                break;
+            }
+        }
+    }
+}
+
 void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<P4>& cornerPointsLessSharp,
                     const std::vector<P4>& surfPointsFlat, const std::vector<P4>& surfPointsLessFlat)
 {
@@ -222,7 +357,8 @@ void Odometry::step(const std::vector<P4>& cornerPointsSharp, const std::vector<
             }
             if (now_frame > cfg.graph_from_frame) {  // LO:794-810
                 std::vector<VertexVote> selected_idx;
-                graph_vote_simple(correspondences, false, selected_idx, nullptr);
+                if (cfg.vote_mode == 1) graph_vote_partial(correspondences, false, selected_idx);   // optional, beyond-reference (dead code LM:321-834)
+                else graph_vote_simple(correspondences, false, selected_idx, nullptr);
                 for (size_t i = 0; i < selected_idx.size(); i++) {
                     const auto& pp = plane_pts[selected_idx[i].index];
                     problem.push_back(make_plane_modify(&pp[0], &pp[3], &pp[6], &pp[9], plane_s[selected_idx[i].index], selected_idx[i].score));

@@ -161,3 +161,28 @@ print("ok", r)
                           "--master-port", "29619", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_config4_chain_prefix_and_anchor_algebra():
+    """bench_configs (BASELINE.json configs[3]): the log-step prefix of the sub-segment transforms equals the sequential
+    LO:830-831 chain, and inverse(anchor) o pose recovers the poses relative to a lane's anchor scan."""
+    import bench_configs as bc
+    rng = np.random.default_rng(4)
+    K = 53
+    q = rng.normal(size=(K, 4)) * 0.05
+    q[:, 3] = 1
+    q /= np.linalg.norm(q, axis=1)[:, None]
+    ends = np.concatenate([q, rng.normal(size=(K, 3))], 1)
+    out = bc.chain_prefix(ends)
+    qq, tt = np.array([0, 0, 0, 1.0]), np.zeros(3)
+    for k in range(K):
+        assert np.allclose(out[k, :4], qq, atol=1e-13) and np.allclose(out[k, 4:], tt, atol=1e-12), k
+        tt = tt + bc._qrot(qq, ends[k, 4:7])
+        qq = bc._qmul(qq, ends[k, :4])
+    # a lane's poses P[j] in its own frame; anchor a: rel[j] = inverse(P[a]) o P[j]; composing back gives P[j]
+    P = np.concatenate([q[:10], rng.normal(size=(10, 3))], 1)
+    rel = bc._qinv_apply(P[3][None, :], P)
+    assert np.allclose(rel[3], [0, 0, 0, 1, 0, 0, 0], atol=1e-14)
+    back_q = bc._qmul(P[3][None, :4], rel[:, :4])
+    back_t = P[3][None, 4:] + bc._qrot(P[3][None, :4], rel[:, 4:])
+    assert np.allclose(back_q, P[:, :4], atol=1e-13) and np.allclose(back_t, P[:, 4:], atol=1e-12)

@@ -336,3 +336,81 @@ def test_lane_status_bad_scan_does_not_advance_the_stream(ll):
             break
     ctx.close()
     ref.close()
+
+
+@pytest.mark.parametrize("distortion,line", [(1, 16), (2, 16), (1, 64), (2, 32)])
+def test_deskew_mode_matches_oracle(ll, orc, distortion, line):
+    """DISTORTION 1 (LO:23, compiled out in the reference build): per-point interpolation ratio s = relTime in
+    TransformToStart (LO:77-95) and in the factors (LF:23-31, 227-235; s != 1 takes the dual-number path of the solve),
+    and - distortion 2 - TransformToEnd of the clouds that become *Last (LO:98-114, 861-880, behind `if (0)` in the
+    reference).  Association index triples equal the oracle's, poses within 1e-9; with mapping on, the mapped pose within 1e-7."""
+    ocfg = orc.config(line, voxel_stable=1, distortion=distortion)
+    ctx = ll.Context(scan_line=line, distortion=distortion)
+    odo = orc.Odometry(ocfg)
+    plain = ll.Context(scan_line=line)
+    moved = False
+    for k in range(8):
+        f = orc.extract_features(ll.synth.scan(line, k), ocfg)
+        po = odo.step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        pg = ctx.odometry_step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        pp = plain.odometry_step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        # distortion 2 rewrites the *Last clouds through slerp + rotate and stores them as fp32: the device's sincos / acos
+        # differ from glibc's in the last bit now and then, which moves a stored coordinate by one fp32 ulp
+        tol = 1e-9 if distortion == 1 else 1e-7
+        assert np.abs(pg["t_w"] - po["t_w"]).max() < tol and np.abs(pg["q_w"] - po["q_w"]).max() < tol, k
+        assert np.abs(pg["t_last"] - po["t_last"]).max() < tol, k
+        if k == 0:
+            continue
+        moved |= bool(np.abs(pg["t_w"] - pp["t_w"]).max() > 1e-6)
+        oc, op = odo.assoc(len(f["sharp"]), len(f["flat"]))
+        gc, gp = ctx.debug_assoc(0)
+        gc, gp = gc[:len(f["sharp"])], gp[:len(f["flat"])]
+        got_c = np.array([[i, a, b] for i, (a, b) in enumerate(gc) if b >= 0], np.int32).reshape(-1, 3)
+        got_p = np.array([[i, a, b, c] for i, (a, b, c, _) in enumerate(gp) if a >= 0], np.int32).reshape(-1, 4)
+        assert np.array_equal(got_c, oc) and np.array_equal(got_p, op), k
+        st, stats = ctx.stats(), odo.stats()
+        assert [int(s[5]) for s in stats] == list(st.lm_jacobian_evals) and [int(s[7]) for s in stats] == list(st.lm_termination), k
+    assert moved      # the mode does change the estimate
+    ctx.close()
+    plain.close()
+
+
+def test_deskew_fused_pipeline_with_mapping(ll, orc):
+    line = 16
+    ctx = ll.Context(scan_line=line, distortion=2, enable_mapping=1, map_capacity=1 << 18)
+    pipe = orc.Pipeline(orc.config(line, voxel_stable=1, distortion=2), with_mapping=True)
+    for k in range(7):
+        scan = ll.synth.scan(line, k)
+        pg, pe = ctx.process_scans([scan])[0], pipe.step(scan)
+        # one-ulp differences of the fp32 clouds TransformToEnd stores (device vs glibc trigonometry) reach the pose at ~1e-8
+        assert np.abs(pg[4:7] - pe["t_odom"]).max() < 1e-6 and np.abs(pg[0:4] - pe["q_odom"]).max() < 1e-6, k
+        assert np.abs(pg[11:14] - pe["t_map"]).max() < 1e-5 and np.abs(pg[7:11] - pe["q_map"]).max() < 1e-5, k
+    ctx.close()
+
+
+@pytest.mark.parametrize("line", [16, 64])
+def test_vote_partial_mode_matches_oracle(ll, orc, line):
+    """vote_mode = 1: the paper-style scoring graph_based_correspondence_vote_partial (LM:321-834, dead code in the
+    reference - beyond-reference behaviour, flagged as such) on the odometry's plane correspondences.  Selected counts equal
+    the oracle's; poses within 1e-6 (the m x m expf / cbrt scores are fp32 roundings of fp64 evaluations on both sides, but
+    not the same libm)."""
+    ocfg = orc.config(line, voxel_stable=1, vote_mode=1)
+    ctx = ll.Context(scan_line=line, vote_mode=1)
+    simple = ll.Context(scan_line=line)
+    odo = orc.Odometry(ocfg)
+    differs = False
+    for k in range(9):
+        f = orc.extract_features(ll.synth.scan(line, k), ocfg)
+        po = odo.step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        pg = ctx.odometry_step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        ps = simple.odometry_step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        assert np.abs(pg["t_w"] - po["t_w"]).max() < 1e-6 and np.abs(pg["q_w"] - po["q_w"]).max() < 1e-6, k
+        if k > 6:
+            st, stats = ctx.stats(), odo.stats()
+            assert [int(s[1]) for s in stats] == list(st.plane_corr), k
+            assert [int(s[2]) for s in stats] == list(st.plane_selected), (k, [int(s[2]) for s in stats], list(st.plane_selected))
+            assert st.plane_selected[2] < st.plane_corr[2]
+            differs |= bool(np.abs(pg["t_w"] - ps["t_w"]).max() > 1e-9)
+    assert differs
+    ctx.close()
+    simple.close()
