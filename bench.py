@@ -166,6 +166,14 @@ def algorithmic_bytes(counts):
     }
 
 
+def config_dict(B, world, n_raw):
+    """The `config` object: identical in both arms (ours and --impl reference), so the two lines describe one workload."""
+    return {"workload": WORKLOAD, "lanes_per_gpu": B, "scans_per_step": B * world, "points_per_scan": int(n_raw), "distinct_scans_in_pool": POOL_SCANS,
+            "gn_linearisations_per_solve_max": 5, "outer_iterations": 3,
+            "parallelism": "independent scan streams sharded per GPU, no data-path collective",
+            "l2": "inputs larger than L2: %d lanes x %.2f MB raw scan = %.0f MB read per step (> 126 MB), no flush" % (B, n_raw * 16 / 1e6, B * n_raw * 16 / 1e6)}
+
+
 def parity_check(ll, ctx, pool, B, rank):
     """Parity gate of THIS configuration in THIS run: the state is reset, PARITY_STEPS steps run through the pool path at
     the full lane count, and PARITY_LANES lanes (first, two inside, last) are compared with the CPU oracle fed the same
@@ -359,11 +367,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": round(value, 1), "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (features, NN) + f64 (residuals, LM)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "lanes_per_gpu": B, "scans_per_step": B * world, "points_per_scan": int(counts["n_raw"]),
-                       "distinct_scans_in_pool": POOL_SCANS,
-                       "gn_linearisations_per_solve_max": 5, "outer_iterations": 3, "parallelism": "independent scan streams sharded per GPU, no data-path collective",
-                       "l2": "inputs larger than L2: %d lanes x %.2f MB raw scan = %.0f MB read per step (> 126 MB), no flush" % (B, counts["n_raw"] * 16 / 1e6, B * counts["n_raw"] * 16 / 1e6),
-                       "cpu_affinity_cores": n_aff},
+            "config": config_dict(B, world, counts["n_raw"]), "host": {"cpu_affinity_cores": n_aff, "cores": os.cpu_count()},
             "e2e": {"value": round(e2e_value, 1), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": B * (14 * 8 + 4),
                     "api": "ll_submit_packed / ll_collect (one pinned host arena of packed xyz records, one H2D copy per step, 2 submissions in flight)",
                     "h2d_gbs": round(h2d / e2e_s / 1e9, 2), "sync_call_value": round(B * world * args.steps / e2e_sync_s, 1)},
@@ -434,7 +438,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(wall / (args.steps + max(args.warmup, 3)) * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (features, NN) + f64 (residuals, LM)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "restated reference CPU path (PCL/Ceres/ROS unavailable offline), one scan stream per host core"},
+            "config": config_dict(args.batch, world, float(np.mean([len(p) for p in _G["pool"]]))),
+            "reference_note": "restated reference CPU path (PCL/Ceres/ROS unavailable offline), one scan stream per host core; the config object is the GPU arm's: same scans, same per-scan work",
             "cpu_baseline": {"value": round(value, 2), "unit": "scans/s", "cores": cores, "kind": "port",
                              "sample": "%d scans per core x %d cores, extract_features + odometry" % (n_scans, cores)},
             "e2e": {"value": round(value, 2), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -401,6 +401,13 @@ __device__ __forceinline__ void for_spans3(const ST& st, int s0, int e0, int s1,
         f(t0); f(t1); f(t2); f(t3);
     }
 }
+// development statistics of the thread pass (compile with -DLL_ASSOC_STATS): candidates per phase and range class
+#ifdef LL_ASSOC_STATS
+__device__ unsigned long long g_assoc_stats[32];
+#define ASTAT(slot, v) (stat[(slot)] += (v))
+#else
+#define ASTAT(slot, v) ((void)0)
+#endif
 struct AssocQuery {
     float qx, qy, qz;
     int closest, cring, n;
@@ -488,15 +495,17 @@ __device__ __forceinline__ float assoc_window_dist(const AssocQuery& Q)
 // Per-thread part: up to dmax bins per side.  Returns false when the window needs more than that (the warp pass
 // restarts it).
 template <bool CORNER, typename ST>
-__device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuery& pq, const ST& st, int NB, int R, int dmax)
+__device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuery& pq, const ST& st, int NB, int R, int dmax, int* stat)
 {
     const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
     auto header = [&](int off, int& s, int& e) { s = st.header(pq.b0 + off, r_lo); e = st.header(pq.b0 + off, r_lo + r_n); };
     auto consider = [&](const float4 t) { assoc_consider<CORNER>(Q, t); };
-    const int near = pq.frac < 0.5f ? -1 : 1;
+    // own bin first: at long range a bin is wider than the distances in play and mostly settles the window alone; the
+    // neighbours follow only as far as rho * sin(azimuth gap) stays inside the distances held
     int s0, e0, s1, e1;
-    header(0, s0, e0); header(near, s1, e1);
-    for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
+    header(0, s0, e0);
+    ASTAT(2, e0 - s0);
+    for_spans3(st, s0, e0, 0, 0, 0, 0, consider);
     int kl, kr;
 #pragma unroll 1
     for (int k = 1;; ++k) {
@@ -504,8 +513,9 @@ __device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuer
         if (k > kl && k > kr) return true;
         if (k > dmax) return false;
         s0 = e0 = s1 = e1 = 0;
-        if (k <= kl && !(k == 1 && near < 0)) header(-k, s0, e0);
-        if (k <= kr && !(k == 1 && near > 0)) header(k, s1, e1);
+        if (k <= kl) header(-k, s0, e0);
+        if (k <= kr) header(k, s1, e1);
+        ASTAT(3, (e0 - s0) + (e1 - s1));
         for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
     }
 }
@@ -630,7 +640,7 @@ __device__ __forceinline__ void nn_consider_ring(u64& best, int& best_ring, floa
 // far, the warp pass restarts from it).
 template <typename ST>
 __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const ST& st, int NB, int R, float qx, float qy, float qz, int kmax, PolarQuery& pq, u64& best,
-                                                     int& best_ring, int& reach_buckets)
+                                                     int& best_ring, int& reach_buckets, int* stat)
 {
     {
         int lo = 0, hi = R;
@@ -639,25 +649,44 @@ __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const S
     }
     auto consider = [&](const float4 t) { nn_consider_ring(best, best_ring, qx, qy, qz, t); };
     auto span = [&](int off, int ra, int rb, int& s, int& e) { s = st.header(pq.b0 + off, ra); e = st.header(pq.b0 + off, rb + 1); };
-    // seed: rings r0-1 .. r0+1 of the own bin and its two neighbours, one stream
+    // seed: rings r0-1 .. r0+1 of the own bin (one contiguous span).  At long range - where the buckets are fullest - a
+    // bin is wider than the match distance, so the seed usually settles the search; the rest of the reach follows below.
     const int sa = max(pq.r0 - 1, 0), sb = min(pq.r0 + 1, R - 1);
-    int s0, e0, s1, e1, s2, e2;
-    span(0, sa, sb, s0, e0); span(-1, sa, sb, s1, e1); span(1, sa, sb, s2, e2);
-    for_spans3(st, s0, e0, s1, e1, s2, e2, consider);
+    int s0, e0, s1, e1;
+    span(0, sa, sb, s0, e0);
+    ASTAT(0, e0 - s0);
+    for_spans3(st, s0, e0, 0, 0, 0, 0, consider);
     PolarReach W = polar_reach(S, pq, NB, R, best);
-    if (W.ra >= sa && W.rb <= sb && W.kl <= 1 && W.kr <= 1) return true;   // nothing closer can lie outside the seed
-    reach_buckets = (W.kl + W.kr + 1) * (W.rb - W.ra + 1);
-    if (W.rb - W.ra > 16 || max(W.kl, W.kr) > kmax) return false;
-    // outward from the own bin over the rings in reach (buckets of the seed are met again: a minimum does not mind);
-    // the reach only shrinks as the best improves
+    if (W.ra >= sa && W.rb <= sb && W.kl == 0 && W.kr == 0) return true;   // nothing closer can lie outside the seed
+    if (W.rb - W.ra > 16 || max(W.kl, W.kr) > kmax) {
+        // the seed found nothing close: its two neighbour bins first (one stream) - they usually pull the reach back
+        // inside what one thread walks; only what is still too wide afterwards goes to the warp pass
+        int s2, e2;
+        span(-1, sa, sb, s0, e0); span(1, sa, sb, s2, e2);
+        ASTAT(1, (e0 - s0) + (e2 - s2));
+        for_spans3(st, s0, e0, s2, e2, 0, 0, consider);
+        W = polar_reach(S, pq, NB, R, best);
+        if (W.ra >= sa && W.rb <= sb && W.kl <= 1 && W.kr <= 1) return true;
+        reach_buckets = (W.kl + W.kr + 1) * (W.rb - W.ra + 1);
+        if (W.rb - W.ra > 16 || max(W.kl, W.kr) > kmax) return false;
+    }
+    // the rings of the own bin the seed left out, then outward over the bins in reach; the reach only shrinks as the best improves
     u64 seen = best;
+    if (W.ra < sa || W.rb > sb) {
+        s0 = e0 = s1 = e1 = 0;
+        if (W.ra < sa) span(0, W.ra, sa - 1, s0, e0);
+        if (W.rb > sb) span(0, sb + 1, W.rb, s1, e1);
+        ASTAT(1, (e0 - s0) + (e1 - s1));
+        for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
+    }
 #pragma unroll 1
-    for (int k = 0;; ++k) {
+    for (int k = 1;; ++k) {
         if (best != seen) { W = polar_reach(S, pq, NB, R, best); seen = best; }
         if (k > W.kl && k > W.kr) return true;
         s0 = e0 = s1 = e1 = 0;
-        if (k >= 1 && k <= W.kl) span(-k, W.ra, W.rb, s0, e0);
+        if (k <= W.kl) span(-k, W.ra, W.rb, s0, e0);
         if (k <= W.kr) span(k, W.ra, W.rb, s1, e1);
+        ASTAT(1, (e0 - s0) + (e1 - s1));
         for_spans3(st, s0, e0, s1, e1, 0, 0, consider);
     }
 }
@@ -783,9 +812,14 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
         const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
         u64 best = NN_NONE;
         int best_ring = 0;
+#ifdef LL_ASSOC_STATS
+        int stat[4] = {0, 0, 0, 0};
+#else
+        int* stat = nullptr;
+#endif
         if (Q.n > 0) {
             int reach_buckets = 0;
-            heavy = !polar_nearest_thread(S, st, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best, best_ring, reach_buckets);
+            heavy = !polar_nearest_thread(S, st, NB, P.R, Q.qx, Q.qy, Q.qz, kmax, pq, best, best_ring, reach_buckets, stat);
             is_long = heavy && reach_buckets > 200;   // these take tens of microseconds each: they must start first
             if (heavy) { entry.y |= ASSOC_OPEN_BIT; entry.z = (int)(unsigned)(best >> 32); entry.w = (int)(unsigned)best; }
         }
@@ -794,7 +828,7 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
             Q.cring = best_ring;               // int(intensity) of the closest point (LO:500 / LO:664): the index carries it for ring-monotone clouds
             int pending = -2;                  // clouds that are not ring-sorted: literal walk
             if (CORNER ? L.mono_corner : L.mono_surf) {
-                pending = assoc_ring_window<CORNER>(Q, pq, st, NB, P.R, dmax) ? -3 : -1;
+                pending = assoc_ring_window<CORNER>(Q, pq, st, NB, P.R, dmax, stat) ? -3 : -1;
                 heavy = pending == -1;
             } else {
                 heavy = true;
@@ -803,6 +837,14 @@ __device__ __forceinline__ void assoc_thread_pass(const OdomParams& P, const Rin
             entry.w = pending;
         }
         if (!heavy) assoc_store<CORNER>(P, b, i, Q);
+#ifdef LL_ASSOC_STATS
+        {
+            const int cls = (CORNER ? 0 : 16) + (pq.rho < 10.f ? 0 : (pq.rho < 20.f ? 5 : 10));
+            atomicAdd(&g_assoc_stats[cls], 1ull);
+            for (int k = 0; k < 4; ++k) atomicAdd(&g_assoc_stats[cls + 1 + k], (unsigned long long)stat[k]);
+            if (heavy) atomicAdd(&g_assoc_stats[CORNER ? 15 : 31], 1ull);
+        }
+#endif
     }
     // the long entries are stored from the front of the queue, the others from its back; the warp pass pops front to back
     // (longest-first: the kernel cannot end before its longest entry does, so that one must not start last)
@@ -1495,6 +1537,14 @@ static int build_grid(ll_ctx* c, KnnGrid& g, const float4* p0, const float4* p1,
     c->launches += 4;
     return LL_OK;
 }
+
+#ifdef LL_ASSOC_STATS
+extern "C" void ll_dev_assoc_stats(unsigned long long out[32], int reset)
+{
+    cudaMemcpyFromSymbol(out, g_assoc_stats, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_assoc_stats, z, sizeof(z)); }
+}
+#endif
 
 int ll_launch_odometry(ll_ctx* c, int n_lanes)
 {

