@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblightloam_b200.so")
+LIB_PATH = os.environ.get("LL_LIB_PATH") or os.path.join(_HERE, "liblightloam_b200.so")   # LL_LIB_PATH: development builds (statistics, tuning variants)
 _LIB = None
 
 LL_OK = 0

@@ -186,6 +186,7 @@ void ll_destroy(ll_ctx* c)
     cudaSetDevice(c->dev);
     if (c->stream) cudaStreamSynchronize(c->stream);
     ll_map_free(c);
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) {
         if (c->ev_staged[k]) cudaEventDestroy(c->ev_staged[k]);
@@ -200,7 +201,7 @@ void ll_destroy(ll_ctx* c)
     if (c->h_ids) cudaFreeHost(c->h_ids);
     if (c->h_status) cudaFreeHost(c->h_status);
     free(c->last_status);
-    void* ptrs[] = {c->d_wide_list, c->d_wide_n, c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
+    void* ptrs[] = {c->d_odom_comm, c->d_odom_seq[0], c->d_odom_seq[1], c->d_wide_list, c->d_wide_n, c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->d_ebound[0], c->d_ebound[1], c->d_bands[0], c->d_bands[1], c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
                     c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n, c->d_vote_src, c->d_vote_tgt};
@@ -308,6 +309,13 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_qa, B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING)));
     CK(dalloc(c->d_qb, B * R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING)));
     CK(dalloc(c->d_qstart, B * (size_t)c->qstart_stride));
+    {   // mailbox of the split odometry solve: [lane][parity][128 contributions][32 doubles] + [lane][128] flags (ll_solve.cuh)
+        c->odom_comm_mbox_bytes = sizeof(double) * B * 2 * 128 * 32;
+        const size_t total = c->odom_comm_mbox_bytes + sizeof(unsigned long long) * B * 128;
+        CK(cudaMalloc(&c->d_odom_comm, total));
+        CK(cudaMemsetAsync(c->d_odom_comm, 0, total, c->stream));
+        for (int k = 0; k < 2; ++k) { CK(dalloc(c->d_odom_seq[k], B)); CK(cudaMemsetAsync(c->d_odom_seq[k], 0, sizeof(unsigned long long) * B, c->stream)); }
+    }
     c->nblk_cap = (int)R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING);
     CK(dalloc(c->d_blocks, B * (size_t)LL_BLOCK_DOUBLES * c->nblk_cap));
     CK(cudaMemsetAsync(c->d_raw, 0, sizeof(uint32_t) * B * N * 8, c->stream));
@@ -394,25 +402,72 @@ static int publish_status(ll_ctx* c, const int* st, int n)
     return first;
 }
 
+// The kernel sequence of one step (SR:100-377 -> LO:425-896 [-> LM:1581-2168]) on the context stream.
+static int launch_pipeline(ll_ctx* c, int n_scans, bool with_events)
+{
+    if (with_events) LL_CUDA_CHECK(c, cudaEventRecord(c->ev[0], c->stream));
+    int rc = ll_launch_features(c, n_scans);
+    if (rc) return rc;
+    if (with_events) LL_CUDA_CHECK(c, cudaEventRecord(c->ev[1], c->stream));
+    rc = ll_launch_odometry(c, n_scans);
+    if (rc) return rc;
+    if (with_events) LL_CUDA_CHECK(c, cudaEventRecord(c->ev[2], c->stream));
+    if (c->cfg.enable_mapping) {
+        rc = ll_launch_mapping(c, n_scans);
+        if (rc) return rc;
+    }
+    if (with_events) LL_CUDA_CHECK(c, cudaEventRecord(c->ev[3], c->stream));
+    return LL_OK;
+}
+
+// Latency path: with few lanes a step is ~30 short kernels and the launches cost as much as the work.  The sequence is
+// captured once per (lane count, mailbox parity) into a CUDA graph and replayed; LL_GRAPH=0 disables, LL_GRAPH=1 forces it
+// for any lane count.  Not used with mapping (its solve alternates argument sets per frame) or while profiling.
+static bool graph_wanted(const ll_ctx* c, int n_scans)
+{
+    if (c->prof || c->cfg.enable_mapping || c->eager_calls < 2) return false;
+    if (const char* e = getenv("LL_GRAPH")) return atoi(e) != 0;
+    return n_scans <= 16;
+}
+
 int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
 {
     if (!c || n_scans < 1 || n_scans > c->B) return LL_E_INVAL;
     LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
     if (c->prof) ll_prof_harvest(c);
-    c->launches = c->pre_launches;   // the header kernel of ll_stage_scans / ll_process_pool belongs to this step
+    const int pre = c->pre_launches;   // the header kernel of ll_stage_scans / ll_process_pool belongs to this step
     c->pre_launches = 0;
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[0], c->stream));
-    int rc = ll_launch_features(c, n_scans);
-    if (rc) return rc;
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[1], c->stream));
-    rc = ll_launch_odometry(c, n_scans);
-    if (rc) return rc;
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[2], c->stream));
-    if (c->cfg.enable_mapping) {
-        rc = ll_launch_mapping(c, n_scans);
+    c->last_call_graph = false;
+    if (graph_wanted(c, n_scans)) {
+        const int key = n_scans * 2 + c->odom_comm_flip;
+        auto it = c->graphs.find(key);
+        if (it == c->graphs.end()) {
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ge = nullptr;
+            const int flip0 = c->odom_comm_flip;
+            LL_CUDA_CHECK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            c->launches = 0;
+            const int rc = launch_pipeline(c, n_scans, false);
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            c->odom_comm_flip = flip0;       // the capture only recorded: nothing ran yet
+            if (rc || e != cudaSuccess) { if (g) cudaGraphDestroy(g); c->last_error = std::string("graph capture: ") + cudaGetErrorString(e); return rc ? rc : LL_E_CUDA; }
+            LL_CUDA_CHECK(c, cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+            c->graph_launches[key] = c->launches;
+            it = c->graphs.emplace(key, ge).first;
+        }
+        LL_CUDA_CHECK(c, cudaGraphLaunch(it->second, c->stream));
+        c->launches = pre + c->graph_launches[key];
+        c->odom_comm_flip ^= c->graph_parity_step;   // three solves per step: the mailbox parity moves as in the eager calls before
+        c->last_call_graph = true;
+    } else {
+        c->launches = pre;
+        const int flip0 = c->odom_comm_flip;
+        const int rc = launch_pipeline(c, n_scans, true);
         if (rc) return rc;
+        c->graph_parity_step = c->odom_comm_flip ^ flip0;
+        c->eager_calls++;
     }
-    LL_CUDA_CHECK(c, cudaEventRecord(c->ev[3], c->stream));
     if (poses_out) {
         LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 14 * n_scans, cudaMemcpyDeviceToHost, c->stream));
         LL_CUDA_CHECK(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int) * n_scans, cudaMemcpyDeviceToHost, c->stream));
@@ -648,6 +703,7 @@ int ll_debug_features(ll_ctx* c, int lane, int counts[5], int* sharp_idx, int* l
 int ll_last_timings(ll_ctx* c, float ms[4])
 {
     if (!c || !ms) return LL_E_INVAL;
+    if (c->last_call_graph) { ms[0] = ms[1] = ms[2] = ms[3] = 0.f; return LL_E_INVAL; }   // a replayed graph records no stage events (LL_GRAPH=0 to time stages)
     LL_CUDA_CHECK(c, cudaEventSynchronize(c->ev[3]));
     LL_CUDA_CHECK(c, cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
     LL_CUDA_CHECK(c, cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));

@@ -143,6 +143,11 @@ struct ll_ctx {
     int* d_qstart = nullptr;       // [B][qstart_stride] slab offsets
     int qstart_stride = 260;
     bool slab_attr_set = false, vp_attr_set = false;
+    // split odometry solve (few lanes, many SMs): `parts` CTAs per lane all-reduce the 28 doubles through a local mailbox (LmComm)
+    void* d_odom_comm = nullptr;               // mailbox doubles followed by the sequence flags
+    size_t odom_comm_mbox_bytes = 0;
+    unsigned long long* d_odom_seq[2] = {nullptr, nullptr};   // [B] collective counters, alternated per solve launch
+    int odom_comm_flip = 0;
     double* d_blocks = nullptr;    // [B][nblk_cap][12]
     int nblk_cap = 0;
 
@@ -163,6 +168,13 @@ struct ll_ctx {
     int* h_ids = nullptr;          // pinned [B]
     int* d_ids = nullptr;          // [B]
     int pool_cap = 0, pool_n = 0;
+
+    // CUDA graphs of the fused pipeline for the latency path (few lanes): key = lanes * 2 + parity of the solve's mailbox counters
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int> graph_launches;   // kernels in each captured graph
+    int graph_parity_step = 0;     // how one step moves odom_comm_flip (1 when the solves are split, else 0)
+    int eager_calls = 0;           // the first call of a context runs eagerly (function attributes, lazy allocations)
+    bool last_call_graph = false;  // ll_last_timings has no events to read after a graph launch
 
     // optional per-kernel device timing (ll_profile_enable): event pairs around every launch
     bool prof = false;

@@ -389,6 +389,9 @@ struct StageShared {
 };
 // Up to three spans as ONE candidate stream (four loads in flight across span boundaries): the spans of neighbouring
 // azimuth bins cost one memory round trip together instead of one each.
+#ifndef ASSOC_W
+#define ASSOC_W 4   // candidate loads in flight per thread and round trip
+#endif
 template <typename ST, typename F>
 __device__ __forceinline__ void for_spans3(const ST& st, int s0, int e0, int s1, int e1, int s2, int e2, F&& f)
 {
@@ -396,9 +399,12 @@ __device__ __forceinline__ void for_spans3(const ST& st, int s0, int e0, int s1,
     const int d1 = s1 - n0, d2 = s2 - n01;   // stream position -> array index: + s0, + d1 or + d2 depending on the span
     auto at = [&](int k) { k = min(k, tot - 1); return k + (k < n0 ? s0 : (k < n01 ? d1 : d2)); };
 #pragma unroll 1
-    for (int k = 0; k < tot; k += 4) {
-        const float4 t0 = st.point(at(k)), t1 = st.point(at(k + 1)), t2 = st.point(at(k + 2)), t3 = st.point(at(k + 3));
-        f(t0); f(t1); f(t2); f(t3);
+    for (int k = 0; k < tot; k += ASSOC_W) {
+        float4 t[ASSOC_W];
+#pragma unroll
+        for (int u = 0; u < ASSOC_W; ++u) t[u] = st.point(at(k + u));
+#pragma unroll
+        for (int u = 0; u < ASSOC_W; ++u) f(t[u]);
     }
 }
 // development statistics of the thread pass (compile with -DLL_ASSOC_STATS): candidates per phase and range class
@@ -1443,13 +1449,21 @@ __global__ void __launch_bounds__(VP_THREADS) k_odom_vote_partial(OdomParams P, 
     if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
 }
 
+// grid (lanes, parts): with few lanes `parts` CTAs share one lane's residual blocks and all-reduce the 28 doubles of every
+// evaluation through the context's mailbox (LmComm, gworld = 1) - the single-stream latency path; parts = 1 is the plain solve
 template <bool DIST>
-__global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P)
+__global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P, LmComm comm, int n_all_lanes)
 {
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, part = blockIdx.y;
     LaneState& L = P.lane[b];
-    if (!L.inited || L.err) return;
-    lm_solve<DIST>(P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap, P.nblk_cap, L.n_blocks, L.para_q, L.para_t, &L, P.outer);
+    const bool split = comm.nparts > 1;
+    if (split && b == 0 && part == 0)   // lanes outside this launch keep their collective counters
+        for (int i = gridDim.x + threadIdx.x; i < n_all_lanes; i += blockDim.x) comm.seq_out[i] = comm.seq_in[i];
+    if (!L.inited || L.err) {
+        if (split && part == 0 && threadIdx.x == 0) comm.seq_out[b] = comm.seq_in[b];
+        return;
+    }
+    lm_solve<DIST>(P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap, P.nblk_cap, L.n_blocks, L.para_q, L.para_t, &L, P.outer, split ? &comm : nullptr, b, part);
 }
 
 // LO:861-880 TransformToEnd of this frame's less-sharp / less-flat clouds (they become *Last at the swap), distortion == 2:
@@ -1571,6 +1585,17 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->dev);
     const int lm_threads = getenv("LL_LM_THREADS") ? atoi(getenv("LL_LM_THREADS")) : (n_lanes > n_sm ? 256 : LM_THREADS);
+    // Splitting a solve over several CTAs (LL_LM_PARTS = 2..16, lanes x parts <= SMs) pays for the 10k-block scan-to-map
+    // problems, not here: with ~1900 blocks the mailbox all-reduce of every evaluation costs more than the split saves
+    // (single stream on B200: 0.124 ms per solve with 16 parts against 0.074 ms with one CTA), so the default is 1.
+    int lm_parts = 1;
+    if (const char* e = getenv("LL_LM_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= LM_MAX_PARTS && v * n_lanes <= n_sm) lm_parts = v; }
+    LmComm comm;
+    for (int g = 0; g < LM_MAX_GPUS; ++g) { comm.mbox[g] = nullptr; comm.flag[g] = nullptr; }
+    comm.mbox[0] = reinterpret_cast<double*>(c->d_odom_comm);
+    comm.flag[0] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_odom_comm) + c->odom_comm_mbox_bytes);
+    comm.grank = 0; comm.gworld = 1; comm.nparts = lm_parts; comm.timeout_ns = 2000000000ull;
+    const int lm_threads_used = lm_parts > 1 ? (getenv("LL_LM_THREADS") ? lm_threads : 128) : lm_threads;   // split: ~1 block per thread
     const int kmax = getenv("LL_ASSOC_KMAX") ? atoi(getenv("LL_ASSOC_KMAX")) : 2;   // 1-NN bins per side a thread walks
     const size_t vote_smem = (size_t)(c->R * LL_FLAT_PER_RING / 10 + 16) * (2 * sizeof(float4) + sizeof(int));
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
@@ -1658,8 +1683,15 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         }
         {
             LLProf pr(c, "k_lm_solve_odom");
-            if (P.distortion) k_lm_solve_odom<true><<<n_lanes, lm_threads, 0, s>>>(P);
-            else k_lm_solve_odom<false><<<n_lanes, lm_threads, 0, s>>>(P);
+            comm.seq_in = c->d_odom_seq[c->odom_comm_flip]; comm.seq_out = c->d_odom_seq[c->odom_comm_flip ^ (lm_parts > 1 ? 1 : 0)];
+            if (lm_parts > 1) {   // the parts of a lane spin on each other's flags: cooperative launch = all resident or refused
+                int a_n = c->B;
+                void* args[] = {&P, &comm, &a_n};
+                const void* fn = P.distortion ? (const void*)k_lm_solve_odom<true> : (const void*)k_lm_solve_odom<false>;
+                LL_CUDA_CHECK(c, cudaLaunchCooperativeKernel(fn, dim3(n_lanes, lm_parts), dim3(lm_threads_used), args, 0, s));
+                c->odom_comm_flip ^= 1;
+            } else if (P.distortion) k_lm_solve_odom<true><<<n_lanes, lm_threads, 0, s>>>(P, comm, c->B);
+            else k_lm_solve_odom<false><<<n_lanes, lm_threads, 0, s>>>(P, comm, c->B);
         }
         c->launches += 5;
     }
