@@ -201,7 +201,7 @@ void ll_destroy(ll_ctx* c)
     if (c->h_ids) cudaFreeHost(c->h_ids);
     if (c->h_status) cudaFreeHost(c->h_status);
     free(c->last_status);
-    void* ptrs[] = {c->d_odom_comm, c->d_odom_seq[0], c->d_odom_seq[1], c->d_wide_list, c->d_wide_n, c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_ori, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
+    void* ptrs[] = {c->d_odom_comm, c->d_odom_seq[0], c->d_odom_seq[1], c->d_wide_list, c->d_wide_n, c->d_status, c->d_pc2, c->d_qa, c->d_qb, c->d_qstart, c->d_pool, c->d_pool_n, c->d_ids, c->d_lane, c->d_pose, c->d_hdr, c->d_raw, c->d_ring8, c->d_rank8, c->d_tile_hist, c->d_full, c->d_curv, c->d_label, c->d_sorted16, c->d_brk, c->d_lf_tmp,
                     c->d_ring_lists, c->d_ring_counts, c->d_sharp, c->d_flat, c->d_sharp_idx, c->d_lsharp_idx, c->d_flat_idx,
                     c->d_lsharp[0], c->d_lsharp[1], c->d_lflat[0], c->d_lflat[1], c->d_ebound[0], c->d_ebound[1], c->d_bands[0], c->d_bands[1], c->a_corner.start, c->a_corner.cursor, c->a_corner.sorted,
                     c->a_corner.partial, c->a_surf.start, c->a_surf.cursor, c->a_surf.sorted, c->a_surf.partial, c->d_corner_assoc, c->d_plane_assoc, c->d_blocks, c->d_assoc_queue, c->d_assoc_queue_n, c->d_vote_src, c->d_vote_tgt};
@@ -263,7 +263,6 @@ int ll_create(const ll_config* cfg, ll_ctx** out)
     CK(dalloc(c->d_raw, B * N * 8));
     CK(dalloc(c->d_ring8, B * N));
     CK(dalloc(c->d_rank8, B * N));
-    CK(dalloc(c->d_ori, B * N));
     CK(dalloc(c->d_tile_hist, B * c->NT * R));
     CK(dalloc(c->d_full, B * N));
     CK(dalloc(c->d_curv, B * N));

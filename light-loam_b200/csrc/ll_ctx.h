@@ -3,7 +3,8 @@
 // Data layout in HBM (per lane = one independent scan stream; all arrays are [batch][...] slabs so one
 // launch covers every lane with blockIdx.y / blockIdx.z = lane):
 //   raw        : the caller's point records as uploaded (stride words per point)
-//   ring8/rank8: per raw point ring id (int8, -1 = dropped) and rank inside its 256-point tile
+//   ring8/rank8: per raw point ring id (int8, -1 = dropped) and rank inside its 256-point tile (the azimuth -atan2(y,x)
+//                is recomputed by k_scatter: cheaper than a 4-byte round trip per point)
 //   tile_hist  : [tiles][rings] counts -> exclusive offsets (stable counting sort by ring, SR:133-221)
 //   full       : ring-sorted float4 x,y,z,intensity (= laserCloud, SR:215-221)
 //   curv       : fp32 curvature per full point (SR:225-235)
@@ -37,6 +38,7 @@ struct LaneState {
     int first_valid, last_valid;     // first / last index surviving the NaN + range filters (SR:109-110)
     int half_idx;                    // index of the point that flips halfPassed (SR:189-192), INT_MAX if none
     float start_ori, end_ori;        // SR:114-126
+    float start_dir[2];              // (cos, sin) of the first valid point's azimuth (= -startOri): the halfPassed prefilter of k_classify
     int n_full;
     int ring_begin[LL_MAX_RINGS + 1];
     int n_sharp, n_less_sharp, n_flat, n_less_flat;
@@ -109,7 +111,6 @@ struct ll_ctx {
     uint32_t* d_raw = nullptr;     // [B][Nmax * 8] words (stride <= 32 B)
     int8_t* d_ring8 = nullptr;     // [B][Nmax]
     uint8_t* d_rank8 = nullptr;    // [B][Nmax]
-    float* d_ori = nullptr;        // [B][Nmax] -atan2(y,x) per raw point
     int* d_tile_hist = nullptr;    // [B][NT][R]
     float4* d_full = nullptr;      // [B][Nmax]
     float* d_curv = nullptr;       // [B][Nmax]

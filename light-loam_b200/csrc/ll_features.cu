@@ -25,7 +25,6 @@ struct FeatParams {
     LaneState* lane;
     int8_t* ring8;
     uint8_t* rank8;
-    float* ori;
     int* tile_hist;
     float4* full;
     float* curv;
@@ -101,20 +100,34 @@ __device__ __forceinline__ int ring_of(const FeatParams& P, float x, float y, fl
     }
     return scanID;
 }
+// SR:177 ori = -atan2(y, x).  The reference's -atan2f is reproduced as the fp64 atan2 rounded once; only DECISIONS need that
+// value to the last bit: the branch thresholds startOri - pi/2, startOri + 3pi/2, (ori - startOri) > pi (SR:180-192),
+// endOri - 3pi/2 and endOri + pi/2 on ori + 2pi (SR:196-205), and the sign of relTime at ori = startOri (SR:207-208:
+// int(intensity) is the ring id the odometry reads).  Modulo 2pi these are startOri + k pi/2 and endOri + pi/2, so a point
+// farther than 1e-5 rad from all of them takes the fp32 atan2f (<= 2 ulp: its intensity moves by at most one ulp of the
+// fraction, which nothing consumes).
+__device__ __forceinline__ float scan_ori(float x, float y, float startOri, float endOri)
+{
+    float ori = -atan2f(y, x);
+    const float qa = (ori - startOri) * 0.63661977f, qb = (ori - endOri) * 0.63661977f;   // in units of pi/2
+    if (fabsf(qa - rintf(qa)) < 1e-5f || fabsf(qb - rintf(qb)) < 1e-5f) ori = -(float)atan2((double)y, (double)x);
+    return ori;
+}
 // One CTA classifies CLS_TPB consecutive 256-point tiles of a lane: the points of all its tiles are requested before
 // the first is used, so the dependent chain (lane state -> raw pointer -> point) is paid once per CTA, not per tile.
 #define CLS_TPB 4
 template <int MINB>
 __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
 {
-    __shared__ int cnt[2][LL_TILE / 32][LL_MAX_RINGS];   // per-warp ring counts of a tile, double-buffered over the tiles
+    __shared__ __align__(16) int cnt[2][LL_TILE / 32][LL_MAX_RINGS];   // per-warp ring counts of a tile, double-buffered over the tiles
     __shared__ int flip_s;
-    for (int k = threadIdx.x; k < 2 * (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE) (&cnt[0][0][0])[k] = 0;
+    reinterpret_cast<int4*>(&cnt[0][0][0])[threadIdx.x] = make_int4(0, 0, 0, 0);   // 2 x 8 x 64 ints = 256 int4
     if (threadIdx.x == 0) flip_s = INT_MAX;
     const int b = blockIdx.y;
     LaneState& L = P.lane[b];
     const int n = L.n_raw, sw = L.stride_words;
     const float startOri = L.start_ori, endOri = L.end_ori;   // found by k_reset_scan_state
+    const float sdir_x = L.start_dir[0], sdir_y = L.start_dir[1];   // unit vector of the first valid point's azimuth
     const int half_seen = *(volatile int*)&L.half_idx;   // filter for the atomic below; a stale (larger) value only costs an atomic
     const int w = warp_id(), lane = lane_id();
     const int tile0 = blockIdx.x * CLS_TPB;
@@ -140,33 +153,28 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
         const float x = px[t], y = py[t], z = pz[t];
         const bool valid = i < n && point_valid(x, y, z, P.thres);
         int ring = -1;
-        float ori = 0.f;
         bool flip = false;
         if (valid) {
             ring = ring_of(P, x, y, z);
-            // SR:177.  The reference's -atan2f is reproduced as the fp64 atan2 rounded once; only DECISIONS need that
-            // value to the last bit: the branch thresholds startOri - pi/2, startOri + 3pi/2, (ori - startOri) > pi
-            // (SR:180-192), endOri - 3pi/2 and endOri + pi/2 on ori + 2pi (SR:196-205), and the sign of relTime at
-            // ori = startOri (SR:207-208: int(intensity) is the ring id the odometry reads).  Modulo 2pi these are
-            // startOri + k pi/2 and endOri + pi/2, so a point farther than 1e-5 rad from all of them takes the fp32
-            // atan2f (<= 2 ulp: its intensity moves by at most one ulp of the fraction, which nothing consumes).
-            ori = -atan2f(y, x);
-            {
-                const float qa = (ori - startOri) * 0.63661977f, qb = (ori - endOri) * 0.63661977f;   // in units of pi/2
-                if (fabsf(qa - rintf(qa)) < 1e-5f || fabsf(qb - rintf(qb)) < 1e-5f) ori = -(float)atan2((double)y, (double)x);
-            }
             if (ring >= 0) {
-                // SR:180-192 in the !halfPassed state: the first point for which this holds flips halfPassed
-                float o = ori;
-                if ((double)o < (double)startOri - LL_PI / 2)
-                    o = (float)((double)o + 2 * LL_PI);
-                else if ((double)o > (double)startOri + LL_PI * 3 / 2)
-                    o = (float)((double)o - 2 * LL_PI);
-                flip = (double)(o - startOri) > LL_PI;
+                // Does this point flip halfPassed (SR:180-192 in the !halfPassed state: (ori - startOri) > pi after the
+                // wrap into [startOri - pi/2, startOri + 3pi/2])?  With a = ori - startOri = (start azimuth) - (point azimuth)
+                // that is a in (pi, 3pi/2]: sin a < 0 and cos a < 0, which two products with the start direction decide without
+                // any arctangent.  Only points within 1e-3 rad of the quadrant's edges take the literal sequence (scan_ori).
+                const float S = sdir_y * x - sdir_x * y, C = sdir_x * x + sdir_y * y, mm = 1e-6f * (x * x + y * y);
+                if ((S > 0.f && S * S > mm) || (C > 0.f && C * C > mm)) flip = false;
+                else if (S < 0.f && S * S > mm && C < 0.f && C * C > mm) flip = true;
+                else {
+                    float o = scan_ori(x, y, startOri, endOri);
+                    if ((double)o < (double)startOri - LL_PI / 2)
+                        o = (float)((double)o + 2 * LL_PI);
+                    else if ((double)o > (double)startOri + LL_PI * 3 / 2)
+                        o = (float)((double)o - 2 * LL_PI);
+                    flip = (double)(o - startOri) > LL_PI;
+                }
             }
         }
         P.ring8[(size_t)b * P.Nmax + i] = (int8_t)ring;
-        P.ori[(size_t)b * P.Nmax + i] = ori;
         if (flip) fl_min = min(fl_min, i);
         // stable rank inside the tile (SR:209 push_back order): warp match on the ring id, then prefix over the tile's warps
         const unsigned m = __match_any_sync(LL_FULL_MASK, ring);
@@ -177,9 +185,9 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_classify(FeatParams P)
             int run = 0;
             for (int ww = 0; ww < LL_TILE / 32; ++ww) { const int v = c[ww][threadIdx.x]; c[ww][threadIdx.x] = run; run += v; }
             P.tile_hist[((size_t)b * P.R + threadIdx.x) * P.NT + tile] = run;  // [lane][ring][tile]: scans run along tiles
-        } else {
+        } else if (threadIdx.x >= 128) {
             // the other buffer (read last by the previous tile's rank write, before the barrier above) is cleared for the next tile
-            for (int k = threadIdx.x - P.R; k < (LL_TILE / 32) * LL_MAX_RINGS; k += LL_TILE - P.R) (&cnt[(t + 1) & 1][0][0])[k] = 0;
+            reinterpret_cast<int4*>(&cnt[(t + 1) & 1][0][0])[threadIdx.x - 128] = make_int4(0, 0, 0, 0);   // 8 x 64 ints = 128 int4
         }
         __syncthreads();
         P.rank8[(size_t)b * P.Nmax + i] = ring >= 0 ? (uint8_t)(c[w][ring] + rank_in_warp) : 0;
@@ -285,7 +293,6 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_scatter(FeatParams P)
     if (threadIdx.x < P.R) ring_begin_s[threadIdx.x] = L.ring_begin[threadIdx.x];
     const int tile0 = blockIdx.x * CLS_TPB;
     int ring[CLS_TPB], rank[CLS_TPB];
-    float orv[CLS_TPB];
     float4 pt[CLS_TPB];
 #pragma unroll
     for (int t = 0; t < CLS_TPB; ++t) {
@@ -293,7 +300,6 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_scatter(FeatParams P)
         ring[t] = -1;
         if (i < n) {
             ring[t] = P.ring8[(size_t)b * P.Nmax + i];
-            orv[t] = P.ori[(size_t)b * P.Nmax + i];
             rank[t] = P.rank8[(size_t)b * P.Nmax + i];
             const uint32_t* p = L.raw + (size_t)i * sw;
             if (sw == 4) pt[t] = __ldg(reinterpret_cast<const float4*>(p));
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(LL_TILE, MINB) k_scatter(FeatParams P)
     for (int t = 0; t < CLS_TPB; ++t) {
         if (ring[t] < 0) continue;
         const int tile = tile0 + t, i = tile * LL_TILE + threadIdx.x;
-        float ori = orv[t];
+        float ori = scan_ori(pt[t].x, pt[t].y, startOri, endOri);   // SR:177
         if (i <= half_idx) {  // SR:178-193 (the flipping point itself still takes this branch)
             if ((double)ori < (double)startOri - LL_PI / 2)
                 ori = (float)((double)ori + 2 * LL_PI);
@@ -882,26 +888,31 @@ __device__ __forceinline__ void ring_lessflat_body(const FeatParams& P, const in
     const bool fast = bits_v + bits_r <= 31 && NS <= KCAP;   // block-uniform; 31: the padding key 0xFFFFFFFF stays above every real key
     unsigned* key32 = reinterpret_cast<unsigned*>(keys);       // [NS] in the lower half of the key buffer
     unsigned* side = key32 + KCAP;                             // [R] in its upper half: run start << 13 | run length
-    const int ro0 = ro;
-    for (int p = p0; p < p1; ++p)
-        if (p == 0 || vid[p] != vid[p - 1]) {
-            if (fast) { key32[ro] = ((unsigned)vid[p] << bits_r) | (unsigned)ro; side[ro] = (unsigned)p << 13; }
-            else keys[ro] = ((u64)(unsigned)vid[p] << 32) | ((unsigned)p << 13);
-            ++ro;
-        }
-    if (fast) { for (int i = R + tid; i < NS; i += NTH) key32[i] = 0xFFFFFFFFu; }
-    else { for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull; }
-    __syncthreads();
-    for (int q = ro0; q < ro; ++q) {   // length = start of the next run - own start
-        if (fast) {
-            const unsigned ps = side[q] >> 13, pn = q + 1 < R ? side[q + 1] >> 13 : (unsigned)m;
-            side[q] |= pn - ps;
-        } else {
-            const unsigned ps = (unsigned)keys[q] >> 13;
-            const unsigned pn = q + 1 < R ? (unsigned)keys[q + 1] >> 13 : (unsigned)m;
-            keys[q] |= (u64)(pn - ps);
+    // every run is written by the thread that owns its head: the key when the run opens, (start, length) when the next head
+    // (or, for the chunk's last run, the end of the run in a neighbour's chunk) closes it - no word is shared between threads
+    {
+        int open_ro = -1, open_p = 0;
+        auto close_run = [&](int end) {
+            const unsigned len = (unsigned)(end - open_p);
+            if (fast) side[open_ro] = ((unsigned)open_p << 13) | len;
+            else keys[open_ro] |= (u64)len;
+        };
+        for (int p = p0; p < p1; ++p)
+            if (p == 0 || vid[p] != vid[p - 1]) {
+                if (open_ro >= 0) close_run(p);
+                if (fast) key32[ro] = ((unsigned)vid[p] << bits_r) | (unsigned)ro;
+                else keys[ro] = ((u64)(unsigned)vid[p] << 32) | ((unsigned)p << 13);
+                open_ro = ro; open_p = p;
+                ++ro;
+            }
+        if (open_ro >= 0) {
+            int e = p1;
+            while (e < m && vid[e] == vid[open_p]) ++e;
+            close_run(e);
         }
     }
+    if (fast) { for (int i = R + tid; i < NS; i += NTH) key32[i] = 0xFFFFFFFFu; }
+    else { for (int i = R + tid; i < NS; i += NTH) keys[i] = ~0ull; }
     __syncthreads();
     if (fast) {
         switch (NS) {   // all 512 threads call; NS / 8 (NS / 4) of them hold keys
@@ -1061,6 +1072,7 @@ __global__ void k_reset_scan_state(LaneState* lane, int n_lanes, float thres, in
         L.last_valid = lv;
         const float so = fv >= 0 ? -(float)atan2((double)sy, (double)sx) : 0.f;   // = the ori k_classify stores for that point
         L.start_ori = so;
+        { float sn, cs; sincosf(so, &sn, &cs); L.start_dir[0] = cs; L.start_dir[1] = -sn; }   // azimuth of the first valid point = -startOri
         L.end_ori = lv >= 0 ? end_ori_of(-(float)atan2((double)ey, (double)ex), so) : 0.f;
         L.half_idx = INT_MAX;
     }
@@ -1085,7 +1097,7 @@ size_t ll_lessflat_smem_bytes(int SCAP)  // k_ring_lessflat: run sort keys, voxe
 int ll_launch_features(ll_ctx* c, int n_lanes)
 {
     FeatParams P;
-    P.lane = c->d_lane; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.ori = c->d_ori; P.tile_hist = c->d_tile_hist;
+    P.lane = c->d_lane; P.ring8 = c->d_ring8; P.rank8 = c->d_rank8; P.tile_hist = c->d_tile_hist;
     P.full = c->d_full; P.curv = c->d_curv; P.label = c->d_label; P.sorted16 = c->d_sorted16; P.brk = c->d_brk; P.brk_words = (c->RCAP + 31) / 32; P.lf_tmp = c->d_lf_tmp; P.ring_lists = c->d_ring_lists; P.ring_counts = c->d_ring_counts;
     P.sharp = c->d_sharp; P.flat = c->d_flat; P.sharp_idx = c->d_sharp_idx; P.lsharp_idx = c->d_lsharp_idx; P.flat_idx = c->d_flat_idx;
     P.lsharp[0] = c->d_lsharp[0]; P.lsharp[1] = c->d_lsharp[1]; P.lflat[0] = c->d_lflat[0]; P.lflat[1] = c->d_lflat[1];
@@ -1098,7 +1110,7 @@ int ll_launch_features(ll_ctx* c, int n_lanes)
     cudaStream_t s = c->stream;
     const dim3 tiles(c->NT, n_lanes);
     { LLProf pr(c, "k_reset_scan_state"); k_reset_scan_state<<<n_lanes, 32, 0, s>>>(c->d_lane, n_lanes, P.thres, c->d_wide_n); }
-    const int cls_minb = getenv("LL_CLS_MINB") ? atoi(getenv("LL_CLS_MINB")) : 8, sct_minb = getenv("LL_SCT_MINB") ? atoi(getenv("LL_SCT_MINB")) : 5;
+    const int cls_minb = getenv("LL_CLS_MINB") ? atoi(getenv("LL_CLS_MINB")) : 8, sct_minb = getenv("LL_SCT_MINB") ? atoi(getenv("LL_SCT_MINB")) : 8;
     {
         LLProf pr(c, "k_classify");
         const dim3 g((c->NT + CLS_TPB - 1) / CLS_TPB, n_lanes);

@@ -599,7 +599,7 @@ __global__ void k_vg_bbox(VgParams P)
         }
     }
 }
-// key = lane (8 bits) | segment (13) | voxel id or element number (31); ~0 = padding / dropped
+// key = lane (up to 12 bits, from bit 44) | segment (13) | voxel id or element number (31); ~0 = padding / dropped
 __global__ void k_vg_keys(VgParams P)
 {
     const int b = blockIdx.y;
@@ -786,7 +786,7 @@ void ll_map_clear(ll_ctx* c)
 
 int ll_map_alloc(ll_ctx* c)
 {
-    if (c->B > 255) { c->last_error = "mapping supports at most 255 lanes"; return LL_E_INVAL; }
+    if (c->B > 4095) { c->last_error = "mapping supports at most 4095 lanes"; return LL_E_INVAL; }   // 12 lane bits in the voxel-filter sort key
     MapState* m = new MapState();
     c->map = m;
     const size_t B = c->B;
@@ -837,7 +837,7 @@ int ll_map_alloc(ll_ctx* c)
     MK(cudaMalloc((void**)&m->seg_count, sizeof(int) * B * MAP_NUM));
     MK(cudaMalloc((void**)&m->lane_base, sizeof(int) * (B + 1)));
     size_t s1 = 0, s2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, s1, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], (long long)B * m->E, 0, 52, c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, s1, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], (long long)B * m->E, 0, 56, c->stream);
     cub::DeviceScan::ExclusiveSum(nullptr, s2, m->vg_head, m->vg_scan, (long long)B * m->E, c->stream);
     m->cub_bytes = s1 > s2 ? s1 : s2;
     MK(cudaMalloc(&m->cub_tmp, m->cub_bytes));
@@ -880,7 +880,9 @@ static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const 
     {
         LLProf pr(c, "cub_radix_sort");
         size_t bytes = m->cub_bytes;
-        LL_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], total, 0, 52, s));
+        int lane_bits = 1;
+        while ((1 << lane_bits) < n_lanes) ++lane_bits;   // only the key bits in use are sorted
+        LL_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], total, 0, 44 + lane_bits, s));
     }
     { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[1], m->vg_head, m->seg_count, nseg, total); }
     {

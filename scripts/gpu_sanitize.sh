@@ -1,4 +1,8 @@
-# compute-sanitizer memcheck + racecheck over a short fused-pipeline run (2 lanes, 64 lines)
+# compute-sanitizer memcheck + racecheck over short runs of every kernel family (scripts/sanitize_run.py)
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-LL_B=2 LL_STEPS=4 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python scripts/prof_run.py > gpurun_out/sanitize_memcheck.log 2>&1; tail -4 gpurun_out/sanitize_memcheck.log
-LL_B=2 LL_STEPS=3 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python scripts/prof_run.py > gpurun_out/sanitize_racecheck.log 2>&1; tail -4 gpurun_out/sanitize_racecheck.log
+TAG=${1:-r02}
+for tool in memcheck racecheck; do
+LL_STEPS=8 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_run.py default > gpurun_out/${TAG}_sanitize_${tool}_default.log 2>&1; tail -3 gpurun_out/${TAG}_sanitize_${tool}_default.log
+LL_ASSOC_SLAB=1 LL_STEPS=4 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_run.py default > gpurun_out/${TAG}_sanitize_${tool}_slab.log 2>&1; tail -3 gpurun_out/${TAG}_sanitize_${tool}_slab.log
+LL_STEPS=8 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_run.py modes > gpurun_out/${TAG}_sanitize_${tool}_modes.log 2>&1; tail -3 gpurun_out/${TAG}_sanitize_${tool}_modes.log
+done

@@ -261,3 +261,23 @@ def test_scan_to_map_graph_vote_matches_oracle(ll, orc):
     assert differs          # the doubled blocks do change the solve
     ctx.close()
     plain.close()
+
+
+def test_cpp_host_driver_reads_kitti_bin_files(ll, tmp_path):
+    """ll_run --bin-dir: KITTI-style .bin files (float32 x, y, z, i records - what kittiHelper.cpp:22-32, 137-147 reads)
+    give the same trajectory file as the generator path fed the same scans."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(ll.__file__)), "host", "ll_run")
+    bins = tmp_path / "velodyne"
+    bins.mkdir()
+    for k in range(5):
+        s = ll.synth.scan(16, k).copy()
+        s[:, 3] = 0.25                                   # reflectance column: ignored by scanRegistration
+        s.astype(np.float32).tofile(bins / ("%06d.bin" % k))
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    subprocess.check_call([exe, "--lines", "16", "--scans", "5", "--out", str(a)])
+    subprocess.check_call([exe, "--lines", "16", "--scans", "9", "--bin-dir", str(bins), "--out", str(b)])   # stops at the first missing file
+    ra, rb = np.loadtxt(a), np.loadtxt(b)
+    assert ra.shape == rb.shape == (5, 12)
+    assert np.array_equal(ra, rb)
