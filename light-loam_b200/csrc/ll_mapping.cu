@@ -16,19 +16,17 @@
 //
 // The cube map is stored per lane and cloud type as CSR over the 21 x 21 x 11 logical cube array and rebuilt once per
 // frame (a streaming copy of the map), which makes the reference's pointer-rotation shifts and per-cube filters one
-// pass.  The two sorts / one scan of the voxel filter use CUB (cub::DeviceRadixSort / DeviceScan, shipped with the
-// CUDA toolkit) — library plumbing on the map-maintenance side ("next" row of SURVEY.md §8f); every other step is a
-// hand-written kernel.
+// pass.  The sort and the prefix sum of the voxel filter are the hand-written ones of ll_sort.cuh (stable LSD radix
+// sort over the key digits in use, three-level scan): no library call on the path.
 #include <limits.h>
 #include <math.h>
 #include <string.h>
-
-#include <cub/cub.cuh>
 
 #include "ll_ctx.h"
 #include "ll_device.cuh"
 #include "ll_knn.cuh"
 #include "ll_solve.cuh"
+#include "ll_sort.cuh"
 
 #define MAP_W 21
 #define MAP_H 21
@@ -65,8 +63,8 @@ struct MapState {
     int* vg_bbox = nullptr;    // [B][nseg][6] ordered-int min xyz / max xyz
     int* seg_count = nullptr;  // [B][MAP_NUM]
     int* lane_base = nullptr;  // [B+1]
-    void* cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    int* sort_hist = nullptr;      // [tiles][256] digit histograms of the radix sort (ll_sort.cuh)
+    int* scan_scratch = nullptr;   // chunk sums of the prefix sums
     double* blocks = nullptr;  // dense records [B][LL_BLOCK_DOUBLES][nblk_cap]
     int nblk_cap = 0;
     // graph vote on the plane correspondences (LM:2057-2072, cfg.map_graph_vote)
@@ -767,7 +765,7 @@ void ll_map_free(ll_ctx* c)
     }
     cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->vg_in); cudaFree(m->vg_seg);
     cudaFree(m->vg_n); cudaFree(m->vg_head); cudaFree(m->vg_scan); cudaFree(m->vg_bbox); cudaFree(m->seg_count); cudaFree(m->lane_base);
-    cudaFree(m->cub_tmp); cudaFree(m->blocks);
+    cudaFree(m->sort_hist); cudaFree(m->scan_scratch); cudaFree(m->blocks);
     cudaFree(m->vote_tgt_raw); cudaFree(m->vote_src); cudaFree(m->vote_tgt); cudaFree(m->vote_cnt);
     for (int g = 0; g < LM_MAX_GPUS; ++g) if (m->peer_ipc[g] && m->peer_buf[g]) cudaIpcCloseMemHandle(m->peer_buf[g]);
     cudaFree(m->comm_buf); cudaFree(m->comm_seq[0]); cudaFree(m->comm_seq[1]);
@@ -836,11 +834,13 @@ int ll_map_alloc(ll_ctx* c)
     MK(cudaMalloc((void**)&m->vg_bbox, sizeof(int) * B * MAP_NUM * 6));
     MK(cudaMalloc((void**)&m->seg_count, sizeof(int) * B * MAP_NUM));
     MK(cudaMalloc((void**)&m->lane_base, sizeof(int) * (B + 1)));
-    size_t s1 = 0, s2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, s1, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], (long long)B * m->E, 0, 56, c->stream);
-    cub::DeviceScan::ExclusiveSum(nullptr, s2, m->vg_head, m->vg_scan, (long long)B * m->E, c->stream);
-    m->cub_bytes = s1 > s2 ? s1 : s2;
-    MK(cudaMalloc(&m->cub_tmp, m->cub_bytes));
+    {
+        const long long total = (long long)B * m->E;
+        const size_t hist = llsort::sort_hist_ints(total);
+        const size_t s1 = llsort::scan_scratch_ints((long long)hist), s2 = llsort::scan_scratch_ints(total);
+        MK(cudaMalloc((void**)&m->sort_hist, sizeof(int) * hist));
+        MK(cudaMalloc((void**)&m->scan_scratch, sizeof(int) * (s1 > s2 ? s1 : s2)));
+    }
     m->nblk_cap = m->stack_cap[0] + m->stack_cap[1];
     MK(cudaMalloc((void**)&m->blocks, sizeof(double) * B * LL_BLOCK_DOUBLES * (size_t)m->nblk_cap));
     if (c->cfg.map_graph_vote > 0) {
@@ -877,23 +877,30 @@ static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const 
     { LLProf pr(c, "k_vg_init"); k_vg_init<<<(n_lanes * nseg + 255) / 256, 256, 0, s>>>(m->vg_bbox, m->seg_count, n_lanes * nseg); }
     { LLProf pr(c, "k_vg_bbox"); k_vg_bbox<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
     { LLProf pr(c, "k_vg_keys"); k_vg_keys<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
+    int sorted = 0;
     {
-        LLProf pr(c, "cub_radix_sort");
-        size_t bytes = m->cub_bytes;
-        int lane_bits = 1;
-        while ((1 << lane_bits) < n_lanes) ++lane_bits;   // only the key bits in use are sorted
-        LL_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(m->cub_tmp, bytes, m->vg_keys[0], m->vg_keys[1], m->vg_vals[0], m->vg_vals[1], total, 0, 44 + lane_bits, s));
+        // stable LSD radix sort of (lane | segment | voxel id): only the 8-bit digits that can differ are sorted - voxel id
+        // bits 0..30, segment bits from 31 (none when there is one segment), lane bits from 44
+        LLProf pr(c, "radix_sort");
+        int lane_bits = 0, seg_bits = 0;
+        while ((1 << lane_bits) < n_lanes) ++lane_bits;
+        while ((1 << seg_bits) < nseg) ++seg_bits;
+        int shifts[8], ns = 0;
+        for (int sh = 0; sh < 64; sh += 8) {
+            const bool voxel = sh < 31, seg = seg_bits > 0 && sh < 31 + seg_bits && sh + 8 > 31, lane = lane_bits > 0 && sh < 44 + lane_bits && sh + 8 > 44;
+            if (voxel || seg || lane) shifts[ns++] = sh;
+        }
+        sorted = llsort::sort_pairs(m->vg_keys, m->vg_vals, total, shifts, ns, m->sort_hist, m->scan_scratch, s, &c->launches);
     }
-    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[1], m->vg_head, m->seg_count, nseg, total); }
+    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_head, m->seg_count, nseg, total); }
     {
-        LLProf pr(c, "cub_scan");
-        size_t bytes = m->cub_bytes;
-        LL_CUDA_CHECK(c, cub::DeviceScan::ExclusiveSum(m->cub_tmp, bytes, m->vg_head, m->vg_scan, total, s));
+        LLProf pr(c, "prefix_sum");
+        c->launches += llsort::scan_exclusive(m->vg_head, m->vg_scan, total, m->scan_scratch, s);
     }
     { LLProf pr(c, "k_vg_offsets"); k_vg_offsets<<<n_lanes, 1024, 0, s>>>(m->seg_count, seg_off, m->lane_base, nseg, n_lanes, nullptr, c->d_lane, which); }
     { LLProf pr(c, "k_vg_lane_prefix"); k_vg_lane_prefix<<<1, 32, 0, s>>>(m->lane_base, n_lanes); }
-    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[1], m->vg_vals[1], m->vg_head, m->vg_scan, m->lane_base, m->vg_in, out, out_cap, total); }
-    c->launches += 9;
+    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_vals[sorted], m->vg_head, m->vg_scan, m->lane_base, m->vg_in, out, out_cap, total); }
+    c->launches += 7;   // + the sort's and the prefix sum's own launches, counted above
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
 }
