@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_map(LaneState* lane, co
     const int b = blockIdx.x, part = blockIdx.y;
     LaneState& L = lane[b];
     const int nb = L.map_ok ? L.n_stack_corner + L.n_stack_surf : 0;
-    if (comm.gworld * comm.nparts > 1 && b == 0 && part == 0)   // lanes outside this launch keep their collective counters
+    if (comm.cluster <= 1 && comm.gworld * comm.nparts > 1 && b == 0 && part == 0)   // lanes outside this launch keep their collective counters
         for (int i = gridDim.x + threadIdx.x; i < n_all_lanes; i += LM_THREADS) comm.seq_out[i] = comm.seq_in[i];
     lm_solve(blocks + (size_t)b * LL_BLOCK_DOUBLES * nblk_cap, nblk_cap, nb, L.map_par, L.map_par + 4, &L, 3 + iter, &comm, b, part);
 }
@@ -949,7 +949,12 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
         comm.flag[g] = base ? reinterpret_cast<unsigned long long*>(base + m->comm_mbox_bytes) : nullptr;
     }
     comm.grank = m->grank; comm.gworld = m->gworld; comm.nparts = parts; comm.timeout_ns = m->timeout_ns;
-    const bool dist = comm.gworld * comm.nparts > 1;
+    // one GPU: the parts of a lane are the CTAs of a thread-block cluster and sum through distributed shared memory (no
+    // mailbox, no cooperative launch); the mailbox path stays for slab sharding over several GPUs (and LL_LM_PARTS)
+    comm.cluster = (m->gworld == 1 && !getenv("LL_LM_PARTS")) ? lm_cluster_size(n_lanes, n_sm) : 1;
+    if (comm.cluster > 1) { parts = comm.cluster; comm.nparts = 1; }
+    else if (m->gworld == 1 && !getenv("LL_LM_PARTS")) { parts = 1; comm.nparts = 1; }   // more lanes than half the SMs: one CTA per lane
+    const bool dist = comm.cluster <= 1 && comm.gworld * comm.nparts > 1;
     for (int iter = 0; iter < 2; ++iter) {  // LM:1834
         { LLProf pr(c, "k_map_reset_corr"); k_map_reset_corr<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
         { LLProf pr(c, "k_map_assoc"); k_map_assoc<<<dim3((m->nblk_cap + 7) / 8, n_lanes), 256, 0, s>>>(A); }
@@ -964,7 +969,9 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
         comm.seq_in = m->comm_seq[m->comm_flip]; comm.seq_out = m->comm_seq[m->comm_flip ^ (dist ? 1 : 0)];
         {
             LLProf pr(c, "k_lm_solve_map");
-            if (dist) {
+            if (comm.cluster > 1) {
+                LL_CUDA_CHECK(c, lm_launch_cluster(k_lm_solve_map, n_lanes, parts, LM_THREADS, s, c->d_lane, (const double*)m->blocks, (int)m->nblk_cap, iter, comm, (int)c->B));
+            } else if (dist) {
                 LaneState* a_lane = c->d_lane; const double* a_blk = m->blocks; int a_cap = m->nblk_cap, a_iter = iter, a_B = c->B;
                 void* args[] = {&a_lane, &a_blk, &a_cap, &a_iter, &comm, &a_B};
                 LL_CUDA_CHECK(c, cudaLaunchCooperativeKernel((const void*)k_lm_solve_map, dim3(n_lanes, parts), dim3(LM_THREADS), args, 0, s));

@@ -223,24 +223,37 @@ __global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
     int tot = 0;
     block_exclusive_scan(s, ws, &tot);
     if (threadIdx.x == 0) S.partial[t][(size_t)b * (nchunk + 1) + chunk] = tot;
-    // the first chunk of each table also decodes the ring elevation bands (complete since k_index_count).  An empty
-    // ring gets an empty band at its predecessor's upper edge, so ordered bands stay ordered through the gaps.
-    if (chunk == 0 && threadIdx.x == 32) {
+    // the first chunk of each table also decodes the ring elevation bands (complete since k_index_count): thread r turns
+    // ring r's tangents into angles, then one thread walks the rings.  An empty ring gets an empty band at its
+    // predecessor's upper edge, so ordered bands stay ordered through the gaps.
+    if (chunk == 0) {   // block-uniform
+        __shared__ float s_lo[LL_MAX_RINGS], s_hi[LL_MAX_RINGS];
+        __shared__ unsigned char s_has[LL_MAX_RINGS];
         const unsigned* eb = S.ebound[t] + (size_t)b * S.rings * 2;
         float* bd = S.bands[t] + (size_t)b * BAND_STRIDE;
-        float plo = -INFINITY, phi = -INFINITY;
-        int ordered = 1;
-        for (int r = 0; r < S.rings; ++r) {
+        const int r = threadIdx.x;
+        if (r < S.rings) {
             const unsigned lo = eb[r * 2], hi = eb[r * 2 + 1];
-            float elo = phi, ehi = phi;
-            if (hi != 0u) {
-                elo = atanf(dec_f32(~lo)) - 1e-5f; ehi = atanf(dec_f32(hi)) + 1e-5f;   // tangents -> angles, widened by the rsqrt / atanf error
-                if (elo < plo || ehi < phi) ordered = 0;
-                plo = elo; phi = ehi;
-            }
-            bd[r] = elo; bd[LL_MAX_RINGS + r] = ehi;
+            s_has[r] = hi != 0u;
+            if (hi != 0u) { s_lo[r] = atanf(dec_f32(~lo)) - 1e-5f; s_hi[r] = atanf(dec_f32(hi)) + 1e-5f; }   // widened by the rsqrt / atanf error
         }
-        reinterpret_cast<int*>(bd)[2 * LL_MAX_RINGS] = ordered;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float plo = -INFINITY, phi = -INFINITY;
+            int ordered = 1;
+            for (int q = 0; q < S.rings; ++q) {
+                float elo = phi, ehi = phi;
+                if (s_has[q]) {
+                    elo = s_lo[q]; ehi = s_hi[q];
+                    if (elo < plo || ehi < phi) ordered = 0;
+                    plo = elo; phi = ehi;
+                }
+                s_lo[q] = elo; s_hi[q] = ehi;
+            }
+            reinterpret_cast<int*>(bd)[2 * LL_MAX_RINGS] = ordered;
+        }
+        __syncthreads();
+        if (r < S.rings) { bd[r] = s_lo[r]; bd[LL_MAX_RINGS + r] = s_hi[r]; }
     }
 }
 __global__ void __launch_bounds__(256) k_index_scan(IndexSet S)
@@ -527,30 +540,32 @@ __device__ __forceinline__ bool assoc_ring_window(AssocQuery& Q, const PolarQuer
 }
 // Warp part: one query's whole ring window, the bins in reach shared out over the lanes (at most 16 per side and
 // round, the reach being re-evaluated between rounds).
+// `step` = bins per side of the first round (doubling up to 16): 16 for the queue's leftovers, which are wide by selection;
+// 2 when the warp takes a fresh query (k_odom_assoc_direct), whose window mostly closes inside its own bin and the next.
 template <bool CORNER>
-__device__ __forceinline__ void assoc_ring_window_warp(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R)
+__device__ __forceinline__ void assoc_ring_window_warp(AssocQuery& Q, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R, int step = 16)
 {
     const int lane = lane_id();
     PolarQuery pq;
     polar_query_init(pq, Q.qx, Q.qy, Q.qz, NB);
     const int r_lo = max(Q.cring - 2, 0), r_n = min(Q.cring + 2, R - 1) + 1 - r_lo;
     int doneL = 0, doneR = -1;   // left offsets 1..doneL and right offsets 0..doneR have been visited
-    for (;;) {
+    for (;; step = min(step * 2, 16)) {
         int kl, kr;
         polar_reach_bins(pq, NB, assoc_window_dist<CORNER>(Q), kl, kr);
         if (doneL >= kl && doneR >= kr) break;
         const int idx = lane >> 1;
         int beg = 0, cnt = 0, off = 0;
         bool on = false;
-        if (lane & 1) { const int k = doneL + 1 + idx; on = k <= kl; off = -k; }
-        else { const int k = doneR + 1 + idx; on = k <= kr; off = k; }
+        if (lane & 1) { const int k = doneL + 1 + idx; on = idx < step && k <= kl; off = -k; }
+        else { const int k = doneR + 1 + idx; on = idx < step && k <= kr; off = k; }
         if (on) {
             const int* h = start + ((pq.b0 + off) & (NB - 1)) * R + r_lo;
             beg = __ldg(h);
             cnt = __ldg(h + r_n) - beg;
         }
         grid_stream_ranges(sorted, beg, cnt, [&](const float4 t) { assoc_consider<CORNER>(Q, t); });
-        doneL += 16; doneR += 16;
+        doneL += step; doneR += step;
         Q.k2 = warp_min_u64(Q.k2);
         if (!CORNER) Q.k3 = warp_min_u64(Q.k3);
         assoc_update_cut<CORNER>(Q);
@@ -699,7 +714,7 @@ __device__ __forceinline__ bool polar_nearest_thread(const RingBands& S, const S
 // Warp version (one query per warp; bands read from global memory): every step streams the rings in reach of up to
 // 16 bins per side.  `best` (warp-uniform) may carry what the thread pass found.
 __device__ __forceinline__ u64 polar_nearest_warp(const float* __restrict__ bands, const int* __restrict__ start, const float4* __restrict__ sorted, int NB, int R,
-                                                  float qx, float qy, float qz, u64 best)
+                                                  float qx, float qy, float qz, u64 best, int wk = 8, int wr = 16)
 {
     const int lane = lane_id();
     PolarQuery pq;
@@ -713,7 +728,9 @@ __device__ __forceinline__ u64 polar_nearest_warp(const float* __restrict__ band
     // The window (bins b0-wk .. b0+wk, rings r0-wr .. r0+wr) doubles every round and is clipped to the reach of the best
     // found so far; the search ends when a round's window covered the whole reach it was clipped to.  The cost is
     // that of the final window (the earlier ones add a third), not that of the 5 m reach a query starts with.
-    int wk = 8, wr = 16;   // what the thread pass hands over nearly always resolves inside this first window
+    int pra = 1 << 20, prb = -1, pkl = -1, pkr = -1;   // rings / bins the previous round streamed (nothing yet)
+    // first window: 8 x 16 by default - what the thread pass hands over nearly always resolves inside it; a fresh query
+    // (k_odom_assoc_direct) starts with its own bin and ring and their neighbours
     for (;;) {
         const float bd = best_dist(best);
         const float g = reach_angle(bd, pq.qn);
@@ -731,7 +748,9 @@ __device__ __forceinline__ u64 polar_nearest_warp(const float* __restrict__ band
             rb = min(rb, R - 1);
         }
         polar_reach_bins(pq, NB, bd, kl, kr);
+        if (ra >= pra && rb <= prb && kl <= pkl && kr <= pkr) break;   // the last window already covered this reach
         const int cra = max(ra, pq.r0 - wr), crb = min(rb, pq.r0 + wr), ckl = min(kl, wk), ckr = min(kr, wk);
+        pra = cra; prb = crb; pkl = ckl; pkr = ckr;
         for (int o0 = -ckl; o0 <= ckr; o0 += 32) {
             const int off = o0 + lane;
             int beg = 0, cnt = 0;
@@ -1090,7 +1109,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, MINB) k_odom_assoc_slab(OdomPara
 // One WARP per queued query, the queue spread over a fixed grid: the long searches (no target nearby, wide ring
 // windows, literal walks) run side by side instead of serialising inside the warp that met them.
 template <bool CORNER>
-__device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int i, bool open, int ez, int ew)
+__device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int i, bool open, int ez, int ew, bool fresh = false)
 {
     const LaneState& L = P.lane[b];
     const int lane = lane_id();
@@ -1100,10 +1119,10 @@ __device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int
     const GridView av = assoc_view(CORNER ? P.ac : P.as_, b);
     const int NB = CORNER ? P.az_bins_corner : P.az_bins_surf;
     int closest = open ? -1 : ez, mode = open ? -1 : ew;
-    if (open) {
+    if (open && Q.n > 0) {
         // 1-NN (kdtree*Last->nearestKSearch(pointSel, 1, ...), LO:494 / LO:656) continued from the thread pass's best
         const u64 best = polar_nearest_warp(P.bands[CORNER ? 0 : 1] + (size_t)b * BAND_STRIDE, av.start, av.sorted, NB, P.R, Q.qx, Q.qy, Q.qz,
-                                            ((u64)(unsigned)ez << 32) | (unsigned)ew);
+                                            ((u64)(unsigned)ez << 32) | (unsigned)ew, fresh ? 1 : 8, fresh ? 1 : 16);
         if (best != NN_NONE) {  // d2 < 25: LO:497 / LO:659
             closest = (int)(unsigned)best;
             mode = (CORNER ? L.mono_corner : L.mono_surf) ? -1 : -2;
@@ -1113,7 +1132,7 @@ __device__ __forceinline__ void assoc_warp_query(const OdomParams& P, int b, int
         Q.closest = closest;
         Q.cring = (int)last[closest].w;  // int(intensity), LO:500 / LO:664
         if (mode == -2) assoc_literal_walk_warp<CORNER>(Q, last);
-        else assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, NB, P.R);
+        else assoc_ring_window_warp<CORNER>(Q, av.start, av.sorted, NB, P.R, fresh ? 2 : 16);
     }
     if (lane == 0) assoc_store<CORNER>(P, b, i, Q);
 }
@@ -1138,6 +1157,21 @@ __global__ void __launch_bounds__(256, 4) k_odom_assoc_heavy(OdomParams P)
             atomicAdd(&P.lane[0].dbg[3 + kind], dt >> 6);
             atomicMax(&P.lane[0].dbg[5 + kind], dt);
         }
+    }
+}
+
+// Few lanes (the single-stream path): a thread per query leaves most of the GPU idle and every query walks its buckets
+// alone, so every query gets a WARP from the start - no thread pass, no queue; the same searches, the same total orders,
+// hence the same correspondences.  Slot w = (lane, feature): corners first, then planes.
+__global__ void __launch_bounds__(256, 4) k_odom_assoc_direct(OdomParams P, int n_lanes)
+{
+    const int nc = P.R * LL_SHARP_PER_RING, per_lane = nc + P.R * LL_FLAT_PER_RING, total = n_lanes * per_lane;
+    for (int w = blockIdx.x * 8 + warp_id(); w < total; w += gridDim.x * 8) {
+        const int b = w / per_lane, e = w - b * per_lane;
+        const LaneState& L = P.lane[b];
+        if (!L.inited || L.err) continue;
+        if (e < nc) { if (e < L.n_sharp) assoc_warp_query<true>(P, b, e, true, (int)(unsigned)(NN_NONE >> 32), 0, true); }
+        else if (e - nc < L.n_flat) assoc_warp_query<false>(P, b, e - nc, true, (int)(unsigned)(NN_NONE >> 32), 0, true);
     }
 }
 
@@ -1456,7 +1490,12 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm_solve_odom(OdomParams P, LmCo
 {
     const int b = blockIdx.x, part = blockIdx.y;
     LaneState& L = P.lane[b];
-    const bool split = comm.nparts > 1;
+    const bool split = comm.nparts > 1, clus = comm.cluster > 1;
+    if (clus) {   // the CTAs of a cluster work on one lane: they take the same decision here
+        if (!L.inited || L.err) return;
+        lm_solve<DIST>(P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap, P.nblk_cap, L.n_blocks, L.para_q, L.para_t, &L, P.outer, &comm, b, part);
+        return;
+    }
     if (split && b == 0 && part == 0)   // lanes outside this launch keep their collective counters
         for (int i = gridDim.x + threadIdx.x; i < n_all_lanes; i += blockDim.x) comm.seq_out[i] = comm.seq_in[i];
     if (!L.inited || L.err) {
@@ -1596,6 +1635,13 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     comm.flag[0] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_odom_comm) + c->odom_comm_mbox_bytes);
     comm.grank = 0; comm.gworld = 1; comm.nparts = lm_parts; comm.timeout_ns = 2000000000ull;
     const int lm_threads_used = lm_parts > 1 ? (getenv("LL_LM_THREADS") ? lm_threads : 128) : lm_threads;   // split: ~1 block per thread
+    // Few lanes (the single-stream path): the CTAs of a thread-block cluster share a lane's blocks and sum their 28 doubles
+    // through distributed shared memory - one hardware cluster barrier per evaluation, no mailbox, no cooperative launch
+    const int lm_cluster = lm_parts > 1 ? 1 : lm_cluster_size(n_lanes, n_sm);
+    comm.cluster = lm_cluster;
+    int lm_cluster_threads = ((c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING) + lm_cluster - 1) / lm_cluster + 63) / 64 * 64;   // ~1 block per thread
+    lm_cluster_threads = lm_cluster_threads < 64 ? 64 : (lm_cluster_threads > LM_THREADS ? LM_THREADS : lm_cluster_threads);
+    if (getenv("LL_LM_THREADS")) lm_cluster_threads = lm_threads;
     const int kmax = getenv("LL_ASSOC_KMAX") ? atoi(getenv("LL_ASSOC_KMAX")) : 2;   // 1-NN bins per side a thread walks
     const size_t vote_smem = (size_t)(c->R * LL_FLAT_PER_RING / 10 + 16) * (2 * sizeof(float4) + sizeof(int));
     // kdtreeCornerLast / kdtreeSurfLast ->setInputCloud (LO:895-896), deferred to the moment the trees are queried:
@@ -1652,9 +1698,17 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     }
     if (slab_mode && slab_smem > (size_t)(slab_minb >= 3 ? 72 : (slab_minb == 2 ? 110 : 220)) * 1024) { c->last_error = "slab stage larger than the shared memory of the chosen occupancy"; return LL_E_INVAL; }
     if (Sp.ns_surf + Sp.ns_corner + 2 > c->qstart_stride) { c->last_error = "too many slabs"; return LL_E_INVAL; }
+    // direct form (a warp per query, one launch) up to LL_ASSOC_DIRECT lanes
+    const int direct_lanes = getenv("LL_ASSOC_DIRECT") ? atoi(getenv("LL_ASSOC_DIRECT")) : 8;
+    const bool direct_mode = !slab_mode && n_lanes <= direct_lanes;
     for (int outer = 0; outer < 3; ++outer) {  // LO:439
         P.outer = outer;
-        if (slab_mode) {
+        if (direct_mode) {
+            LLProf pr(c, "k_odom_assoc_direct");
+            const int want = (n_lanes * c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING) + 7) / 8;
+            k_odom_assoc_direct<<<want < n_sm * 16 ? want : n_sm * 16, 256, 0, s>>>(P, n_lanes);
+            c->launches -= 1;   // one launch instead of the thread pass + the queue pass (5 counted per iteration below)
+        } else if (slab_mode) {
             { LLProf pr(c, "k_odom_queries"); k_odom_queries<<<n_lanes, QPREP_THREADS, 0, s>>>(P, Sp); }
             LLProf pr(c, "k_odom_assoc");
             const dim3 g(Sp.ns_surf + Sp.ns_corner, n_lanes);
@@ -1670,7 +1724,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
             else if (minb >= 8) k_odom_assoc<8><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
             else k_odom_assoc<6><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
         }
-        { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
+        if (!direct_mode) { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
         { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
         if (c->cfg.vote_mode == 1) {
             const int mcap = c->R * LL_FLAT_PER_RING / 10 + 16;
@@ -1690,6 +1744,9 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
                 const void* fn = P.distortion ? (const void*)k_lm_solve_odom<true> : (const void*)k_lm_solve_odom<false>;
                 LL_CUDA_CHECK(c, cudaLaunchCooperativeKernel(fn, dim3(n_lanes, lm_parts), dim3(lm_threads_used), args, 0, s));
                 c->odom_comm_flip ^= 1;
+            } else if (lm_cluster > 1) {
+                if (P.distortion) LL_CUDA_CHECK(c, lm_launch_cluster(k_lm_solve_odom<true>, n_lanes, lm_cluster, lm_cluster_threads, s, P, comm, (int)c->B));
+                else LL_CUDA_CHECK(c, lm_launch_cluster(k_lm_solve_odom<false>, n_lanes, lm_cluster, lm_cluster_threads, s, P, comm, (int)c->B));
             } else if (P.distortion) k_lm_solve_odom<true><<<n_lanes, lm_threads, 0, s>>>(P, comm, c->B);
             else k_lm_solve_odom<false><<<n_lanes, lm_threads, 0, s>>>(P, comm, c->B);
         }

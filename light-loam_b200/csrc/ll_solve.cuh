@@ -15,6 +15,7 @@
 // One CTA per problem (or several, see LmComm); LM_THREADS threads stride over the residual blocks; the reduction
 // order is fixed (lane tree, then warps in order, then CTAs in rank order), so results are run-to-run deterministic.
 #pragma once
+#include <cooperative_groups.h>
 #include <float.h>
 
 #include "ll_ctx.h"
@@ -42,6 +43,8 @@ struct LmComm {
     unsigned long long* seq_out;                // [B] written by part 0 of this launch (the host alternates the two arrays)
     int grank, gworld, nparts;
     unsigned long long timeout_ns;              // a peer that never shows up must not hang the GPU
+    int cluster;                                // > 1: the parts of a problem are the CTAs of one thread-block cluster (gworld = 1) and
+                                                // exchange their partial sums through distributed shared memory, not the mailbox
 };
 
 struct LmCtl {   // trust-region controller state (thread 0 only); kept out of the registers of the evaluation loops
@@ -54,6 +57,7 @@ struct LmShared {
     double x[7], cand[7];
     double red[LM_THREADS / 32][LM_NRED];
     double out[LM_NRED];
+    double pub[2][LM_NRED];   // cluster mode: this CTA's partial sums as its peers read them (slot = parity of the collective)
     int go;
     int comm_dead;
 };
@@ -99,6 +103,26 @@ __device__ __forceinline__ void lm_allreduce(LmShared& S, const LmComm& C, int b
         volatile const double* src = C.mbox[C.grank] + slot;
         double v = 0.0;
         for (int r = 0; r < W; ++r) v += src[(size_t)r * LM_MBOX_DOUBLES + tid];  // rank order: same bits in every CTA
+        S.out[tid] = v;
+    }
+    __syncthreads();
+}
+
+// The same sum over the CTAs of a thread-block cluster (the single-stream path: few problems, many idle SMs).  Every CTA
+// publishes its partial sums in its own shared memory, one cluster barrier later every CTA reads all of them in rank
+// order through DSMEM - identical bits everywhere again.  One barrier per collective: a CTA can only overwrite a slot
+// two collectives later, and it cannot pass the barrier in between before every peer is done reading.
+__device__ __forceinline__ void lm_allreduce_cluster(LmShared& S, int nparts, unsigned long long seq, int first)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int tid = threadIdx.x;
+    double* pub = S.pub[seq & 1];
+    if (tid < LM_NRED && tid >= first) pub[tid] = S.out[tid];
+    cl.sync();
+    if (tid < LM_NRED && tid >= first) {
+        double v = 0.0;
+        for (int r = 0; r < nparts; ++r) v += *cl.map_shared_rank(pub + tid, r);
         S.out[tid] = v;
     }
     __syncthreads();
@@ -434,8 +458,9 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
 {
     __shared__ LmShared S;
     const int tid = threadIdx.x;
-    const bool dist = comm != nullptr && comm->gworld * comm->nparts > 1;
-    const int nparts = dist ? comm->nparts : 1;
+    const bool clus = comm != nullptr && comm->cluster > 1;   // parts = CTAs of a cluster: same lane, same nb, DSMEM exchange
+    const bool dist = comm != nullptr && !clus && comm->gworld * comm->nparts > 1;
+    const int nparts = clus ? comm->cluster : (dist ? comm->nparts : 1);
     unsigned long long seq = dist ? comm->seq_in[comm_b] : 0ull;   // collectives so far; every thread keeps its own copy
     if (tid == 0) S.comm_dead = 0;
     if (tid < 4) S.x[tid] = q_io[tid];
@@ -466,6 +491,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
     lm_reduce<true>(S, acc);
     if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
+    if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
     if (tid == 0) {
         for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
         for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
@@ -538,6 +564,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         lm_accumulate<false, DIST>(blk, cap, nb, S.cand, acc, part, nparts);
         lm_reduce<false>(S, acc);
         if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 27, L);
+        if (clus) lm_allreduce_cluster(S, nparts, ++seq, 27);
         if (tid == 0) {
             const double cand_cost = S.out[27];
             ++C.cost_evals;
@@ -576,6 +603,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
             lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
             lm_reduce<true>(S, acc);
             if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
+            if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
             if (tid == 0) {
                 for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
                 for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
@@ -590,6 +618,7 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         }
         __syncthreads();
     }
+    if (clus) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still be reading its shared memory
     if (tid == 0 && part == 0) {  // every part holds the same result; one writes it
         if (!S.comm_dead) {       // a collective that timed out leaves partial sums behind: the parameters stay untouched (L->err = LL_E_NCCL)
             for (int i = 0; i < 4; ++i) q_io[i] = S.x[i];
@@ -605,3 +634,26 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         }
     }
 }
+
+// host side: launch `kern` on grid (lanes, parts) with the parts of a lane forming one thread-block cluster
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lm_launch_cluster(void (*kern)(KArgs...), int n_lanes, int parts, int threads, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_lanes, parts); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)parts; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+// CTAs per cluster for a solve over n_lanes problems: the largest of 8 / 4 / 2 that leaves every CTA an SM of its own
+// (LL_LM_CLUSTER overrides; 1 = off)
+static inline int lm_cluster_size(int n_lanes, int n_sm)
+{
+    int p = 1;
+    for (int q = 8; q >= 2; q >>= 1) if (n_lanes * q <= n_sm) { p = q; break; }
+    if (const char* e = getenv("LL_LM_CLUSTER")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4 || v == 8) && v * n_lanes <= n_sm) p = v; }
+    return p;
+}
+

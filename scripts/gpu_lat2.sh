@@ -1,0 +1,7 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_odometry.py tests/test_gpu_mapping.py -m gpu -x -q 2>&1 | tail -8
+python scripts/time_latency.py 2>&1 | tail -3
+echo "--- direct off"; LL_ASSOC_DIRECT=0 python scripts/time_latency.py 2>&1 | head -1
+echo "--- cluster off"; LL_LM_CLUSTER=1 python scripts/time_latency.py 2>&1 | head -2
+echo "--- cluster 4"; LL_LM_CLUSTER=4 python scripts/time_latency.py 2>&1 | head -1
+echo "--- graph off"; LL_GRAPH=0 python scripts/time_latency.py 2>&1 | head -1

@@ -151,14 +151,19 @@ def _config5_inputs(ll, line=32):
 
 
 def test_split_solve_matches_single_cta(ll, monkeypatch):
-    """The LM solve split over 16 CTAs (in-kernel all-reduce through the mailbox) vs one CTA: same pose to fp64
-    summation-order noise, same iteration counts and termination."""
+    """The LM solve split over 16 / 5 CTAs (in-kernel all-reduce through the mailbox) and over a thread-block cluster of 8
+    (sums through distributed shared memory: the default on one GPU) vs one CTA: same pose to fp64 summation-order noise,
+    same iteration counts and termination."""
     corner, surf = _config5_inputs(ll)
     q0 = np.array([0, 0, np.sin(np.pi / 4), np.cos(np.pi / 4)])
     t0 = np.array([25.0, 0.0, 0.0])
     res = {}
-    for parts in (1, 16, 5):
-        monkeypatch.setenv("LL_LM_PARTS", str(parts))
+    for parts in (1, 16, 5, "cluster8", "cluster4"):
+        if isinstance(parts, int):
+            monkeypatch.setenv("LL_LM_PARTS", str(parts))
+        else:
+            monkeypatch.delenv("LL_LM_PARTS", raising=False)
+            monkeypatch.setenv("LL_LM_CLUSTER", parts[7:])
         ctx = ll.Context(scan_line=32, map_capacity=1 << 19)
         f = ctx.extract_features(ll.synth.scan(32, 0, mode=1))
         ctx.map_insert(corner, surf)
@@ -169,7 +174,7 @@ def test_split_solve_matches_single_cta(ll, monkeypatch):
             out.append((m["q"].copy(), m["t"].copy(), list(st.map_jacobian_evals), list(st.map_termination), st.map_corner_corr, st.map_surf_corr))
         res[parts] = out
         ctx.close()
-    for parts in (16, 5):
+    for parts in (16, 5, "cluster8", "cluster4"):
         for a, b in zip(res[1], res[parts]):
             assert np.abs(a[0] - b[0]).max() < 1e-11 and np.abs(a[1] - b[1]).max() < 1e-10, (parts, a, b)
             assert a[2:] == b[2:], (parts, a[2:], b[2:])

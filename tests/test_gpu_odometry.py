@@ -15,10 +15,19 @@ def _ang(qa, qb):
     return 2 * np.arccos(min(1.0, d))
 
 
-@pytest.mark.parametrize("line,n,az,lm_threads", [(16, 10, None, None), (64, 9, None, None), (32, 8, 1200, None), (64, 8, None, "256")])
+@pytest.mark.parametrize("line,n,az,lm_threads", [(16, 10, None, None), (64, 9, None, None), (32, 8, 1200, None), (64, 8, None, "256"),
+                                                  (64, 9, None, "many-lanes"), (16, 8, None, "many-lanes"), (64, 8, None, "cluster2")])
 def test_fused_pipeline_trajectory_matches_oracle(ll, orc, line, n, az, lm_threads, monkeypatch):
-    if lm_threads:   # the CTA shape the solve uses when there are more scan streams than SMs (bench: 256 lanes)
+    # one lane runs the single-stream forms by default: a warp per query (k_odom_assoc_direct) and the solve spread over a
+    # thread-block cluster of 8; "many-lanes" forces the forms the batched path uses (thread pass + queue, one CTA per solve)
+    if lm_threads == "many-lanes":
+        monkeypatch.setenv("LL_ASSOC_DIRECT", "0")
+        monkeypatch.setenv("LL_LM_CLUSTER", "1")
+    elif lm_threads == "cluster2":
+        monkeypatch.setenv("LL_LM_CLUSTER", "2")
+    elif lm_threads:   # the CTA shape the solve uses when there are more scan streams than SMs (bench: 256 lanes)
         monkeypatch.setenv("LL_LM_THREADS", lm_threads)
+        monkeypatch.setenv("LL_LM_CLUSTER", "1")
     ctx = ll.Context(scan_line=line)
     exact = orc.Pipeline(orc.config(line, voxel_stable=1), with_mapping=False)
     faithful = orc.Pipeline(orc.config(line, voxel_stable=0), with_mapping=False)
