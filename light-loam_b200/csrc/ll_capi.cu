@@ -812,6 +812,7 @@ int ll_get_last_stats(ll_ctx* c, ll_stats* o)
     o->frame = L.now_frame;
     o->map_vote_corr = L.n_map_vote; o->map_vote_selected = L.n_map_vote_sel;
     if (getenv("LL_DEBUG_ASSOC")) fprintf(stderr, "assoc dbg (all lanes, cumulative): queued with the 1-NN open %d (kcycles %d, longest %d cycles), queued for the ring window %d (kcycles %d, longest %d cycles)\n", L.dbg[1], L.dbg[3], L.dbg[5] * 16, L.dbg[2], L.dbg[4], L.dbg[6] * 16);
+    if (getenv("LL_DEBUG_LM")) fprintf(stderr, "lm dbg (lane, cumulative cycles; LL_LM_TIMING build): linearise %d  reduce %d  step %d  cost %d  reduce %d  accept %d  gradient %d\n", L.dbg[0], L.dbg[1], L.dbg[2], L.dbg[3], L.dbg[4], L.dbg[5], L.dbg[6]);
     o->kernel_launches = c->launches;
     return LL_OK;
 }

@@ -121,8 +121,11 @@ __device__ __forceinline__ void lm_allreduce_cluster(LmShared& S, int nparts, un
     if (tid < LM_NRED && tid >= first) pub[tid] = S.out[tid];
     cl.sync();
     if (tid < LM_NRED && tid >= first) {
-        double v = 0.0;
-        for (int r = 0; r < nparts; ++r) v += *cl.map_shared_rank(pub + tid, r);
+        double t[8], v = 0.0;   // nparts <= 8 (portable cluster size); the remote loads are issued together
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = r < nparts ? *cl.map_shared_rank(pub + tid, r) : 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v += t[r];
         S.out[tid] = v;
     }
     __syncthreads();
@@ -481,6 +484,12 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     }
     double acc[LM_NRED];
     LmCtl& C = S.ctl;
+#ifdef LL_LM_TIMING   // development build: cycles per phase of the solve, summed into LaneState::dbg (LL_DEBUG_LM prints them)
+    long long tmark = clock64();
+#define LMT(slot) do { if (tid == 0 && part == 0 && L) { const long long now_ = clock64(); atomicAdd(&L->dbg[slot], (int)(now_ - tmark)); tmark = now_; } } while (0)
+#else
+#define LMT(slot) ((void)0)
+#endif
     if (tid == 0) {
         C.x_cost = 0; C.x_norm = 0; C.radius = 1e4; C.decrease_factor = 2.0; C.se_cost = 0; C.model_cost_change = 0; C.gmax = 0; C.initial_cost = 0;
         C.reuse_diagonal = 0; C.last_successful = 1; C.atleast_one = 0; C.iteration = 0; C.invalid = 0; C.term = 0; C.jac_evals = 0; C.cost_evals = 0;
@@ -489,9 +498,11 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
 
     // IterationZero: cost, gradient, Jacobian (as JtJ) at x
     lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
+    LMT(0);
     lm_reduce<true>(S, acc);
     if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
     if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
+    LMT(1);
     if (tid == 0) {
         for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
         for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
@@ -559,16 +570,22 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
             S.go = go;
         }
         __syncthreads();
+        LMT(2);
         if (!S.go) break;
-        // ---- all threads: cost at the candidate --------------------------------------------------------
-        lm_accumulate<false, DIST>(blk, cap, nb, S.cand, acc, part, nparts);
-        lm_reduce<false>(S, acc);
-        if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 27, L);
-        if (clus) lm_allreduce_cluster(S, nparts, ++seq, 27);
+        // ---- all threads: cost at the candidate - and its linearisation in the same pass.  Ceres evaluates the cost
+        // first and the Jacobian only once the step is accepted; accepted steps are the rule (and a cost-only pass costs
+        // nearly as much as a full one: the records dominate), so the Jacobian sums are taken speculatively and simply
+        // dropped when the step is rejected.  Same numbers, one pass and one reduction per iteration instead of two.
+        lm_accumulate<true, DIST>(blk, cap, nb, S.cand, acc, part, nparts);
+        LMT(3);
+        lm_reduce<true>(S, acc);
+        if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
+        if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
+        LMT(4);
         if (tid == 0) {
             const double cand_cost = S.out[27];
             ++C.cost_evals;
-            int go = 2;  // 2: accepted -> re-linearise, 1: rejected -> next step, 0: stop
+            int go = 2;  // 2: accepted, 1: rejected -> next step, 0: stop
             double sn = 0;
             for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
             if (C.atleast_one && sqrt(sn) <= 1e-8 * (C.x_norm + 1e-8)) { C.term = 2; go = 0; }           // parameter_tolerance
@@ -586,6 +603,16 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
                     C.atleast_one = true;
                     C.last_successful = true;
                     go = 2;
+                    // EvaluateGradientAndJacobian at the accepted point: the sums are already here
+                    for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
+                    for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
+                    C.x_cost = cand_cost;
+                    ++C.jac_evals;
+                    double ng[6], xp[7];
+                    for (int c = 0; c < 6; ++c) ng[c] = -C.g[c];
+                    lm_plus(S.x, ng, xp);
+                    C.gmax = 0;
+                    for (int i = 0; i < 7; ++i) C.gmax = fmax(C.gmax, fabs(S.x[i] - xp[i]));
                 } else {  // StepRejected
                     C.radius = C.radius / C.decrease_factor;
                     C.decrease_factor *= 2.0;
@@ -597,26 +624,8 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
             S.go = go;
         }
         __syncthreads();
-        const int go = S.go;
-        if (go == 0) break;
-        if (go == 2) {
-            lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
-            lm_reduce<true>(S, acc);
-            if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
-            if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
-            if (tid == 0) {
-                for (int k = 0; k < 21; ++k) C.H[k] = S.out[k];
-                for (int k = 0; k < 6; ++k) C.g[k] = S.out[21 + k];
-                C.x_cost = S.out[27];
-                ++C.jac_evals;
-                double ng[6], xp[7];
-                for (int c = 0; c < 6; ++c) ng[c] = -C.g[c];
-                lm_plus(S.x, ng, xp);
-                C.gmax = 0;
-                for (int i = 0; i < 7; ++i) C.gmax = fmax(C.gmax, fabs(S.x[i] - xp[i]));
-            }
-        }
-        __syncthreads();
+        LMT(5);
+        if (S.go == 0) break;
     }
     if (clus) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still be reading its shared memory
     if (tid == 0 && part == 0) {  // every part holds the same result; one writes it
@@ -647,12 +656,16 @@ static inline cudaError_t lm_launch_cluster(void (*kern)(KArgs...), int n_lanes,
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
-// CTAs per cluster for a solve over n_lanes problems: the largest of 8 / 4 / 2 that leaves every CTA an SM of its own
+// CTAs per cluster for a solve over n_lanes problems
 // (LL_LM_CLUSTER overrides; 1 = off)
 static inline int lm_cluster_size(int n_lanes, int n_sm)
 {
+    // measured on B200 (256-thread to 512-thread CTAs, ~2000 blocks per problem): 8 or 4 CTAs pay while half the SMs stay
+    // free for the other problems' CTAs, 2 CTAs as long as every CTA has an SM
     int p = 1;
-    for (int q = 8; q >= 2; q >>= 1) if (n_lanes * q <= n_sm) { p = q; break; }
+    if (n_lanes * 8 <= n_sm / 2) p = 8;
+    else if (n_lanes * 4 <= n_sm / 2) p = 4;
+    else if (n_lanes * 2 <= n_sm) p = 2;
     if (const char* e = getenv("LL_LM_CLUSTER")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4 || v == 8) && v * n_lanes <= n_sm) p = v; }
     return p;
 }
