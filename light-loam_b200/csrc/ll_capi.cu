@@ -421,10 +421,12 @@ static int launch_pipeline(ll_ctx* c, int n_scans, bool with_events)
 
 // Latency path: with few lanes a step is ~30 short kernels and the launches cost as much as the work.  The sequence is
 // captured once per (lane count, mailbox parity) into a CUDA graph and replayed; LL_GRAPH=0 disables, LL_GRAPH=1 forces it
-// for any lane count.  Not used with mapping (its solve alternates argument sets per frame) or while profiling.
+// for any lane count.  With mapping the key also carries which cube-map buffer is current (the frames alternate).  Not used
+// while profiling, nor when the mapping solve runs its collectives through the mailbox (several GPUs, LL_LM_PARTS).
 static bool graph_wanted(const ll_ctx* c, int n_scans)
 {
-    if (c->prof || c->cfg.enable_mapping || c->eager_calls < 2) return false;
+    if (c->prof || c->eager_calls < 2) return false;
+    if (c->cfg.enable_mapping && ll_map_graph_state(c) < 0) return false;
     if (const char* e = getenv("LL_GRAPH")) return atoi(e) != 0;
     return n_scans <= 16;
 }
@@ -438,7 +440,8 @@ int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
     c->pre_launches = 0;
     c->last_call_graph = false;
     if (graph_wanted(c, n_scans)) {
-        const int key = n_scans * 2 + c->odom_comm_flip;
+        const int map_state = c->cfg.enable_mapping ? ll_map_graph_state(c) : 0;
+        const int key = (n_scans * 2 + c->odom_comm_flip) * 2 + map_state;
         auto it = c->graphs.find(key);
         if (it == c->graphs.end()) {
             cudaGraph_t g = nullptr;
@@ -449,6 +452,7 @@ int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
             const int rc = launch_pipeline(c, n_scans, false);
             const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             c->odom_comm_flip = flip0;       // the capture only recorded: nothing ran yet
+            if (c->cfg.enable_mapping) ll_map_graph_set_state(c, map_state);
             if (rc || e != cudaSuccess) { if (g) cudaGraphDestroy(g); c->last_error = std::string("graph capture: ") + cudaGetErrorString(e); return rc ? rc : LL_E_CUDA; }
             LL_CUDA_CHECK(c, cudaGraphInstantiate(&ge, g, 0));
             cudaGraphDestroy(g);
@@ -458,6 +462,7 @@ int ll_process_staged(ll_ctx* c, int n_scans, double* poses_out)
         LL_CUDA_CHECK(c, cudaGraphLaunch(it->second, c->stream));
         c->launches = pre + c->graph_launches[key];
         c->odom_comm_flip ^= c->graph_parity_step;   // three solves per step: the mailbox parity moves as in the eager calls before
+        if (c->cfg.enable_mapping) ll_map_graph_set_state(c, map_state ^ 1);   // the frame wrote the other cube-map buffer
         c->last_call_graph = true;
     } else {
         c->launches = pre;

@@ -229,3 +229,7 @@ int ll_map_alloc(ll_ctx* c);
 void ll_map_free(ll_ctx* c);
 void ll_map_clear(ll_ctx* c);                                   // forget the map contents, keep the allocations
 int ll_launch_mapping(ll_ctx* c, int n_lanes);                  // LM:1581-2168
+// host-side state a captured mapping frame depends on (which of the two cube-map buffers is current): part of the CUDA graph
+// key; -1 = this context's mapping cannot be replayed from a graph (slab sharding over several GPUs, mailbox split)
+int ll_map_graph_state(const ll_ctx* c);
+void ll_map_graph_set_state(ll_ctx* c, int state);

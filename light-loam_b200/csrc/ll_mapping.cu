@@ -996,6 +996,14 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     return LL_OK;
 }
 
+int ll_map_graph_state(const ll_ctx* c)
+{
+    const MapState* m = c->map;
+    if (!m || m->gworld > 1 || getenv("LL_LM_PARTS")) return -1;   // mailbox collectives carry per-frame sequence state
+    return m->buf;
+}
+void ll_map_graph_set_state(ll_ctx* c, int state) { if (c->map) c->map->buf = state & 1; }
+
 int ll_launch_mapping(ll_ctx* c, int n_lanes)
 {
     MapState* m = c->map;

@@ -286,3 +286,19 @@ def test_cpp_host_driver_reads_kitti_bin_files(ll, tmp_path):
     ra, rb = np.loadtxt(a), np.loadtxt(b)
     assert ra.shape == rb.shape == (5, 12)
     assert np.array_equal(ra, rb)
+
+
+@pytest.mark.parametrize("mapping", [0, 1])
+def test_graph_replay_equals_eager_launches(ll, monkeypatch, mapping):
+    """After two eager calls a context with few lanes replays the step from a CUDA graph (with mapping: one graph per current
+    cube-map buffer).  Same kernels, same arguments: the poses must be identical to the bit with LL_GRAPH=0."""
+    line, n = 16, 9
+    scans = [ll.synth.scan(line, k) for k in range(n)]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LL_GRAPH", mode)
+        ctx = ll.Context(scan_line=line, batch=2, enable_mapping=mapping, map_capacity=1 << 18)
+        out[mode] = np.stack([ctx.process_scans([scans[k], scans[(k + 3) % n]]) for k in range(n)])
+        ctx.close()
+    assert np.array_equal(out["1"], out["0"])
+    assert np.abs(out["1"][-1, 0, 4:7]).max() > 0.1     # the trajectory moved
