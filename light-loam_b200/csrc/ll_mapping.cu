@@ -63,6 +63,7 @@ struct MapState {
     int* vg_bbox = nullptr;    // [B][nseg][6] ordered-int min xyz / max xyz
     int* seg_count = nullptr;  // [B][MAP_NUM]
     int* lane_base = nullptr;  // [B+1]
+    int* vg_pos_off = nullptr;     // [B + 1] lane offsets of the compact key array; [n_lanes] = elements in use
     int* sort_hist = nullptr;      // [tiles][256] digit histograms of the radix sort (ll_sort.cuh)
     int* scan_scratch = nullptr;   // chunk sums of the prefix sums
     double* blocks = nullptr;  // dense records [B][LL_BLOCK_DOUBLES][nblk_cap]
@@ -550,11 +551,26 @@ struct VgParams {
     u64* keys;
     int* vals;
     float inv_leaf;
+    const int* pos_off;  // [n_lanes + 1] exclusive prefix of n over the lanes: lane b's keys sit at pos_off[b] .. (compact: the sort
+                         // and everything after it work on pos_off[n_lanes] elements, not on the capacity)
 };
 
-__global__ void k_vg_init(int* bbox, int* seg_count, int nseg_total)
+// exclusive prefix of cnt[0..n) by one CTA of 256 threads (n_lanes <= 4095: up to 16 per thread): out[i], out[n] = total; out may alias cnt
+__device__ __forceinline__ void cta_prefix_small(const int* cnt, int* out, int n, int* ws)
 {
+    const int per = (n + 255) / 256, i0 = min((int)threadIdx.x * per, n), i1 = min(i0 + per, n);
+    int v[16], s = 0;
+    for (int i = i0; i < i1; ++i) { v[i - i0] = cnt[i]; s += v[i - i0]; }
+    int tot = 0;
+    int run = block_exclusive_scan(s, ws, &tot);
+    for (int i = i0; i < i1; ++i) { out[i] = run; run += v[i - i0]; }
+    if (threadIdx.x == 0) out[n] = tot;
+}
+__global__ void __launch_bounds__(256) k_vg_init(int* bbox, int* seg_count, int nseg_total, const int* n, int* pos_off, int n_lanes)
+{
+    __shared__ int ws[40];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) cta_prefix_small(n, pos_off, n_lanes, ws);   // where each lane's elements start in the compact key array
     if (i < nseg_total) {
         for (int a = 0; a < 3; ++a) { bbox[i * 6 + a] = INT_MAX; bbox[i * 6 + 3 + a] = INT_MIN; }
         seg_count[i] = 0;
@@ -601,40 +617,38 @@ __global__ void k_vg_bbox(VgParams P)
 __global__ void k_vg_keys(VgParams P)
 {
     const int b = blockIdx.y;
-    const int n = P.n[b];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P.E; e += gridDim.x * blockDim.x) {
+    const int n = P.n[b], off = P.pos_off[b];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const size_t g = (size_t)b * P.E + e;
         u64 key = ~0ull;
-        if (e < n) {
-            const int s = P.seg[g];
-            if (s >= 0) {
-                const float4 p = P.in[g];
-                const int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
-                const float inv = P.inv_leaf;
-                const float mn[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])}, mx[3] = {ord2f(bb[3]), ord2f(bb[4]), ord2f(bb[5])};
-                bool ds = P.ds_mask ? P.ds_mask[(size_t)b * P.nseg + s] != 0 : true;
-                const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
-                                dz = (long long)((mx[2] - mn[2]) * inv) + 1;
-                if (dx * dy * dz > (long long)INT_MAX) ds = false;  // PCL: leaf too small -> output = input
-                unsigned v = (unsigned)e;
-                if (ds) {
-                    const int mb0 = (int)floorf(mn[0] * inv), mb1 = (int)floorf(mn[1] * inv), mb2 = (int)floorf(mn[2] * inv);
-                    const int div0 = (int)floorf(mx[0] * inv) - mb0 + 1, div1 = (int)floorf(mx[1] * inv) - mb1 + 1;
-                    const int i0 = (int)(floorf(p.x * inv) - (float)mb0), i1 = (int)(floorf(p.y * inv) - (float)mb1),
-                              i2 = (int)(floorf(p.z * inv) - (float)mb2);
-                    v = (unsigned)(i0 + i1 * div0 + i2 * div0 * div1);
-                }
-                key = ((u64)b << 44) | ((u64)s << 31) | (u64)(v & 0x7FFFFFFFu);
+        const int s = P.seg[g];
+        if (s >= 0) {
+            const float4 p = P.in[g];
+            const int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
+            const float inv = P.inv_leaf;
+            const float mn[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])}, mx[3] = {ord2f(bb[3]), ord2f(bb[4]), ord2f(bb[5])};
+            bool ds = P.ds_mask ? P.ds_mask[(size_t)b * P.nseg + s] != 0 : true;
+            const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
+                            dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+            if (dx * dy * dz > (long long)INT_MAX) ds = false;  // PCL: leaf too small -> output = input
+            unsigned v = (unsigned)e;
+            if (ds) {
+                const int mb0 = (int)floorf(mn[0] * inv), mb1 = (int)floorf(mn[1] * inv), mb2 = (int)floorf(mn[2] * inv);
+                const int div0 = (int)floorf(mx[0] * inv) - mb0 + 1, div1 = (int)floorf(mx[1] * inv) - mb1 + 1;
+                const int i0 = (int)(floorf(p.x * inv) - (float)mb0), i1 = (int)(floorf(p.y * inv) - (float)mb1),
+                          i2 = (int)(floorf(p.z * inv) - (float)mb2);
+                v = (unsigned)(i0 + i1 * div0 + i2 * div0 * div1);
             }
+            key = ((u64)b << 44) | ((u64)s << 31) | (u64)(v & 0x7FFFFFFFu);
         }
-        P.keys[g] = key;
-        P.vals[g] = (int)g;
+        P.keys[off + e] = key;   // dropped elements (~0) sort behind every lane's real keys
+        P.vals[off + e] = (int)g;
     }
 }
-__global__ void k_vg_heads(const u64* keys, int* head, int* seg_count, int nseg, long long total)
+__global__ void k_vg_heads(const u64* keys, int* head, int* seg_count, int nseg, const int* total_dev)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total) return;
+    if (p >= *total_dev) return;
     const u64 k = keys[p];
     int h = 0;
     if (k != ~0ull && (p == 0 || keys[p - 1] != k)) {
@@ -667,19 +681,17 @@ __global__ void __launch_bounds__(1024) k_vg_offsets(const int* seg_count, int* 
     }
     (void)n_out_field0;
 }
-__global__ void k_vg_lane_prefix(int* lane_base, int n_lanes)
+__global__ void __launch_bounds__(256) k_vg_lane_prefix(int* lane_base, int n_lanes)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int run = 0;
-        for (int b = 0; b < n_lanes; ++b) { const int c = lane_base[b]; lane_base[b] = run; run += c; }
-        lane_base[n_lanes] = run;
-    }
+    __shared__ int ws[40];
+    cta_prefix_small(lane_base, lane_base, n_lanes, ws);
 }
 // centroid of x,y,z,intensity over every run of equal keys, fp32 sums in sorted (= input) order
 __global__ void k_vg_centroid(const u64* keys, const int* vals, const int* head, const int* scan, const int* lane_base, const float4* in,
-                              float4* out, int out_cap, long long total)
+                              float4* out, int out_cap, const int* total_dev)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = *total_dev;
     if (p >= total || !head[p]) return;
     const u64 k = keys[p];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
@@ -765,7 +777,7 @@ void ll_map_free(ll_ctx* c)
     }
     cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->vg_in); cudaFree(m->vg_seg);
     cudaFree(m->vg_n); cudaFree(m->vg_head); cudaFree(m->vg_scan); cudaFree(m->vg_bbox); cudaFree(m->seg_count); cudaFree(m->lane_base);
-    cudaFree(m->sort_hist); cudaFree(m->scan_scratch); cudaFree(m->blocks);
+    cudaFree(m->sort_hist); cudaFree(m->scan_scratch); cudaFree(m->vg_pos_off); cudaFree(m->blocks);
     cudaFree(m->vote_tgt_raw); cudaFree(m->vote_src); cudaFree(m->vote_tgt); cudaFree(m->vote_cnt);
     for (int g = 0; g < LM_MAX_GPUS; ++g) if (m->peer_ipc[g] && m->peer_buf[g]) cudaIpcCloseMemHandle(m->peer_buf[g]);
     cudaFree(m->comm_buf); cudaFree(m->comm_seq[0]); cudaFree(m->comm_seq[1]);
@@ -829,6 +841,7 @@ int ll_map_alloc(ll_ctx* c)
     MK(cudaMalloc((void**)&m->vg_in, sizeof(float4) * B * m->E));
     MK(cudaMalloc((void**)&m->vg_seg, sizeof(int) * B * m->E));
     MK(cudaMalloc((void**)&m->vg_n, sizeof(int) * B));
+    MK(cudaMalloc((void**)&m->vg_pos_off, sizeof(int) * (B + 1)));
     MK(cudaMalloc((void**)&m->vg_head, sizeof(int) * B * m->E));
     MK(cudaMalloc((void**)&m->vg_scan, sizeof(int) * B * m->E));
     MK(cudaMalloc((void**)&m->vg_bbox, sizeof(int) * B * MAP_NUM * 6));
@@ -837,9 +850,8 @@ int ll_map_alloc(ll_ctx* c)
     {
         const long long total = (long long)B * m->E;
         const size_t hist = llsort::sort_hist_ints(total);
-        const size_t s1 = llsort::scan_scratch_ints((long long)hist), s2 = llsort::scan_scratch_ints(total);
         MK(cudaMalloc((void**)&m->sort_hist, sizeof(int) * hist));
-        MK(cudaMalloc((void**)&m->scan_scratch, sizeof(int) * (s1 > s2 ? s1 : s2)));
+        MK(cudaMalloc((void**)&m->scan_scratch, sizeof(int) * llsort::scan_scratch_ints(total)));
     }
     m->nblk_cap = m->stack_cap[0] + m->stack_cap[1];
     MK(cudaMalloc((void**)&m->blocks, sizeof(double) * B * LL_BLOCK_DOUBLES * (size_t)m->nblk_cap));
@@ -871,10 +883,11 @@ static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const 
     cudaStream_t s = c->stream;
     VgParams P;
     P.lane = c->d_lane; P.in = m->vg_in; P.seg = m->vg_seg; P.n = m->vg_n; P.E = E_used; P.nseg = nseg; P.ds_mask = ds_mask; P.bbox = m->vg_bbox;
-    P.keys = m->vg_keys[0]; P.vals = m->vg_vals[0]; P.inv_leaf = 1.0f / leaf;
-    const long long total = (long long)n_lanes * E_used;
+    P.keys = m->vg_keys[0]; P.vals = m->vg_vals[0]; P.inv_leaf = 1.0f / leaf; P.pos_off = m->vg_pos_off;
+    const long long total = (long long)n_lanes * E_used;   // capacity: sizes the grids; the kernels work on *n_dev elements
+    const int* n_dev = m->vg_pos_off + n_lanes;
     const int gx = 296;
-    { LLProf pr(c, "k_vg_init"); k_vg_init<<<(n_lanes * nseg + 255) / 256, 256, 0, s>>>(m->vg_bbox, m->seg_count, n_lanes * nseg); }
+    { LLProf pr(c, "k_vg_init"); k_vg_init<<<(n_lanes * nseg + 255) / 256, 256, 0, s>>>(m->vg_bbox, m->seg_count, n_lanes * nseg, m->vg_n, m->vg_pos_off, n_lanes); }
     { LLProf pr(c, "k_vg_bbox"); k_vg_bbox<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
     { LLProf pr(c, "k_vg_keys"); k_vg_keys<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
     int sorted = 0;
@@ -890,16 +903,16 @@ static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const 
             const bool voxel = sh < 31, seg = seg_bits > 0 && sh < 31 + seg_bits && sh + 8 > 31, lane = lane_bits > 0 && sh < 44 + lane_bits && sh + 8 > 44;
             if (voxel || seg || lane) shifts[ns++] = sh;
         }
-        sorted = llsort::sort_pairs(m->vg_keys, m->vg_vals, total, shifts, ns, m->sort_hist, m->scan_scratch, s, &c->launches);
+        sorted = llsort::sort_pairs(m->vg_keys, m->vg_vals, total, n_dev, shifts, ns, m->sort_hist, s, &c->launches);
     }
-    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_head, m->seg_count, nseg, total); }
+    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_head, m->seg_count, nseg, n_dev); }
     {
         LLProf pr(c, "prefix_sum");
-        c->launches += llsort::scan_exclusive(m->vg_head, m->vg_scan, total, m->scan_scratch, s);
+        c->launches += llsort::scan_exclusive(m->vg_head, m->vg_scan, total, llsort::LenSpec{n_dev, 0}, m->scan_scratch, s);
     }
     { LLProf pr(c, "k_vg_offsets"); k_vg_offsets<<<n_lanes, 1024, 0, s>>>(m->seg_count, seg_off, m->lane_base, nseg, n_lanes, nullptr, c->d_lane, which); }
-    { LLProf pr(c, "k_vg_lane_prefix"); k_vg_lane_prefix<<<1, 32, 0, s>>>(m->lane_base, n_lanes); }
-    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_vals[sorted], m->vg_head, m->vg_scan, m->lane_base, m->vg_in, out, out_cap, total); }
+    { LLProf pr(c, "k_vg_lane_prefix"); k_vg_lane_prefix<<<1, 256, 0, s>>>(m->lane_base, n_lanes); }
+    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_vals[sorted], m->vg_head, m->vg_scan, m->lane_base, m->vg_in, out, out_cap, n_dev); }
     c->launches += 7;   // + the sort's and the prefix sum's own launches, counted above
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
