@@ -173,29 +173,32 @@ __device__ __forceinline__ int shifted_source(int id, const int sh[3])
     return oi + MAP_W * oj + MAP_W * MAP_H * ok;
 }
 
-// LM:1805-1811: one CTA per (valid cube slot, lane, type)
-__global__ void k_map_gather(LaneState* lane, const int* valid_ind, const float4* map0, const int* off0, float4* out0, const float4* map1,
-                             const int* off1, float4* out1, int map_cap)
+// LM:1805-1811: `split` CTAs per (valid cube slot, lane, type) share the copy of one cube (a cube of a dense map holds tens
+// of thousands of points; with many lanes there are CTAs enough without splitting); where the cube goes = the sizes of the
+// valid cubes before it, one per thread
+__global__ void __launch_bounds__(256) k_map_gather(LaneState* lane, const int* valid_ind, const float4* map0, const int* off0, float4* out0, const float4* map1,
+                                                    const int* off1, float4* out1, int map_cap, int split)
 {
-    __shared__ int base_s, src_s, cnt_s;
-    const int v = blockIdx.x, b = blockIdx.y, t = blockIdx.z;
+    __shared__ int ws[40];
+    __shared__ int src_s, cnt_s;
+    const int v = blockIdx.x, b = blockIdx.y, t = blockIdx.z & 1, part = blockIdx.z >> 1;
     LaneState& L = lane[b];
     if (v >= L.n_valid) return;
     const int* off = (t == 0 ? off0 : off1) + (size_t)b * (MAP_NUM + 1);
     const float4* src = (t == 0 ? map0 : map1) + (size_t)b * map_cap;
     float4* dst = (t == 0 ? out0 : out1) + (size_t)b * map_cap;
-    if (threadIdx.x == 0) {
-        int base = 0;
-        for (int u = 0; u <= v; ++u) {
-            const int s = shifted_source(valid_ind[b * MAP_MAXVALID + u], L.map_shift);
-            const int cnt = s >= 0 ? off[s + 1] - off[s] : 0;
-            if (u == v) { src_s = s >= 0 ? off[s] : 0; cnt_s = cnt; } else base += cnt;
-        }
-        base_s = base;
-        if (v == L.n_valid - 1) { if (t == 0) L.n_map_corner = base + cnt_s; else L.n_map_surf = base + cnt_s; }
+    int before = 0;
+    if ((int)threadIdx.x <= v) {   // v < MAP_MAXVALID <= blockDim.x
+        const int sc = shifted_source(valid_ind[b * MAP_MAXVALID + threadIdx.x], L.map_shift);
+        const int cnt = sc >= 0 ? off[sc + 1] - off[sc] : 0;
+        if ((int)threadIdx.x == v) { src_s = sc >= 0 ? off[sc] : 0; cnt_s = cnt; } else before = cnt;
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < cnt_s; k += blockDim.x) dst[base_s + k] = src[src_s + k];
+    int base = 0;
+    block_exclusive_scan(before, ws, &base);
+    const int cnt = cnt_s;
+    if (part == 0 && threadIdx.x == 0 && v == L.n_valid - 1) { if (t == 0) L.n_map_corner = base + cnt; else L.n_map_surf = base + cnt; }
+    const int per = (cnt + split - 1) / split, k0 = part * per, k1 = min(k0 + per, cnt);
+    for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) dst[base + k] = src[src_s + k];
 }
 
 __global__ void k_map_guard(LaneState* lane, int n_lanes)
@@ -576,42 +579,49 @@ __global__ void __launch_bounds__(256) k_vg_init(int* bbox, int* seg_count, int 
         seg_count[i] = 0;
     }
 }
-// Elements arrive grouped by segment (CSR order of the old map, then the stack), so a warp's 32 elements nearly
-// always share one segment: reduce in the warp and issue six atomics per warp instead of six per point.
-__global__ void k_vg_bbox(VgParams P)
+// Elements arrive grouped by segment (CSR order of the old map, then the stack).  Every CTA takes one contiguous chunk of the
+// lane's elements, a thread keeps the bounding box of the segment it is in, and the warp hands a segment's box over only when
+// its lanes leave the segment (and at the end): the lanes that share the segment reduce among themselves and one of them issues
+// the six atomics - a few atomics per warp and segment instead of six per 32 points.
+__global__ void __launch_bounds__(256) k_vg_bbox(VgParams P)
 {
     const int b = blockIdx.y;
     const int n = P.n[b];
     const int lane = lane_id();
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += gridDim.x * blockDim.x) {
-        const int e = base + lane;
-        int s = -1;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < n) {
-            s = P.seg[(size_t)b * P.E + e];
-            if (s >= 0) p = P.in[(size_t)b * P.E + e];
-        }
-        const unsigned have = __ballot_sync(LL_FULL_MASK, s >= 0);
-        if (!have) continue;
-        const int s0 = __shfl_sync(LL_FULL_MASK, s, __ffs(have) - 1);
-        const bool uniform = __all_sync(LL_FULL_MASK, s < 0 || s == s0);
-        if (uniform) {
-            const bool v = s >= 0;
-            const int lo0 = __reduce_min_sync(LL_FULL_MASK, v ? f2ord(p.x) : INT_MAX), lo1 = __reduce_min_sync(LL_FULL_MASK, v ? f2ord(p.y) : INT_MAX),
-                      lo2 = __reduce_min_sync(LL_FULL_MASK, v ? f2ord(p.z) : INT_MAX);
-            const int hi0 = __reduce_max_sync(LL_FULL_MASK, v ? f2ord(p.x) : INT_MIN), hi1 = __reduce_max_sync(LL_FULL_MASK, v ? f2ord(p.y) : INT_MIN),
-                      hi2 = __reduce_max_sync(LL_FULL_MASK, v ? f2ord(p.z) : INT_MIN);
-            if (lane == 0) {
-                int* bb = P.bbox + ((size_t)b * P.nseg + s0) * 6;
-                atomicMin(&bb[0], lo0); atomicMin(&bb[1], lo1); atomicMin(&bb[2], lo2);
-                atomicMax(&bb[3], hi0); atomicMax(&bb[4], hi1); atomicMax(&bb[5], hi2);
+    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 255) & ~255;   // multiple of the CTA size: whole warps inside a chunk
+    const int e0 = blockIdx.x * per, e1 = min(e0 + per, n);
+    int cur = -1, lo0 = INT_MAX, lo1 = INT_MAX, lo2 = INT_MAX, hi0 = INT_MIN, hi1 = INT_MIN, hi2 = INT_MIN;
+    auto flush = [&](bool mine) {   // warp-collective; `mine`: this lane hands its box over
+        const unsigned grp = __match_any_sync(LL_FULL_MASK, mine ? cur : -1 - lane);
+        if (mine) {
+            const int a0 = __reduce_min_sync(grp, lo0), a1 = __reduce_min_sync(grp, lo1), a2 = __reduce_min_sync(grp, lo2);
+            const int c0 = __reduce_max_sync(grp, hi0), c1 = __reduce_max_sync(grp, hi1), c2 = __reduce_max_sync(grp, hi2);
+            if (lane == __ffs(grp) - 1) {
+                int* bb = P.bbox + ((size_t)b * P.nseg + cur) * 6;
+                atomicMin(&bb[0], a0); atomicMin(&bb[1], a1); atomicMin(&bb[2], a2);
+                atomicMax(&bb[3], c0); atomicMax(&bb[4], c1); atomicMax(&bb[5], c2);
             }
-        } else if (s >= 0) {
-            int* bb = P.bbox + ((size_t)b * P.nseg + s) * 6;
-            atomicMin(&bb[0], f2ord(p.x)); atomicMin(&bb[1], f2ord(p.y)); atomicMin(&bb[2], f2ord(p.z));
-            atomicMax(&bb[3], f2ord(p.x)); atomicMax(&bb[4], f2ord(p.y)); atomicMax(&bb[5], f2ord(p.z));
+            lo0 = lo1 = lo2 = INT_MAX; hi0 = hi1 = hi2 = INT_MIN; cur = -1;
+        }
+    };
+    for (int base = e0 + (threadIdx.x & ~31); base < e1; base += blockDim.x) {
+        const int e = base + lane;
+        int sg = -1;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < e1) {
+            sg = P.seg[(size_t)b * P.E + e];
+            if (sg >= 0) p = P.in[(size_t)b * P.E + e];
+        }
+        const bool leave = sg >= 0 && cur >= 0 && sg != cur;
+        if (__any_sync(LL_FULL_MASK, leave)) flush(leave);
+        if (sg >= 0) {
+            cur = sg;
+            const int ox = f2ord(p.x), oy = f2ord(p.y), oz = f2ord(p.z);
+            lo0 = min(lo0, ox); lo1 = min(lo1, oy); lo2 = min(lo2, oz);
+            hi0 = max(hi0, ox); hi1 = max(hi1, oy); hi2 = max(hi2, oz);
         }
     }
+    flush(cur >= 0);
 }
 // key = lane (up to 12 bits, from bit 44) | segment (13) | voxel id or element number (31); ~0 = padding / dropped
 __global__ void k_vg_keys(VgParams P)
@@ -932,7 +942,12 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
         if (rc) return rc;
     }
     // LM:1805-1811 local map, LM:1826 guard, LM:1830-1831 search structures
-    { LLProf pr(c, "k_map_gather"); k_map_gather<<<dim3(MAP_MAXVALID, n_lanes, 2), 256, 0, s>>>(c->d_lane, m->valid_ind, m->map_pts[0][cur], m->cube_off[0][cur], m->frommap[0], m->map_pts[1][cur], m->cube_off[1][cur], m->frommap[1], m->map_cap); }
+    {
+        LLProf pr(c, "k_map_gather");
+        int split = 2048 / (n_lanes * 75);
+        split = split < 1 ? 1 : (split > 16 ? 16 : split);
+        k_map_gather<<<dim3(MAP_MAXVALID, n_lanes, 2 * split), 256, 0, s>>>(c->d_lane, m->valid_ind, m->map_pts[0][cur], m->cube_off[0][cur], m->frommap[0], m->map_pts[1][cur], m->cube_off[1][cur], m->frommap[1], m->map_cap, split);
+    }
     { LLProf pr(c, "k_map_guard"); k_map_guard<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
     c->launches += 5;
     for (int t = 0; t < 2; ++t) {
