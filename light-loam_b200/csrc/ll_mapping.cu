@@ -52,20 +52,27 @@ struct MapState {
     unsigned char* valid_mask = nullptr;        // [B][MAP_NUM]
     int* valid_ind = nullptr;                   // [B][MAP_MAXVALID]
     double* pose_in = nullptr;                  // [B][7] q_wodom_curr, t_wodom_curr
-    // voxel filter work space (one filter runs at a time)
-    float4* vg_in = nullptr;   // [B][E]
-    int* vg_seg = nullptr;     // [B][E]
-    int* vg_n = nullptr;       // [B] elements per lane
-    u64* vg_keys[2] = {nullptr, nullptr};
-    int* vg_vals[2] = {nullptr, nullptr};
-    int* vg_head = nullptr;
-    int* vg_scan = nullptr;
-    int* vg_bbox = nullptr;    // [B][nseg][6] ordered-int min xyz / max xyz
-    int* seg_count = nullptr;  // [B][MAP_NUM]
-    int* lane_base = nullptr;  // [B+1]
-    int* vg_pos_off = nullptr;     // [B + 1] lane offsets of the compact key array; [n_lanes] = elements in use
-    int* sort_hist = nullptr;      // [tiles][256] digit histograms of the radix sort (ll_sort.cuh)
-    int* scan_scratch = nullptr;   // chunk sums of the prefix sums
+    // voxel filter work space.  Contexts with few lanes (the latency regime, <= 16) hold two sets and a side stream: the corner
+    // and the surf filter of a frame are independent chains of short kernels and run side by side; larger batches keep one set
+    // (the work fills the GPU anyway, the scratch is 50 bytes per map point and lane).
+    struct VgScratch {
+        float4* in = nullptr;      // [B][E]
+        int* seg = nullptr;        // [B][E]
+        int* n = nullptr;          // [B] elements per lane
+        u64* keys[2] = {nullptr, nullptr};
+        int* vals[2] = {nullptr, nullptr};
+        int* head = nullptr;
+        int* scan = nullptr;
+        int* bbox = nullptr;       // [B][nseg][6] ordered-int min xyz / max xyz
+        int* seg_count = nullptr;  // [B][MAP_NUM]
+        int* lane_base = nullptr;  // [B+1]
+        int* pos_off = nullptr;    // [B + 1] lane offsets of the compact key array; [n_lanes] = elements in use
+        int* sort_hist = nullptr;  // [tiles][256] digit histograms + 256 row totals of the radix sort (ll_sort.cuh)
+        int* scan_scratch = nullptr;   // chunk sums of the prefix sum
+    } vgs[2];
+    int n_vgs = 1;
+    cudaStream_t side = nullptr;               // second stream of the two-set mode
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double* blocks = nullptr;  // dense records [B][LL_BLOCK_DOUBLES][nblk_cap]
     int nblk_cap = 0;
     // graph vote on the plane correspondences (LM:2057-2072, cfg.map_graph_vote)
@@ -783,11 +790,17 @@ void ll_map_free(ll_ctx* c)
         for (int k = 0; k < 2; ++k) { cudaFree(m->map_pts[t][k]); cudaFree(m->cube_off[t][k]); }
         cudaFree(m->in_cloud[t]); cudaFree(m->stack[t]); cudaFree(m->frommap[t]);
         cudaFree(m->grid[t].start); cudaFree(m->grid[t].cursor); cudaFree(m->grid[t].sorted); cudaFree(m->grid[t].partial);
-        cudaFree(m->vg_keys[t]); cudaFree(m->vg_vals[t]);
     }
-    cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->vg_in); cudaFree(m->vg_seg);
-    cudaFree(m->vg_n); cudaFree(m->vg_head); cudaFree(m->vg_scan); cudaFree(m->vg_bbox); cudaFree(m->seg_count); cudaFree(m->lane_base);
-    cudaFree(m->sort_hist); cudaFree(m->scan_scratch); cudaFree(m->vg_pos_off); cudaFree(m->blocks);
+    cudaFree(m->in_n); cudaFree(m->valid_mask); cudaFree(m->valid_ind); cudaFree(m->pose_in); cudaFree(m->blocks);
+    for (int k = 0; k < m->n_vgs; ++k) {
+        MapState::VgScratch& W = m->vgs[k];
+        cudaFree(W.in); cudaFree(W.seg); cudaFree(W.n); cudaFree(W.keys[0]); cudaFree(W.keys[1]); cudaFree(W.vals[0]); cudaFree(W.vals[1]);
+        cudaFree(W.head); cudaFree(W.scan); cudaFree(W.bbox); cudaFree(W.seg_count); cudaFree(W.lane_base); cudaFree(W.pos_off);
+        cudaFree(W.sort_hist); cudaFree(W.scan_scratch);
+    }
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     cudaFree(m->vote_tgt_raw); cudaFree(m->vote_src); cudaFree(m->vote_tgt); cudaFree(m->vote_cnt);
     for (int g = 0; g < LM_MAX_GPUS; ++g) if (m->peer_ipc[g] && m->peer_buf[g]) cudaIpcCloseMemHandle(m->peer_buf[g]);
     cudaFree(m->comm_buf); cudaFree(m->comm_seq[0]); cudaFree(m->comm_seq[1]);
@@ -840,28 +853,34 @@ int ll_map_alloc(ll_ctx* c)
         MK(cudaMalloc((void**)&g.sorted, sizeof(float4) * B * (size_t)g.cap));
         MK(cudaMalloc((void**)&g.partial, sizeof(int) * B * (size_t)(g.T / 2048 + 1)));
     }
-    for (int k = 0; k < 2; ++k) {
-        MK(cudaMalloc((void**)&m->vg_keys[k], sizeof(u64) * B * m->E));
-        MK(cudaMalloc((void**)&m->vg_vals[k], sizeof(int) * B * m->E));
-    }
     MK(cudaMalloc((void**)&m->in_n, sizeof(int) * B * 2));
     MK(cudaMalloc((void**)&m->valid_mask, B * MAP_NUM));
     MK(cudaMalloc((void**)&m->valid_ind, sizeof(int) * B * MAP_MAXVALID));
     MK(cudaMalloc((void**)&m->pose_in, sizeof(double) * B * 7));
-    MK(cudaMalloc((void**)&m->vg_in, sizeof(float4) * B * m->E));
-    MK(cudaMalloc((void**)&m->vg_seg, sizeof(int) * B * m->E));
-    MK(cudaMalloc((void**)&m->vg_n, sizeof(int) * B));
-    MK(cudaMalloc((void**)&m->vg_pos_off, sizeof(int) * (B + 1)));
-    MK(cudaMalloc((void**)&m->vg_head, sizeof(int) * B * m->E));
-    MK(cudaMalloc((void**)&m->vg_scan, sizeof(int) * B * m->E));
-    MK(cudaMalloc((void**)&m->vg_bbox, sizeof(int) * B * MAP_NUM * 6));
-    MK(cudaMalloc((void**)&m->seg_count, sizeof(int) * B * MAP_NUM));
-    MK(cudaMalloc((void**)&m->lane_base, sizeof(int) * (B + 1)));
-    {
+    m->n_vgs = (c->B <= 16 && !(getenv("LL_MAP_STREAMS") && atoi(getenv("LL_MAP_STREAMS")) == 1)) ? 2 : 1;
+    for (int k = 0; k < m->n_vgs; ++k) {
+        MapState::VgScratch& W = m->vgs[k];
+        for (int q = 0; q < 2; ++q) {
+            MK(cudaMalloc((void**)&W.keys[q], sizeof(u64) * B * m->E));
+            MK(cudaMalloc((void**)&W.vals[q], sizeof(int) * B * m->E));
+        }
+        MK(cudaMalloc((void**)&W.in, sizeof(float4) * B * m->E));
+        MK(cudaMalloc((void**)&W.seg, sizeof(int) * B * m->E));
+        MK(cudaMalloc((void**)&W.n, sizeof(int) * B));
+        MK(cudaMalloc((void**)&W.pos_off, sizeof(int) * (B + 1)));
+        MK(cudaMalloc((void**)&W.head, sizeof(int) * B * m->E));
+        MK(cudaMalloc((void**)&W.scan, sizeof(int) * B * m->E));
+        MK(cudaMalloc((void**)&W.bbox, sizeof(int) * B * MAP_NUM * 6));
+        MK(cudaMalloc((void**)&W.seg_count, sizeof(int) * B * MAP_NUM));
+        MK(cudaMalloc((void**)&W.lane_base, sizeof(int) * (B + 1)));
         const long long total = (long long)B * m->E;
-        const size_t hist = llsort::sort_hist_ints(total);
-        MK(cudaMalloc((void**)&m->sort_hist, sizeof(int) * hist));
-        MK(cudaMalloc((void**)&m->scan_scratch, sizeof(int) * llsort::scan_scratch_ints(total)));
+        MK(cudaMalloc((void**)&W.sort_hist, sizeof(int) * llsort::sort_hist_ints(total)));
+        MK(cudaMalloc((void**)&W.scan_scratch, sizeof(int) * llsort::scan_scratch_ints(total)));
+    }
+    if (m->n_vgs == 2) {
+        MK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+        MK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        MK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     }
     m->nblk_cap = m->stack_cap[0] + m->stack_cap[1];
     MK(cudaMalloc((void**)&m->blocks, sizeof(double) * B * LL_BLOCK_DOUBLES * (size_t)m->nblk_cap));
@@ -884,20 +903,52 @@ int ll_map_alloc(ll_ctx* c)
     return LL_OK;
 }
 
-// pcl::VoxelGrid over the elements currently assembled in vg_in / vg_seg / vg_n. Writes the filtered points to `out`
+// Fork / join of the two per-type chains of a mapping frame.  begin(0) marks the fork point on the main stream, begin(1) points
+// c->stream at the side stream (made to wait for the fork point), end(1) restores it and makes the main stream wait for the side chain; type 0
+// stays on the main stream.  With one scratch set (many lanes, profiling) everything stays on the main stream, one chain after
+// the other.  Works the same inside a stream capture: the side stream joins the capture through the fork event and is joined
+// back before the capture ends.
+struct MapTwoStreams {
+    ll_ctx* c;
+    MapState* m;
+    cudaStream_t main_stream;
+    bool two, bad = false;
+    explicit MapTwoStreams(ll_ctx* ctx) : c(ctx), m(ctx->map), main_stream(ctx->stream), two(ctx->map->n_vgs == 2 && !ctx->prof) {}
+    MapState::VgScratch& begin(int t)
+    {
+        if (two && t == 0) bad |= cudaEventRecord(m->ev_fork, main_stream) != cudaSuccess;   // the fork point: before either chain is issued
+        if (two && t == 1) {
+            bad |= cudaStreamWaitEvent(m->side, m->ev_fork, 0) != cudaSuccess;
+            c->stream = m->side;
+        }
+        return m->vgs[two ? t : 0];
+    }
+    void end(int t)
+    {
+        if (two && t == 1) {
+            c->stream = main_stream;
+            bad |= cudaEventRecord(m->ev_join, m->side) != cudaSuccess;
+            bad |= cudaStreamWaitEvent(main_stream, m->ev_join, 0) != cudaSuccess;
+        }
+    }
+    bool failed() { if (bad) c->last_error = "mapping: fork / join of the side stream failed"; return bad; }
+    ~MapTwoStreams() { c->stream = main_stream; }
+};
+
+// pcl::VoxelGrid over the elements currently assembled in W.in / W.seg / W.n, on the stream c->stream names at the time of the
+// call (see MapTwoStreams). Writes the filtered points to `out`
 // (lane slabs of out_cap) in (segment, voxel id) order; seg_off (optional) receives the CSR offsets; which = 0 / 1
 // additionally stores the lane totals into n_stack_corner / n_stack_surf.
-static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const unsigned char* ds_mask, float leaf, float4* out, int out_cap, int* seg_off, int which)
+static int run_voxel_filter(ll_ctx* c, MapState::VgScratch& W, int n_lanes, int E_used, int nseg, const unsigned char* ds_mask, float leaf, float4* out, int out_cap, int* seg_off, int which)
 {
-    MapState* m = c->map;
     cudaStream_t s = c->stream;
     VgParams P;
-    P.lane = c->d_lane; P.in = m->vg_in; P.seg = m->vg_seg; P.n = m->vg_n; P.E = E_used; P.nseg = nseg; P.ds_mask = ds_mask; P.bbox = m->vg_bbox;
-    P.keys = m->vg_keys[0]; P.vals = m->vg_vals[0]; P.inv_leaf = 1.0f / leaf; P.pos_off = m->vg_pos_off;
+    P.lane = c->d_lane; P.in = W.in; P.seg = W.seg; P.n = W.n; P.E = E_used; P.nseg = nseg; P.ds_mask = ds_mask; P.bbox = W.bbox;
+    P.keys = W.keys[0]; P.vals = W.vals[0]; P.inv_leaf = 1.0f / leaf; P.pos_off = W.pos_off;
     const long long total = (long long)n_lanes * E_used;   // capacity: sizes the grids; the kernels work on *n_dev elements
-    const int* n_dev = m->vg_pos_off + n_lanes;
+    const int* n_dev = W.pos_off + n_lanes;
     const int gx = 296;
-    { LLProf pr(c, "k_vg_init"); k_vg_init<<<(n_lanes * nseg + 255) / 256, 256, 0, s>>>(m->vg_bbox, m->seg_count, n_lanes * nseg, m->vg_n, m->vg_pos_off, n_lanes); }
+    { LLProf pr(c, "k_vg_init"); k_vg_init<<<(n_lanes * nseg + 255) / 256, 256, 0, s>>>(W.bbox, W.seg_count, n_lanes * nseg, W.n, W.pos_off, n_lanes); }
     { LLProf pr(c, "k_vg_bbox"); k_vg_bbox<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
     { LLProf pr(c, "k_vg_keys"); k_vg_keys<<<dim3(gx, n_lanes), 256, 0, s>>>(P); }
     int sorted = 0;
@@ -913,16 +964,16 @@ static int run_voxel_filter(ll_ctx* c, int n_lanes, int E_used, int nseg, const 
             const bool voxel = sh < 31, seg = seg_bits > 0 && sh < 31 + seg_bits && sh + 8 > 31, lane = lane_bits > 0 && sh < 44 + lane_bits && sh + 8 > 44;
             if (voxel || seg || lane) shifts[ns++] = sh;
         }
-        sorted = llsort::sort_pairs(m->vg_keys, m->vg_vals, total, n_dev, shifts, ns, m->sort_hist, s, &c->launches);
+        sorted = llsort::sort_pairs(W.keys, W.vals, total, n_dev, shifts, ns, W.sort_hist, s, &c->launches);
     }
-    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_head, m->seg_count, nseg, n_dev); }
+    { LLProf pr(c, "k_vg_heads"); k_vg_heads<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W.keys[sorted], W.head, W.seg_count, nseg, n_dev); }
     {
         LLProf pr(c, "prefix_sum");
-        c->launches += llsort::scan_exclusive(m->vg_head, m->vg_scan, total, llsort::LenSpec{n_dev, 0}, m->scan_scratch, s);
+        c->launches += llsort::scan_exclusive(W.head, W.scan, total, llsort::LenSpec{n_dev, 0}, W.scan_scratch, s);
     }
-    { LLProf pr(c, "k_vg_offsets"); k_vg_offsets<<<n_lanes, 1024, 0, s>>>(m->seg_count, seg_off, m->lane_base, nseg, n_lanes, nullptr, c->d_lane, which); }
-    { LLProf pr(c, "k_vg_lane_prefix"); k_vg_lane_prefix<<<1, 256, 0, s>>>(m->lane_base, n_lanes); }
-    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(m->vg_keys[sorted], m->vg_vals[sorted], m->vg_head, m->vg_scan, m->lane_base, m->vg_in, out, out_cap, n_dev); }
+    { LLProf pr(c, "k_vg_offsets"); k_vg_offsets<<<n_lanes, 1024, 0, s>>>(W.seg_count, seg_off, W.lane_base, nseg, n_lanes, nullptr, c->d_lane, which); }
+    { LLProf pr(c, "k_vg_lane_prefix"); k_vg_lane_prefix<<<1, 256, 0, s>>>(W.lane_base, n_lanes); }
+    { LLProf pr(c, "k_vg_centroid"); k_vg_centroid<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W.keys[sorted], W.vals[sorted], W.head, W.scan, W.lane_base, W.in, out, out_cap, n_dev); }
     c->launches += 7;   // + the sort's and the prefix sum's own launches, counted above
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
@@ -936,11 +987,15 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     { LLProf pr(c, "k_map_begin"); k_map_begin<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, m->pose_in, m->valid_mask, m->valid_ind, from_odom, n_lanes); }
     // LM:1814-1822: voxel-filter the incoming clouds
     const float leaf[2] = {c->cfg.line_res, c->cfg.plane_res};
+    MapTwoStreams two(c);   // corner chain on the context's stream, surf chain on the side stream (when the context has one)
     for (int t = 0; t < 2; ++t) {
-        { LLProf pr(c, "k_vg_fill_incoming"); k_vg_fill_incoming<<<dim3(64, n_lanes), 256, 0, s>>>(m->in_cloud[t], m->in_cap[t], m->in_n, t, m->vg_in, m->vg_seg, m->vg_n, m->in_cap[t]); }
-        const int rc = run_voxel_filter(c, n_lanes, m->in_cap[t], 1, nullptr, leaf[t], m->stack[t], m->stack_cap[t], nullptr, t);
+        MapState::VgScratch& W = two.begin(t);
+        { LLProf pr(c, "k_vg_fill_incoming"); k_vg_fill_incoming<<<dim3(64, n_lanes), 256, 0, c->stream>>>(m->in_cloud[t], m->in_cap[t], m->in_n, t, W.in, W.seg, W.n, m->in_cap[t]); }
+        const int rc = run_voxel_filter(c, W, n_lanes, m->in_cap[t], 1, nullptr, leaf[t], m->stack[t], m->stack_cap[t], nullptr, t);
+        two.end(t);
         if (rc) return rc;
     }
+    if (two.failed()) return LL_E_CUDA;
     // LM:1805-1811 local map, LM:1826 guard, LM:1830-1831 search structures
     {
         LLProf pr(c, "k_map_gather");
@@ -951,9 +1006,12 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     { LLProf pr(c, "k_map_guard"); k_map_guard<<<(n_lanes + 31) / 32, 32, 0, s>>>(c->d_lane, n_lanes); }
     c->launches += 5;
     for (int t = 0; t < 2; ++t) {
+        two.begin(t);
         const int rc = ll_build_map_grid(c, m->grid[t], m->frommap[t], (size_t)m->map_cap, 2 + t, n_lanes, m->map_cap);
+        two.end(t);
         if (rc) return rc;
     }
+    if (two.failed()) return LL_E_CUDA;
     MapAssocParams A;
     A.lane = c->d_lane; A.stack[0] = m->stack[0]; A.stack[1] = m->stack[1]; A.frommap[0] = m->frommap[0]; A.frommap[1] = m->frommap[1];
     A.stack_cap[0] = m->stack_cap[0]; A.stack_cap[1] = m->stack_cap[1]; A.map_cap = m->map_cap; A.g[0] = m->grid[0]; A.g[1] = m->grid[1];
@@ -1014,11 +1072,14 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     c->launches += 1;
     // LM:2104-2168: insert + per-cube filter + shift, one CSR rebuild per cloud type
     for (int t = 0; t < 2; ++t) {
-        { LLProf pr(c, "k_vg_fill_rebuild"); k_vg_fill_rebuild<<<dim3(296, n_lanes), 256, 0, s>>>(c->d_lane, m->map_pts[t][cur], m->cube_off[t][cur], m->map_cap, m->stack[t], m->stack_cap[t], t, m->vg_in, m->vg_seg, m->vg_n, m->E); }
+        MapState::VgScratch& W = two.begin(t);
+        { LLProf pr(c, "k_vg_fill_rebuild"); k_vg_fill_rebuild<<<dim3(296, n_lanes), 256, 0, c->stream>>>(c->d_lane, m->map_pts[t][cur], m->cube_off[t][cur], m->map_cap, m->stack[t], m->stack_cap[t], t, W.in, W.seg, W.n, m->E); }
         c->launches += 1;
-        const int rc = run_voxel_filter(c, n_lanes, m->E, MAP_NUM, m->valid_mask, leaf[t], m->map_pts[t][nxt], m->map_cap, m->cube_off[t][nxt], -1);
+        const int rc = run_voxel_filter(c, W, n_lanes, m->E, MAP_NUM, m->valid_mask, leaf[t], m->map_pts[t][nxt], m->map_cap, m->cube_off[t][nxt], -1);
+        two.end(t);
         if (rc) return rc;
     }
+    if (two.failed()) return LL_E_CUDA;
     m->buf = nxt;
     LL_CUDA_CHECK(c, cudaGetLastError());
     return LL_OK;
@@ -1122,8 +1183,9 @@ extern "C" int ll_map_insert(ll_ctx* c, ll_cloud_view corner, ll_cloud_view surf
         LL_CUDA_CHECK(c, cudaMemsetAsync(m->valid_mask, 0, MAP_NUM, c->stream));
         const int cur = m->buf, nxt = m->buf ^ 1;
         for (int t = 0; t < 2; ++t) {
-            k_vg_fill_rebuild<<<dim3(296, 1), 256, 0, c->stream>>>(c->d_lane, m->map_pts[t][cur], m->cube_off[t][cur], m->map_cap, m->stack[t], m->stack_cap[t], t, m->vg_in, m->vg_seg, m->vg_n, m->E);
-            const int rc = run_voxel_filter(c, 1, m->E, MAP_NUM, m->valid_mask, 1.0f, m->map_pts[t][nxt], m->map_cap, m->cube_off[t][nxt], -1);
+            MapState::VgScratch& W = m->vgs[0];
+            k_vg_fill_rebuild<<<dim3(296, 1), 256, 0, c->stream>>>(c->d_lane, m->map_pts[t][cur], m->cube_off[t][cur], m->map_cap, m->stack[t], m->stack_cap[t], t, W.in, W.seg, W.n, m->E);
+            const int rc = run_voxel_filter(c, W, 1, m->E, MAP_NUM, m->valid_mask, 1.0f, m->map_pts[t][nxt], m->map_cap, m->cube_off[t][nxt], -1);
             if (rc) return rc;
         }
         m->buf = nxt;
