@@ -58,7 +58,8 @@ struct LmShared {
     double red[LM_THREADS / 32][LM_NRED];
     double out[LM_NRED];
     double pub[2][LM_NRED];   // cluster mode: this CTA's partial sums as its peers read them (slot = parity of the collective)
-    int go;
+    int go, go2;   // decisions of the step phase / of the accept phase (two words: the next step phase may write go while
+                   // slower threads still read go2)
     int comm_dead;
 };
 __device__ __forceinline__ unsigned long long lm_globaltimer()
@@ -621,11 +622,11 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
                     go = 1;
                 }
             }
-            S.go = go;
+            S.go2 = go;
         }
         __syncthreads();
         LMT(5);
-        if (S.go == 0) break;
+        if (S.go2 == 0) break;
     }
     if (clus) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still be reading its shared memory
     if (tid == 0 && part == 0) {  // every part holds the same result; one writes it
