@@ -182,6 +182,11 @@ int ll_debug_assoc(ll_ctx* ctx, int lane, int* corner, int corner_cap, int* plan
 /* Parity: feature indices (into the lane's ring-sorted cloud) of the last extraction of lane `lane`.
  * counts = {n_full, n_sharp, n_less_sharp, n_flat, n_less_flat}; index arrays sized scan_line * 12 / 120 / 24 (or NULL). */
 int ll_debug_features(ll_ctx* ctx, int lane, int counts[5], int* sharp_idx, int* less_sharp_idx, int* flat_idx);
+/* Parity of the map filter's device-wide primitives (csrc/ll_sort.cuh) on their own: sorts n (key, value) pairs by the low
+ * `key_bits` bits of the key, stable, in place on the host arrays; if scan_io is not NULL it is replaced by its exclusive
+ * prefix sum (n_scan ints).  The device arrays are sized for `capacity` >= n elements, as in the filter, so the kernels'
+ * device-side length handling is exercised too. */
+int ll_debug_sort_scan(ll_ctx* ctx, unsigned long long* keys_io, int* vals_io, int n, int key_bits, int capacity, int* scan_io, int n_scan);
 /* Raw CUDA stream of the context (cudaStream_t as void*), so a host can order its own work after ours. */
 void* ll_cuda_stream(ll_ctx* ctx);
 /* Kernels of this library launched by the last call (no synchronisation; the same number ll_stats::kernel_launches reports). */

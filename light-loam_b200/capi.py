@@ -18,7 +18,7 @@ LL_W_FEW_CORRESPONDENCES = 1
 SYMBOLS = ["ll_default_config", "ll_create", "ll_destroy", "ll_strerror", "ll_last_error", "ll_get_last_stats", "ll_reset",
            "ll_extract_features", "ll_fetch_pointcloud2", "ll_odometry_step", "ll_mapping_step", "ll_map_insert", "ll_process_scans", "ll_stage_scans",
            "ll_process_staged", "ll_submit_scans", "ll_submit_packed", "ll_collect", "ll_get_lane_status", "ll_debug_features", "ll_pool_upload", "ll_process_pool", "ll_profile_enable", "ll_profile_read", "ll_last_timings",
-           "ll_debug_assoc", "ll_cuda_stream", "ll_launch_count", "ll_comm_export", "ll_comm_local_ptr", "ll_comm_attach", "ll_comm_detach", "ll_map_set_slab"]
+           "ll_debug_assoc", "ll_debug_sort_scan", "ll_cuda_stream", "ll_launch_count", "ll_comm_export", "ll_comm_local_ptr", "ll_comm_attach", "ll_comm_detach", "ll_map_set_slab"]
 
 
 class LLConfig(ctypes.Structure):
@@ -87,6 +87,7 @@ def lib():
         L.ll_submit_packed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.ll_get_lane_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.ll_debug_features.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.ll_debug_sort_scan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ll_pool_upload.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(LLCloudView)]
         L.ll_process_pool.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.ll_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -326,6 +327,16 @@ class Context:
         f = np.zeros(self.R * 24, np.int32)
         self._check(self.L.ll_debug_features(self.h, lane, cnt.ctypes.data, s_.ctypes.data, ls.ctypes.data, f.ctypes.data), "ll_debug_features")
         return dict(counts=cnt, sharp_idx=s_[:cnt[1]], less_sharp_idx=ls[:cnt[2]], flat_idx=f[:cnt[3]])
+
+    def debug_sort_scan(self, keys, vals, key_bits=64, capacity=None, scan=None):
+        """The map filter's radix sort / prefix sum on caller data (ll_debug_sort_scan): returns (keys, vals, scan) after the call."""
+        k = np.ascontiguousarray(keys, np.uint64).copy()
+        v = np.ascontiguousarray(vals, np.int32).copy()
+        sc = None if scan is None else np.ascontiguousarray(scan, np.int32).copy()
+        cap = max(len(k), 0 if sc is None else len(sc)) if capacity is None else capacity
+        self._check(self.L.ll_debug_sort_scan(self.h, k.ctypes.data, v.ctypes.data, len(k), key_bits, cap, None if sc is None else sc.ctypes.data,
+                                              0 if sc is None else len(sc)), "ll_debug_sort_scan")
+        return k, v, sc
 
     def debug_assoc(self, lane=0):
         c = np.zeros((self.R * 12, 2), np.int32)

@@ -1283,3 +1283,44 @@ extern "C" int ll_map_set_slab(ll_ctx* c, double x_lo, double x_hi)
     c->map->slab_lo = x_lo; c->map->slab_hi = x_hi;
     return LL_OK;
 }
+
+// Test hook (include/lightloam_b200.h): the radix sort and the prefix sum of the voxel filter on caller data.
+extern "C" int ll_debug_sort_scan(ll_ctx* c, unsigned long long* keys_io, int* vals_io, int n, int key_bits, int capacity, int* scan_io, int n_scan)
+{
+    if (!c || n < 0 || capacity < n || capacity < n_scan || key_bits < 1 || key_bits > 64 || (n > 0 && (!keys_io || !vals_io))) return LL_E_INVAL;
+    LL_CUDA_CHECK(c, cudaSetDevice(c->dev));
+    const long long cap = capacity > 0 ? capacity : 1;
+    u64* keys[2] = {nullptr, nullptr};
+    int* vals[2] = {nullptr, nullptr};
+    int *hist = nullptr, *n_dev = nullptr, *scan = nullptr, *scratch = nullptr;
+    cudaStream_t s = c->stream;
+    int rc = LL_OK;
+#define DB(expr) do { if (rc == LL_OK && (expr) != cudaSuccess) { c->last_error = #expr; rc = LL_E_CUDA; } } while (0)
+    for (int k = 0; k < 2; ++k) { DB(cudaMalloc((void**)&keys[k], sizeof(u64) * cap)); DB(cudaMalloc((void**)&vals[k], sizeof(int) * cap)); }
+    DB(cudaMalloc((void**)&hist, sizeof(int) * llsort::sort_hist_ints(cap)));
+    DB(cudaMalloc((void**)&n_dev, sizeof(int) * 2));
+    DB(cudaMalloc((void**)&scan, sizeof(int) * cap));
+    DB(cudaMalloc((void**)&scratch, sizeof(int) * llsort::scan_scratch_ints(cap)));
+    if (rc == LL_OK) {
+        const int nn[2] = {n, n_scan};
+        DB(cudaMemcpyAsync(n_dev, nn, sizeof(nn), cudaMemcpyHostToDevice, s));
+        DB(cudaMemsetAsync(keys[0], 0xFF, sizeof(u64) * cap, s));
+        if (n > 0) { DB(cudaMemcpyAsync(keys[0], keys_io, sizeof(u64) * n, cudaMemcpyHostToDevice, s)); DB(cudaMemcpyAsync(vals[0], vals_io, sizeof(int) * n, cudaMemcpyHostToDevice, s)); }
+        int shifts[8], ns = 0, launches = 0;
+        for (int sh = 0; sh < key_bits; sh += 8) shifts[ns++] = sh;
+        const int res = llsort::sort_pairs(keys, vals, cap, n_dev, shifts, ns, hist, s, &launches);
+        if (n > 0) { DB(cudaMemcpyAsync(keys_io, keys[res], sizeof(u64) * n, cudaMemcpyDeviceToHost, s)); DB(cudaMemcpyAsync(vals_io, vals[res], sizeof(int) * n, cudaMemcpyDeviceToHost, s)); }
+        if (scan_io && n_scan > 0) {
+            DB(cudaMemcpyAsync(scan, scan_io, sizeof(int) * n_scan, cudaMemcpyHostToDevice, s));
+            llsort::scan_exclusive(scan, scan, cap, llsort::LenSpec{n_dev + 1, 0}, scratch, s);
+            DB(cudaMemcpyAsync(scan_io, scan, sizeof(int) * n_scan, cudaMemcpyDeviceToHost, s));
+        }
+        DB(cudaStreamSynchronize(s));
+        DB(cudaGetLastError());
+    }
+#undef DB
+    for (int k = 0; k < 2; ++k) { cudaFree(keys[k]); cudaFree(vals[k]); }
+    cudaFree(hist); cudaFree(n_dev); cudaFree(scan); cudaFree(scratch);
+    return rc;
+}
+

@@ -302,3 +302,25 @@ def test_graph_replay_equals_eager_launches(ll, monkeypatch, mapping):
         ctx.close()
     assert np.array_equal(out["1"], out["0"])
     assert np.abs(out["1"][-1, 0, 4:7]).max() > 0.1     # the trajectory moved
+
+
+@pytest.mark.parametrize("n,key_bits,cap_extra", [(0, 32, 10), (1, 64, 0), (2047, 31, 1), (2048, 44, 0), (2049, 48, 4097), (100003, 56, 50000), (700001, 64, 0)])
+def test_radix_sort_and_prefix_sum_primitives(ll, n, key_bits, cap_extra):
+    """csrc/ll_sort.cuh on its own (the hand-written replacements of cub::DeviceRadixSort / DeviceScan in the map filter): random
+    keys with many duplicates, sizes around the 2048-element tiles, arrays larger than the data (device-side lengths).
+    Bar: bit-exact against numpy's stable sort / cumsum."""
+    rng = np.random.default_rng(n + key_bits)
+    ctx = ll.Context(scan_line=16)
+    mask = np.uint64((1 << key_bits) - 1) if key_bits < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    keys &= mask
+    if n > 10:
+        keys[rng.integers(0, n, size=n // 2)] = keys[rng.integers(0, n, size=n // 2)]     # duplicates: stability matters
+        keys[: n // 8] &= np.uint64(0xFF)                                                # and a crowd in the low digit only
+    vals = np.arange(n, dtype=np.int32)
+    scan_in = rng.integers(0, 3, size=n + 5, dtype=np.int32)
+    k, v, sc = ctx.debug_sort_scan(keys, vals, key_bits=key_bits, capacity=n + 5 + cap_extra, scan=scan_in)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
+    assert np.array_equal(sc, np.concatenate([[0], np.cumsum(scan_in[:-1])]).astype(np.int32))
+    ctx.close()
