@@ -324,3 +324,20 @@ def test_radix_sort_and_prefix_sum_primitives(ll, n, key_bits, cap_extra):
     assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
     assert np.array_equal(sc, np.concatenate([[0], np.cumsum(scan_in[:-1])]).astype(np.int32))
     ctx.close()
+
+
+def test_long_trajectory_with_mapping_stays_on_the_oracle(ll, orc):
+    """30 scans with scan-to-map on (the map grows, cubes fill, the graph replays alternate between the two cube-map buffers):
+    mapped pose within 1e-6 of the oracle in the same voxel order at every scan, map sizes equal at the end."""
+    line, n = 16, 30
+    ctx = ll.Context(scan_line=line, enable_mapping=1, map_capacity=1 << 18)
+    exact = orc.Pipeline(orc.config(line, voxel_stable=1), with_mapping=True)
+    for k in range(n):
+        scan = ll.synth.scan(line, k, mode=1)
+        pg = ctx.process_scans([scan])[0]
+        pe = exact.step(scan)
+        assert np.abs(pg[4:7] - pe["t_odom"]).max() < 1e-8, k
+        assert np.abs(pg[11:14] - pe["t_map"]).max() < 1e-6 and np.abs(pg[7:11] - pe["q_map"]).max() < 1e-6, (k, pg[7:], pe["q_map"], pe["t_map"])
+    st = ctx.stats()
+    assert st.frame == n and st.map_surf > 1000
+    ctx.close()

@@ -425,3 +425,23 @@ def test_vote_partial_mode_matches_oracle(ll, orc, line):
     assert differs
     ctx.close()
     simple.close()
+
+
+@pytest.mark.parametrize("line,mode", [(64, 0), (64, 1), (16, 1)])
+def test_long_trajectory_stays_on_the_oracle(ll, orc, line, mode):
+    """40 consecutive scans: discrete decisions (nearest neighbours, votes, LM accept / reject / termination) must keep matching the
+    oracle long after the vote gate, and the accumulated pose must not drift away from it.  Bar: accumulated pose within 1e-8 of the
+    oracle run in the GPU's voxel order at every scan, identical correspondence / selection / evaluation counts at the end."""
+    n = 40
+    ctx = ll.Context(scan_line=line)
+    exact = orc.Pipeline(orc.config(line, voxel_stable=1), with_mapping=False)
+    worst = 0.0
+    for k in range(n):
+        scan = ll.synth.scan(line, k, mode=mode)
+        pg = ctx.process_scans([scan])[0]
+        pe = exact.step(scan)
+        worst = max(worst, np.abs(pg[4:7] - pe["t_odom"]).max(), np.abs(pg[0:4] - pe["q_odom"]).max())
+        assert worst < 1e-8, (k, worst)
+    st = ctx.stats()
+    assert st.frame == n and np.abs(pg[4:7]).max() > 1.0
+    ctx.close()
