@@ -210,7 +210,7 @@ __global__ void k_index_count(IndexSet S, LaneState* lane)
         }
     }
 }
-__global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
+__global__ void __launch_bounds__(256) k_index_partial(IndexSet S, LaneState* lane)
 {
     __shared__ int ws[40];
     const int b = blockIdx.y;
@@ -226,6 +226,10 @@ __global__ void __launch_bounds__(256) k_index_partial(IndexSet S)
     // the first chunk of each table also decodes the ring elevation bands (complete since k_index_count): thread r turns
     // ring r's tangents into angles, then one thread walks the rings.  An empty ring gets an empty band at its
     // predecessor's upper edge, so ordered bands stay ordered through the gaps.
+    if (chunk == 0 && t == 0 && threadIdx.x == 0) {   // once per lane and step: the selection counters the vote CTAs add to
+        LaneState& L = lane[b];
+        L.plane_sel[0] = L.plane_sel[1] = L.plane_sel[2] = 0;
+    }
     if (chunk == 0) {   // block-uniform
         __shared__ float s_lo[LL_MAX_RINGS], s_hi[LL_MAX_RINGS];
         __shared__ unsigned char s_has[LL_MAX_RINGS];
@@ -1254,10 +1258,9 @@ __global__ void __launch_bounds__(PREP_THREADS) k_odom_prep(OdomParams P)
         L.n_blocks = ncorner + nplane;
         L.n_corner_corr = ncorner;
         L.n_plane_corr = nplane;
-        L.n_plane_sel = vote ? 0 : nplane;       // k_odom_vote adds the selected ones
         L.corner_corr[P.outer] = ncorner;
         L.plane_corr[P.outer] = nplane;
-        L.plane_sel[P.outer] = vote ? 0 : nplane;
+        L.plane_sel[P.outer] = vote ? 0 : nplane;   // the vote kernels add the selected ones
     }
 }
 
@@ -1334,7 +1337,152 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_odom_vote(OdomParams P)
     }
     if (sel) atomicAdd(&nsel_s, sel);
     __syncthreads();
-    if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
+    if (tid == 0 && nsel_s) atomicAdd(&L.plane_sel[P.outer], nsel_s);
+}
+
+// k_odom_prep + k_odom_vote in one launch (the default vote mode): one CTA per (region, lane).  Every CTA counts the lane's
+// matches itself (two block scans over the association tables), so it knows the compacted order; it then writes the records of
+// ITS share - a tenth of the corners and the plane matches of its vote region - and keeps the region's Corre_Match points in
+// shared memory for the vote instead of sending them through global memory to a second kernel.  Same records, same votes.
+__global__ void __launch_bounds__(VOTE_THREADS) k_odom_prep_vote(OdomParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int ws[40];
+    __shared__ int nsel_s;
+    const int b = blockIdx.y, reg = blockIdx.x, tid = threadIdx.x;
+    LaneState& L = P.lane[b];
+    if (!L.inited || L.err) { if (reg == 0 && tid == 0) L.n_blocks = 0; return; }
+    const int maxc = P.R * LL_SHARP_PER_RING, maxp = P.R * LL_FLAT_PER_RING;
+    const int mcap = maxp / 10 + 16;
+    float4* src = reinterpret_cast<float4*>(smem_raw);
+    float4* tgt = src + mcap;
+    int* votes = reinterpret_cast<int*>(tgt + mcap);
+    const int ns = L.n_sharp, nf = L.n_flat, slot = last_slot(L);
+    const bool vote = L.now_frame > P.graph_from_frame;   // LO:781 / LO:794
+    const float4* sharp = P.sharp + (size_t)b * maxc;
+    const float4* flat = P.flat + (size_t)b * maxp;
+    const float4* lastc = P.lsharp[slot] + (size_t)b * P.R * LL_LSHARP_PER_RING;
+    const float4* lasts = P.lflat[slot] + (size_t)b * P.Nmax;
+    const int* ca = P.corner_assoc + (size_t)b * maxc * 2;
+    int* pa = P.plane_assoc + (size_t)b * maxp * 4;
+    double* blk = P.blocks + (size_t)b * LL_BLOCK_DOUBLES * P.nblk_cap;
+    const int cap = P.nblk_cap;
+    if (tid == 0) nsel_s = 0;
+
+    // ---- corners (LO:556-618): compacted order from a scan over all of them, records for positions [c0, c1) ----------
+    int ncorner = 0;
+    {
+        const int per = (maxc + VOTE_THREADS - 1) / VOTE_THREADS;
+        const int i0 = min(tid * per, ns), i1 = min(i0 + per, ns);
+        int mine = 0;
+        for (int i = i0; i < i1; ++i) mine += ca[i * 2 + 1] >= 0;
+        int pos = block_exclusive_scan(mine, ws, &ncorner);
+        const int c0 = (int)((long long)ncorner * reg / 10), c1 = (int)((long long)ncorner * (reg + 1) / 10);
+        for (int i = i0; i < i1; ++i) {
+            const int2 m = *reinterpret_cast<const int2*>(ca + i * 2);
+            if (m.y < 0) continue;
+            if (pos >= c0 && pos < c1) {
+                const float4 cp = sharp[i], a = lastc[m.x], c = lastc[m.y];
+                blk[0 * cap + pos] = 0.0;
+                blk[1 * cap + pos] = cp.x; blk[2 * cap + pos] = cp.y; blk[3 * cap + pos] = cp.z;
+                blk[4 * cap + pos] = a.x; blk[5 * cap + pos] = a.y; blk[6 * cap + pos] = a.z;
+                blk[7 * cap + pos] = c.x; blk[8 * cap + pos] = c.y; blk[9 * cap + pos] = c.z;
+                blk[10 * cap + pos] = 1.0;
+                if (P.distortion) blk[11 * cap + pos] = point_ratio(cp);   // feature_s, LO:569-573
+            }
+            ++pos;
+        }
+    }
+    // ---- planes: compacted order, this CTA's vote region [r0, r1) (LO:202-215) ----------------------------------------
+    int nplane = 0;
+    const int per = (maxp + VOTE_THREADS - 1) / VOTE_THREADS;
+    const int i0 = min(tid * per, nf), i1 = min(i0 + per, nf);
+    int mine = 0;
+    for (int i = i0; i < i1; ++i) mine += pa[i * 4] >= 0;
+    int pos = block_exclusive_scan(mine, ws, &nplane);
+    const int region_len = nplane / 10;
+    const int r0 = region_len * reg, r1 = reg == 9 ? nplane : region_len * (reg + 1);
+    const int m = r1 - r0;
+    for (int i = i0; i < i1; ++i) {
+        const int4 mt = *reinterpret_cast<const int4*>(pa + i * 4);
+        if (mt.x < 0) continue;
+        if (pos >= r0 && pos < r1) {
+            const float4 cp = flat[i], pj = lasts[mt.x], pl = lasts[mt.y], pm = lasts[mt.z];
+            src[pos - r0] = make_float4(cp.x, cp.y, cp.z, __int_as_float(i));  // Corre_Match src / tgt, LO:753-754 (+ the feature index)
+            tgt[pos - r0] = pj;
+            votes[pos - r0] = 0;
+            // LF:210-211  ljm_norm = (j - l).cross(j - m); normalize()
+            const double ax = (double)pj.x - (double)pl.x, ay = (double)pj.y - (double)pl.y, az = (double)pj.z - (double)pl.z;
+            const double bx = (double)pj.x - (double)pm.x, by = (double)pj.y - (double)pm.y, bz = (double)pj.z - (double)pm.z;
+            double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+            const double z = nx * nx + ny * ny + nz * nz;
+            if (z > 0.0) { const double nn = sqrt(z); nx = nx / nn; ny = ny / nn; nz = nz / nn; }
+            const int o = ncorner + pos;
+            blk[0 * cap + o] = 1.0;
+            blk[1 * cap + o] = cp.x; blk[2 * cap + o] = cp.y; blk[3 * cap + o] = cp.z;
+            blk[4 * cap + o] = pj.x; blk[5 * cap + o] = pj.y; blk[6 * cap + o] = pj.z;
+            blk[7 * cap + o] = nx; blk[8 * cap + o] = ny; blk[9 * cap + o] = nz;
+            blk[10 * cap + o] = 1.0;             // LO:783: weight 1 while now_frame <= 5
+            if (P.distortion) blk[11 * cap + o] = point_ratio(cp);   // feature_s, LO:739-743
+            if (!vote) pa[i * 4 + 3] = 1000;
+        }
+        ++pos;
+    }
+    if (reg == 0 && tid == 0) {
+        L.n_blocks = ncorner + nplane;
+        L.n_corner_corr = ncorner;
+        L.n_plane_corr = nplane;
+        L.corner_corr[P.outer] = ncorner;
+        L.plane_corr[P.outer] = nplane;
+    }
+    if (!vote) {   // every match is selected with weight 1 (LO:781-787)
+        if (tid == 0 && m > 0) atomicAdd(&L.plane_sel[P.outer], m);
+        return;
+    }
+    __syncthreads();
+    if (m <= 0) return;
+    // ---- graph_based_correspondence_vote_simple on the region (LO:165-342), as k_odom_vote ---------------------------------
+    const float t_min = P.vote_t_min;
+    const float g_mid = sqrtf(t_min);
+    for (int k = tid >> 2; k < (m + 1) / 2; k += VOTE_THREADS / 4) {
+        const int q = tid & 3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int row = half == 0 ? k : m - 1 - k;
+            if (half == 1 && row == k) break;
+            const float4 a = src[row], c = tgt[row];
+            int cnt = 0;
+            for (int j = row + 1 + q; j < m; j += 4) {
+                const float4 sj = src[j], tj = tgt[j];
+                const float d1 = sqdist3(a.x, a.y, a.z, sj.x, sj.y, sj.z), d2 = sqdist3(c.x, c.y, c.z, tj.x, tj.y, tj.z);
+                const float ge = fabsf(d1 * rsqrtf(fmaxf(d1, 1e-30f)) - d2 * rsqrtf(fmaxf(d2, 1e-30f)));
+                bool v = ge > g_mid;
+                if (fabsf(ge - g_mid) < 1e-3f) {  // too close to call with the approximation: LO:236-242 to the letter
+                    const float gap = fabsf(sqrtf(d1) - sqrtf(d2));
+                    v = gap * gap >= t_min;
+                }
+                if (v) { ++cnt; atomicAdd(&votes[j], 1); }
+            }
+            if (cnt) atomicAdd(&votes[row], cnt);
+        }
+    }
+    __syncthreads();
+    const float num_selected = 0.90f * (float)m;                    // LO:299-300
+    int sel = 0;
+    for (int k = tid; k < m; k += VOTE_THREADS) {
+        const float fv = (float)votes[k];
+        float w;
+        if (fv > num_selected) w = 0.f;                              // LO:312-316: this and all worse are dropped
+        else if (fv <= 50.f) w = 5.0f;                               // LO:317-318
+        else w = 1.0f;
+        const int o = ncorner + r0 + k;
+        if (w > 0.f) { blk[10 * cap + o] = (double)w; ++sel; }
+        else blk[o] = -1.0;                                          // not selected: no residual block (LO:797-808)
+        pa[__float_as_int(src[k].w) * 4 + 3] = (int)(w * 1000.f);
+    }
+    if (sel) atomicAdd(&nsel_s, sel);
+    __syncthreads();
+    if (tid == 0 && nsel_s) atomicAdd(&L.plane_sel[P.outer], nsel_s);
 }
 
 // graph_based_correspondence_vote_partial (laserMapping.cpp:321-834, graph_construction_partial LM:261-318): the paper-style
@@ -1480,7 +1628,7 @@ __global__ void __launch_bounds__(VP_THREADS) k_odom_vote_partial(OdomParams P, 
     }
     if (sel) atomicAdd(&nsel_s, sel);
     __syncthreads();
-    if (tid == 0 && nsel_s) { atomicAdd(&L.n_plane_sel, nsel_s); atomicAdd(&L.plane_sel[P.outer], nsel_s); }
+    if (tid == 0 && nsel_s) atomicAdd(&L.plane_sel[P.outer], nsel_s);
 }
 
 // grid (lanes, parts): with few lanes `parts` CTAs share one lane's residual blocks and all-reduce the 28 doubles of every
@@ -1669,7 +1817,7 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
         const int gx_surf = (c->Nmax * 5 / 16 + per_block - 1) / per_block;
         const dim3 gidx(S.gx_corner + gx_surf, n_lanes);
         { LLProf pr(c, "k_index_count"); k_index_count<<<gidx, 256, 0, s>>>(S, c->d_lane); }
-        { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
+        { LLProf pr(c, "k_index_partial"); k_index_partial<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S, c->d_lane); }
         { LLProf pr(c, "k_index_scan"); k_index_scan<<<dim3(S.chunk_begin[2], n_lanes), 256, 0, s>>>(S); }
         { LLProf pr(c, "k_index_scatter"); k_index_scatter<<<gidx, 256, 0, s>>>(S, c->d_lane); }
         c->launches += 4;
@@ -1725,8 +1873,17 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
             else k_odom_assoc<6><<<g, assoc_threads, 0, s>>>(P, cblocks, dmax, kmax);
         }
         if (!direct_mode) { LLProf pr(c, "k_odom_assoc_heavy"); k_odom_assoc_heavy<<<heavy_blocks, 256, 0, s>>>(P); }
-        { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
-        if (c->cfg.vote_mode == 1) {
+        // records + vote in one launch for few lanes (two dependent launches less per iteration: 0.440 -> 0.423 ms per scan on one
+        // stream); with many lanes the ten CTAs per lane each repeating the match count cost more than the launch saves
+        // (3.61 vs 3.56 ms per 256-lane step), so the batched path keeps k_odom_prep + k_odom_vote.  LL_VOTE_FUSED = 0 / 1 forces.
+        const char* fv_env = getenv("LL_VOTE_FUSED");
+        const bool fused_vote = c->cfg.vote_mode != 1 && (fv_env ? atoi(fv_env) != 0 : n_lanes <= 16);
+        if (fused_vote) {
+            LLProf pr(c, "k_odom_prep_vote"); k_odom_prep_vote<<<dim3(10, n_lanes), VOTE_THREADS, vote_smem + 64, s>>>(P);
+            c->launches -= 1;   // one launch for the records and the vote (5 counted per iteration below)
+        } else { LLProf pr(c, "k_odom_prep"); k_odom_prep<<<n_lanes, PREP_THREADS, 0, s>>>(P); }
+        if (fused_vote) {
+        } else if (c->cfg.vote_mode == 1) {
             const int mcap = c->R * LL_FLAT_PER_RING / 10 + 16;
             const size_t vp_smem = ((size_t)mcap * mcap + (size_t)mcap * (VP_WORDS + 3)) * 4;
             if (!c->vp_attr_set) { LL_CUDA_CHECK(c, cudaFuncSetAttribute(k_odom_vote_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vp_smem)); c->vp_attr_set = true; }

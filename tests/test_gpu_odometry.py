@@ -19,10 +19,12 @@ def _ang(qa, qb):
                                                   (64, 9, None, "many-lanes"), (16, 8, None, "many-lanes"), (64, 8, None, "cluster2")])
 def test_fused_pipeline_trajectory_matches_oracle(ll, orc, line, n, az, lm_threads, monkeypatch):
     # one lane runs the single-stream forms by default: a warp per query (k_odom_assoc_direct) and the solve spread over a
-    # thread-block cluster of 8; "many-lanes" forces the forms the batched path uses (thread pass + queue, one CTA per solve)
+    # thread-block cluster of 8, records + vote in one kernel; "many-lanes" forces the forms the batched path uses (thread pass +
+    # queue, separate record and vote kernels, one CTA per solve)
     if lm_threads == "many-lanes":
         monkeypatch.setenv("LL_ASSOC_DIRECT", "0")
         monkeypatch.setenv("LL_LM_CLUSTER", "1")
+        monkeypatch.setenv("LL_VOTE_FUSED", "0")
     elif lm_threads == "cluster2":
         monkeypatch.setenv("LL_LM_CLUSTER", "2")
     elif lm_threads:   # the CTA shape the solve uses when there are more scan streams than SMs (bench: 256 lanes)
