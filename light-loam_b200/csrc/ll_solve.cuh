@@ -249,19 +249,9 @@ __device__ __forceinline__ int lm_functor_s(int type, const double* rec /* cp, p
     res[0] = ((lp[0] - j[0]) * n[0] + (lp[1] - j[1]) * n[1] + (lp[2] - j[2]) * n[2]) * T(rec[9]);
     return 1;
 }
-// one block of the de-skew mode: cost (+ JtJ / Jtr when FULL) into acc
-template <bool FULL>
-__device__ __noinline__ void lm_block_distort(int type, const double* rec, double s, const double* x, double acc[LM_NRED])
+// one block of the de-skew mode: cost, JtJ and Jtr into acc
+static __device__ __noinline__ void lm_block_distort(int type, const double* rec, double s, const double* x, double acc[LM_NRED])
 {
-    if (!FULL) {
-        double r[3];
-        const int nr = lm_functor_s<double>(type, rec, s, x, x + 4, r);
-        double ss = 0.0;
-        for (int k = 0; k < nr; ++k) ss += r[k] * r[k];
-        double sq;
-        acc[27] += 0.5 * lm_huber(ss, sq);
-        return;
-    }
     LmJet q[4], t[3], r[3];
     for (int k = 0; k < 4; ++k) q[k] = LmJet(x[k], k);
     for (int k = 0; k < 3; ++k) t[k] = LmJet(x[4 + k], 4 + k);
@@ -290,7 +280,7 @@ __device__ __forceinline__ void lm_load_record(LmRecord& r, const double* __rest
 #pragma unroll
     for (int k = 0; k < 11; ++k) r.v[k] = __ldg(blk + (size_t)k * cap + i);
 }
-template <bool FULL, bool DIST = false>
+template <bool DIST = false>
 __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, int cap, int nb, const double* x, double acc[LM_NRED], int part = 0, int nparts = 1)
 {
 #pragma unroll
@@ -305,7 +295,7 @@ __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, in
         if (i + stride < nb) lm_load_record(nxt, blk, cap, i + stride);
         const int type = (int)cur.v[0];
         if (DIST && (type == 0 || type == 1)) {   // de-skew mode: per-point interpolation ratio s in record slot 11
-            lm_block_distort<FULL>(type, &cur.v[1], __ldg(blk + (size_t)11 * cap + i), x, acc);
+            lm_block_distort(type, &cur.v[1], __ldg(blk + (size_t)11 * cap + i), x, acc);
         } else
         if (type >= 0) {  // dense mapping records: type -1 = slot without a correspondence
         const double cpx = cur.v[1], cpy = cur.v[2], cpz = cur.v[3];
@@ -325,11 +315,9 @@ __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, in
             const double s = (r0 * r0 + r1 * r1) + r2 * r2;
             double sq;
             acc[27] += 0.5 * lm_huber(s, sq);
-            if (FULL) {
-                lm_row(acc, 0.0, -ez, ey, r0, Rx, Ry, Rz, sq);
-                lm_row(acc, ez, 0.0, -ex, r1, Rx, Ry, Rz, sq);
-                lm_row(acc, -ey, ex, 0.0, r2, Rx, Ry, Rz, sq);
-            }
+            lm_row(acc, 0.0, -ez, ey, r0, Rx, Ry, Rz, sq);
+            lm_row(acc, ez, 0.0, -ex, r1, Rx, Ry, Rz, sq);
+            lm_row(acc, -ey, ex, 0.0, r2, Rx, Ry, Rz, sq);
         } else {
             // type 1 LidarPlaneFactor_modify: r = w (lp - j) . n ; type 2 LidarPlaneNormFactor: r = n . lp + d
             const double r0 = type == 1 ? ((lx - ax) * bx + (ly - ay) * by + (lz - az) * bz) * w : (ax * lx + ay * ly + az * lz) + w;
@@ -339,7 +327,7 @@ __device__ __forceinline__ void lm_accumulate(const double* __restrict__ blk, in
             double sq;
             const double rho = lm_huber(0.0 + r0 * r0, sq);
             acc[27] += twice ? rho : 0.5 * rho;
-            if (FULL) lm_row(acc, d0, d1, d2, r0, Rx, Ry, Rz, twice ? sq * 1.4142135623730951 : sq);
+            lm_row(acc, d0, d1, d2, r0, Rx, Ry, Rz, twice ? sq * 1.4142135623730951 : sq);
         }
         }
         cur = nxt;
@@ -361,35 +349,27 @@ __device__ __forceinline__ void lm_fold(double (&v)[32], int lane)
         v[k] = keep + shfl_xor_f64(send, M);
     }
 }
-template <bool FULL>
 __device__ __forceinline__ void lm_reduce(LmShared& S, double acc[LM_NRED])
 {
     const int lane = lane_id(), w = warp_id();
-    if (FULL) {
-        double v[32];
+    double v[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = k < LM_NRED ? acc[k] : 0.0;
-        lm_fold<32, 16>(v, lane);
-        lm_fold<16, 8>(v, lane);
-        lm_fold<8, 4>(v, lane);
-        lm_fold<4, 2>(v, lane);
-        lm_fold<2, 1>(v, lane);
-        // the lane's value index: bit 4 of the lane picked the upper half of 32, bit 3 of 16, ... bit 0 of 2
-        const int idx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
-        if (idx < LM_NRED) S.red[w][idx] = v[0];
-    } else {
-        double v = acc[27];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += shfl_down_f64(v, d);
-        if (lane == 0) S.red[w][27] = v;
-    }
+    for (int k = 0; k < 32; ++k) v[k] = k < LM_NRED ? acc[k] : 0.0;
+    lm_fold<32, 16>(v, lane);
+    lm_fold<16, 8>(v, lane);
+    lm_fold<8, 4>(v, lane);
+    lm_fold<4, 2>(v, lane);
+    lm_fold<2, 1>(v, lane);
+    // the lane's value index: bit 4 of the lane picked the upper half of 32, bit 3 of 16, ... bit 0 of 2
+    const int idx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+    if (idx < LM_NRED) S.red[w][idx] = v[0];
     __syncthreads();
-    if (threadIdx.x < LM_NRED && (FULL || threadIdx.x == 27)) {
-        double v = 0.0;
+    if (threadIdx.x < LM_NRED) {
+        double t = 0.0;
         const int nw = (int)blockDim.x >> 5;
 #pragma unroll 4
-        for (int ww = 0; ww < nw; ++ww) v += S.red[ww][threadIdx.x];
-        S.out[threadIdx.x] = v;
+        for (int ww = 0; ww < nw; ++ww) t += S.red[ww][threadIdx.x];
+        S.out[threadIdx.x] = t;
     }
     __syncthreads();
 }
@@ -498,9 +478,9 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
     auto norm7 = [](const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); };
 
     // IterationZero: cost, gradient, Jacobian (as JtJ) at x
-    lm_accumulate<true, DIST>(blk, cap, nb, S.x, acc, part, nparts);
+    lm_accumulate<DIST>(blk, cap, nb, S.x, acc, part, nparts);
     LMT(0);
-    lm_reduce<true>(S, acc);
+    lm_reduce(S, acc);
     if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
     if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
     LMT(1);
@@ -577,9 +557,9 @@ static __device__ __noinline__ void lm_solve(const double* blk, int cap, int nb,
         // first and the Jacobian only once the step is accepted; accepted steps are the rule (and a cost-only pass costs
         // nearly as much as a full one: the records dominate), so the Jacobian sums are taken speculatively and simply
         // dropped when the step is rejected.  Same numbers, one pass and one reduction per iteration instead of two.
-        lm_accumulate<true, DIST>(blk, cap, nb, S.cand, acc, part, nparts);
+        lm_accumulate<DIST>(blk, cap, nb, S.cand, acc, part, nparts);
         LMT(3);
-        lm_reduce<true>(S, acc);
+        lm_reduce(S, acc);
         if (dist) lm_allreduce(S, *comm, comm_b, part, ++seq, 0, L);
         if (clus) lm_allreduce_cluster(S, nparts, ++seq, 0);
         LMT(4);
