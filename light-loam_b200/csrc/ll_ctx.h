@@ -89,6 +89,7 @@ struct ll_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
+    int cluster_ok[3] = {-1, -1, -1};   // can the device run the solve kernels (odometry, odometry de-skew, mapping) as clusters? -1 = not asked yet
     int launches = 0;
     int pre_launches = 0;     // launches issued by the staging half of a call, folded into `launches` by the processing half
     float vote_t_min = 0.f;   // smallest fp32 t with expf(-t) < 0.96f on this host's libm (LO:239-242)

@@ -1038,6 +1038,10 @@ static int mapping_frame(ll_ctx* c, int n_lanes, int from_odom)
     // one GPU: the parts of a lane are the CTAs of a thread-block cluster and sum through distributed shared memory (no
     // mailbox, no cooperative launch); the mailbox path stays for slab sharding over several GPUs (and LL_LM_PARTS)
     comm.cluster = (m->gworld == 1 && !getenv("LL_LM_PARTS")) ? lm_cluster_size(n_lanes, n_sm) : 1;
+    if (comm.cluster > 1) {
+        if (c->cluster_ok[2] < 0) c->cluster_ok[2] = lm_cluster_fits(k_lm_solve_map, 8, LM_THREADS) ? 1 : 0;
+        if (!c->cluster_ok[2]) comm.cluster = 1;
+    }
     if (comm.cluster > 1) { parts = comm.cluster; comm.nparts = 1; }
     else if (m->gworld == 1 && !getenv("LL_LM_PARTS")) { parts = 1; comm.nparts = 1; }   // more lanes than half the SMs: one CTA per lane
     const bool dist = comm.cluster <= 1 && comm.gworld * comm.nparts > 1;

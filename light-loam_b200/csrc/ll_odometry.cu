@@ -1785,7 +1785,12 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     const int lm_threads_used = lm_parts > 1 ? (getenv("LL_LM_THREADS") ? lm_threads : 128) : lm_threads;   // split: ~1 block per thread
     // Few lanes (the single-stream path): the CTAs of a thread-block cluster share a lane's blocks and sum their 28 doubles
     // through distributed shared memory - one hardware cluster barrier per evaluation, no mailbox, no cooperative launch
-    const int lm_cluster = lm_parts > 1 ? 1 : lm_cluster_size(n_lanes, n_sm);
+    int lm_cluster = lm_parts > 1 ? 1 : lm_cluster_size(n_lanes, n_sm);
+    if (lm_cluster > 1) {
+        int& ok = c->cluster_ok[P.distortion ? 1 : 0];
+        if (ok < 0) ok = (P.distortion ? lm_cluster_fits(k_lm_solve_odom<true>, 8, LM_THREADS) : lm_cluster_fits(k_lm_solve_odom<false>, 8, LM_THREADS)) ? 1 : 0;
+        if (!ok) lm_cluster = 1;
+    }
     comm.cluster = lm_cluster;
     int lm_cluster_threads = ((c->R * (LL_SHARP_PER_RING + LL_FLAT_PER_RING) + lm_cluster - 1) / lm_cluster + 63) / 64 * 64;   // ~1 block per thread
     lm_cluster_threads = lm_cluster_threads < 64 ? 64 : (lm_cluster_threads > LM_THREADS ? LM_THREADS : lm_cluster_threads);

@@ -637,6 +637,21 @@ static inline cudaError_t lm_launch_cluster(void (*kern)(KArgs...), int n_lanes,
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
+// Can the device schedule a cluster of `parts` CTAs of `kern` at all (enough SMs per GPC, MIG slices, ...)?  Asked once per
+// kernel and context; a refusal makes the caller fall back to one CTA per problem instead of failing the launch.
+template <typename... KArgs>
+static inline bool lm_cluster_fits(void (*kern)(KArgs...), int parts, int threads)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, parts); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)parts; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return n >= 1;
+}
 // CTAs per cluster for a solve over n_lanes problems
 // (LL_LM_CLUSTER overrides; 1 = off)
 static inline int lm_cluster_size(int n_lanes, int n_sm)
