@@ -2,14 +2,16 @@
 //
 //   k_map_begin     LM:1581 transformAssociateToMap, LM:1584-1779 centre cube + shifts, LM:1781-1803 valid cubes
 //   voxel grid      LM:1814-1822 (incoming clouds) and LM:2155-2168 (every valid cube): pcl::VoxelGrid restated as
-//                   bbox (atomics) -> voxel id -> stable radix sort of (lane, segment, voxel id) -> run-sum centroids
+//                   bbox (per-thread boxes, warp hand-over) -> voxel id -> stable radix sort of (lane, segment, voxel id)
+//                   over a compact key array -> run heads -> prefix sum -> run-sum centroids
 //   k_map_gather    LM:1805-1811 concatenation of the 5x5x3 valid cubes into the local map
 //   grid build      kdtree*FromMap->setInputCloud (LM:1830-1831) -> hashed uniform grid, cell 1.05 m (>= the 1 m
 //                   acceptance radius of LM:1884 / LM:1952, so one 27-cell pass is exact)
 //   k_map_assoc     LM:1877-1940 / LM:1943-2055: pointAssociateToMap, exact 5-NN, line fit (3x3 symmetric eigen,
 //                   lambda2 > 3 lambda1) -> LidarEdgeFactor record; plane fit (5x3 pivoted Householder QR, all
 //                   residuals <= 0.2) -> LidarPlaneNormFactor record; one warp per stack point, dense records
-//   k_lm_solve_map  ceres::Solve LM:2079-2087 (shared LM controller, ll_solve.cuh)
+//   k_lm_solve_map  ceres::Solve LM:2079-2087 (shared LM controller, ll_solve.cuh): a thread-block cluster per lane on one GPU,
+//                   mailbox all-reduce across GPUs when the map is sharded by slab
 //   k_map_end       LM:2101 transformUpdate
 //   rebuild         LM:2104-2168: insert the stack points into their cubes, voxel-filter every valid cube, and
 //                   re-emit the whole cube array as CSR (cube_off + points) with this frame's shift applied
@@ -17,7 +19,8 @@
 // The cube map is stored per lane and cloud type as CSR over the 21 x 21 x 11 logical cube array and rebuilt once per
 // frame (a streaming copy of the map), which makes the reference's pointer-rotation shifts and per-cube filters one
 // pass.  The sort and the prefix sum of the voxel filter are the hand-written ones of ll_sort.cuh (stable LSD radix
-// sort over the key digits in use, three-level scan): no library call on the path.
+// sort over the key digits in use, three-level scan): no library call on the path.  Contexts of up to 16 lanes run the
+// corner and the surf chain of a frame on two streams (MapTwoStreams).
 #include <limits.h>
 #include <math.h>
 #include <string.h>

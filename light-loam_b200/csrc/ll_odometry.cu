@@ -1772,9 +1772,10 @@ int ll_launch_odometry(ll_ctx* c, int n_lanes)
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->dev);
     const int lm_threads = getenv("LL_LM_THREADS") ? atoi(getenv("LL_LM_THREADS")) : (n_lanes > n_sm ? 256 : LM_THREADS);
-    // Splitting a solve over several CTAs (LL_LM_PARTS = 2..16, lanes x parts <= SMs) pays for the 10k-block scan-to-map
-    // problems, not here: with ~1900 blocks the mailbox all-reduce of every evaluation costs more than the split saves
-    // (single stream on B200: 0.124 ms per solve with 16 parts against 0.074 ms with one CTA), so the default is 1.
+    // Splitting a solve over several CTAs through the MAILBOX (LL_LM_PARTS = 2..16, lanes x parts <= SMs; the form the
+    // multi-GPU scan-to-map solve uses) does not pay here: with ~1900 blocks the global-memory all-reduce of every evaluation
+    // costs more than the split saves (single stream on B200: 0.124 ms per solve with 16 parts against 0.074 ms with one
+    // CTA), so its default is 1.  The split that does pay on one GPU is the thread-block cluster below.
     int lm_parts = 1;
     if (const char* e = getenv("LL_LM_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= LM_MAX_PARTS && v * n_lanes <= n_sm) lm_parts = v; }
     LmComm comm;
