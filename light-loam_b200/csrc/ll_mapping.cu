@@ -832,6 +832,7 @@ int ll_map_alloc(ll_ctx* c)
     m->stack_cap[0] = m->in_cap[0];
     m->stack_cap[1] = m->in_cap[1];
     m->E = m->map_cap + m->stack_cap[1];
+    if ((long long)c->B * m->E > (long long)INT_MAX) { c->last_error = "mapping: lanes x (map_capacity + max_points) exceeds 2^31 - 1 elements"; delete m; c->map = nullptr; return LL_E_INVAL; }   // the filter's positions are ints
 #define MK(expr)                                                              \
     do {                                                                      \
         cudaError_t e__ = (expr);                                             \
